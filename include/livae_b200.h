@@ -1,0 +1,183 @@
+/*
+ * livae_b200.h -- C ABI of liblivae_sm100.so, the B200 (sm_100a) kernels under the
+ * LI-VAE rVAE/VAE training-step hot path.
+ *
+ * The reference (jerrydzhang/LI-VAE) is pure Python/PyTorch and exposes NO FFI or
+ * operator/plugin layer; the drop-in boundary towards users is the
+ * Python API in li-vae_b200/livae/.  This header is the thin C-ABI underneath those
+ * classes: plain device pointers and sizes, no torch types.  Each entry point cites
+ * the reference code (path under /root/reference, file:line) whose arithmetic it
+ * replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all activation tensors are NHWC ("pixels x channels"), contiguous;
+ *     1-channel images are therefore identical to the reference's NCHW layout;
+ *   - `dt` selects the storage type of activations/packed weights:
+ *       LIVAE_F32 (0) float, LIVAE_F16 (1) __half, LIVAE_BF16 (2) __nv_bfloat16;
+ *     accumulation is always fp32, parameters and their gradients are always fp32
+ *     in torch's own layouts (Conv2d [Cout,Cin,kh,kw], ConvTranspose2d
+ *     [Cin,Cout,kh,kw], Linear [out,in] with NCHW flatten order);
+ *   - return 0 on success, <0 argument error, >0 cudaError_t; message via
+ *     livae_last_error() (thread local).  Nothing is allocated, retained or freed
+ *     by the library; workspaces are passed in.  All work is enqueued on `stream`.
+ */
+#ifndef LIVAE_B200_H
+#define LIVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* livae_stream_t; /* cudaStream_t */
+
+enum { LIVAE_F32 = 0, LIVAE_F16 = 1, LIVAE_BF16 = 2 };
+enum { LIVAE_ACT_NONE = 0, LIVAE_ACT_RELU = 1, LIVAE_ACT_SIGMOID = 2 };
+
+/* conv "kinds": which torch weight layout is read and which side is the strided one */
+enum {
+  LIVAE_CONV = 0,        /* nn.Conv2d, zero padding                      (model.py:204,207,290-296) */
+  LIVAE_CONVT = 2        /* nn.ConvTranspose2d(k4,s2,p1)                 (model.py:90-96) */
+};
+
+int livae_abi_version(void);
+const char* livae_last_error(void);
+/* kernels launched by this library since load (bench.py reports the delta as gpu_launches) */
+int64_t livae_launch_count(void);
+/* 1 if the running device is sm_100 (B200); kernels refuse to launch otherwise */
+int livae_device_ok(void);
+
+/* ---- a1: peak-centred integer patch gather ------------------------------------------
+ * replaces PatchDataset.__getitem__ with transform=None (data.py:211-250): whole-image
+ * translate + center_crop == float32(img)[cy-P/2:cy+P/2, cx-P/2:cx+P/2], bit exact.
+ * images: [n_img,H,W] (float or double, cast to float like data.py:226);
+ * sites: int32 [N,3] = (img_idx, cy, cx); out: float [N,P,P].  Out-of-image pixels -> 0. */
+int livae_patch_gather_f32(const float* images, int n_img, int H, int W,
+                           const int32_t* sites, int N, int P, float* out, livae_stream_t stream);
+int livae_patch_gather_f64(const double* images, int n_img, int H, int W,
+                           const int32_t* sites, int N, int P, float* out, livae_stream_t stream);
+/* a2 tail: per-patch min-max normalisation to [0,1] (data.py:553-558), in place */
+int livae_patch_minmax(float* patches, int N, int P, livae_stream_t stream);
+
+/* ---- a6: fused rotate + bilinear sample (affine_grid + grid_sample) ------------------
+ * replaces F.affine_grid + F.grid_sample(bilinear, reflection, align_corners=False) at
+ * model.py:254-258, model.py:467-470 and train.py:675-677.  cs: [B,2] = (cos, sin);
+ * the matrix used is [[c,-sgn*s,0],[sgn*s,c,0]] so sgn=-1 gives the inverse rotation.
+ * img/out: float [B,C,H,W].  No [B,H,W,2] grid is materialised. */
+int livae_rot_sample_fwd(const float* img, const float* cs, float sgn, int B, int C, int H, int W,
+                         float* out, livae_stream_t stream);
+/* gimg may be NULL (x never requires grad).  gcs: [B,2] = dL/d(cos), dL/d(sin) (written,
+ * not accumulated; already multiplied by sgn for the sin component). */
+int livae_rot_sample_bwd(const float* img, const float* cs, float sgn, const float* gout,
+                         int B, int C, int H, int W, float* gimg, float* gcs, livae_stream_t stream);
+
+/* ---- a4 tail: rotation head ------------------------------------------------------------
+ * F.normalize(vec, eps=1e-6) -> (cos, sin); theta = atan2(sin, cos)   (model.py:245-261) */
+int livae_stn_head_fwd(const float* vec, int B, float* cs, float* theta, livae_stream_t stream);
+/* gvec = J^T (gcs + gtheta * (-s, c));  gcs / gtheta may be NULL */
+int livae_stn_head_bwd(const float* vec, const float* gcs, const float* gtheta, int B,
+                       float* gvec, livae_stream_t stream);
+/* (cos, sin) of an angle tensor, for get_rotation_matrix(theta) (model.py:220-235) */
+int livae_angle_to_cs(const float* theta, int B, float* cs, livae_stream_t stream);
+/* gtheta = -sin*gc + cos*gs */
+int livae_angle_to_cs_bwd(const float* theta, const float* gcs, int B, float* gtheta, livae_stream_t stream);
+
+/* ---- a8: reparameterisation (model.py:426-440; eps drawn by torch, passed in) ---------- */
+int livae_reparam_fwd(const float* mu, const float* logvar, const float* eps, int n, float* z,
+                      livae_stream_t stream);
+/* gmu = gz, glv = gz*eps*0.5*exp(0.5*lv) */
+int livae_reparam_bwd(const float* gz, const float* logvar, const float* eps, int n, float* gmu,
+                      float* glv, livae_stream_t stream);
+
+/* ---- a12/a13/a14: fused ELBO reductions ---------------------------------------------------
+ * RVAELoss (loss.py:162-169): recon = sum((r-x)^2)/B, kld = mean_b(-0.5*sum_l(1+lv-mu^2-e^lv))
+ * VAELoss  (loss.py:116-119): recon = mean((r-x)^2),  kld = -0.5*mean(1+lv-mu^2-e^lv)
+ * canonical MSE (train.py:391-393): mean((recon - canonical_input)^2)   (n_lat = 0)
+ * One launch: sums[0] = sum((r-x)^2), sums[1] = sum(-0.5*(1+lv-mu^2-e^lv)) (raw; the host side
+ * applies 1/B, 1/n, beta to the two device scalars).  Deterministic two-stage reduction.
+ * scratch: livae_elbo_scratch_floats() floats, zeroed once by the caller (self-resetting). */
+int64_t livae_elbo_scratch_floats(void);
+int livae_elbo_fwd(const float* recon, const float* x, int64_t n_pix, const float* mu,
+                   const float* logvar, int n_lat, float* sums, float* scratch, livae_stream_t stream);
+/* g: device pointer to the two upstream gradients (dL/dsums[0], dL/dsums[1]).
+ * d_recon = g[0]*2(r-x); d_x = -d_recon; d_mu = g[1]*mu; d_lv = g[1]*0.5(e^lv-1).
+ * d_recon / d_x may be NULL; d_mu, d_lv required when n_lat > 0. */
+int livae_elbo_bwd(const float* recon, const float* x, int64_t n_pix, const float* mu,
+                   const float* logvar, int n_lat, const float* g, float* d_recon, float* d_x,
+                   float* d_mu, float* d_lv, livae_stream_t stream);
+/* cycle_consistency_loss (loss.py:52-94): loss[0] = mean(1-cos(th_r - th + angle)) */
+int livae_cycle_fwd(const float* theta, const float* theta_rot, const float* angle, int B,
+                    float* loss, livae_stream_t stream);
+/* d_theta = -g[0]*sin(d)/B, d_theta_rot = +g[0]*sin(d)/B (either may be NULL) */
+int livae_cycle_bwd(const float* theta, const float* theta_rot, const float* angle, const float* g,
+                    int B, float* d_theta, float* d_theta_rot, livae_stream_t stream);
+/* out = a*x + b*y elementwise (y may be NULL); a_dev/b_dev are device pointers to one float
+ * each (NULL = 1), so scaling by a device scalar needs no host sync. */
+int livae_axpby_dev(const float* x, const float* a_dev, const float* y, const float* b_dev,
+                    int64_t n, float* out, livae_stream_t stream);
+
+/* ---- a4/a7/a9/a11: convolution / linear layers, engine 0 (exact fp32) -----------------------
+ * One descriptor covers nn.Conv2d (+ReLU/Sigmoid, +MaxPool2d(2,2)) and
+ * nn.ConvTranspose2d(k4,s2,p1) (model.py:204-209, 290-296, 359-371, 90-96).  A Linear over a
+ * flattened NHWC feature map is the LIVAE_CONV whose kernel covers the whole map (kh=Hin,
+ * kw=Win, pad 0): torch's Linear weight [N, C*H*W] in NCHW flatten order IS that conv's
+ * [N,C,H,W] weight (model.py:210-213, 321-324).
+ * x: [B,Hin,Win,Cin] NHWC fp32; y: [B,Ho,Wo,Cout] (Ho,Wo AFTER pooling when pool=1);
+ * w, bias: fp32 in torch's own layouts (Conv2d [Cout,Cin,kh,kw]; ConvTranspose2d [Cin,Cout,kh,kw]). */
+typedef struct {
+  int kind;                 /* LIVAE_CONV / LIVAE_CONVT */
+  int B, Hin, Win, Cin;
+  int Cout, kh, kw, stride, pad;
+  int act;                  /* LIVAE_ACT_* applied after bias */
+  int pool;                 /* 1: MaxPool2d(2,2) after the activation (LIVAE_CONV only) */
+} livae_conv_desc;
+
+void livae_conv_out_shape(const livae_conv_desc* d, int* Ho, int* Wo);
+int64_t livae_conv_fwd_ws_bytes(const livae_conv_desc* d);   /* non-zero only when pool=1 */
+/* y = [pool](act(conv(x, w) + bias)); pool_idx: uint8 argmax position, same shape as y */
+int livae_conv_fwd(const livae_conv_desc* d, const float* x, const float* w, const float* bias,
+                   float* y, uint8_t* pool_idx, void* ws, livae_stream_t stream);
+/* gy: gradient w.r.t. y (post-activation, post-pool).  The activation derivative and the pool
+ * routing are applied while loading gy (y, pool_idx are the forward outputs).  gw, gb, gx are
+ * written, not accumulated; each may be NULL. */
+int livae_conv_bwd(const livae_conv_desc* d, const float* x, const float* w, const float* y,
+                   const float* gy, const uint8_t* pool_idx, float* gw, float* gb, float* gx,
+                   livae_stream_t stream);
+
+/* Upsample(x2, bilinear, align_corners=False) + ReflectionPad2d(1) (model.py:357-358 etc.):
+ * x [B,H,W,C] -> out [B,2H+2,2W+2,C]; the decoder's 3x3 p0 conv then runs on `out`. */
+int livae_upsample_pad_fwd(const float* x, int B, int H, int W, int C, float* out, livae_stream_t stream);
+/* adjoint (gather form, no atomics).  relu_mask_y (may be NULL): post-ReLU tensor that x was;
+ * when given, gx is multiplied by (relu_mask_y > 0), i.e. it is already the pre-activation
+ * gradient of the layer that produced x. */
+int livae_upsample_pad_bwd(const float* g, int B, int H, int W, int C, const float* relu_mask_y,
+                           float* gx, livae_stream_t stream);
+
+/* Decoder.fc / VAEDecoder.fc (model.py:353, 383-384; 84, 108-110):
+ * out[b,h,w,c] = relu(z[b,:] . w[(c,h,w),:] + bias[(c,h,w)]), w: torch Linear [C*HW, L]. */
+int livae_decfc_fwd(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,
+                    float* out, livae_stream_t stream);
+/* gy: gradient w.r.t. out (post-ReLU; masked with y>0 on load).  gw [C*HW,L], gb [C*HW], gz [B,L]. */
+int livae_decfc_bwd(const float* z, const float* w, const float* y, const float* gy, int B, int L,
+                    int C, int HW, float* gw, float* gb, float* gz, livae_stream_t stream);
+
+/* ---- optimiser side (train.py:396-405): global L2 norm of a flat fp32 gradient buffer;
+ * out[0] = norm, out[1] = min(1, max_norm/(norm+1e-6)) (torch clip_grad_norm_); apply != 0
+ * scales grads in place.  scratch: livae_l2norm_scratch_floats() floats. */
+int64_t livae_l2norm_scratch_floats(void);
+int livae_l2norm_clip(float* grads, int64_t n, float max_norm, float* out_norm_coef, float* scratch,
+                      int apply, livae_stream_t stream);
+/* fused Adam/AdamW on flat fp32 buffers (torch.optim semantics; scripts/train_rvae.py:157-159,
+ * scripts/train_vae.py:142).  decoupled=1: AdamW.  step_dev: device float step counter, read as
+ * t = step+1 and incremented when inc_step != 0; gscale_dev: optional device multiplier applied
+ * to the gradient (the clip coefficient). */
+int livae_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int decoupled, float* step_dev,
+                const float* gscale_dev, int inc_step, livae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIVAE_B200_H */

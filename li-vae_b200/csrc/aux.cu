@@ -1,0 +1,329 @@
+// Memory-bound helpers around the GEMM layers:
+//   * Upsample(x2, bilinear, align_corners=False) + ReflectionPad2d(1)      (model.py:357-370) fwd/adjoint
+//   * Decoder.fc / VAEDecoder.fc: relu(Linear(L -> 256 q q)) viewed [B,256,q,q] (model.py:353,383-384; 84,108-110)
+//   * global L2 norm + clip coefficient, fused AdamW on flat fp32 buffers    (train.py:396; scripts/train_rvae.py:157-159)
+#include "common.cuh"
+
+namespace livae {
+
+// source index / lerp weight of nn.Upsample(scale 2, bilinear, align_corners=False):
+// src = max(0.5*(dst+0.5)-0.5, 0); i0 = floor(src); i1 = min(i0+1, n-1); lambda = src - i0
+__device__ __forceinline__ void up_src(int u, int n, int* i0, int* i1, float* f) {
+  float s = fmaxf(0.5f * ((float)u + 0.5f) - 0.5f, 0.f);
+  int a = (int)s;
+  *i0 = a;
+  *i1 = a < n - 1 ? a + 1 : a;
+  *f = s - (float)a;
+}
+// ReflectionPad2d(1): padded index Y in [0, 2n+2) -> upsampled index in [0, 2n)
+__device__ __forceinline__ int unpad(int Y, int n2) {
+  int u = Y - 1;
+  if (u < 0) u = -u;
+  if (u >= n2) u = 2 * n2 - 2 - u;
+  return u;
+}
+
+// x: [B,H,W,C] -> out: [B,2H+2,2W+2,C]
+__global__ void __launch_bounds__(256) upsample_pad_fwd_kernel(const float* __restrict__ x, int B, int H,
+                                                               int W, int C, float* __restrict__ out) {
+  int Ho = 2 * H + 2, Wo = 2 * W + 2;
+  int64_t n = (int64_t)B * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); int64_t q = i / C; int X = (int)(q % Wo); q /= Wo; int Y = (int)(q % Ho);
+    int b = (int)(q / Ho);
+    int y0, y1, x0, x1; float fy, fx;
+    up_src(unpad(Y, 2 * H), H, &y0, &y1, &fy);
+    up_src(unpad(X, 2 * W), W, &x0, &x1, &fx);
+    const float* s = x + (int64_t)b * H * W * C + c;
+    float v00 = s[((int64_t)y0 * W + x0) * C], v01 = s[((int64_t)y0 * W + x1) * C];
+    float v10 = s[((int64_t)y1 * W + x0) * C], v11 = s[((int64_t)y1 * W + x1) * C];
+    // ATen: h0lambda*(w0lambda*v00 + w1lambda*v01) + h1lambda*(w0lambda*v10 + w1lambda*v11)
+    out[i] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+  }
+}
+
+// 1-D adjoint weights: for source index i, sum over upsampled u in [2i-2, 2i+2] of
+// w(u,i) * (sum of padded positions that map to u).  Done as a gather so no atomics are needed.
+// gx[b,i,j,c] = relu_mask * sum_{u,v} wy(u,i) wx(v,j) G[u,v],  G[u,v] = sum_{Y in pre(u), X in pre(v)} g[Y,X]
+__global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(const float* __restrict__ g, int B, int H,
+                                                               int W, int C, const float* __restrict__ mask_y,
+                                                               float* __restrict__ gx) {
+  int Ho = 2 * H + 2, Wo = 2 * W + 2;
+  int64_t n = (int64_t)B * H * W * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C); int64_t q = idx / C; int j = (int)(q % W); q /= W; int i = (int)(q % H);
+    int b = (int)(q / H);
+    if (mask_y && !(mask_y[idx] > 0.f)) { gx[idx] = 0.f; continue; }
+    const float* gb = g + (int64_t)b * Ho * Wo * C + c;
+    float acc = 0.f;
+    for (int u = max(0, 2 * i - 2); u <= min(2 * H - 1, 2 * i + 2); ++u) {
+      int y0, y1; float fy;
+      up_src(u, H, &y0, &y1, &fy);
+      float wy = (y0 == i ? 1.f - fy : 0.f) + (y1 == i ? fy : 0.f);
+      if (wy == 0.f) continue;
+      // padded rows that read upsampled row u: Y = u+1, plus the reflected border rows
+      int Ys[2]; int ny = 0;
+      Ys[ny++] = u + 1;
+      if (u == 1) Ys[ny++] = 0;
+      if (u == 2 * H - 2) Ys[ny++] = 2 * H + 1;
+      for (int v = max(0, 2 * j - 2); v <= min(2 * W - 1, 2 * j + 2); ++v) {
+        int x0, x1; float fx;
+        up_src(v, W, &x0, &x1, &fx);
+        float wx = (x0 == j ? 1.f - fx : 0.f) + (x1 == j ? fx : 0.f);
+        if (wx == 0.f) continue;
+        int Xs[2]; int nx = 0;
+        Xs[nx++] = v + 1;
+        if (v == 1) Xs[nx++] = 0;
+        if (v == 2 * W - 2) Xs[nx++] = 2 * W + 1;
+        float s = 0.f;
+        for (int a = 0; a < ny; ++a)
+          for (int d = 0; d < nx; ++d) s += gb[((int64_t)Ys[a] * Wo + Xs[d]) * C];
+        acc += wy * wx * s;
+      }
+    }
+    gx[idx] = acc;
+  }
+}
+
+// out[b, (h,w,c)] = relu(sum_l z[b,l] * w[(c,h,w), l] + bias[(c,h,w)])  -- NHWC output of the
+// reference's h.view(B, 256, q, q)
+__global__ void __launch_bounds__(256) decfc_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int B, int L, int C,
+                                                        int HW, float* __restrict__ out) {
+  int64_t n = (int64_t)B * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); int64_t q = i / C; int p = (int)(q % HW); int b = (int)(q / HW);
+    int row = c * HW + p;
+    float a = bias[row];
+    for (int l = 0; l < L; ++l) a = fmaf(z[b * L + l], w[(int64_t)row * L + l], a);
+    out[i] = fmaxf(a, 0.f);
+  }
+}
+
+// gz[b,l] = sum_n gpre[b,n] w[n,l]; one CTA per sample
+__global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                          const float* __restrict__ w, int L, int C, int HW,
+                                                          float* __restrict__ gz) {
+  __shared__ float red[32];
+  int b = blockIdx.x;
+  int N = C * HW;
+  const float* gyb = gy + (int64_t)b * N;
+  const float* yb = y + (int64_t)b * N;
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      float g = yb[i] > 0.f ? gyb[i] : 0.f;
+      int c = i % C, p = i / C;
+      const float* wr = w + (int64_t)(c * HW + p) * L;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (l0 + t < L) a[t] = fmaf(g, wr[l0 + t], a[t]);
+    }
+    for (int t = 0; t < 4; ++t) {
+      float s = block_sum(a[t], red);
+      if (threadIdx.x == 0 && l0 + t < L) gz[b * L + l0 + t] = s;
+      __syncthreads();
+    }
+  }
+}
+
+// gw[n,l] = sum_b gpre[b,n] z[b,l], gb[n] = sum_b gpre[b,n]; thread per output feature n (NHWC
+// order so that a warp reads contiguous gy), loop over the batch.  Batch is split over
+// blockIdx.y and combined with atomics on the (zeroed) outputs.
+template <int LT>
+__global__ void __launch_bounds__(128) decfc_bwd_w_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                          const float* __restrict__ z, int B, int L, int C, int HW,
+                                                          float* __restrict__ gw, float* __restrict__ gb) {
+  int N = C * HW;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int c = i % C, p = i / C;
+  int row = c * HW + p;
+  int bchunk = (B + gridDim.y - 1) / gridDim.y;
+  int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  for (int l0 = 0; l0 < L; l0 += LT) {
+    float a[LT];
+#pragma unroll
+    for (int t = 0; t < LT; ++t) a[t] = 0.f;
+    float sb = 0.f;
+    for (int b = b0; b < b1; ++b) {
+      float g = gy[(int64_t)b * N + i];
+      g = y[(int64_t)b * N + i] > 0.f ? g : 0.f;
+      sb += g;
+#pragma unroll
+      for (int t = 0; t < LT; ++t)
+        if (l0 + t < L) a[t] = fmaf(g, __ldg(z + b * L + l0 + t), a[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < LT; ++t)
+      if (l0 + t < L) atomicAdd(gw + (int64_t)row * L + l0 + t, a[t]);
+    if (l0 == 0 && gb) atomicAdd(gb + row, sb);
+  }
+}
+
+// ---- optimiser side ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n,
+                                                    float* __restrict__ partial) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i];
+    a = fmaf(v, v, a);
+  }
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = a;
+}
+
+// out[0] = norm, out[1] = clip coefficient min(1, max_norm / (norm + 1e-6))  (torch clip_grad_norm_)
+__global__ void __launch_bounds__(256) norm_finish_kernel(const float* __restrict__ partial, int nparts,
+                                                          float max_norm, float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += partial[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) {
+    float nrm = sqrtf(a);
+    out[0] = nrm;
+    out[1] = fminf(1.f, max_norm / (nrm + 1e-6f));
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ g, int64_t n,
+                                                    const float* __restrict__ coef) {
+  float c = coef[0];
+  if (c == 1.f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    g[i] *= c;
+}
+
+// torch.optim.AdamW / Adam (decoupled = 1 / 0), single flat tensor.  step_dev holds the step
+// count as a float and is incremented by thread 0 AFTER all reads (separate tiny kernel order).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                    float lr, float b1, float b2, float eps, float wd,
+                                                    int decoupled, const float* __restrict__ step_dev,
+                                                    const float* __restrict__ gscale) {
+  float t = step_dev[0] + 1.f;
+  float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  float gs = gscale ? gscale[0] : 1.f;
+  float step_size = lr / bc1;
+  float bc2s = sqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], gi = g[i] * gs;
+    if (decoupled) pi *= (1.f - lr * wd);
+    else gi = fmaf(wd, pi, gi);
+    float mi = m[i] + (1.f - b1) * (gi - m[i]);       // lerp, as torch does
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2s + eps;
+    p[i] = pi - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+__global__ void inc_step_kernel(float* step_dev) { step_dev[0] += 1.f; }
+
+static inline int sgrid(int64_t n, int per = 4) {
+  int64_t blocks = (n + 256LL * per - 1) / (256LL * per);
+  if (blocks < 1) blocks = 1;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace livae
+
+using namespace livae;
+
+extern "C" int livae_upsample_pad_fwd(const float* x, int B, int H, int W, int C, float* out,
+                                      livae_stream_t stream) {
+  LIVAE_CHECK_ARG(x && out && B >= 0 && H > 1 && W > 1 && C > 0, "upsample_pad_fwd: bad args");
+  if (int e = require_sm100()) return e;
+  if (B == 0) return 0;
+  int64_t n = (int64_t)B * (2 * H + 2) * (2 * W + 2) * C;
+  upsample_pad_fwd_kernel<<<sgrid(n, 2), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_upsample_pad_bwd(const float* g, int B, int H, int W, int C, const float* relu_mask_y,
+                                      float* gx, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(g && gx && B >= 0 && H > 1 && W > 1 && C > 0, "upsample_pad_bwd: bad args");
+  if (int e = require_sm100()) return e;
+  if (B == 0) return 0;
+  int64_t n = (int64_t)B * H * W * C;
+  upsample_pad_bwd_kernel<<<sgrid(n, 1), 256, 0, (cudaStream_t)stream>>>(g, B, H, W, C, relu_mask_y, gx);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_decfc_fwd(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,
+                               float* out, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(z && w && bias && out && B >= 0 && L > 0 && C > 0 && HW > 0, "decfc_fwd: bad args");
+  if (int e = require_sm100()) return e;
+  if (B == 0) return 0;
+  decfc_fwd_kernel<<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C, HW, out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_decfc_bwd(const float* z, const float* w, const float* y, const float* gy, int B, int L,
+                               int C, int HW, float* gw, float* gb, float* gz, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(z && w && y && gy && B >= 0 && L > 0 && C > 0 && HW > 0, "decfc_bwd: bad args");
+  if (int e = require_sm100()) return e;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int N = C * HW;
+  if (gz) {
+    decfc_bwd_z_kernel<<<B, 256, 0, st>>>(gy, y, w, L, C, HW, gz);
+    LIVAE_CUDA_LAUNCH_CHECK();
+  }
+  if (gw) {
+    cudaError_t ce;
+    if ((ce = cudaMemsetAsync(gw, 0, (size_t)N * L * sizeof(float), st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (gb && (ce = cudaMemsetAsync(gb, 0, (size_t)N * sizeof(float), st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    int nb = (N + 127) / 128;
+    int ysplit = (kNumSMs * 8 + nb - 1) / nb;
+    if (ysplit > (B + 15) / 16) ysplit = (B + 15) / 16;
+    if (ysplit < 1) ysplit = 1;
+    dim3 grid(nb, ysplit);
+    decfc_bwd_w_kernel<4><<<grid, 128, 0, st>>>(gy, y, z, B, L, C, HW, gw, gb);
+    LIVAE_CUDA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int64_t livae_l2norm_scratch_floats(void) { return kNumSMs * 16 + 8; }
+
+extern "C" int livae_l2norm_clip(float* grads, int64_t n, float max_norm, float* out_norm_coef, float* scratch,
+                                 int apply, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(grads && out_norm_coef && scratch && n >= 0, "l2norm_clip: bad args");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = sgrid(n, 8);
+  sumsq_kernel<<<grid, 256, 0, st>>>(grads, n, scratch);
+  norm_finish_kernel<<<1, 256, 0, st>>>(scratch, grid, max_norm, out_norm_coef);
+  if (apply) scale_kernel<<<sgrid(n, 4), 256, 0, st>>>(grads, n, out_norm_coef + 1);
+  count_launch(apply ? 2 : 1);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int decoupled, float* step_dev,
+                           const float* gscale_dev, int inc_step, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(p && g && m && v && step_dev && n >= 0, "adamw: bad args");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0)
+    adamw_kernel<<<sgrid(n, 4), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                              step_dev, gscale_dev);
+  if (inc_step) inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  if (inc_step && n > 0) count_launch(1);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}

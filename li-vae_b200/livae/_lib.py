@@ -1,0 +1,142 @@
+"""ctypes binding of liblivae_sm100.so (C ABI declared in include/livae_b200.h).
+
+There is NO fallback: if the shared library is missing, cannot be loaded, or the device is not
+sm_100, every op raises.  Tensors are passed as raw device pointers; every kernel is enqueued on
+torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblivae_sm100.so")
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class ConvDesc(C.Structure):
+    """mirror of livae_conv_desc"""
+    _fields_ = [(n, C.c_int) for n in ("kind", "B", "Hin", "Win", "Cin", "Cout", "kh", "kw", "stride",
+                                       "pad", "act", "pool")]
+
+
+CONV, CONVT = 0, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+# name -> argument type codes: p pointer, i int, l int64, f float, s stream, d ConvDesc*
+_SIGS = {
+    "livae_patch_gather_f32": "piiipiips",
+    "livae_patch_gather_f64": "piiipiips",
+    "livae_patch_minmax": "piis",
+    "livae_rot_sample_fwd": "ppfiiiips",
+    "livae_rot_sample_bwd": "ppfpiiiipps",
+    "livae_stn_head_fwd": "pipps",
+    "livae_stn_head_bwd": "pppips",
+    "livae_angle_to_cs": "pips",
+    "livae_angle_to_cs_bwd": "ppips",
+    "livae_reparam_fwd": "pppips",
+    "livae_reparam_bwd": "pppipps",
+    "livae_elbo_fwd": "pplppipps",
+    "livae_elbo_bwd": "pplppi" + "ppppp" + "s",
+    "livae_cycle_fwd": "pppips",
+    "livae_cycle_bwd": "ppppipps",
+    "livae_axpby_dev": "pppplps",
+    "livae_conv_fwd": "d" + "p" * 6 + "s",
+    "livae_conv_bwd": "d" + "p" * 8 + "s",
+    "livae_upsample_pad_fwd": "piiiips",
+    "livae_upsample_pad_bwd": "piiiipps",
+    "livae_decfc_fwd": "pppiiiips",
+    "livae_decfc_bwd": "ppppiiiippps",
+    "livae_l2norm_clip": "plfppis",
+    "livae_adamw": "pppplfffffippis",
+}
+_CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P, "d": C.POINTER(ConvDesc)}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python li-vae_b200/build.py` "
+            "(livae has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.livae_last_error.restype = C.c_char_p
+    L.livae_abi_version.restype = C.c_int
+    L.livae_device_ok.restype = C.c_int
+    for n in ("livae_elbo_scratch_floats", "livae_l2norm_scratch_floats", "livae_launch_count"):
+        getattr(L, n).restype = C.c_int64
+        getattr(L, n).argtypes = []
+    L.livae_conv_fwd_ws_bytes.restype = C.c_int64
+    L.livae_conv_fwd_ws_bytes.argtypes = [C.POINTER(ConvDesc)]
+    L.livae_conv_out_shape.restype = None
+    L.livae_conv_out_shape.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for name, sig in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = [_CODE[c] for c in sig]
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
+    return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
+                                 "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
+                                 "livae_launch_count", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# When set to a list, every call is bracketed by CUDA events on the launching stream and
+# (name, args, start_event, end_event) is appended: bench.py uses it to time each kernel family.
+PROFILE = None
+
+
+def call(name, *args):
+    """invoke an int-returning entry point; tensors -> device pointers; raises on error"""
+    L = lib()
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, name)(*conv, stream())
+        e1.record()
+        PROFILE.append((name, args, e0, e1))
+    else:
+        rc = getattr(L, name)(*conv, stream())
+    if rc != 0:
+        msg = L.livae_last_error().decode(errors="replace")
+        raise RuntimeError(f"{name} failed (rc={rc}): {msg}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("livae: tensors must live on a CUDA (sm_100) device; there is no CPU path")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"livae: expected float32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("livae: tensors must be contiguous")

@@ -1,0 +1,383 @@
+"""torch.autograd seams over the C-ABI kernels (one Function per kernel family).
+
+Activations between layers are NHWC float32 ([B,H,W,C], contiguous); 1-channel images are the
+same memory as the reference's NCHW tensors.  Parameters keep torch's own layouts and dtypes
+(SURVEY.md section 8b), so state_dicts and optimisers are interchangeable with the reference.
+No op here has a CPU or ATen fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, CONV, CONVT, ConvDesc, call, require_cuda
+
+_scratch = {}
+
+
+def _get_scratch(dev, key, nfloats):
+    k = (dev.index, key)
+    t = _scratch.get(k)
+    if t is None or t.numel() < nfloats:
+        t = torch.zeros(nfloats, dtype=torch.float32, device=dev)
+        _scratch[k] = t
+    return t
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# convolution / linear layers
+# ------------------------------------------------------------------------------------------
+class _ConvFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, kind, kh, kw, stride, pad, act, pool):
+        x = _c(x); w = _c(w)
+        require_cuda(x, w, b)
+        B, Hin, Win, Cin = x.shape
+        if kind == CONV:
+            Cout = w.shape[0]
+            assert w.numel() == Cout * Cin * kh * kw, "conv weight shape mismatch"
+        else:
+            assert w.shape[0] == Cin, "conv_transpose weight shape mismatch"
+            Cout = w.shape[1]
+        d = ConvDesc(kind, B, Hin, Win, Cin, Cout, kh, kw, stride, pad, act, int(pool))
+        ho, wo = C.c_int(), C.c_int()
+        L.lib().livae_conv_out_shape(C.byref(d), C.byref(ho), C.byref(wo))
+        y = torch.empty((B, ho.value, wo.value, Cout), dtype=torch.float32, device=x.device)
+        idx = ws = None
+        if pool:
+            idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+            ws = torch.empty(L.lib().livae_conv_fwd_ws_bytes(C.byref(d)) // 4, dtype=torch.float32,
+                             device=x.device)
+        call("livae_conv_fwd", C.byref(d), x, w, b, y, idx, ws)
+        ctx.desc = d
+        ctx.save_for_backward(x, w, y, idx)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, y, idx = ctx.saved_tensors
+        gy = _c(gy)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty_like(w) if need_w else None
+        gb = torch.empty(y.shape[-1], dtype=torch.float32, device=x.device) if need_b else None
+        if need_x or need_w or need_b:
+            call("livae_conv_bwd", C.byref(ctx.desc), x, w, y, gy, idx, gw, gb, gx)
+        return gx, gw, gb, None, None, None, None, None, None, None
+
+
+def conv2d(x, w, b, kh, kw, stride, pad, act=ACT_NONE, pool=False):
+    """nn.Conv2d (+ReLU/Sigmoid, +MaxPool2d(2,2)) on NHWC input (model.py:204-209, 290-296, 359-371)"""
+    return _ConvFn.apply(x, w, b, CONV, kh, kw, stride, pad, act, pool)
+
+
+def conv_transpose2d(x, w, b, kh, kw, stride, pad, act=ACT_NONE):
+    """nn.ConvTranspose2d (+ReLU/Sigmoid) on NHWC input (model.py:90-96)"""
+    return _ConvFn.apply(x, w, b, CONVT, kh, kw, stride, pad, act, False)
+
+
+def linear_nhwc(x, w, b, act=ACT_NONE):
+    """nn.Linear applied to the reference's NCHW flatten of an NHWC feature map x [B,H,W,C]
+    (model.py:210-213, 321-324): the conv whose kernel covers the whole map."""
+    B, H, W, _ = x.shape
+    return _ConvFn.apply(x, w, b, CONV, H, W, 1, 0, act, False).view(B, -1)
+
+
+class _UpsamplePadFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        require_cuda(x)
+        B, H, W, Cc = x.shape
+        out = torch.empty((B, 2 * H + 2, 2 * W + 2, Cc), dtype=torch.float32, device=x.device)
+        call("livae_upsample_pad_fwd", x, B, H, W, Cc, out)
+        ctx.shape = (B, H, W, Cc)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        B, H, W, Cc = ctx.shape
+        g = _c(g)
+        gx = torch.empty((B, H, W, Cc), dtype=torch.float32, device=g.device)
+        call("livae_upsample_pad_bwd", g, B, H, W, Cc, None, gx)
+        return gx
+
+
+def upsample_pad(x):
+    """nn.Upsample(x2, bilinear, align_corners=False) + nn.ReflectionPad2d(1) (model.py:357-358)"""
+    return _UpsamplePadFn.apply(x)
+
+
+class _DecFcFn(Function):
+    @staticmethod
+    def forward(ctx, z, w, b, Cc, q):
+        z = _c(z); w = _c(w)
+        require_cuda(z, w, b)
+        B, Ld = z.shape
+        assert w.shape == (Cc * q * q, Ld)
+        out = torch.empty((B, q, q, Cc), dtype=torch.float32, device=z.device)
+        call("livae_decfc_fwd", z, w, b, B, Ld, Cc, q * q, out)
+        ctx.save_for_backward(z, w, out)
+        ctx.dims = (B, Ld, Cc, q * q)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        z, w, y = ctx.saved_tensors
+        B, Ld, Cc, HW = ctx.dims
+        gy = _c(gy)
+        gw = torch.empty_like(w)
+        gb = torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+        gz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        call("livae_decfc_bwd", z, w, y, gy, B, Ld, Cc, HW, gw, gb, gz)
+        return gz, gw, gb, None, None
+
+
+def decoder_fc(z, w, b, channels, q):
+    """relu(Linear(z)).view(B, channels, q, q) as an NHWC tensor (model.py:353, 383-384)"""
+    return _DecFcFn.apply(z, w, b, channels, q)
+
+
+# ------------------------------------------------------------------------------------------
+# rotation: head, angle -> (cos, sin), fused affine_grid + grid_sample
+# ------------------------------------------------------------------------------------------
+class _StnHeadFn(Function):
+    @staticmethod
+    def forward(ctx, vec):
+        vec = _c(vec)
+        require_cuda(vec)
+        B = vec.shape[0]
+        cs = torch.empty((B, 2), dtype=torch.float32, device=vec.device)
+        theta = torch.empty((B, 1), dtype=torch.float32, device=vec.device)
+        call("livae_stn_head_fwd", vec, B, cs, theta)
+        ctx.save_for_backward(vec)
+        return cs, theta
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gcs, gtheta):
+        (vec,) = ctx.saved_tensors
+        gvec = torch.empty_like(vec)
+        call("livae_stn_head_bwd", vec, _c(gcs) if gcs is not None else None,
+             _c(gtheta) if gtheta is not None else None, vec.shape[0], gvec)
+        return gvec
+
+
+def stn_head(vec):
+    """F.normalize(vec, eps=1e-6) -> (cos, sin) [B,2]; theta = atan2(sin, cos) [B,1] (model.py:245-261)"""
+    return _StnHeadFn.apply(vec)
+
+
+class _AngleToCsFn(Function):
+    @staticmethod
+    def forward(ctx, theta):
+        theta = _c(theta)
+        require_cuda(theta)
+        B = theta.numel()
+        cs = torch.empty((B, 2), dtype=torch.float32, device=theta.device)
+        call("livae_angle_to_cs", theta, B, cs)
+        ctx.save_for_backward(theta)
+        return cs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gcs):
+        (theta,) = ctx.saved_tensors
+        g = torch.empty_like(theta)
+        call("livae_angle_to_cs_bwd", theta, _c(gcs), theta.numel(), g)
+        return g
+
+
+def angle_to_cs(theta):
+    """(cos theta, sin theta) [B,2] -- the two free entries of get_rotation_matrix (model.py:220-235)"""
+    return _AngleToCsFn.apply(theta)
+
+
+class _RotSampleFn(Function):
+    @staticmethod
+    def forward(ctx, img, cs, sgn):
+        img = _c(img); cs = _c(cs)
+        require_cuda(img, cs)
+        B, Cc, H, W = img.shape
+        out = torch.empty_like(img)
+        call("livae_rot_sample_fwd", img, cs, float(sgn), B, Cc, H, W, out)
+        ctx.save_for_backward(img, cs)
+        ctx.sgn = float(sgn)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        img, cs = ctx.saved_tensors
+        B, Cc, H, W = img.shape
+        gout = _c(gout)
+        gimg = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        gcs = torch.empty_like(cs) if ctx.needs_input_grad[1] else None
+        if gimg is not None or gcs is not None:
+            call("livae_rot_sample_bwd", img, cs, ctx.sgn, gout, B, Cc, H, W, gimg, gcs)
+        return gimg, gcs, None
+
+
+def rot_sample(img, cs, sgn=1.0):
+    """F.grid_sample(img, F.affine_grid([[c,-sgn*s,0],[sgn*s,c,0]], img.size(), align_corners=False),
+    padding_mode='reflection', align_corners=False) for NCHW img (model.py:250-258, 465-470;
+    train.py:675-677); sgn=-1 applies the inverse rotation."""
+    return _RotSampleFn.apply(img, cs, sgn)
+
+
+# ------------------------------------------------------------------------------------------
+# reparameterisation and losses
+# ------------------------------------------------------------------------------------------
+class _ReparamFn(Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu = _c(mu); logvar = _c(logvar); eps = _c(eps)
+        require_cuda(mu, logvar, eps)
+        z = torch.empty_like(mu)
+        call("livae_reparam_fwd", mu, logvar, eps, mu.numel(), z)
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz):
+        logvar, eps = ctx.saved_tensors
+        gz = _c(gz)
+        gmu = torch.empty_like(gz)
+        glv = torch.empty_like(gz)
+        call("livae_reparam_bwd", gz, logvar, eps, gz.numel(), gmu, glv)
+        return gmu, glv, None
+
+
+def reparam(mu, logvar, eps):
+    """z = mu + eps * exp(0.5 * logvar) (model.py:436-439) with eps drawn by the caller"""
+    return _ReparamFn.apply(mu, logvar, eps)
+
+
+class _ElboSumsFn(Function):
+    @staticmethod
+    def forward(ctx, recon, x, mu, logvar):
+        recon = _c(recon); x = _c(x)
+        require_cuda(recon, x, mu, logvar)
+        assert recon.numel() == x.numel()
+        n_lat = 0
+        if mu is not None:
+            mu = _c(mu); logvar = _c(logvar)
+            n_lat = mu.numel()
+        sums = torch.empty(2, dtype=torch.float32, device=x.device)
+        scratch = _get_scratch(x.device, "elbo", L.lib().livae_elbo_scratch_floats())
+        call("livae_elbo_fwd", recon, x, recon.numel(), mu, logvar, n_lat, sums, scratch)
+        ctx.save_for_backward(recon, x, mu, logvar)
+        return sums
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        recon, x, mu, logvar = ctx.saved_tensors
+        g = _c(g)
+        d_recon = torch.empty_like(recon) if ctx.needs_input_grad[0] else None
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        n_lat = 0 if mu is None else mu.numel()
+        d_mu = torch.empty_like(mu) if n_lat else None
+        d_lv = torch.empty_like(logvar) if n_lat else None
+        call("livae_elbo_bwd", recon, x, recon.numel(), mu, logvar, n_lat, g, d_recon, d_x, d_mu, d_lv)
+        return d_recon, d_x, d_mu, d_lv
+
+
+def elbo_sums(recon, x, mu=None, logvar=None):
+    """-> tensor[2] = (sum((recon-x)^2), sum(-0.5*(1+logvar-mu^2-exp(logvar)))) in one launch
+    (loss.py:116-119, 165-169; train.py:391-393).  With mu=None only the first entry is meaningful."""
+    return _ElboSumsFn.apply(recon, x, mu, logvar)
+
+
+class _CycleFn(Function):
+    @staticmethod
+    def forward(ctx, theta, theta_rot, angle):
+        theta = _c(theta); theta_rot = _c(theta_rot); angle = _c(angle)
+        require_cuda(theta, theta_rot, angle)
+        B = theta.numel()
+        assert theta_rot.numel() == B and angle.numel() == B
+        loss = torch.empty((), dtype=torch.float32, device=theta.device)
+        call("livae_cycle_fwd", theta, theta_rot, angle, B, loss)
+        ctx.save_for_backward(theta, theta_rot, angle)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        theta, theta_rot, angle = ctx.saved_tensors
+        g = _c(g)
+        d_t = torch.empty_like(theta) if ctx.needs_input_grad[0] else None
+        d_r = torch.empty_like(theta_rot) if ctx.needs_input_grad[1] else None
+        if d_t is not None or d_r is not None:
+            call("livae_cycle_bwd", theta, theta_rot, angle, g, theta.numel(), d_t, d_r)
+        return d_t, d_r, None
+
+
+def cycle_loss(theta, theta_rot, angle):
+    """mean(1 - cos(theta_rot - theta + angle)) (loss.py:52-94)"""
+    return _CycleFn.apply(theta, theta_rot, angle)
+
+
+# ------------------------------------------------------------------------------------------
+# data side
+# ------------------------------------------------------------------------------------------
+def patch_gather(images, sites, P, out=None):
+    """images [n_img,H,W] float32/float64 (device), sites int32 [N,3] (img, cy, cx) ->
+    float32 [N,1,P,P] == float32(img)[cy-P/2:cy+P/2, cx-P/2:cx+P/2] (data.py:211-250, transform=None)"""
+    if not images.is_cuda or not sites.is_cuda:
+        raise RuntimeError("livae.patch_gather: device tensors required; there is no CPU path")
+    assert images.dim() == 3 and images.is_contiguous()
+    assert sites.dtype == torch.int32 and sites.dim() == 2 and sites.shape[1] == 3 and sites.is_contiguous()
+    n_img, H, W = images.shape
+    N = sites.shape[0]
+    if out is None:
+        out = torch.empty((N, 1, P, P), dtype=torch.float32, device=images.device)
+    if images.dtype == torch.float32:
+        call("livae_patch_gather_f32", images, n_img, H, W, sites, N, P, out)
+    elif images.dtype == torch.float64:
+        call("livae_patch_gather_f64", images, n_img, H, W, sites, N, P, out)
+    else:
+        raise RuntimeError(f"patch_gather: unsupported image dtype {images.dtype}")
+    return out
+
+
+def patch_minmax_(patches):
+    """in-place per-patch min-max normalisation to [0,1] (data.py:553-558)"""
+    require_cuda(patches)
+    N = patches.shape[0]
+    P = patches.shape[-1]
+    assert patches.numel() == N * P * P
+    call("livae_patch_minmax", patches, N, P)
+    return patches
+
+
+# ------------------------------------------------------------------------------------------
+# optimiser side
+# ------------------------------------------------------------------------------------------
+def l2norm_clip_(flat_grads, max_norm, apply=True):
+    """-> tensor[2] (norm, clip coefficient); scales flat_grads in place when apply (train.py:396)"""
+    require_cuda(flat_grads)
+    out = torch.empty(2, dtype=torch.float32, device=flat_grads.device)
+    scratch = _get_scratch(flat_grads.device, "l2", L.lib().livae_l2norm_scratch_floats())
+    call("livae_l2norm_clip", flat_grads, flat_grads.numel(), float(max_norm), out, scratch, int(apply))
+    return out
+
+
+def adamw_(p, g, m, v, step_dev, lr, betas, eps, weight_decay, decoupled=True, gscale=None, inc_step=True):
+    require_cuda(p, g, m, v, step_dev)
+    call("livae_adamw", p, g, m, v, p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+         float(weight_decay), int(decoupled), step_dev, gscale, int(inc_step))

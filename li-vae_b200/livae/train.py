@@ -1,0 +1,334 @@
+"""livae.train -- drop-in for the training-step part of the reference's src/livae/train.py.
+
+Same function names, signatures and metric keys (reference train.py:33-165, 168-278, 286-445,
+448-556, 559-573, 670-677).  Differences that do not change results:
+  * per-step metrics are accumulated ON DEVICE and read back once per epoch (the reference does
+    >= 38 `.item()` syncs per step, train.py:399-427); the reported epoch averages are the same
+    quantities;
+  * clipping / gradient norm use one fused L2-norm kernel when the parameters' gradients live in a
+    livae.optim flat buffer, torch.nn.utils.clip_grad_norm_ otherwise;
+  * `scaler` (AMP GradScaler) is accepted for signature compatibility; the B200 path keeps fp32
+    master tensors and does its own operand rounding inside the tensor-core kernels, so the scaler
+    is not used.
+Reference quirks preserved on purpose: `train_canonical_loss` is reported as 0.0
+(train.py:310,436: never accumulated); evaluate_rvae reports only the LAST batch
+(train.py:521-541 sit outside the loop); clipping is always on (max_norm 20 / 5).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Any
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+__all__ = [
+    "train_one_epoch", "evaluate", "train_rvae_one_epoch", "evaluate_rvae", "rotate_to_canonical",
+    "rvae_step_loss", "train_rvae_step", "MetricLogger", "compute_psnr", "compute_ssim", "get_rotation_stats",
+]
+
+
+class MetricLogger:
+    """reference train.py:559-573"""
+
+    def __init__(self):
+        self.metrics = defaultdict(list)
+
+    def update(self, **kwargs):
+        for k, v in kwargs.items():
+            if isinstance(v, torch.Tensor):
+                v = v.item()
+            self.metrics[k].append(v)
+
+    def get_averages(self) -> dict[str, Any]:
+        return {k: np.mean(v) for k, v in self.metrics.items()}
+
+    def reset(self):
+        self.metrics.clear()
+
+
+def get_rotation_stats(rotations: torch.Tensor) -> tuple[float, float]:
+    """reference train.py:576-580"""
+    angles = torch.atan2(rotations[:, 1], rotations[:, 0]) * (180.0 / np.pi)
+    return torch.mean(angles).item(), torch.std(angles).item()
+
+
+def _psnr_dev(img1, img2, max_val: float = 1.0):
+    mse = ops.elbo_sums(img1, img2)[0] / img1.numel()
+    return 20.0 * torch.log10(max_val / torch.sqrt(mse))
+
+
+def compute_psnr(img1: torch.Tensor, img2: torch.Tensor, max_val: float = 1.0) -> float:
+    """reference train.py:583-603 (MSE via the fused reduction kernel)"""
+    with torch.no_grad():
+        v = _psnr_dev(img1, img2, max_val).item()
+    return float("inf") if np.isinf(v) else v
+
+
+def _ssim_dev(img1, img2, window_size: int = 11, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2):
+    # Observability metric (SURVEY.md section 8f "next #1"), not part of the five hot-path stages:
+    # kept on the 11x11 box filter of the reference (train.py:606-667).
+    ap = lambda t: torch.nn.functional.avg_pool2d(t, window_size, stride=1, padding=window_size // 2)
+    mu1, mu2 = ap(img1), ap(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = ap(img1 * img1) - mu1_sq
+    sigma2_sq = ap(img2 * img2) - mu2_sq
+    sigma12 = ap(img1 * img2) - mu1_mu2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def compute_ssim(img1, img2, window_size: int = 11, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2) -> float:
+    with torch.no_grad():
+        return _ssim_dev(img1, img2, window_size, C1, C2).item()
+
+
+def rotate_to_canonical(x: torch.Tensor, theta: torch.Tensor, rotation_stn: nn.Module = None) -> torch.Tensor:
+    """Rotate a batch to the canonical frame with the predicted angles (reference train.py:670-677):
+    grid_sample(x, affine_grid(get_rotation_matrix(theta))) as ONE fused kernel; gradients flow to
+    theta (x needs none)."""
+    return ops.rot_sample(x, ops.angle_to_cs(theta), 1.0)
+
+
+def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_weight: float = 0.2,
+                   elide_dead_encoder: bool = False):
+    """forward + loss of one rVAE training step, reference train.py:373-394 (fp32 branch).
+    -> (loss, recon_loss, kld_loss, cycle_loss, canonical_loss, outputs)
+
+    train.py:376-377 runs the FULL Encoder on x_rotated although only theta is consumed; that is
+    reproduced by default.  elide_dead_encoder=True evaluates only the STN localisation (same
+    results, the conv stack's mu/logvar are discarded at the call site)."""
+    rotated_recon, canonical_recon, theta, mu, logvar = model(x)
+    theta_rotated = None
+    if x_rotated is not None:
+        if elide_dead_encoder:
+            _, theta_rotated = model.encoder.rotation_stn.localize(x_rotated)
+        else:
+            _, _, theta_rotated = model.encoder(x_rotated)
+    loss, recon_loss, kld_loss, cycle_loss = criterion(rotated_recon, x, mu, logvar, theta, theta_rotated, angle)
+    canonical_loss = torch.zeros((), device=loss.device)
+    if canonical_weight > 0 and canonical_recon is not None:
+        canonical_input = rotate_to_canonical(x, theta, model.encoder.rotation_stn)
+        canonical_loss = ops.elbo_sums(canonical_recon, canonical_input)[0] / canonical_recon.numel()
+        loss = loss + canonical_weight * canonical_loss
+    return loss, recon_loss, kld_loss, cycle_loss, canonical_loss, (rotated_recon, canonical_recon, theta, mu, logvar)
+
+
+def _unpack_rvae_batch(batch, device):
+    """reference train.py:316-339"""
+    if isinstance(batch, (list, tuple)):
+        if len(batch) == 3:
+            x, x_rotated, angle = batch
+            x = x.to(device, non_blocking=True)
+            x_rotated = x_rotated.to(device, non_blocking=True)
+            angle = (angle.to(device, non_blocking=True) if isinstance(angle, torch.Tensor)
+                     else torch.tensor(angle, dtype=torch.float32, device=device))
+            return x, x_rotated, angle.to(torch.float32)
+        if len(batch) == 2:
+            x, x_rotated = batch
+            return x.to(device, non_blocking=True), x_rotated.to(device, non_blocking=True), None
+        return batch[0].to(device, non_blocking=True), None, None
+    return batch.to(device, non_blocking=True), None, None
+
+
+def _clip_and_norm(model, optimizer, max_norm):
+    """-> device scalar: pre-clip global gradient norm (what clip_grad_norm_ returns)"""
+    flat = getattr(optimizer, "flat_grad", None)
+    if flat is not None:
+        return ops.l2norm_clip_(flat, max_norm, apply=True)[0]
+    return torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
+
+
+def _post_clip_norm(pre_norm, max_norm):
+    # the reference measures the norm AFTER clipping (train.py:399-405): min(norm, ~max_norm)
+    coef = torch.clamp(max_norm / (pre_norm + 1e-6), max=1.0)
+    return pre_norm * coef
+
+
+class _DevAccum:
+    """sums of device scalars, read back once"""
+
+    def __init__(self, device):
+        self.device = device
+        self.sums = {}
+
+    def add(self, **kw):
+        for k, v in kw.items():
+            v = v.detach().reshape(()) if isinstance(v, torch.Tensor) else torch.tensor(float(v), device=self.device)
+            self.sums[k] = v if k not in self.sums else self.sums[k] + v
+
+    def averages(self, n):
+        if not self.sums:
+            return {}
+        keys = list(self.sums)
+        vals = torch.stack([self.sums[k].to(torch.float32) for k in keys]).cpu().tolist()
+        return {k: v / n for k, v in zip(keys, vals)}
+
+
+def train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight: float = 0.2,
+                    max_norm: float = 20.0, reduce_grads=None):
+    """ONE batch of the reference's rVAE training loop (train.py:315-397): unpack + host->device
+    copy, forward, loss, backward, [gradient all-reduce], clip, optimizer step.
+    -> (loss, recon, kld, cycle, canonical, outputs, pre_clip_grad_norm), all device tensors."""
+    x, x_rotated, angle = _unpack_rvae_batch(batch, device)
+    optimizer.zero_grad(set_to_none=getattr(optimizer, "flat_grad", None) is None)
+    loss, recon_l, kld_l, cycle_l, can_l, outs = rvae_step_loss(model, criterion, x, x_rotated, angle,
+                                                              canonical_weight)
+    loss.backward()
+    if reduce_grads is not None:
+        reduce_grads()
+    pre = _clip_and_norm(model, optimizer, max_norm)
+    optimizer.step()
+    return x, loss, recon_l, kld_l, cycle_l, can_l, outs, pre
+
+
+def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger, device,
+                         canonical_weight: float = 0.2, scaler=None, grad_max_norm: float | None = None) -> None:
+    """reference train.py:286-445"""
+    model.train()
+    acc = _DevAccum(device)
+    n_batches = 0
+    max_norm = grad_max_norm if grad_max_norm is not None else 20.0
+    for batch in data_loader:
+        x, loss, recon_l, kld_l, cycle_l, _can_l, outs, pre = train_rvae_step(
+            model, optimizer, criterion, batch, device, canonical_weight, max_norm)
+        rotated_recon, canonical_recon, theta, mu, logvar = outs
+        with torch.no_grad():
+            m = dict(train_loss=loss, train_recon_loss=recon_l, train_kld_loss=kld_l, train_cycle_loss=cycle_l,
+                     train_psnr=_psnr_dev(rotated_recon, x), train_ssim=_ssim_dev(rotated_recon, x),
+                     train_latent_mean_abs=mu.abs().mean(), train_latent_std=torch.exp(0.5 * logvar).mean(),
+                     train_grad_norm=_post_clip_norm(pre, max_norm))
+            if theta is not None:
+                m["train_rotation_std"] = torch.std(theta)
+            if canonical_recon is not None:
+                canonical_input = rotate_to_canonical(x, theta)
+                m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
+                m["train_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
+            acc.add(**m)
+        n_batches += 1
+    avg = acc.averages(max(n_batches, 1))
+    for k in ("train_rotation_std", "train_canonical_psnr", "train_canonical_ssim"):
+        avg.setdefault(k, 0.0)
+    avg["train_canonical_loss"] = 0.0   # reference never accumulates it (train.py:310, 436)
+    metric_logger.update(**avg)
+
+
+def train_one_epoch(model, data_loader, optimizer, criterion, metric_logger, device, scaler=None,
+                    canonical_weight: float = 0.0) -> None:
+    """reference train.py:33-165 (VAE and rVAE outputs both accepted; criterion returns 3 values)"""
+    model.train()
+    acc = _DevAccum(device)
+    n_batches = 0
+    canonical_batches = 0
+    for x in data_loader:
+        if isinstance(x, (list, tuple)):
+            x = x[0]
+        x = x.to(device, non_blocking=True)
+        optimizer.zero_grad(set_to_none=getattr(optimizer, "flat_grad", None) is None)
+        outputs = model(x)
+        canonical_recon = None
+        theta = None
+        if len(outputs) == 3:
+            recon, mu, logvar = outputs
+            rotated_recon = recon
+            loss, recon_l, kld_l = criterion(recon, x, mu, logvar)
+        elif len(outputs) == 5:
+            rotated_recon, canonical_recon, theta, mu, logvar = outputs
+            loss, recon_l, kld_l = criterion(rotated_recon, x, mu, logvar)
+        else:
+            raise ValueError(f"Unexpected model output length: {len(outputs)}")
+        loss.backward()
+        pre = _clip_and_norm(model, optimizer, 5.0)
+        optimizer.step()
+        with torch.no_grad():
+            m = dict(train_loss=loss, train_recon_loss=recon_l, train_kld_loss=kld_l,
+                     train_psnr=_psnr_dev(rotated_recon, x), train_ssim=_ssim_dev(rotated_recon, x),
+                     train_latent_mean_abs=mu.abs().mean(), train_latent_std=torch.exp(0.5 * logvar).mean(),
+                     train_grad_norm=_post_clip_norm(pre, 5.0))
+            m["train_rotation_std"] = torch.std(theta) if theta is not None else torch.zeros((), device=device)
+            if canonical_recon is not None and theta is not None:
+                canonical_input = rotate_to_canonical(x, theta)
+                m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
+                m["train_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
+                canonical_batches += 1
+            acc.add(**m)
+        n_batches += 1
+    avg = acc.averages(max(n_batches, 1))
+    if canonical_batches == 0:
+        avg.pop("train_canonical_psnr", None)
+        avg.pop("train_canonical_ssim", None)
+    metric_logger.update(**avg)
+
+
+def evaluate(model, data_loader, criterion, metric_logger, device, canonical_weight: float = 0.0) -> None:
+    """reference train.py:168-278"""
+    model.eval()
+    acc = _DevAccum(device)
+    n_batches = 0
+    canonical_batches = 0
+    with torch.no_grad():
+        for x in data_loader:
+            if isinstance(x, (list, tuple)):
+                x = x[0]
+            x = x.to(device)
+            outputs = model(x)
+            canonical_recon = None
+            theta = None
+            if len(outputs) == 3:
+                rotated_recon, mu, logvar = outputs
+            elif len(outputs) == 5:
+                rotated_recon, canonical_recon, theta, mu, logvar = outputs
+            else:
+                raise ValueError(f"Unexpected model output length: {len(outputs)}")
+            loss, recon_l, kld_l = criterion(rotated_recon, x, mu, logvar)
+            has_can = canonical_recon is not None and theta is not None
+            if canonical_weight > 0 and has_can:
+                canonical_input = rotate_to_canonical(x, theta)
+                loss = loss + canonical_weight * (ops.elbo_sums(canonical_recon, canonical_input)[0]
+                                                  / canonical_recon.numel())
+            m = dict(val_loss=loss, val_recon_loss=recon_l, val_kld_loss=kld_l,
+                     val_psnr=_psnr_dev(rotated_recon, x), val_ssim=_ssim_dev(rotated_recon, x),
+                     val_latent_mean_abs=mu.abs().mean(), val_latent_std=torch.exp(0.5 * logvar).mean())
+            m["val_rotation_std"] = torch.std(theta) if theta is not None else torch.zeros((), device=device)
+            if has_can:
+                canonical_input = rotate_to_canonical(x, theta)
+                m["val_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
+                m["val_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
+                canonical_batches += 1
+            acc.add(**m)
+            n_batches += 1
+    avg = acc.averages(max(n_batches, 1))
+    if canonical_batches == 0:
+        avg.pop("val_canonical_psnr", None)
+        avg.pop("val_canonical_ssim", None)
+    metric_logger.update(**avg)
+
+
+def evaluate_rvae(model, data_loader, criterion, metric_logger, device, canonical_weight: float = 0.2) -> None:
+    """reference train.py:448-556.  The reference's accumulators sit outside its batch loop, so it
+    reports the metrics of the LAST validation batch only; that behaviour is preserved."""
+    model.eval()
+    last = None
+    with torch.no_grad():
+        for batch in data_loader:
+            x, x_rotated, angle = _unpack_rvae_batch(batch, device)
+            loss, recon_l, kld_l, cycle_l, can_l, outs = rvae_step_loss(model, criterion, x, x_rotated, angle,
+                                                                      canonical_weight)
+            last = (x, loss, recon_l, kld_l, cycle_l, can_l, outs)
+        if last is None:
+            raise ZeroDivisionError("evaluate_rvae: empty data loader")
+        x, loss, recon_l, kld_l, cycle_l, can_l, (rotated_recon, canonical_recon, theta, mu, logvar) = last
+        acc = _DevAccum(device)
+        m = dict(val_loss=loss, val_recon_loss=recon_l, val_kld_loss=kld_l, val_cycle_loss=cycle_l,
+                 val_canonical_loss=canonical_weight * can_l,
+                 val_psnr=_psnr_dev(rotated_recon, x), val_ssim=_ssim_dev(rotated_recon, x),
+                 val_latent_mean_abs=mu.abs().mean(), val_latent_std=torch.exp(0.5 * logvar).mean(),
+                 val_rotation_std=torch.std(theta))
+        canonical_input = rotate_to_canonical(x, theta)
+        m["val_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
+        m["val_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
+        acc.add(**m)
+    metric_logger.update(**acc.averages(1))

@@ -1,0 +1,212 @@
+"""GPU parity of the whole training step through the drop-in `livae` API (which calls the C ABI)
+against (a) the committed golden vectors produced by the UNMODIFIED reference and (b) the oracle
+restatement on fresh seeded inputs.  fp32 engine: reconstructions/gradients 1e-4 relative
+(2e-4 on sampled gradient entries, as the oracle's own pin), ELBO 1e-3 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rvae as O
+from tests.util import check_grads_against_golden, fp32_noise_floor, grad_tolerances, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+class FixedEps:
+    """inject the reparameterisation noise (CPU and CUDA generators differ; model.py:438)"""
+
+    def __init__(self, eps):
+        self.eps = eps
+
+    def __enter__(self):
+        self.orig = torch.randn_like
+        torch.randn_like = lambda t, **k: self.eps.to(device=t.device, dtype=t.dtype).reshape(t.shape)
+
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
+def _rvae(P, L, params):
+    import livae
+    m = livae.RVAE(latent_dim=L, in_channels=1, patch_size=P)
+    m.load_state_dict(params, strict=True)
+    return m.cuda()
+
+
+def _run_rvae_step(P, L, params, x, xr, ang, eps, beta=10.0, gamma=10.0, cw=0.2):
+    import livae
+    from livae.train import rvae_step_loss
+    m = _rvae(P, L, params)
+    crit = livae.RVAELoss(beta=beta, gamma=gamma)
+    with FixedEps(eps):
+        loss, rl, kl, cyc, can, outs = rvae_step_loss(m, crit, x.cuda(), xr.cuda() if xr is not None else None,
+                                                      ang.cuda() if ang is not None else None, cw)
+    loss.backward()
+    grads = {k: (p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu())
+             for k, p in m.named_parameters()}
+    return dict(loss=loss.item(), recon_loss=rl.item(), kld=kl.item(), cycle=float(cyc), canonical=float(can),
+                rotated_recon=outs[0].detach().cpu(), recon=outs[1].detach().cpu(), theta=outs[2].detach().cpu(),
+                mu=outs[3].detach().cpu(), logvar=outs[4].detach().cpu()), grads
+
+
+def _golden_case(tag):
+    g = load_golden(f"rvae_step_{tag}.npz")
+    P, L, B, seed = int(g["P"]), int(g["L"]), int(g["B"]), int(g["seed"])
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    x, xr, ang = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    return g, P, L, params, x, xr, ang, eps
+
+
+@pytest.mark.parametrize("tag", ["p32", "p128"])
+def test_rvae_step_matches_reference_golden(tag):
+    g, P, L, params, x, xr, ang, eps = _golden_case(tag)
+    outs, grads = _run_rvae_step(P, L, params, x, xr, ang, eps)
+    assert rel_l2(outs["theta"], g["theta"]) < 1e-4
+    assert rel_l2(outs["mu"], g["mu"]) < 1e-4
+    assert rel_l2(outs["logvar"], g["logvar"]) < 1e-4
+    # per-batch ELBO within 1e-3 relative (north_star); fp32 engine is far inside that
+    assert abs(outs["loss"] - float(g["metric/train_loss"])) <= 1e-4 * abs(float(g["metric/train_loss"]))
+    assert abs(outs["recon_loss"] - float(g["metric/train_recon_loss"])) <= 1e-4 * float(g["metric/train_recon_loss"])
+    assert abs(outs["kld"] - float(g["metric/train_kld_loss"])) <= 1e-3 * float(g["metric/train_kld_loss"]) + 1e-8
+    assert abs(outs["cycle"] - float(g["metric/train_cycle_loss"])) <= 1e-4
+    if "recon" in g.files:
+        assert np.abs(outs["recon"].numpy() - g["recon"]).max() < 1e-4
+        assert np.abs(outs["rotated_recon"].numpy() - g["rotated_recon"]).max() < 1e-4
+    else:
+        assert np.abs(outs["recon"][0, 0, ::8, ::8].numpy() - g["recon_b0"]).max() < 1e-4
+        assert np.abs(outs["rotated_recon"][0, 0, ::8, ::8].numpy() - g["rotated_recon_b0"]).max() < 1e-4
+    # end-to-end gradients: 1e-3, or 3x the reference's own fp32-vs-fp64 reproducibility where
+    # that is larger (tests/util.py:fp32_noise_floor)
+    floor = fp32_noise_floor(O.rvae_full_step, params, x, xr, ang, eps, beta=10.0, gamma=10.0, canonical_weight=0.2)
+    check_grads_against_golden(grads, g, rtol=grad_tolerances(floor))
+
+
+def test_rvae_step_matches_oracle_fresh_seed():
+    P, L, B, seed = 64, 3, 5, 4321
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    x, xr, ang = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    want, wgrads = O.rvae_full_step(params, x, xr, ang, eps, beta=10.0, gamma=10.0, canonical_weight=0.2)
+    outs, grads = _run_rvae_step(P, L, params, x, xr, ang, eps)
+    assert abs(outs["loss"] - float(want["loss"])) <= 1e-4 * abs(float(want["loss"]))
+    assert abs(outs["canonical"] - float(want["canonical"])) <= 1e-4 * abs(float(want["canonical"]))
+    assert np.abs(outs["rotated_recon"].numpy() - want["rotated_recon"].numpy()).max() < 1e-4
+    tol = grad_tolerances(fp32_noise_floor(O.rvae_full_step, params, x, xr, ang, eps, beta=10.0, gamma=10.0,
+                                           canonical_weight=0.2))
+    for k in wgrads:
+        assert rel_l2(grads[k], wgrads[k]) < tol[k], k
+
+
+def test_rvae_no_pair_no_canonical_and_diversity():
+    """criterion branches: gamma = 0; diversity loss; canonical_weight = 0 (loss.py:171-182)"""
+    import livae
+    P, L, B, seed = 32, 2, 6, 99
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    x, xr, ang = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    want, wgrads = O.rvae_full_step(params, x, None, None, eps, beta=2.0, gamma=0.0, canonical_weight=0.0)
+    outs, grads = _run_rvae_step(P, L, params, x, None, None, eps, beta=2.0, gamma=0.0, cw=0.0)
+    assert abs(outs["loss"] - float(want["loss"])) <= 1e-4 * abs(float(want["loss"]))
+    tol = grad_tolerances(fp32_noise_floor(O.rvae_full_step, params, x, None, None, eps, beta=2.0, gamma=0.0,
+                                           canonical_weight=0.0))
+    for k in wgrads:
+        assert rel_l2(grads[k], wgrads[k]) < tol[k] or float(wgrads[k].norm()) < 1e-7, k
+    want, wgrads = O.rvae_full_step(params, x, xr, ang, eps, beta=1.0, gamma=3.0, canonical_weight=0.2,
+                                    use_diversity=True)
+    tol = grad_tolerances(fp32_noise_floor(O.rvae_full_step, params, x, xr, ang, eps, beta=1.0, gamma=3.0,
+                                           canonical_weight=0.2, use_diversity=True))
+    m = _rvae(P, L, params)
+    crit = livae.RVAELoss(beta=1.0, gamma=3.0, use_diversity=True)
+    from livae.train import rvae_step_loss
+    with FixedEps(eps):
+        loss = rvae_step_loss(m, crit, x.cuda(), xr.cuda(), ang.cuda(), 0.2)[0]
+    loss.backward()
+    assert abs(loss.item() - float(want["loss"])) <= 1e-4 * abs(float(want["loss"]))
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad.cpu(), wgrads[k]) < tol[k] or float(wgrads[k].norm()) < 1e-7, k
+
+
+def test_vae_step_matches_reference_golden():
+    import livae
+    g = load_golden("vae_step_p64.npz")
+    P, L, B, seed = int(g["P"]), int(g["L"]), int(g["B"]), int(g["seed"])
+    params = O.make_params(O.vae_param_shapes(P, L), seed=seed)
+    x, _, _ = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    m = livae.VAE(latent_dim=L, in_channels=1, patch_size=P)
+    m.load_state_dict(params, strict=True)
+    m.cuda()
+    crit = livae.VAELoss(beta=1.0)
+    with FixedEps(eps):
+        recon, mu, logvar = m(x.cuda())
+    loss, rl, kl = crit(recon, x.cuda(), mu, logvar)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    assert np.abs(recon.detach().cpu().numpy() - g["recon"]).max() < 1e-4
+    assert rel_l2(mu.detach().cpu(), g["mu"]) < 1e-4
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+    floor = fp32_noise_floor(O.vae_full_step, params, x, eps, beta=1.0)
+    check_grads_against_golden(grads, g, rtol=grad_tolerances(floor))
+
+
+def test_stn_pretrain_step_matches_reference_golden():
+    """scripts/pretrain_stn.py:104-112: two encoder passes + cycle loss"""
+    import livae
+    g = load_golden("stn_pretrain_p32.npz")
+    P, B, seed = int(g["P"]), int(g["B"]), int(g["seed"])
+    params = O.make_params(O.rvae_param_shapes(P, 2), seed=seed, stn_head_std=0.5)
+    x, xr, ang = O.make_lattice_batch(B, P, seed=seed + 1)
+    m = _rvae(P, 2, params)
+    _, _, th0 = m.encoder(x.cuda())
+    _, _, th1 = m.encoder(xr.cuda())
+    loss = livae.cycle_consistency_loss(th0, th1, ang.cuda())
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    assert rel_l2(th0.detach().cpu(), g["theta"]) < 1e-4
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
+    floor = fp32_noise_floor(O.stn_pretrain_step, params, x, xr, ang)
+    floor = {k: floor.get(k, 0.0) for k in grads}
+    check_grads_against_golden(grads, g, rtol=grad_tolerances(floor))
+
+
+def test_train_rvae_one_epoch_runs_and_learns():
+    """drop-in trainer API (train.py:286-445): metric keys, loss decreases over a few epochs"""
+    import livae
+    torch.manual_seed(0)
+    P, L, B = 32, 2, 16
+    x, xr, ang = O.make_lattice_batch(B * 2, P, seed=7)
+    loader = [(x[:B], xr[:B], ang[:B]), (x[B:], xr[B:], ang[B:])]
+    m = livae.RVAE(L, 1, P).cuda()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    crit = livae.RVAELoss(beta=1.0, gamma=10.0)
+    log = livae.MetricLogger()
+    for _ in range(6):
+        livae.train_rvae_one_epoch(m, loader, opt, crit, log, torch.device("cuda"))
+    losses = log.metrics["train_loss"]
+    assert len(losses) == 6 and np.isfinite(losses).all() and losses[-1] < losses[0]
+    for k in ("train_recon_loss", "train_kld_loss", "train_cycle_loss", "train_canonical_loss", "train_psnr",
+              "train_ssim", "train_latent_mean_abs", "train_latent_std", "train_rotation_std", "train_grad_norm",
+              "train_canonical_psnr", "train_canonical_ssim"):
+        assert k in log.metrics, k
+    vlog = livae.MetricLogger()
+    livae.evaluate_rvae(m, loader, crit, vlog, torch.device("cuda"))
+    assert np.isfinite(vlog.metrics["val_loss"][0])
+
+
+def test_train_one_epoch_vae_runs():
+    import livae
+    torch.manual_seed(0)
+    P, L, B = 32, 4, 8
+    x, _, _ = O.make_lattice_batch(B * 2, P, seed=8)
+    loader = [x[:B], x[B:]]
+    m = livae.VAE(L, 1, P).cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    log = livae.MetricLogger()
+    for _ in range(4):
+        livae.train_one_epoch(m, loader, opt, livae.VAELoss(1.0), log, torch.device("cuda"))
+    losses = log.metrics["train_loss"]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    vlog = livae.MetricLogger()
+    livae.evaluate(m, loader, livae.VAELoss(1.0), vlog, torch.device("cuda"))
+    assert "val_psnr" in vlog.metrics

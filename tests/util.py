@@ -42,6 +42,27 @@ def check_grads_against_golden(grads, gold, rtol, atol_frac=1e-6, names=None):
         err = np.linalg.norm(samp - want) / max(np.linalg.norm(want), atol_frac * max(gn, 1e-30))
         nerr = abs(float(g.norm()) - gn) / max(gn, 1e-30)
         worst = max(worst, err, nerr)
-        assert err <= rtol, f"{k}: sampled-grad rel err {err:.3e} > {rtol}"
-        assert nerr <= rtol, f"{k}: grad-norm rel err {nerr:.3e} > {rtol}"
+        tol = rtol[k] if isinstance(rtol, dict) else rtol
+        assert err <= tol, f"{k}: sampled-grad rel err {err:.3e} > {tol:.3e}"
+        assert nerr <= tol, f"{k}: grad-norm rel err {nerr:.3e} > {tol:.3e}"
     return worst
+
+
+def fp32_noise_floor(step_fn, params, *inputs, **kw):
+    """How reproducible the REFERENCE algorithm's own fp32 gradients are: relative L2 distance, per
+    parameter, between the oracle step evaluated in float32 and in float64 on the same inputs.
+    ReLU / max-pool / bilinear-cell decisions flip under 1e-7 perturbations, so end-to-end
+    gradients of the full step are only defined to this level (1e-3..1e-2 for the STN/encoder at
+    P=128); single-kernel parity is tested at 1e-4 in test_gpu_kernels.py."""
+    f64 = lambda t: t.double() if isinstance(t, torch.Tensor) and t.is_floating_point() else t
+    _, g32 = step_fn(params, *inputs, **kw)
+    _, g64 = step_fn({k: v.double() for k, v in params.items()}, *[f64(t) for t in inputs], **kw)
+    out = {}
+    for k in g32:
+        d = float(g64[k].norm())
+        out[k] = float((g32[k].double() - g64[k]).norm()) / d if d > 0 else 0.0
+    return out
+
+
+def grad_tolerances(floor, base=1e-3, factor=3.0):
+    return {k: max(base, factor * v) for k, v in floor.items()}
