@@ -146,6 +146,31 @@ int livae_conv_bwd(const livae_conv_desc* d, const float* x, const float* w, con
                    const float* gy, const uint8_t* pool_idx, float* gw, float* gb, float* gx,
                    livae_stream_t stream);
 
+/* ---- a4/a7/a9: convolution layers, engine 1 (tcgen05 + TMA, bf16 operands, fp32 accumulate) ---
+ * The dense mid layers (encoder c2-c4, decoder d1-d3, STN conv2; model.py:207, 292-296, 359-367)
+ * as a tap-decomposed implicit GEMM: per 128-pixel output tile and per filter tap one TMA box
+ * load of the shifted NHWC input (zero padding = TMA OOB fill) feeds tcgen05.mma; accumulators
+ * live in TMEM.  Parity class 1e-2 (bf16 GEMM inputs).
+ * x: bf16 [B,Hin,Win,Cin]; wpacked: bf16 [kh*kw][Cout][Cin] from livae_tc_pack_weights;
+ * y: bf16 (or fp32 when out_f32) [B,Ho,Wo,Cout]; relu_mask (optional): bf16, same shape as y,
+ * y *= (relu_mask > 0) -- used when y is the gradient of a post-ReLU tensor. */
+typedef struct {
+  int B, Hin, Win, Cin;
+  int Cout, kh, kw, stride, pad;
+  int act;
+  int out_f32;
+} livae_tc_conv_desc;
+int livae_tc_conv_supported(const livae_tc_conv_desc* d);
+/* w: fp32 torch layout [Cs][Cb][kh][kw].  mode 0 -> [tap][Cs][Cb] (forward of Conv2d with
+ * Cout=Cs, Cin=Cb); mode 1 -> [flipped tap][Cb][Cs] (its stride-1 data gradient run as a
+ * forward convolution over gy with pad' = k-1-pad). */
+int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
+                          livae_stream_t stream);
+int livae_tc_conv(const livae_tc_conv_desc* d, const void* x, const void* wpacked, const float* bias,
+                  void* y, const void* relu_mask, livae_stream_t stream);
+/* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
+int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
+
 /* Upsample(x2, bilinear, align_corners=False) + ReflectionPad2d(1) (model.py:357-358 etc.):
  * x [B,H,W,C] -> out [B,2H+2,2W+2,C]; the decoder's 3x3 p0 conv then runs on `out`. */
 int livae_upsample_pad_fwd(const float* x, int B, int H, int W, int C, float* out, livae_stream_t stream);

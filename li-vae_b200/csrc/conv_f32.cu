@@ -65,6 +65,24 @@ struct P2 {  // small -> big (Conv2d dgrad / ConvTranspose2d forward)
   }
 };
 
+// P2 specialised for a "full-map" kernel (Linear over a flattened feature map: Hs = Ws = 1,
+// kh = Hb, kw = Wb, pad 0): each big-side pixel matches exactly one tap, so the data gradient is
+// the plain GEMM [B, Cs] x [Cs, Cb*taps] with the output index permuted to NHWC.
+struct P2Lin {
+  ConvGeom g; TensorRef small; const float* w; float* out;
+  static constexpr bool kAContigK = true, kBContigK = false;
+  __device__ int M() const { return g.B; }
+  __device__ int N() const { return g.Cb * g.kh * g.kw; }
+  __device__ int K() const { return g.Cs; }
+  __device__ float A(int m, int k) const { return ref_load(small, m, 0, 0, k, 1, 1, g.Cs); }
+  __device__ float Bv(int k, int n) const { return __ldg(w + (int64_t)k * g.Cb * g.kh * g.kw + n); }
+  __device__ void store(int m, int n, float v) const {
+    int taps = g.kh * g.kw;
+    int cb = n / taps, tap = n - cb * taps;
+    out[((int64_t)m * taps + tap) * g.Cb + cb] = v;
+  }
+};
+
 struct P3 {  // weight gradient, reduction over (b, oy, ox); split-K with fp32 atomics
   ConvGeom g; TensorRef big; TensorRef small; float* gw;
   static constexpr bool kAContigK = false, kBContigK = false;
@@ -342,8 +360,13 @@ extern "C" int livae_conv_bwd(const livae_conv_desc* d, const float* x, const fl
       LIVAE_CUDA_LAUNCH_CHECK();
     }
     if (gx) {
-      P2 p{g, grad, w, nullptr, gx, LIVAE_ACT_NONE};
-      if (int e = launch_gemm(p, g.B * g.Hb * g.Wb, g.Cb, g.kh * g.kw * g.Cs, false, st)) return e;
+      if (g.Hs == 1 && g.Ws == 1 && g.pad == 0 && g.kh == g.Hb && g.kw == g.Wb && !d->pool) {
+        P2Lin p{g, grad, w, gx};
+        if (int e = launch_gemm(p, g.B, g.Cb * g.kh * g.kw, g.Cs, false, st)) return e;
+      } else {
+        P2 p{g, grad, w, nullptr, gx, LIVAE_ACT_NONE};
+        if (int e = launch_gemm(p, g.B * g.Hb * g.Wb, g.Cb, g.kh * g.kw * g.Cs, false, st)) return e;
+      }
     }
   } else {
     if (gw) {

@@ -1,0 +1,337 @@
+// Engine 1: tcgen05 / TMA implicit-GEMM convolution for the dense layers of the step (encoder
+// c2-c4, decoder d1-d3, STN conv2; reference model.py:207, 292-296, 359-367), bf16 operands,
+// fp32 accumulation in TMEM.  Parity class: 1e-2 relative (bf16 GEMM inputs, north_star).
+//
+// Formulation ("tap decomposition"): for a 128-pixel output tile (nb images x th x tw pixels),
+//     D[128, Cout] = sum over taps (ky,kx) and Cin-chunks c of  A_tap,c[128, kc] * W_tap,c[Cout, kc]^T
+// where A_tap,c is the input tile shifted by the tap -- ONE TMA box load from the NHWC tensor
+// (zero padding = TMA out-of-bounds fill; stride 2 = tensor-map elementStrides), landing in shared
+// memory already in the swizzled K-major layout tcgen05.mma consumes.  No im2col, no thread gathers.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/activation/ReLU-mask -> bf16/fp32 NHWC).
+// A ring of STAGES {A,B} buffers with full/empty mbarriers decouples TMA from the MMA issue.
+#include "tc_common.cuh"
+
+namespace livae {
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides, int inner_bytes) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
+  CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : inner_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return -3; }
+  return 0;
+}
+
+struct ConvTcParams {
+  int tiles_x, tiles_y;   // tiles per image in x / y
+  int tw, th, nb;         // tile = nb images x th rows x tw cols = 128 pixels
+  int Ho, Wo;             // output spatial size
+  int ntaps, kw, stride, pad;
+  int kc, nkc;            // channels per k-block, k-blocks per tap
+  int N;                  // output channels (UMMA N)
+  void* out;              // [B,Ho,Wo,N] bf16 or fp32
+  int out_f32;
+  const float* bias;      // may be null
+  int act;
+  const __nv_bfloat16* relu_mask;  // may be null: out *= (relu_mask > 0), same shape as out
+};
+
+static constexpr int kThreads = 192;
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)p.kc * 2u;
+  const uint32_t a_bytes = 128u * row_bytes;
+  const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
+  const uint32_t a_slot = (a_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_slot + b_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)p.N) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+  const int b0 = tile * p.nb;
+  const int nk = p.ntaps * p.nkc;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int x0 = tx * p.tw * p.stride - p.pad, y0 = ty * p.th * p.stride - p.pad;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
+        const int tap = kb / p.nkc, c = kb - tap * p.nkc;
+        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+        uint8_t* a_s = smem + (uint32_t)s * stage_bytes;
+        tma_load_4d(a_s, &tmA, &full_bar[s], c * p.kc, x0 + kx, y0 + ky, b0);
+        tma_load_3d(a_s + a_slot, &tmB, &full_bar[s], c * p.kc, 0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+      const uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+      const uint32_t sbo = 8u * row_bytes;
+      const int ksteps = p.kc / 16;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (uint32_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + a_slot;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+          const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(&accum_bar);        // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int px = row % p.tw;
+    const int t2 = row / p.tw;
+    const int py = t2 % p.th;
+    const int bi = t2 / p.th;
+    const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (ty * p.th + py)) * p.Wo + (tx * p.tw + px);
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(v[i]);
+        if (p.bias) a += __ldg(p.bias + c0 + i);
+        if (p.act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (p.act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
+        f[i] = a;
+      }
+      if (p.relu_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + pix * p.N + c0);
+        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
+        const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!(__bfloat162float(mb0[i]) > 0.f)) f[i] = 0.f;
+          if (!(__bfloat162float(mb1[i]) > 0.f)) f[8 + i] = 0.f;
+        }
+      }
+      if (p.out_f32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.N + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.N + c0);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+// w fp32 [Cs][Cb][kh][kw] (torch) -> bf16
+//   mode 0: out[tap][cs][cb]                      (P1: big -> small, K = cb)
+//   mode 1: out[tap'][cb][cs], tap' = flipped tap (P2 at stride 1 run as a P1 over the small side)
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb, int kh, int kw, int mode,
+                                    __nv_bfloat16* __restrict__ out) {
+  int n = Cs * Cb * kh * kw;
+  int taps = kh * kw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int tap, cs, cb;
+    if (mode == 0) { cb = i % Cb; int t = i / Cb; cs = t % Cs; tap = t / Cs; }
+    else { cs = i % Cs; int t = i / Cs; cb = t % Cb; tap = taps - 1 - t / Cb; }
+    out[i] = __float2bfloat16_rn(w[((int64_t)cs * Cb + cb) * taps + tap]);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ y) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __bfloat162float(x[i]);
+}
+
+}  // namespace tc
+}  // namespace livae
+
+using namespace livae;
+using namespace livae::tc;
+
+// Can the tensor-core engine run this convolution?  (channel counts a multiple of 16, a 128-pixel
+// tile that divides the output, Cout a valid UMMA N)
+extern "C" int livae_tc_conv_supported(const livae_tc_conv_desc* d) {
+  if (!d) return 0;
+  if (d->Cin % 16 != 0 || d->Cout % 16 != 0 || d->Cout < 16 || d->Cout > 256) return 0;
+  if (d->Cin > 64 && d->Cin % 64 != 0) return 0;
+  if (d->Cin < 64 && d->Cin != 16 && d->Cin != 32) return 0;
+  int Ho = (d->Hin + 2 * d->pad - d->kh) / d->stride + 1, Wo = (d->Win + 2 * d->pad - d->kw) / d->stride + 1;
+  if (Ho <= 0 || Wo <= 0) return 0;
+  if (d->stride != 1 && d->stride != 2) return 0;
+  int tw = Wo >= 16 ? 16 : Wo;
+  if ((tw & (tw - 1)) != 0 || Wo % tw != 0) return 0;
+  int th = 128 / tw;
+  int nb = 1;
+  if (th > Ho) { if (th % Ho != 0) return 0; nb = th / Ho; th = Ho; }
+  if (Ho % th != 0 || d->B % nb != 0) return 0;
+  if (tw * d->stride > 256 || th * d->stride > 256) return 0;
+  return 1;
+}
+
+extern "C" int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
+                                     livae_stream_t stream) {
+  LIVAE_CHECK_ARG(w && out_bf16 && Cs > 0 && Cb > 0 && kh > 0 && kw > 0 && (mode == 0 || mode == 1),
+                  "tc_pack_weights: bad args");
+  if (int e = require_sm100()) return e;
+  int n = Cs * Cb * kh * kw;
+  pack_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cs, Cb, kh, kw, mode,
+                                                                          (__nv_bfloat16*)out_bf16);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(n >= 0, "cast: bad size");
+  if (n == 0) return 0;
+  LIVAE_CHECK_ARG(src && dst, "cast: null pointer");
+  if (int e = require_sm100()) return e;
+  int64_t blocks = (n + 1023) / 1024;
+  int grid = (int)(blocks < kNumSMs * 16 ? blocks : kNumSMs * 16);
+  if (dt_src == LIVAE_F32 && dt_dst == LIVAE_BF16)
+    cast_f32_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, n, (__nv_bfloat16*)dst);
+  else if (dt_src == LIVAE_BF16 && dt_dst == LIVAE_F32)
+    cast_bf16_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, (float*)dst);
+  else { set_error("cast: unsupported dtype pair %d -> %d", dt_src, dt_dst); return -1; }
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// y[B,Ho,Wo,Cout] = act(conv(x[B,Hin,Win,Cin] (bf16), wpacked[tap][Cout][Cin] (bf16)) + bias) [* (mask > 0)]
+extern "C" int livae_tc_conv(const livae_tc_conv_desc* d, const void* x, const void* wpacked, const float* bias,
+                             void* y, const void* relu_mask, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(d, "tc_conv: null descriptor");
+  if (d->B == 0) return 0;
+  LIVAE_CHECK_ARG(x && wpacked && y, "tc_conv: null pointer");
+  LIVAE_CHECK_ARG(livae_tc_conv_supported(d), "tc_conv: shape not supported by the tensor-core engine");
+  LIVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)wpacked | (uintptr_t)y | (uintptr_t)relu_mask) & 15) == 0,
+                  "tc_conv: pointers must be 16-byte aligned");
+  if (int e = require_sm100()) return e;
+  const int Ho = (d->Hin + 2 * d->pad - d->kh) / d->stride + 1, Wo = (d->Win + 2 * d->pad - d->kw) / d->stride + 1;
+  ConvTcParams p;
+  p.tw = Wo >= 16 ? 16 : Wo;
+  p.th = 128 / p.tw;
+  p.nb = 1;
+  if (p.th > Ho) { p.nb = p.th / Ho; p.th = Ho; }
+  p.tiles_x = Wo / p.tw; p.tiles_y = Ho / p.th;
+  p.Ho = Ho; p.Wo = Wo;
+  p.ntaps = d->kh * d->kw; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
+  p.kc = d->Cin >= 64 ? 64 : d->Cin;
+  p.nkc = d->Cin / p.kc;
+  p.N = d->Cout;
+  p.out = y; p.out_f32 = d->out_f32; p.bias = bias; p.act = d->act;
+  p.relu_mask = (const __nv_bfloat16*)relu_mask;
+  const int row_bytes = p.kc * 2;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->Win * d->Cin * 2, (uint64_t)d->Hin * d->Win * d->Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.tw * d->stride), (uint32_t)(p.th * d->stride), (uint32_t)p.nb};
+    uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+    if (int e = make_tmap_bf16(&tmA, x, 4, dims, str, box, es, row_bytes)) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)p.ntaps};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout * d->Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)d->Cout, 1};
+    if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
+  }
+  const uint32_t a_slot = (128u * row_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
+  constexpr int STAGES = 4;
+  const size_t smem = (size_t)STAGES * (a_slot + b_slot) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * (d->B / p.nb);
+  conv_tc_kernel<STAGES><<<tiles, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}

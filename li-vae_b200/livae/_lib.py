@@ -23,7 +23,14 @@ class ConvDesc(C.Structure):
                                        "pad", "act", "pool")]
 
 
+class TcConvDesc(C.Structure):
+    """mirror of livae_tc_conv_desc"""
+    _fields_ = [(n, C.c_int) for n in ("B", "Hin", "Win", "Cin", "Cout", "kh", "kw", "stride", "pad", "act",
+                                       "out_f32")]
+
+
 CONV, CONVT = 0, 2
+F32, F16, BF16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 
 # name -> argument type codes: p pointer, i int, l int64, f float, s stream, d ConvDesc*
@@ -46,6 +53,9 @@ _SIGS = {
     "livae_axpby_dev": "pppplps",
     "livae_conv_fwd": "d" + "p" * 6 + "s",
     "livae_conv_bwd": "d" + "p" * 8 + "s",
+    "livae_tc_pack_weights": "piiiiips",
+    "livae_tc_conv": "t" + "p" * 5 + "s",
+    "livae_cast": "pipils",
     "livae_upsample_pad_fwd": "piiiips",
     "livae_upsample_pad_bwd": "piiiipps",
     "livae_decfc_fwd": "pppiiiips",
@@ -53,7 +63,7 @@ _SIGS = {
     "livae_l2norm_clip": "plfppis",
     "livae_adamw": "pppplfffffippis",
 }
-_CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P, "d": C.POINTER(ConvDesc)}
+_CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P, "d": C.POINTER(ConvDesc), "t": C.POINTER(TcConvDesc)}
 
 _lib = None
 
@@ -75,6 +85,8 @@ def lib():
         getattr(L, n).argtypes = []
     L.livae_conv_fwd_ws_bytes.restype = C.c_int64
     L.livae_conv_fwd_ws_bytes.argtypes = [C.POINTER(ConvDesc)]
+    L.livae_tc_conv_supported.restype = C.c_int
+    L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_conv_out_shape.restype = None
     L.livae_conv_out_shape.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for name, sig in _SIGS.items():
@@ -89,7 +101,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
 
 
 def ptr(t):

@@ -381,3 +381,48 @@ def adamw_(p, g, m, v, step_dev, lr, betas, eps, weight_decay, decoupled=True, g
     require_cuda(p, g, m, v, step_dev)
     call("livae_adamw", p, g, m, v, p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
          float(weight_decay), int(decoupled), step_dev, gscale, int(inc_step))
+
+
+# ------------------------------------------------------------------------------------------
+# engine 1: tcgen05 / TMA convolution (bf16 operands, fp32 accumulate)
+# ------------------------------------------------------------------------------------------
+def cast(t, dtype):
+    """fp32 <-> bf16 conversion kernel"""
+    t = _c(t)
+    if t.dtype == dtype:
+        return t
+    codes = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    call("livae_cast", t, codes[t.dtype], out, codes[dtype], t.numel())
+    return out
+
+
+def tc_pack_weights(w, Cs, Cb, kh, kw, mode):
+    """torch-layout fp32 weight [Cs,Cb,kh,kw] -> bf16 [tap][Cs][Cb] (mode 0) / [flipped tap][Cb][Cs] (mode 1)"""
+    w = _c(w)
+    assert w.numel() == Cs * Cb * kh * kw and w.dtype == torch.float32 and w.is_cuda
+    shape = (kh * kw, Cs, Cb) if mode == 0 else (kh * kw, Cb, Cs)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    call("livae_tc_pack_weights", w, Cs, Cb, kh, kw, mode, out)
+    return out
+
+
+def tc_conv_supported(B, Hin, Win, Cin, Cout, kh, kw, stride, pad):
+    d = L.TcConvDesc(B, Hin, Win, Cin, Cout, kh, kw, stride, pad, 0, 0)
+    return bool(L.lib().livae_tc_conv_supported(C.byref(d)))
+
+
+def tc_conv(x, wpacked, bias, kh, kw, stride, pad, act=ACT_NONE, out_f32=False, relu_mask=None):
+    """raw tensor-core convolution (no autograd): x bf16 [B,H,W,Cin], wpacked bf16 [taps,Cout,Cin]"""
+    assert x.dtype == torch.bfloat16 and wpacked.dtype == torch.bfloat16 and x.is_cuda and x.is_contiguous()
+    B, Hin, Win, Cin = x.shape
+    taps, Cout, Cin2 = wpacked.shape
+    assert Cin2 == Cin and taps == kh * kw
+    d = L.TcConvDesc(B, Hin, Win, Cin, Cout, kh, kw, stride, pad, act, int(out_f32))
+    Ho = (Hin + 2 * pad - kh) // stride + 1
+    Wo = (Win + 2 * pad - kw) // stride + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    if relu_mask is not None:
+        assert relu_mask.dtype == torch.bfloat16 and relu_mask.shape == y.shape and relu_mask.is_contiguous()
+    call("livae_tc_conv", C.byref(d), x, wpacked, bias, y, relu_mask)
+    return y

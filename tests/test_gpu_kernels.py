@@ -198,7 +198,11 @@ CONV_CASES = [
     (2, 32, 8, 8, 64, 4, 2, 1, "relu", False),      # encoder c2..c4 (model.py:292-296)
     (2, 24, 10, 10, 40, 3, 1, 0, "relu", False),    # decoder 3x3 p0 (model.py:359-367)
     (2, 32, 10, 12, 1, 3, 1, 0, "sigmoid", False),  # decoder last layer (model.py:371-372)
+    (2, 64, 8, 8, 128, 4, 2, 1, "relu", False),     # encoder c3/c4 widths: 64-wide N tiles in dgrad
+    (5, 128, 4, 4, 256, 4, 2, 1, "relu", False),    # encoder c4 at P=32 (odd batch)
+    (3, 64, 6, 6, 48, 3, 1, 0, "relu", False),      # decoder widths, stride 1
     (5, 8, 4, 4, 7, 4, 1, 0, "none", False),        # Linear over a flattened map (model.py:302-303)
+    (6, 256, 2, 2, 2, 2, 1, 0, "none", False),      # encoder heads at P=32 (model.py:302-303)
     (5, 32, 1, 1, 2, 1, 1, 0, "none", False),       # Linear(32, 2) (model.py:213)
 ]
 _ACT = {"none": 0, "relu": 1, "sigmoid": 2}
@@ -266,6 +270,40 @@ def test_linear_nhwc_matches_nchw_flatten(ops):
     assert rel_l2(yd.detach().cpu(), y.detach()) < 1e-5
     assert rel_l2(xd.grad.cpu(), _nhwc(x.grad)) < 1e-4
     assert rel_l2(wd.grad.cpu(), w.grad) < 1e-4 and rel_l2(bd.grad.cpu(), b.grad) < 1e-4
+
+
+def test_encoder_chain_strict(ops):
+    """4 strided convs + two Linear heads composed through autograd, identical inputs on both
+    sides: every activation, activation gradient and weight gradient within 1e-5 (model.py:289-324)"""
+    torch.manual_seed(0)
+    B, P, Ld = 6, 32, 2
+    chans = [(1, 32), (32, 64), (64, 128), (128, 256)]
+    ws = [torch.randn(co, ci, 4, 4) / (ci * 16) ** 0.5 for ci, co in chans]
+    bs = [torch.randn(co) * 0.1 for ci, co in chans]
+    q = P // 16
+    wm = torch.randn(Ld, 256 * q * q) * 0.05; wl = torch.randn(Ld, 256 * q * q) * 0.05
+    x = torch.rand(B, 1, P, P)
+    gm = torch.randn(B, Ld); gl = torch.randn(B, Ld)
+    xc = x.clone().requires_grad_(True)
+    hs = []; h = xc
+    pw = [w.clone().requires_grad_(True) for w in ws]
+    for w, b in zip(pw, bs):
+        h = torch.relu(F.conv2d(h, w, b, stride=2, padding=1)); h.retain_grad(); hs.append(h)
+    mu = F.linear(h.flatten(1), wm); lv = F.linear(h.flatten(1), wl)
+    ((mu * gm).sum() + (lv * gl).sum()).backward()
+    xd = x.cuda().reshape(B, P, P, 1).requires_grad_(True)
+    hd = xd; hds = []
+    dw = [w.cuda().requires_grad_(True) for w in ws]
+    for w, b in zip(dw, bs):
+        hd = ops.conv2d(hd, w, b.cuda(), 4, 4, 2, 1, 1); hd.retain_grad(); hds.append(hd)
+    mud = ops.linear_nhwc(hd, wm.cuda(), None); lvd = ops.linear_nhwc(hd, wl.cuda(), None)
+    ((mud * gm.cuda()).sum() + (lvd * gl.cuda()).sum()).backward()
+    assert rel_l2(mud.detach().cpu(), mu.detach()) < 1e-5
+    for i in range(4):
+        assert rel_l2(hds[i].detach().cpu(), hs[i].detach().permute(0, 2, 3, 1)) < 1e-5
+        assert rel_l2(hds[i].grad.cpu(), hs[i].grad.permute(0, 2, 3, 1)) < 1e-5
+        assert rel_l2(dw[i].grad.cpu(), pw[i].grad) < 1e-5
+    assert rel_l2(xd.grad.cpu().reshape(B, 1, P, P), xc.grad) < 1e-5
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 2, 2), (2, 5, 4, 6), (1, 8, 8, 8)])

