@@ -163,11 +163,23 @@ typedef struct {
 int livae_tc_conv_supported(const livae_tc_conv_desc* d);
 /* w: fp32 torch layout [Cs][Cb][kh][kw].  mode 0 -> [tap][Cs][Cb] (forward of Conv2d with
  * Cout=Cs, Cin=Cb); mode 1 -> [flipped tap][Cb][Cs] (its stride-1 data gradient run as a
- * forward convolution over gy with pad' = k-1-pad). */
+ * forward convolution over gy with pad' = k-1-pad); mode 2 -> [tap][Cb][Cs] (livae_tc_conv_dgrad). */
 int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
                           livae_stream_t stream);
 int livae_tc_conv(const livae_tc_conv_desc* d, const void* x, const void* wpacked, const float* bias,
                   void* y, const void* relu_mask, livae_stream_t stream);
+/* Data gradient of the convolution d (= nn.ConvTranspose2d forward with x := gy, model.py:90-96):
+ * gx[B,Hin,Win,Cin] = act(sum gy[b,(iy+pad-ky)/s,(ix+pad-kx)/s,co] * w[co,ci,ky,kx] + bias) [* (relu_mask>0)].
+ * gy: bf16 [B,Ho,Wo,Cout]; wpacked: mode-2 packing; stride 2 runs as four output-parity phases. */
+int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, const void* wpacked,
+                        const float* bias, void* gx, const void* relu_mask, livae_stream_t stream);
+/* Weight (+ bias) gradient of the convolution d on tensor cores.  x: bf16 [B,Hin,Win,Cin];
+ * gy: bf16 [B,Ho,Wo,Cout], already the PRE-activation gradient; gw: fp32 torch layout
+ * [Cout][Cin][kh][kw] (written); gb: fp32 [Cout] (written, may be NULL);
+ * ws: livae_tc_wgrad_ws_bytes(d) bytes of scratch. */
+int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d);
+int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
+                        void* ws, livae_stream_t stream);
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

@@ -46,13 +46,20 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   return 0;
 }
 
+static constexpr int kMaxTaps = 32;
 struct ConvTcParams {
-  int tiles_x, tiles_y;   // tiles per image in x / y
-  int tw, th, nb;         // tile = nb images x th rows x tw cols = 128 pixels
-  int Ho, Wo;             // output spatial size
-  int ntaps, kw, stride, pad;
+  int tiles_x, tiles_y;   // tiles per image in x / y (ragged last tiles are predicated)
+  int tw, th, nb;         // tile = nb images x th rows x tw cols <= 128 pixels
+  int Hq, Wq;             // tile-grid extent in output-grid units (Ho/os, Wo/os)
+  int Ho, Wo;             // full output spatial size
+  int os, oy0, ox0;       // output pixel = (q * os + o?0): os = 2 for the stride-2 phase kernels
+  int in_stride;          // input coordinate of grid point q is q * in_stride + tap offset
+  int ntaps;
+  int8_t tap_dy[kMaxTaps], tap_dx[kMaxTaps];  // input offset of each tap (pad already folded in)
+  int8_t tap_w[kMaxTaps];                     // index of each tap in the packed weight tensor
   int kc, nkc;            // channels per k-block, k-blocks per tap
   int N;                  // output channels (UMMA N)
+  int B;
   void* out;              // [B,Ho,Wo,N] bf16 or fp32
   int out_f32;
   const float* bias;      // may be null
@@ -74,9 +81,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)p.kc * 2u;
-  const uint32_t a_bytes = 128u * row_bytes;
+  const uint32_t a_bytes = (uint32_t)(p.nb * p.th * p.tw) * row_bytes;   // bytes one A box delivers
   const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
-  const uint32_t a_slot = (a_bytes + 1023u) & ~1023u;
+  const uint32_t a_slot = (128u * row_bytes + 1023u) & ~1023u;
   const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_slot + b_slot;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -107,17 +114,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      const int x0 = tx * p.tw * p.stride - p.pad, y0 = ty * p.th * p.stride - p.pad;
+      const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
         const int tap = kb / p.nkc, c = kb - tap * p.nkc;
-        const int ky = tap / p.kw, kx = tap - ky * p.kw;
         uint8_t* a_s = smem + (uint32_t)s * stage_bytes;
-        tma_load_4d(a_s, &tmA, &full_bar[s], c * p.kc, x0 + kx, y0 + ky, b0);
-        tma_load_3d(a_s + a_slot, &tmB, &full_bar[s], c * p.kc, 0, tap);
+        tma_load_4d(a_s, &tmA, &full_bar[s], c * p.kc, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+        tma_load_3d(a_s + a_slot, &tmB, &full_bar[s], c * p.kc, 0, (int)p.tap_w[tap]);
       }
     }
   } else if (warp == 1) {
@@ -150,14 +156,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int t2 = row / p.tw;
     const int py = t2 % p.th;
     const int bi = t2 / p.th;
-    const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (ty * p.th + py)) * p.Wo + (tx * p.tw + px);
+    const int qy = ty * p.th + py, qx = tx * p.tw + px;
+    const bool valid = bi < p.nb && (b0 + bi) < p.B && qy < p.Hq && qx < p.Wq;
+    const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int c0 = 0; c0 < p.N; c0 += 16) {
       uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld16(taddr + (uint32_t)c0, v);   // warp-collective: issued by all lanes, stores predicated
       tmem_ld_wait();
+      if (!valid) continue;
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // w fp32 [Cs][Cb][kh][kw] (torch) -> bf16
 //   mode 0: out[tap][cs][cb]                      (P1: big -> small, K = cb)
 //   mode 1: out[tap'][cb][cs], tap' = flipped tap (P2 at stride 1 run as a P1 over the small side)
+//   mode 2: out[tap][cb][cs]                      (data gradient / ConvTranspose2d forward, K = cs)
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb, int kh, int kw, int mode,
                                     __nv_bfloat16* __restrict__ out) {
   int n = Cs * Cb * kh * kw;
@@ -213,7 +223,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb,
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int tap, cs, cb;
     if (mode == 0) { cb = i % Cb; int t = i / Cb; cs = t % Cs; tap = t / Cs; }
-    else { cs = i % Cs; int t = i / Cs; cb = t % Cb; tap = taps - 1 - t / Cb; }
+    else { cs = i % Cs; int t = i / Cs; cb = t % Cb; tap = mode == 1 ? taps - 1 - t / Cb : t / Cb; }
     out[i] = __float2bfloat16_rn(w[((int64_t)cs * Cb + cb) * taps + tap]);
   }
 }
@@ -233,29 +243,106 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_
 using namespace livae;
 using namespace livae::tc;
 
-// Can the tensor-core engine run this convolution?  (channel counts a multiple of 16, a 128-pixel
-// tile that divides the output, Cout a valid UMMA N)
+namespace livae {
+namespace tc {
+
+// Pick the (nb, th, tw) pixel tile (<= 128 pixels = UMMA M rows) that covers an Hq x Wq grid with
+// the fewest tiles; ragged edges are handled by TMA zero fill + predicated stores.
+static void choose_tile(int Hq, int Wq, int B, int* tw, int* th, int* nb) {
+  if (Hq * Wq <= 64) {
+    *tw = Wq; *th = Hq;
+    int n = 128 / (Hq * Wq);
+    if (n > B) n = B;
+    *nb = n < 1 ? 1 : n;
+    return;
+  }
+  *nb = 1;
+  int best = 1 << 30, btw = 1, bth = 1;
+  for (int w = 1; w <= (Wq < 128 ? Wq : 128); ++w) {
+    int h = 128 / w;
+    if (h > Hq) h = Hq;
+    if (h < 1) continue;
+    int tiles = ((Wq + w - 1) / w) * ((Hq + h - 1) / h);
+    if (tiles < best || (tiles == best && w > btw)) { best = tiles; btw = w; bth = h; }
+  }
+  *tw = btw; *th = bth;
+}
+
+static bool channels_ok(int Cin, int Cout) {
+  if (Cout % 16 != 0 || Cout < 16 || Cout > 256) return false;
+  if (Cin >= 64) return Cin % 64 == 0;
+  return Cin == 16 || Cin == 32;
+}
+
+// One launch: out[b, q*os+o0, :, N] = epilogue( sum_taps in[b, q*in_stride + d(tap), :, Cin] * W[wtap][N][Cin] )
+static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
+                          int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
+                          const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
+                          const float* bias, int act, const void* relu_mask, cudaStream_t st) {
+  LIVAE_CHECK_ARG(ntaps >= 1 && ntaps <= kMaxTaps, "tc_conv: too many taps (%d)", ntaps);
+  ConvTcParams p;
+  choose_tile(Hq, Wq, B, &p.tw, &p.th, &p.nb);
+  LIVAE_CHECK_ARG(p.tw * in_stride <= 256 && p.th * in_stride <= 256, "tc_conv: TMA box too large");
+  p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + p.th - 1) / p.th;
+  p.Hq = Hq; p.Wq = Wq; p.Ho = Ho; p.Wo = Wo; p.os = os; p.oy0 = oy0; p.ox0 = ox0; p.in_stride = in_stride;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { p.tap_dy[t] = (int8_t)tdy[t]; p.tap_dx[t] = (int8_t)tdx[t]; p.tap_w[t] = (int8_t)tw_idx[t]; }
+  p.kc = Cin >= 64 ? 64 : Cin;
+  p.nkc = Cin / p.kc;
+  p.N = N; p.B = B;
+  p.out = out; p.out_f32 = out_f32; p.bias = bias; p.act = act;
+  p.relu_mask = (const __nv_bfloat16*)relu_mask;
+  const int row_bytes = p.kc * 2;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.tw * in_stride), (uint32_t)(p.th * in_stride), (uint32_t)p.nb};
+    uint32_t es[4] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1};
+    if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)wtaps};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)N, 1};
+    if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
+  }
+  const uint32_t a_slot = (128u * row_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)N * row_bytes + 1023u) & ~1023u;
+  constexpr int STAGES = 4;
+  const size_t smem = (size_t)STAGES * (a_slot + b_slot) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * ((B + p.nb - 1) / p.nb);
+  conv_tc_kernel<STAGES><<<tiles, kThreads, smem, st>>>(tmA, tmB, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace livae
+
+using namespace livae;
+using namespace livae::tc;
+
+// Can the tensor-core engine run this convolution (forward AND both gradients)?
 extern "C" int livae_tc_conv_supported(const livae_tc_conv_desc* d) {
   if (!d) return 0;
-  if (d->Cin % 16 != 0 || d->Cout % 16 != 0 || d->Cout < 16 || d->Cout > 256) return 0;
-  if (d->Cin > 64 && d->Cin % 64 != 0) return 0;
-  if (d->Cin < 64 && d->Cin != 16 && d->Cin != 32) return 0;
+  if (!channels_ok(d->Cin, d->Cout)) return 0;
+  if (d->stride != 1 && d->stride != 2) return 0;
+  if (d->kh * d->kw > kMaxTaps) return 0;
   int Ho = (d->Hin + 2 * d->pad - d->kh) / d->stride + 1, Wo = (d->Win + 2 * d->pad - d->kw) / d->stride + 1;
   if (Ho <= 0 || Wo <= 0) return 0;
-  if (d->stride != 1 && d->stride != 2) return 0;
-  int tw = Wo >= 16 ? 16 : Wo;
-  if ((tw & (tw - 1)) != 0 || Wo % tw != 0) return 0;
-  int th = 128 / tw;
-  int nb = 1;
-  if (th > Ho) { if (th % Ho != 0) return 0; nb = th / Ho; th = Ho; }
-  if (Ho % th != 0 || d->B % nb != 0) return 0;
-  if (tw * d->stride > 256 || th * d->stride > 256) return 0;
+  if (d->stride == 2 && ((d->Hin | d->Win) & 1)) return 0;
   return 1;
 }
 
 extern "C" int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
                                      livae_stream_t stream) {
-  LIVAE_CHECK_ARG(w && out_bf16 && Cs > 0 && Cb > 0 && kh > 0 && kw > 0 && (mode == 0 || mode == 1),
+  LIVAE_CHECK_ARG(w && out_bf16 && Cs > 0 && Cb > 0 && kh > 0 && kw > 0 && mode >= 0 && mode <= 2,
                   "tc_pack_weights: bad args");
   if (int e = require_sm100()) return e;
   int n = Cs * Cb * kh * kw;
@@ -287,51 +374,58 @@ extern "C" int livae_tc_conv(const livae_tc_conv_desc* d, const void* x, const v
   LIVAE_CHECK_ARG(d, "tc_conv: null descriptor");
   if (d->B == 0) return 0;
   LIVAE_CHECK_ARG(x && wpacked && y, "tc_conv: null pointer");
-  LIVAE_CHECK_ARG(livae_tc_conv_supported(d), "tc_conv: shape not supported by the tensor-core engine");
+  LIVAE_CHECK_ARG(channels_ok(d->Cin, d->Cout) && (d->stride == 1 || d->stride == 2) && d->kh * d->kw <= kMaxTaps,
+                  "tc_conv: shape not supported by the tensor-core engine");
   LIVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)wpacked | (uintptr_t)y | (uintptr_t)relu_mask) & 15) == 0,
                   "tc_conv: pointers must be 16-byte aligned");
   if (int e = require_sm100()) return e;
   const int Ho = (d->Hin + 2 * d->pad - d->kh) / d->stride + 1, Wo = (d->Win + 2 * d->pad - d->kw) / d->stride + 1;
-  ConvTcParams p;
-  p.tw = Wo >= 16 ? 16 : Wo;
-  p.th = 128 / p.tw;
-  p.nb = 1;
-  if (p.th > Ho) { p.nb = p.th / Ho; p.th = Ho; }
-  p.tiles_x = Wo / p.tw; p.tiles_y = Ho / p.th;
-  p.Ho = Ho; p.Wo = Wo;
-  p.ntaps = d->kh * d->kw; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad;
-  p.kc = d->Cin >= 64 ? 64 : d->Cin;
-  p.nkc = d->Cin / p.kc;
-  p.N = d->Cout;
-  p.out = y; p.out_f32 = d->out_f32; p.bias = bias; p.act = d->act;
-  p.relu_mask = (const __nv_bfloat16*)relu_mask;
-  const int row_bytes = p.kc * 2;
+  LIVAE_CHECK_ARG(Ho > 0 && Wo > 0, "tc_conv: empty output");
+  int tdy[kMaxTaps], tdx[kMaxTaps], tw[kMaxTaps];
+  for (int ky = 0; ky < d->kh; ++ky)
+    for (int kx = 0; kx < d->kw; ++kx) {
+      int t = ky * d->kw + kx;
+      tdy[t] = ky - d->pad; tdx[t] = kx - d->pad; tw[t] = t;
+    }
+  return launch_conv_tc(x, d->B, d->Hin, d->Win, d->Cin, wpacked, d->kh * d->kw, d->Cout, Ho, Wo, Ho, Wo, 1, 0, 0,
+                        d->stride, d->kh * d->kw, tdy, tdx, tw, y, d->out_f32, bias, d->act, relu_mask,
+                        (cudaStream_t)stream);
+}
 
-  CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->B};
-    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->Win * d->Cin * 2, (uint64_t)d->Hin * d->Win * d->Cin * 2};
-    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.tw * d->stride), (uint32_t)(p.th * d->stride), (uint32_t)p.nb};
-    uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
-    if (int e = make_tmap_bf16(&tmA, x, 4, dims, str, box, es, row_bytes)) return e;
-  }
-  {
-    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)p.ntaps};
-    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout * d->Cin * 2};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)d->Cout, 1};
-    if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
-  }
-  const uint32_t a_slot = (128u * row_bytes + 1023u) & ~1023u;
-  const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
-  constexpr int STAGES = 4;
-  const size_t smem = (size_t)STAGES * (a_slot + b_slot) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(conv_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
-  const int tiles = p.tiles_x * p.tiles_y * (d->B / p.nb);
-  conv_tc_kernel<STAGES><<<tiles, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
-  LIVAE_CUDA_LAUNCH_CHECK();
+// Data gradient of the convolution described by d (also nn.ConvTranspose2d forward, model.py:90-96):
+//   gx[B,Hin,Win,Cin] = act( sum_{ky,kx,co} gy[b,(iy+pad-ky)/s,(ix+pad-kx)/s,co] * w[co,ci,ky,kx] + bias ) [* (mask>0)]
+// gy: bf16 [B,Ho,Wo,Cout]; wpacked: mode-2 packing [tap][Cin][Cout].  Stride 2 runs as four
+// output-parity phases, each a stride-1 convolution over gy with the taps of matching parity.
+extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, const void* wpacked,
+                                   const float* bias, void* gx, const void* relu_mask, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(d, "tc_conv_dgrad: null descriptor");
+  if (d->B == 0) return 0;
+  LIVAE_CHECK_ARG(gy && wpacked && gx, "tc_conv_dgrad: null pointer");
+  LIVAE_CHECK_ARG(channels_ok(d->Cout, d->Cin) && (d->stride == 1 || d->stride == 2) && d->kh * d->kw <= kMaxTaps,
+                  "tc_conv_dgrad: shape not supported by the tensor-core engine");
+  LIVAE_CHECK_ARG((((uintptr_t)gy | (uintptr_t)wpacked | (uintptr_t)gx | (uintptr_t)relu_mask) & 15) == 0,
+                  "tc_conv_dgrad: pointers must be 16-byte aligned");
+  if (int e = require_sm100()) return e;
+  const int s = d->stride;
+  const int Ho = (d->Hin + 2 * d->pad - d->kh) / s + 1, Wo = (d->Win + 2 * d->pad - d->kw) / s + 1;
+  LIVAE_CHECK_ARG(Ho > 0 && Wo > 0, "tc_conv_dgrad: empty output");
+  LIVAE_CHECK_ARG(s == 1 || ((d->Hin % 2) == 0 && (d->Win % 2) == 0), "tc_conv_dgrad: stride 2 needs even input size");
+  for (int py = 0; py < s; ++py)
+    for (int px = 0; px < s; ++px) {
+      int tdy[kMaxTaps], tdx[kMaxTaps], tw[kMaxTaps], nt = 0;
+      for (int ky = 0; ky < d->kh; ++ky) {
+        if ((py + d->pad - ky) % s != 0) continue;
+        for (int kx = 0; kx < d->kw; ++kx) {
+          if ((px + d->pad - kx) % s != 0) continue;
+          tdy[nt] = (py + d->pad - ky) / s; tdx[nt] = (px + d->pad - kx) / s; tw[nt] = ky * d->kw + kx;
+          ++nt;
+        }
+      }
+      LIVAE_CHECK_ARG(nt > 0, "tc_conv_dgrad: a phase without taps is not supported");
+      if (int e = launch_conv_tc(gy, d->B, Ho, Wo, d->Cout, wpacked, d->kh * d->kw, d->Cin, d->Hin / s, d->Win / s,
+                                 d->Hin, d->Win, s, py, px, 1, nt, tdy, tdx, tw, gx, d->out_f32, bias, d->act,
+                                 relu_mask, (cudaStream_t)stream))
+        return e;
+    }
   return 0;
 }

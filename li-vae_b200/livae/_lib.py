@@ -55,6 +55,8 @@ _SIGS = {
     "livae_conv_bwd": "d" + "p" * 8 + "s",
     "livae_tc_pack_weights": "piiiiips",
     "livae_tc_conv": "t" + "p" * 5 + "s",
+    "livae_tc_conv_dgrad": "t" + "p" * 5 + "s",
+    "livae_tc_conv_wgrad": "t" + "p" * 5 + "s",
     "livae_cast": "pipils",
     "livae_upsample_pad_fwd": "piiiips",
     "livae_upsample_pad_bwd": "piiiipps",
@@ -85,6 +87,8 @@ def lib():
         getattr(L, n).argtypes = []
     L.livae_conv_fwd_ws_bytes.restype = C.c_int64
     L.livae_conv_fwd_ws_bytes.argtypes = [C.POINTER(ConvDesc)]
+    L.livae_tc_wgrad_ws_bytes.restype = C.c_int64
+    L.livae_tc_wgrad_ws_bytes.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_tc_conv_supported.restype = C.c_int
     L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_conv_out_shape.restype = None
@@ -101,7 +105,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
 
 
 def ptr(t):

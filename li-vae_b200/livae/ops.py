@@ -401,7 +401,7 @@ def tc_pack_weights(w, Cs, Cb, kh, kw, mode):
     """torch-layout fp32 weight [Cs,Cb,kh,kw] -> bf16 [tap][Cs][Cb] (mode 0) / [flipped tap][Cb][Cs] (mode 1)"""
     w = _c(w)
     assert w.numel() == Cs * Cb * kh * kw and w.dtype == torch.float32 and w.is_cuda
-    shape = (kh * kw, Cs, Cb) if mode == 0 else (kh * kw, Cb, Cs)
+    shape = (kh * kw, Cs, Cb) if mode == 0 else (kh * kw, Cb, Cs)   # modes 1, 2: K axis = Cs
     out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
     call("livae_tc_pack_weights", w, Cs, Cb, kh, kw, mode, out)
     return out
@@ -426,3 +426,32 @@ def tc_conv(x, wpacked, bias, kh, kw, stride, pad, act=ACT_NONE, out_f32=False, 
         assert relu_mask.dtype == torch.bfloat16 and relu_mask.shape == y.shape and relu_mask.is_contiguous()
     call("livae_tc_conv", C.byref(d), x, wpacked, bias, y, relu_mask)
     return y
+
+
+def tc_conv_dgrad(gy, wpacked2, bias, Hin, Win, kh, kw, stride, pad, act=ACT_NONE, out_f32=False, relu_mask=None):
+    """raw tensor-core data gradient of conv(Cin->Cout) / ConvTranspose2d forward: gy bf16 [B,Ho,Wo,Cout],
+    wpacked2 bf16 [taps,Cin,Cout] (mode-2 packing) -> gx [B,Hin,Win,Cin]"""
+    assert gy.dtype == torch.bfloat16 and wpacked2.dtype == torch.bfloat16 and gy.is_cuda and gy.is_contiguous()
+    B, Ho, Wo, Cout = gy.shape
+    taps, Cin, Cout2 = wpacked2.shape
+    assert Cout2 == Cout and taps == kh * kw
+    d = L.TcConvDesc(B, Hin, Win, Cin, Cout, kh, kw, stride, pad, act, int(out_f32))
+    gx = torch.empty((B, Hin, Win, Cin), dtype=torch.float32 if out_f32 else torch.bfloat16, device=gy.device)
+    if relu_mask is not None:
+        assert relu_mask.dtype == torch.bfloat16 and relu_mask.shape == gx.shape and relu_mask.is_contiguous()
+    call("livae_tc_conv_dgrad", C.byref(d), gy, wpacked2, bias, gx, relu_mask)
+    return gx
+
+
+def tc_conv_wgrad(x, gy, kh, kw, stride, pad, want_bias=True):
+    """raw tensor-core weight gradient: x bf16 [B,Hin,Win,Cin], gy bf16 [B,Ho,Wo,Cout] (pre-activation
+    gradient) -> gw fp32 [Cout,Cin,kh,kw], gb fp32 [Cout] or None"""
+    assert x.dtype == torch.bfloat16 and gy.dtype == torch.bfloat16 and x.is_contiguous() and gy.is_contiguous()
+    B, Hin, Win, Cin = x.shape
+    Cout = gy.shape[-1]
+    d = L.TcConvDesc(B, Hin, Win, Cin, Cout, kh, kw, stride, pad, 0, 0)
+    gw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=x.device)
+    gb = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    ws = torch.empty(L.lib().livae_tc_wgrad_ws_bytes(C.byref(d)) // 4, dtype=torch.float32, device=x.device)
+    call("livae_tc_conv_wgrad", C.byref(d), x, gy, gw, gb, ws)
+    return gw, gb

@@ -69,6 +69,69 @@ def test_tc_conv_as_stride1_dgrad_with_relu_mask():
     assert rel_l2(gx.cpu(), want) < 1e-4
 
 
+DGRAD_CASES = [
+    # (B, Cin, H, W, Cout, k, stride, pad): gradient w.r.t. the [B,Cin,H,W] input
+    (2, 64, 18, 18, 32, 3, 1, 0),     # decoder 3x3 p0 over an up-padded map: ragged 18x18 tiles
+    (1, 128, 34, 34, 64, 3, 1, 0),    # decoder d2
+    (3, 16, 16, 16, 32, 5, 1, 2),     # STN conv2 (N = 16)
+    (2, 32, 32, 32, 64, 4, 2, 1),     # encoder c2: four output-parity phases
+    (2, 64, 16, 16, 128, 4, 2, 1),    # encoder c3
+    (3, 128, 8, 8, 256, 4, 2, 1),     # encoder c4: 4x4 phase grids, several images per tile, ragged batch
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_tc_conv_dgrad(case):
+    from livae import ops
+    B, Ci, H, W, Co, k, s, p = case
+    rng = np.random.default_rng(sum(case) + 1)
+    x = torch.tensor(rng.standard_normal((B, Ci, H, W)).astype(np.float32), requires_grad=True)
+    w = _bf(torch.tensor((rng.standard_normal((Co, Ci, k, k)) / np.sqrt(Ci * k * k)).astype(np.float32)))
+    y = F.conv2d(x, w, stride=s, padding=p)
+    gy = _bf(torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32)))
+    (y * gy).sum().backward()
+    wp = ops.tc_pack_weights(w.cuda(), Co, Ci, k, k, 2)
+    mask = torch.tensor(rng.standard_normal((B, H, W, Ci)).astype(np.float32)).cuda().to(torch.bfloat16)
+    gx = ops.tc_conv_dgrad(_nhwc(gy).cuda().to(torch.bfloat16), wp, None, H, W, k, k, s, p, 0, out_f32=True,
+                           relu_mask=mask)
+    want = _nhwc(x.grad) * (mask.float().cpu() > 0)
+    assert rel_l2(gx.cpu(), want) < 1e-4
+    # the same kernel is nn.ConvTranspose2d forward (+bias, +ReLU, bf16 out)
+    if s == 2:
+        b = torch.tensor(rng.standard_normal(Ci).astype(np.float32) * 0.1)
+        want_t = torch.relu(F.conv_transpose2d(gy, w, b, stride=2, padding=p))
+        got_t = ops.tc_conv_dgrad(_nhwc(gy).cuda().to(torch.bfloat16), wp, b.cuda(), H, W, k, k, s, p, 1)
+        assert rel_l2(got_t.float().cpu(), _nhwc(want_t)) < 5e-3
+
+
+WGRAD_CASES = [
+    (2, 64, 18, 18, 32, 3, 1, 0),     # decoder d3-like: 2 taps per 128-row group, N = 32 (SW64 gy)
+    (2, 128, 18, 18, 64, 3, 1, 0),    # decoder d2-like: 1 tap per group
+    (2, 256, 18, 18, 128, 3, 1, 0),   # decoder d1: 2 groups per tap, 18 groups over 5 CTAs-sets
+    (3, 16, 16, 16, 32, 5, 1, 2),     # STN conv2: 8 taps per group (SW32 x boxes), padded last group
+    (2, 32, 32, 32, 64, 4, 2, 1),     # encoder c2 (stride 2 via elementStrides)
+    (2, 64, 16, 16, 128, 4, 2, 1),    # encoder c3
+    (4, 128, 16, 16, 256, 4, 2, 1),   # encoder c4: N = 256, G = 2
+    (16, 64, 4, 4, 128, 4, 2, 1),     # tiny maps: 16 images per 64-pixel tile
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_tc_conv_wgrad(case):
+    from livae import ops
+    B, Ci, H, W, Co, k, s, p = case
+    rng = np.random.default_rng(sum(case) + 2)
+    x = _bf(torch.tensor(rng.standard_normal((B, Ci, H, W)).astype(np.float32)))
+    w = torch.zeros(Co, Ci, k, k, requires_grad=True)
+    b = torch.zeros(Co, requires_grad=True)
+    y = F.conv2d(x, w, b, stride=s, padding=p)
+    gy = _bf(torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32)))
+    (y * gy).sum().backward()
+    gw, gb = ops.tc_conv_wgrad(_nhwc(x).cuda().to(torch.bfloat16), _nhwc(gy).cuda().to(torch.bfloat16), k, k, s, p)
+    assert rel_l2(gw.cpu(), w.grad) < 1e-4
+    assert rel_l2(gb.cpu(), b.grad) < 1e-4
+
+
 def test_cast_roundtrip():
     from livae import ops
     x = torch.randn(1000003).cuda()
