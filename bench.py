@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--nbatches", type=int, default=3)
-    ap.add_argument("--engine", default="f32", help="convolution engine: f32 (exact SIMT) | tc (tcgen05 bf16)")
+    ap.add_argument("--engine", default="tc", help="convolution engine: tc (tcgen05, bf16 storage) | f32 (exact SIMT)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -261,8 +261,7 @@ def main():
     import livae
     from livae import _lib, optim
     from livae.train import train_rvae_step
-    if hasattr(livae, "set_engine"):
-        livae.set_engine(args.engine)
+    livae.set_engine(args.engine)
 
     torch.manual_seed(1234)
     model = livae.RVAE(latent_dim=LATENT, in_channels=1, patch_size=P).to(device)

@@ -164,8 +164,11 @@ int livae_tc_conv_supported(const livae_tc_conv_desc* d);
 /* w: fp32 torch layout [Cs][Cb][kh][kw].  mode 0 -> [tap][Cs][Cb] (forward of Conv2d with
  * Cout=Cs, Cin=Cb); mode 1 -> [flipped tap][Cb][Cs] (its stride-1 data gradient run as a
  * forward convolution over gy with pad' = k-1-pad); mode 2 -> [tap][Cb][Cs] (livae_tc_conv_dgrad). */
-int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
-                          livae_stream_t stream);
+/* modes 3 / 4: nn.Linear over an NHWC-flattened [kh,kw,Cb] map (model.py:210-213, 321-324), seen as a
+ * 1x1 convolution with K = kh*kw*Cb in (h,w,c) order: mode 3 -> [Cs][tap][Cb] (forward), mode 4 ->
+ * [tap][Cb][Cs] (data gradient).  Cs may be padded: rows >= Cs_real are written as zeros. */
+int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, int Cs_real,
+                          void* out_bf16, livae_stream_t stream);
 int livae_tc_conv(const livae_tc_conv_desc* d, const void* x, const void* wpacked, const float* bias,
                   void* y, const void* relu_mask, livae_stream_t stream);
 /* Data gradient of the convolution d (= nn.ConvTranspose2d forward with x := gy, model.py:90-96):
@@ -180,6 +183,47 @@ int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, const void*
 int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d);
 int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
                         void* ws, livae_stream_t stream);
+/* Linear weight gradient: tensor-core layout [N][(h,w,c)] -> torch [N][(c,h,w)] */
+int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float* dst_chw, livae_stream_t stream);
+
+/* ---- thin 1-channel layers around the tensor-core convolutions (SIMT, bf16 on the wide side) ----
+ * kind 0: STN conv1 1->16 5x5 p2 +ReLU +MaxPool (model.py:204-206): out bf16 [B,H/2,W/2,16] + pool_idx
+ * kind 1: encoder c1 1->32 4x4 s2 p1 +ReLU (model.py:290):          out bf16 [B,H/2,W/2,32]
+ * kind 2: data gradient of decoder d4 (32->1 3x3 p0, model.py:371): img = fp32 pre-activation
+ *         gradient [B,H,W], out bf16 [B,H+2,W+2,32] */
+int livae_thin_conv1c_fwd(int kind, const float* img, const float* w, const float* bias, int B, int H,
+                          int W, void* out_bf16, uint8_t* pool_idx, livae_stream_t stream);
+/* weight/bias gradients of kinds 0, 1; g: bf16 PRE-activation gradient (kind 0: pooled, routed by pool_idx) */
+int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g_bf16, const uint8_t* pool_idx, int B,
+                            int H, int W, float* gw, float* gb, livae_stream_t stream);
+/* encoder c1 data gradient: g bf16 [B,H/2,W/2,32] -> gimg fp32 [B,H,W] */
+int livae_thin_conv1c_dgrad(const void* g_bf16, const float* w, int B, int H, int W, float* gimg,
+                            livae_stream_t stream);
+/* decoder d4 forward (32->1 3x3 p0 + activation): x bf16 [B,H,W,32] -> out fp32 [B,H-2,W-2] */
+int livae_thin_convc1_fwd(const void* x_bf16, const float* w, const float* bias, int B, int H, int W,
+                          int act, float* out, livae_stream_t stream);
+/* decoder d4 weight/bias gradient; g fp32 [B,H-2,W-2] pre-activation gradient */
+int livae_thin_convc1_wgrad(const void* x_bf16, const float* g, int B, int H, int W, float* gw, float* gb,
+                            livae_stream_t stream);
+/* out = (g1 + g2) * y * (1 - y); g2 may be NULL */
+int livae_sigmoid_bwd(const float* y, const float* g1, const float* g2, int64_t n, float* out,
+                      livae_stream_t stream);
+/* out_bf16 = g * (y > 0) (y may be NULL: plain cast) */
+int livae_relu_mask_cast_bf16(const float* g, const float* y, int64_t n, void* out_bf16, livae_stream_t stream);
+int livae_maxpool_bf16(const void* full, int B, int H, int W, int C, void* pooled, uint8_t* idx,
+                       livae_stream_t stream);
+int livae_unpool_bf16(const void* g_pooled, const uint8_t* idx, int B, int H, int W, int C, void* g_full,
+                      livae_stream_t stream);
+/* bf16 variants of upsample_pad / decoder fc for the tensor-core path; gradients handed in are
+ * PRE-activation gradients, so decfc_bwd_bf16 does not re-apply the ReLU mask */
+int livae_upsample_pad_fwd_bf16(const void* x, int B, int H, int W, int C, void* out, livae_stream_t stream);
+int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
+                                livae_stream_t stream);
+int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,
+                         void* out, livae_stream_t stream);
+int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, int L, int C, int HW,
+                         float* gw, float* gb, float* gz, livae_stream_t stream);
+
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

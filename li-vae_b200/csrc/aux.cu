@@ -24,8 +24,9 @@ __device__ __forceinline__ int unpad(int Y, int n2) {
 }
 
 // x: [B,H,W,C] -> out: [B,2H+2,2W+2,C]
-__global__ void __launch_bounds__(256) upsample_pad_fwd_kernel(const float* __restrict__ x, int B, int H,
-                                                               int W, int C, float* __restrict__ out) {
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_pad_fwd_kernel(const T* __restrict__ x, int B, int H,
+                                                               int W, int C, T* __restrict__ out) {
   int Ho = 2 * H + 2, Wo = 2 * W + 2;
   int64_t n = (int64_t)B * Ho * Wo * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -35,28 +36,29 @@ __global__ void __launch_bounds__(256) upsample_pad_fwd_kernel(const float* __re
     int y0, y1, x0, x1; float fy, fx;
     up_src(unpad(Y, 2 * H), H, &y0, &y1, &fy);
     up_src(unpad(X, 2 * W), W, &x0, &x1, &fx);
-    const float* s = x + (int64_t)b * H * W * C + c;
-    float v00 = s[((int64_t)y0 * W + x0) * C], v01 = s[((int64_t)y0 * W + x1) * C];
-    float v10 = s[((int64_t)y1 * W + x0) * C], v11 = s[((int64_t)y1 * W + x1) * C];
+    const T* s = x + (int64_t)b * H * W * C + c;
+    float v00 = Cvt<T>::ld(s, ((int64_t)y0 * W + x0) * C), v01 = Cvt<T>::ld(s, ((int64_t)y0 * W + x1) * C);
+    float v10 = Cvt<T>::ld(s, ((int64_t)y1 * W + x0) * C), v11 = Cvt<T>::ld(s, ((int64_t)y1 * W + x1) * C);
     // ATen: h0lambda*(w0lambda*v00 + w1lambda*v01) + h1lambda*(w0lambda*v10 + w1lambda*v11)
-    out[i] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+    Cvt<T>::st(out, i, (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11));
   }
 }
 
 // 1-D adjoint weights: for source index i, sum over upsampled u in [2i-2, 2i+2] of
 // w(u,i) * (sum of padded positions that map to u).  Done as a gather so no atomics are needed.
 // gx[b,i,j,c] = relu_mask * sum_{u,v} wy(u,i) wx(v,j) G[u,v],  G[u,v] = sum_{Y in pre(u), X in pre(v)} g[Y,X]
-__global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(const float* __restrict__ g, int B, int H,
-                                                               int W, int C, const float* __restrict__ mask_y,
-                                                               float* __restrict__ gx) {
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(const T* __restrict__ g, int B, int H,
+                                                               int W, int C, const T* __restrict__ mask_y,
+                                                               T* __restrict__ gx) {
   int Ho = 2 * H + 2, Wo = 2 * W + 2;
   int64_t n = (int64_t)B * H * W * C;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(idx % C); int64_t q = idx / C; int j = (int)(q % W); q /= W; int i = (int)(q % H);
     int b = (int)(q / H);
-    if (mask_y && !(mask_y[idx] > 0.f)) { gx[idx] = 0.f; continue; }
-    const float* gb = g + (int64_t)b * Ho * Wo * C + c;
+    if (mask_y && !(Cvt<T>::ld(mask_y, idx) > 0.f)) { Cvt<T>::st(gx, idx, 0.f); continue; }
+    const T* gb = g + (int64_t)b * Ho * Wo * C + c;
     float acc = 0.f;
     for (int u = max(0, 2 * i - 2); u <= min(2 * H - 1, 2 * i + 2); ++u) {
       int y0, y1; float fy;
@@ -79,19 +81,20 @@ __global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(const float* __re
         if (v == 2 * W - 2) Xs[nx++] = 2 * W + 1;
         float s = 0.f;
         for (int a = 0; a < ny; ++a)
-          for (int d = 0; d < nx; ++d) s += gb[((int64_t)Ys[a] * Wo + Xs[d]) * C];
+          for (int d = 0; d < nx; ++d) s += Cvt<T>::ld(gb, ((int64_t)Ys[a] * Wo + Xs[d]) * C);
         acc += wy * wx * s;
       }
     }
-    gx[idx] = acc;
+    Cvt<T>::st(gx, idx, acc);
   }
 }
 
 // out[b, (h,w,c)] = relu(sum_l z[b,l] * w[(c,h,w), l] + bias[(c,h,w)])  -- NHWC output of the
 // reference's h.view(B, 256, q, q)
+template <typename T>
 __global__ void __launch_bounds__(256) decfc_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int B, int L, int C,
-                                                        int HW, float* __restrict__ out) {
+                                                        int HW, T* __restrict__ out) {
   int64_t n = (int64_t)B * HW * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -99,23 +102,26 @@ __global__ void __launch_bounds__(256) decfc_fwd_kernel(const float* __restrict_
     int row = c * HW + p;
     float a = bias[row];
     for (int l = 0; l < L; ++l) a = fmaf(z[b * L + l], w[(int64_t)row * L + l], a);
-    out[i] = fmaxf(a, 0.f);
+    Cvt<T>::st(out, i, fmaxf(a, 0.f));
   }
 }
 
 // gz[b,l] = sum_n gpre[b,n] w[n,l]; one CTA per sample
-__global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+// y == nullptr: gy is already the pre-activation gradient (tensor-core path convention)
+template <typename T>
+__global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const T* __restrict__ gy, const T* __restrict__ y,
                                                           const float* __restrict__ w, int L, int C, int HW,
                                                           float* __restrict__ gz) {
   __shared__ float red[32];
   int b = blockIdx.x;
   int N = C * HW;
-  const float* gyb = gy + (int64_t)b * N;
-  const float* yb = y + (int64_t)b * N;
+  const T* gyb = gy + (int64_t)b * N;
+  const T* yb = y ? y + (int64_t)b * N : nullptr;
   for (int l0 = 0; l0 < L; l0 += 4) {
     float a[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      float g = yb[i] > 0.f ? gyb[i] : 0.f;
+      float g = Cvt<T>::ld(gyb, i);
+      if (yb && !(Cvt<T>::ld(yb, i) > 0.f)) g = 0.f;
       int c = i % C, p = i / C;
       const float* wr = w + (int64_t)(c * HW + p) * L;
 #pragma unroll
@@ -133,8 +139,8 @@ __global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const float* __restric
 // gw[n,l] = sum_b gpre[b,n] z[b,l], gb[n] = sum_b gpre[b,n]; thread per output feature n (NHWC
 // order so that a warp reads contiguous gy), loop over the batch.  Batch is split over
 // blockIdx.y and combined with atomics on the (zeroed) outputs.
-template <int LT>
-__global__ void __launch_bounds__(128) decfc_bwd_w_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+template <int LT, typename T>
+__global__ void __launch_bounds__(128) decfc_bwd_w_kernel(const T* __restrict__ gy, const T* __restrict__ y,
                                                           const float* __restrict__ z, int B, int L, int C, int HW,
                                                           float* __restrict__ gw, float* __restrict__ gb) {
   int N = C * HW;
@@ -150,8 +156,8 @@ __global__ void __launch_bounds__(128) decfc_bwd_w_kernel(const float* __restric
     for (int t = 0; t < LT; ++t) a[t] = 0.f;
     float sb = 0.f;
     for (int b = b0; b < b1; ++b) {
-      float g = gy[(int64_t)b * N + i];
-      g = y[(int64_t)b * N + i] > 0.f ? g : 0.f;
+      float g = Cvt<T>::ld(gy, (int64_t)b * N + i);
+      if (y && !(Cvt<T>::ld(y, (int64_t)b * N + i) > 0.f)) g = 0.f;
       sb += g;
 #pragma unroll
       for (int t = 0; t < LT; ++t)
@@ -245,7 +251,7 @@ extern "C" int livae_upsample_pad_fwd(const float* x, int B, int H, int W, int C
   if (int e = require_sm100()) return e;
   if (B == 0) return 0;
   int64_t n = (int64_t)B * (2 * H + 2) * (2 * W + 2) * C;
-  upsample_pad_fwd_kernel<<<sgrid(n, 2), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
+  upsample_pad_fwd_kernel<float><<<sgrid(n, 2), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -256,7 +262,7 @@ extern "C" int livae_upsample_pad_bwd(const float* g, int B, int H, int W, int C
   if (int e = require_sm100()) return e;
   if (B == 0) return 0;
   int64_t n = (int64_t)B * H * W * C;
-  upsample_pad_bwd_kernel<<<sgrid(n, 1), 256, 0, (cudaStream_t)stream>>>(g, B, H, W, C, relu_mask_y, gx);
+  upsample_pad_bwd_kernel<float><<<sgrid(n, 1), 256, 0, (cudaStream_t)stream>>>(g, B, H, W, C, relu_mask_y, gx);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -266,7 +272,7 @@ extern "C" int livae_decfc_fwd(const float* z, const float* w, const float* bias
   LIVAE_CHECK_ARG(z && w && bias && out && B >= 0 && L > 0 && C > 0 && HW > 0, "decfc_fwd: bad args");
   if (int e = require_sm100()) return e;
   if (B == 0) return 0;
-  decfc_fwd_kernel<<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C, HW, out);
+  decfc_fwd_kernel<float><<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C, HW, out);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -279,7 +285,7 @@ extern "C" int livae_decfc_bwd(const float* z, const float* w, const float* y, c
   cudaStream_t st = (cudaStream_t)stream;
   int N = C * HW;
   if (gz) {
-    decfc_bwd_z_kernel<<<B, 256, 0, st>>>(gy, y, w, L, C, HW, gz);
+    decfc_bwd_z_kernel<float><<<B, 256, 0, st>>>(gy, y, w, L, C, HW, gz);
     LIVAE_CUDA_LAUNCH_CHECK();
   }
   if (gw) {
@@ -291,9 +297,93 @@ extern "C" int livae_decfc_bwd(const float* z, const float* w, const float* y, c
     if (ysplit > (B + 15) / 16) ysplit = (B + 15) / 16;
     if (ysplit < 1) ysplit = 1;
     dim3 grid(nb, ysplit);
-    decfc_bwd_w_kernel<4><<<grid, 128, 0, st>>>(gy, y, z, B, L, C, HW, gw, gb);
+    decfc_bwd_w_kernel<4, float><<<grid, 128, 0, st>>>(gy, y, z, B, L, C, HW, gw, gb);
     LIVAE_CUDA_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// ---- bf16 variants used by the tensor-core path (gradients are pre-activation: no ReLU re-masking) ----
+extern "C" int livae_upsample_pad_fwd_bf16(const void* x, int B, int H, int W, int C, void* out, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 1 && W > 1 && C > 0, "upsample_pad_fwd_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(x && out, "upsample_pad_fwd_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  int64_t n = (int64_t)B * (2 * H + 2) * (2 * W + 2) * C;
+  upsample_pad_fwd_kernel<__nv_bfloat16><<<sgrid(n, 2), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y,
+                                           void* gx, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 1 && W > 1 && C > 0, "upsample_pad_bwd_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(g && gx, "upsample_pad_bwd_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  int64_t n = (int64_t)B * H * W * C;
+  upsample_pad_bwd_kernel<__nv_bfloat16><<<sgrid(n, 1), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g, B, H, W, C, (const __nv_bfloat16*)relu_mask_y, (__nv_bfloat16*)gx);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,
+                                    void* out, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && L > 0 && C > 0 && HW > 0, "decfc_fwd_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(z && w && bias && out, "decfc_fwd_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  decfc_fwd_kernel<__nv_bfloat16><<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(
+      z, w, bias, B, L, C, HW, (__nv_bfloat16*)out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// gy: bf16 PRE-activation gradient w.r.t. the fc output (already masked by the producer)
+extern "C" int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, int L, int C, int HW,
+                                    float* gw, float* gb, float* gz, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && L > 0 && C > 0 && HW > 0, "decfc_bwd_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(z && w && gy, "decfc_bwd_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* g = (const __nv_bfloat16*)gy;
+  int N = C * HW;
+  if (gz) {
+    decfc_bwd_z_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);
+    LIVAE_CUDA_LAUNCH_CHECK();
+  }
+  if (gw) {
+    cudaError_t ce;
+    if ((ce = cudaMemsetAsync(gw, 0, (size_t)N * L * sizeof(float), st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (gb && (ce = cudaMemsetAsync(gb, 0, (size_t)N * sizeof(float), st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    int nb = (N + 127) / 128;
+    int ysplit = (kNumSMs * 8 + nb - 1) / nb;
+    if (ysplit > (B + 15) / 16) ysplit = (B + 15) / 16;
+    if (ysplit < 1) ysplit = 1;
+    decfc_bwd_w_kernel<4, __nv_bfloat16><<<dim3(nb, ysplit), 128, 0, st>>>(g, (const __nv_bfloat16*)nullptr, z, B, L, C, HW,
+                                                                            gw, gb);
+    LIVAE_CUDA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// Linear weight gradient from the tensor-core kernel's [Npad][(h,w,c)] layout to torch's
+// [N][(c,h,w)] (model.py:210, 321: NCHW flatten), dropping padded rows.
+__global__ void permute_linear_grad_kernel(const float* __restrict__ src, int N, int C, int HW, float* __restrict__ dst) {
+  int64_t n = (int64_t)N * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW); int64_t q = i / HW; int c = (int)(q % C); int r = (int)(q / C);
+    dst[i] = src[((int64_t)r * HW + p) * C + c];
+  }
+}
+extern "C" int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float* dst_chw, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(src_hwc && dst_chw && N > 0 && C > 0 && HW > 0, "permute_linear_grad: bad args");
+  if (int e = require_sm100()) return e;
+  permute_linear_grad_kernel<<<sgrid((int64_t)N * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(src_hwc, N, C, HW, dst_chw);
+  LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
 

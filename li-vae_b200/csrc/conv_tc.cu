@@ -58,7 +58,8 @@ struct ConvTcParams {
   int8_t tap_dy[kMaxTaps], tap_dx[kMaxTaps];  // input offset of each tap (pad already folded in)
   int8_t tap_w[kMaxTaps];                     // index of each tap in the packed weight tensor
   int kc, nkc;            // channels per k-block, k-blocks per tap
-  int N;                  // output channels (UMMA N)
+  int N;                  // output channels per CTA (UMMA N); blockIdx.y selects the chunk
+  int Ntot;               // total output channels (row pitch of out / relu_mask / bias)
   int B;
   void* out;              // [B,Ho,Wo,N] bf16 or fp32
   int out_f32;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         const int tap = kb / p.nkc, c = kb - tap * p.nkc;
         uint8_t* a_s = smem + (uint32_t)s * stage_bytes;
         tma_load_4d(a_s, &tmA, &full_bar[s], c * p.kc, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
-        tma_load_3d(a_s + a_slot, &tmB, &full_bar[s], c * p.kc, 0, (int)p.tap_w[tap]);
+        tma_load_3d(a_s + a_slot, &tmB, &full_bar[s], c * p.kc, (int)blockIdx.y * p.N, (int)p.tap_w[tap]);
       }
     }
   } else if (warp == 1) {
@@ -162,11 +163,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
+    const int nbase = (int)blockIdx.y * p.N;
+    for (int cc = 0; cc < p.N; cc += 16) {
       uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);   // warp-collective: issued by all lanes, stores predicated
+      tmem_ld16(taddr + (uint32_t)cc, v);   // warp-collective: issued by all lanes, stores predicated
       tmem_ld_wait();
       if (!valid) continue;
+      const int c0 = nbase + cc;
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         f[i] = a;
       }
       if (p.relu_mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + pix * p.N + c0);
+        const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + pix * p.Ntot + c0);
         uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
         const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
         const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         }
       }
       if (p.out_f32) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.N + c0);
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Ntot + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
       } else {
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
           __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
           w[i] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.N + c0);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Ntot + c0);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
         o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
@@ -216,15 +219,20 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 //   mode 0: out[tap][cs][cb]                      (P1: big -> small, K = cb)
 //   mode 1: out[tap'][cb][cs], tap' = flipped tap (P2 at stride 1 run as a P1 over the small side)
 //   mode 2: out[tap][cb][cs]                      (data gradient / ConvTranspose2d forward, K = cs)
+//   mode 3: Linear over an NHWC-flattened map, forward:  out[cs][tap][cb] = w[cs][cb][tap]
+//           (one "tap", K = taps*Cb in (h,w,c) order; torch keeps the K axis in (c,h,w) order)
+//   mode 4: the same Linear, data gradient:              out[tap][cb][cs] (N = taps*Cb rows of K = cs)
+// Rows cs >= Cs_real (padding up to Cs) are written as zeros (modes 3, 4).
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb, int kh, int kw, int mode,
-                                    __nv_bfloat16* __restrict__ out) {
+                                    int Cs_real, __nv_bfloat16* __restrict__ out) {
   int n = Cs * Cb * kh * kw;
   int taps = kh * kw;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int tap, cs, cb;
     if (mode == 0) { cb = i % Cb; int t = i / Cb; cs = t % Cs; tap = t / Cs; }
+    else if (mode == 3) { cb = i % Cb; int t = i / Cb; tap = t % taps; cs = t / taps; }
     else { cs = i % Cs; int t = i / Cs; cb = t % Cb; tap = mode == 1 ? taps - 1 - t / Cb : t / Cb; }
-    out[i] = __float2bfloat16_rn(w[((int64_t)cs * Cb + cb) * taps + tap]);
+    out[i] = cs < Cs_real ? __float2bfloat16_rn(w[((int64_t)cs * Cb + cb) * taps + tap]) : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -269,7 +277,7 @@ static void choose_tile(int Hq, int Wq, int B, int* tw, int* th, int* nb) {
 }
 
 static bool channels_ok(int Cin, int Cout) {
-  if (Cout % 16 != 0 || Cout < 16 || Cout > 256) return false;
+  if (Cout % 16 != 0 || Cout < 16) return false;
   if (Cin >= 64) return Cin % 64 == 0;
   return Cin == 16 || Cin == 32;
 }
@@ -289,7 +297,12 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
   for (int t = 0; t < ntaps; ++t) { p.tap_dy[t] = (int8_t)tdy[t]; p.tap_dx[t] = (int8_t)tdx[t]; p.tap_w[t] = (int8_t)tw_idx[t]; }
   p.kc = Cin >= 64 ? 64 : Cin;
   p.nkc = Cin / p.kc;
-  p.N = N; p.B = B;
+  int nchunk = N;
+  if (N > 256) {
+    nchunk = 256;
+    while (N % nchunk != 0) nchunk -= 16;
+  }
+  p.N = nchunk; p.Ntot = N; p.B = B;
   p.out = out; p.out_f32 = out_f32; p.bias = bias; p.act = act;
   p.relu_mask = (const __nv_bfloat16*)relu_mask;
   const int row_bytes = p.kc * 2;
@@ -304,11 +317,11 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)wtaps};
     uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)N, 1};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.N, 1};
     if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
   }
   const uint32_t a_slot = (128u * row_bytes + 1023u) & ~1023u;
-  const uint32_t b_slot = ((uint32_t)N * row_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
   constexpr int STAGES = 4;
   const size_t smem = (size_t)STAGES * (a_slot + b_slot) + 1024;
   static bool attr_done = false;
@@ -317,7 +330,7 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
     attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * ((B + p.nb - 1) / p.nb);
-  conv_tc_kernel<STAGES><<<tiles, kThreads, smem, st>>>(tmA, tmB, p);
+  conv_tc_kernel<STAGES><<<dim3(tiles, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -340,14 +353,15 @@ extern "C" int livae_tc_conv_supported(const livae_tc_conv_desc* d) {
   return 1;
 }
 
-extern "C" int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, void* out_bf16,
-                                     livae_stream_t stream) {
-  LIVAE_CHECK_ARG(w && out_bf16 && Cs > 0 && Cb > 0 && kh > 0 && kw > 0 && mode >= 0 && mode <= 2,
+extern "C" int livae_tc_pack_weights(const float* w, int Cs, int Cb, int kh, int kw, int mode, int Cs_real,
+                                     void* out_bf16, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(w && out_bf16 && Cs > 0 && Cb > 0 && kh > 0 && kw > 0 && mode >= 0 && mode <= 4 &&
+                      Cs_real > 0 && Cs_real <= Cs && (Cs_real == Cs || mode >= 3),
                   "tc_pack_weights: bad args");
   if (int e = require_sm100()) return e;
   int n = Cs * Cb * kh * kw;
-  pack_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cs, Cb, kh, kw, mode,
-                                                                          (__nv_bfloat16*)out_bf16);
+  pack_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cs, Cb, kh, kw, mode == 4 ? 2 : mode,
+                                                                          Cs_real, (__nv_bfloat16*)out_bf16);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

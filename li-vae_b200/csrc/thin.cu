@@ -1,0 +1,498 @@
+// Thin layers around the tensor-core convolutions: the 1-channel ends of the networks
+//   STN conv1  1->16 5x5 p2 +ReLU +MaxPool   (model.py:204-206)
+//   encoder c1 1->32 4x4 s2 p1 +ReLU          (model.py:290)
+//   decoder d4 32->1 3x3 p0 +Sigmoid          (model.py:371-372)
+// Their GEMM shapes have N = 1 or K <= 25, useless for a 128xN MMA tile, and they are bound by the
+// bf16 activation traffic on the C-channel side, so they are SIMT kernels: fp32 FMA, bf16 NHWC
+// storage on the wide side, fp32 images on the 1-channel side.  Gradient conventions follow the
+// tensor-core engine: tensors handed between layers are PRE-activation gradients.
+#include "common.cuh"
+
+namespace livae {
+
+__device__ __forceinline__ float bf(const __nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---------------------------------------------------------------------------------------------
+// 1 -> C convolution forward (also: data gradient of a C -> 1 convolution, with flip = 1).
+// img fp32 [B,H,W]; w fp32 [C][K*K] (torch [C,1,K,K] or [1,C,K,K]); out bf16 NHWC.
+// POOL: ReLU + 2x2 max-pool fused, idx = argmax position (torch scan order).
+template <int C, int K, int S, bool POOL>
+__global__ void __launch_bounds__(256) conv1c_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int H, int W,
+                                                         int Ho, int Wo, int pad, int act, int flip,
+                                                         __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  __shared__ float sw[K * K][C];
+  __shared__ float sb[C];
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
+    int c = i % C, t = i / C;
+    sw[t][c] = w[c * K * K + (flip ? K * K - 1 - t : t)];
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* im = img + (int64_t)b * H * W;
+  if (POOL) {
+    const int Hp = Ho >> 1, Wp = Wo >> 1;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Hp * Wp; q += gridDim.x * blockDim.x) {
+      const int py = q / Wp, px = q - py * Wp;
+      float best[C]; int bi[C];
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const int oy = 2 * py + (sub >> 1), ox = 2 * px + (sub & 1);
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = sb[c];
+        for (int ky = 0; ky < K; ++ky) {
+          const int iy = oy * S - pad + ky;
+          if (iy < 0 || iy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int ix = ox * S - pad + kx;
+            if (ix < 0 || ix >= W) continue;
+            const float v = __ldg(im + iy * W + ix);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(v, sw[ky * K + kx][c], acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float a = fmaxf(acc[c], 0.f);
+          if (sub == 0 || a > best[c]) { best[c] = a; bi[c] = sub; }
+        }
+      }
+      __nv_bfloat16* o = out + (((int64_t)b * Hp + py) * Wp + px) * C;
+      uint8_t* oi = idx + (((int64_t)b * Hp + py) * Wp + px) * C;
+#pragma unroll
+      for (int c = 0; c < C; c += 2) {
+        *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(best[c], best[c + 1]);
+        oi[c] = (uint8_t)bi[c]; oi[c + 1] = (uint8_t)bi[c + 1];
+      }
+    }
+  } else {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Ho * Wo; q += gridDim.x * blockDim.x) {
+      const int oy = q / Wo, ox = q - oy * Wo;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = sb[c];
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - pad + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox * S - pad + kx;
+          if (ix < 0 || ix >= W) continue;
+          const float v = __ldg(im + iy * W + ix);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(v, sw[ky * K + kx][c], acc[c]);
+        }
+      }
+      __nv_bfloat16* o = out + ((int64_t)b * Ho * Wo + q) * C;
+#pragma unroll
+      for (int c = 0; c < C; c += 2) {
+        float a0 = acc[c], a1 = acc[c + 1];
+        if (act == LIVAE_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(a0, a1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1 -> C convolution weight (+bias) gradient: gw[c][tap] = sum img[b, oy*S-pad+ky, ox*S-pad+kx] * g[b,oy,ox,c]
+// g bf16: [B,Ho,Wo,C] pre-activation gradient, or (POOL) the pooled gradient [B,Ho/2,Wo/2,C] routed by idx.
+// Thread = (tap row ky, 4 channels, output row of the band); accumulators stay in registers over all
+// images the CTA walks, then shared-memory reduction and one global atomic per weight per CTA.
+template <int C, int K, int S, bool POOL>
+__global__ void __launch_bounds__(256) conv1c_wgrad_kernel(const float* __restrict__ img,
+                                                           const __nv_bfloat16* __restrict__ g,
+                                                           const uint8_t* __restrict__ idx, int B, int H, int W, int Ho,
+                                                           int Wo, int pad, float* __restrict__ gw,
+                                                           float* __restrict__ gb) {
+  constexpr int CG = C / 4;
+  constexpr int COMBOS = K * CG;
+  constexpr int RB = 256 / COMBOS;          // output rows per band
+  __shared__ float sacc[K * K][C];
+  __shared__ float sbias[C];
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) (&sacc[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sbias[i] = 0.f;
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int ky = t % K, cg = (t / K) % CG, r = t / COMBOS;
+  const bool active = r < RB;
+  const int oy = blockIdx.x * RB + r;
+  float acc[K][4];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (active && oy < Ho) {
+    const int iy = oy * S - pad + ky;
+    const bool row_ok = iy >= 0 && iy < H;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+      const float* im = img + ((int64_t)b * H + (row_ok ? iy : 0)) * W;
+      for (int ox = 0; ox < Wo; ++ox) {
+        float g4[4];
+        if (POOL) {
+          const int64_t pi = ((((int64_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1)) + (ox >> 1)) * C + cg * 4;
+          const int pos = ((oy & 1) << 1) | (ox & 1);
+          const uint32_t id4 = *reinterpret_cast<const uint32_t*>(idx + pi);
+          const uint2 gv = *reinterpret_cast<const uint2*>(g + pi);
+          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(&gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g4[j] = (int)((id4 >> (8 * j)) & 0xff) == pos ? bf(gp[j]) : 0.f;
+        } else {
+          const uint2 gv = *reinterpret_cast<const uint2*>(g + (((int64_t)b * Ho + oy) * Wo + ox) * C + cg * 4);
+          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(&gv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g4[j] = bf(gp[j]);
+        }
+        if (ky == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accb[j] += g4[j];
+        }
+        if (row_ok) {
+          const int ix0 = ox * S - pad;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int ix = ix0 + kx;
+            const float v = (ix >= 0 && ix < W) ? __ldg(im + ix) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[kx][j] = fmaf(v, g4[j], acc[kx][j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sacc[ky * K + kx][cg * 4 + j], acc[kx][j]);
+    if (ky == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sbias[cg * 4 + j], accb[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
+    int c = i % C, tp = i / C;
+    atomicAdd(gw + c * K * K + tp, sacc[tp][c]);
+  }
+  if (gb)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(gb + i, sbias[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C -> 1 convolution forward, stride 1 (decoder d4): out[b,oy,ox] = act(sum_{tap,c} x[b,oy+ky,ox+kx,c] w[c][tap] + bias)
+// x bf16 [B,H,W,C] (already padded: pad 0), w fp32 [1][C][K][K], out fp32 [B,Ho,Wo].
+template <int C, int K>
+__global__ void __launch_bounds__(256) convc1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int H, int W, int Ho,
+                                                         int Wo, int act, float* __restrict__ out) {
+  __shared__ float sw[K * K][C];
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) { int c = i % C, t = i / C; sw[t][c] = w[c * K * K + t]; }
+  __syncthreads();
+  const float b0 = bias ? bias[0] : 0.f;
+  const int64_t n = (int64_t)B * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo); int64_t q = i / Wo; const int oy = (int)(q % Ho); const int b = (int)(q / Ho);
+    float acc = b0;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const uint4* p = reinterpret_cast<const uint4*>(x + (((int64_t)b * H + oy + ky) * W + ox + kx) * C);
+#pragma unroll
+        for (int v = 0; v < C / 8; ++v) {
+          const uint4 u = __ldg(p + v);
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(bf(e[j]), sw[ky * K + kx][v * 8 + j], acc);
+        }
+      }
+    if (act == LIVAE_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+    else if (act == LIVAE_ACT_RELU) acc = fmaxf(acc, 0.f);
+    out[i] = acc;
+  }
+}
+
+// C -> 1 convolution weight (+bias) gradient: gw[c][tap] = sum x[b,oy+ky,ox+kx,c] * g[b,oy,ox]  (g fp32, pre-activation)
+// thread = (tap, c); CTA = a band of output rows, walking over images with register accumulators.
+template <int C, int K>
+__global__ void __launch_bounds__(C* K* K) convc1_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ g, int B, int H, int W,
+                                                               int Ho, int Wo, int rows_per_band,
+                                                               float* __restrict__ gw, float* __restrict__ gb) {
+  extern __shared__ float sg[];   // rows_per_band x Wo of g
+  const int t = threadIdx.x;
+  const int c = t % C, tap = t / C;
+  const int ky = tap / K, kx = tap % K;
+  const int oy0 = blockIdx.x * rows_per_band;
+  const int nrows = min(rows_per_band, Ho - oy0);
+  float acc = 0.f, accb = 0.f;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    __syncthreads();
+    for (int i = t; i < nrows * Wo; i += blockDim.x) sg[i] = g[((int64_t)b * Ho + oy0) * Wo + i];
+    __syncthreads();
+    for (int r = 0; r < nrows; ++r) {
+      const __nv_bfloat16* xr = x + (((int64_t)b * H + oy0 + r + ky) * W + kx) * C + c;
+      const float* gr = sg + r * Wo;
+#pragma unroll 4
+      for (int ox = 0; ox < Wo; ++ox) acc = fmaf(bf(xr[(int64_t)ox * C]), gr[ox], acc);
+    }
+    for (int i = t; i < nrows * Wo; i += blockDim.x) accb += sg[i];
+  }
+  atomicAdd(gw + c * K * K + tap, acc);
+  if (gb) {
+    accb = warp_sum(accb);
+    if ((t & 31) == 0) atomicAdd(gb, accb);
+  }
+}
+
+// Data gradient of a 1 -> C strided convolution (encoder c1): gimg[b,iy,ix] = sum_{ky,kx,c} g[b,oy,ox,c] w[c][ky][kx]
+// with oy = (iy+pad-ky)/S.  g bf16 [B,Ho,Wo,C] pre-activation gradient; gimg fp32 [B,H,W].
+template <int C, int K, int S>
+__global__ void __launch_bounds__(256) conv1c_dgrad_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
+                                                           int B, int H, int W, int Ho, int Wo, int pad,
+                                                           float* __restrict__ gimg) {
+  __shared__ float sw[K * K][C];
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) { int c = i % C, t = i / C; sw[t][c] = w[c * K * K + t]; }
+  __syncthreads();
+  const int64_t n = (int64_t)B * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % W); int64_t q = i / W; const int iy = (int)(q % H); const int b = (int)(q / H);
+    float acc = 0.f;
+    for (int ky = 0; ky < K; ++ky) {
+      const int ty = iy + pad - ky;
+      if (ty < 0 || ty % S != 0) continue;
+      const int oy = ty / S;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int tx = ix + pad - kx;
+        if (tx < 0 || tx % S != 0) continue;
+        const int ox = tx / S;
+        if (ox >= Wo) continue;
+        const uint4* p = reinterpret_cast<const uint4*>(g + (((int64_t)b * Ho + oy) * Wo + ox) * C);
+#pragma unroll
+        for (int v = 0; v < C / 8; ++v) {
+          const uint4 u = __ldg(p + v);
+          const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(bf(e[j]), sw[ky * K + kx][v * 8 + j], acc);
+        }
+      }
+    }
+    gimg[i] = acc;
+  }
+}
+
+// out = (g1 + g2) * y * (1 - y): pre-activation gradient of the decoder's sigmoid (model.py:372)
+__global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g1,
+                                                          const float* __restrict__ g2, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = y[i], g = g1[i] + (g2 ? g2[i] : 0.f);
+    out[i] = g * v * (1.f - v);
+  }
+}
+
+// out_bf16 = g * (y > 0): pre-activation gradient of a small fp32 ReLU layer, cast for the tensor-core path
+__global__ void __launch_bounds__(256) relu_mask_cast_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                             int64_t n, __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn((!y || y[i] > 0.f) ? g[i] : 0.f);
+}
+
+// ---- bf16 max-pool / un-pool ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_bf16_kernel(const __nv_bfloat16* __restrict__ full, int B, int H, int W,
+                                                           int C, __nv_bfloat16* __restrict__ pooled,
+                                                           uint8_t* __restrict__ idx) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int64_t n = (int64_t)B * Hp * Wp * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t q = i / C; const int px = (int)(q % Wp); q /= Wp; const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    const __nv_bfloat16* s = full + (((int64_t)b * H + 2 * py) * W + 2 * px) * C + c;
+    float best = bf(s[0]); int bi = 0;
+    float v = bf(s[C]); if (v > best) { best = v; bi = 1; }
+    v = bf(s[(int64_t)W * C]); if (v > best) { best = v; bi = 2; }
+    v = bf(s[(int64_t)W * C + C]); if (v > best) { best = v; bi = 3; }
+    pooled[i] = __float2bfloat16_rn(best);
+    idx[i] = (uint8_t)bi;
+  }
+}
+// full[b,y,x,c] = (idx[pooled] == pos) ? g[pooled] : 0
+__global__ void __launch_bounds__(256) unpool_bf16_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ idx,
+                                                          int B, int H, int W, int C, __nv_bfloat16* __restrict__ full) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int64_t n = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); int64_t q = i / C; const int x = (int)(q % W); q /= W; const int y = (int)(q % H);
+    const int b = (int)(q / H);
+    const int64_t pi = (((int64_t)b * Hp + (y >> 1)) * Wp + (x >> 1)) * C + c;
+    full[i] = idx[pi] == (((y & 1) << 1) | (x & 1)) ? g[pi] : __float2bfloat16_rn(0.f);
+  }
+}
+
+static inline int tgrid(int64_t n, int per = 1) {
+  int64_t blocks = (n + 256LL * per - 1) / (256LL * per);
+  if (blocks < 1) blocks = 1;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace livae
+
+using namespace livae;
+
+// kind: 0 = STN conv1 (C=16,K=5,S=1,+ReLU+pool), 1 = encoder c1 (C=32,K=4,S=2,+ReLU),
+//       2 = decoder d4 data gradient (C=32,K=3,S=1, flipped taps, no activation)
+extern "C" int livae_thin_conv1c_fwd(int kind, const float* img, const float* w, const float* bias, int B, int H,
+                                     int W, void* out_bf16, uint8_t* pool_idx, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && kind >= 0 && kind <= 2, "thin_conv1c_fwd: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(img && w && out_bf16, "thin_conv1c_fwd: null pointer");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+  if (kind == 0) {
+    LIVAE_CHECK_ARG(pool_idx && (H % 2) == 0 && (W % 2) == 0, "thin_conv1c_fwd: STN conv1 needs pool_idx and even size");
+    int quads = (H / 2) * (W / 2);
+    dim3 grid((quads + 255) / 256, B);
+    conv1c_fwd_kernel<16, 5, 1, true><<<grid, 256, 0, st>>>(img, w, bias, B, H, W, H, W, 2, LIVAE_ACT_RELU, 0, o, pool_idx);
+  } else if (kind == 1) {
+    LIVAE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "thin_conv1c_fwd: encoder c1 needs even size");
+    int px = (H / 2) * (W / 2);
+    dim3 grid((px + 255) / 256, B);
+    conv1c_fwd_kernel<32, 4, 2, false><<<grid, 256, 0, st>>>(img, w, bias, B, H, W, H / 2, W / 2, 1, LIVAE_ACT_RELU, 0, o, nullptr);
+  } else {
+    int px = (H + 2) * (W + 2);
+    dim3 grid((px + 255) / 256, B);
+    conv1c_fwd_kernel<32, 3, 1, false><<<grid, 256, 0, st>>>(img, w, nullptr, B, H, W, H + 2, W + 2, 2, LIVAE_ACT_NONE, 1, o, nullptr);
+  }
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// kind 0: STN conv1 (g = pooled pre-activation gradient bf16 [B,H/2,W/2,16] + pool_idx);
+// kind 1: encoder c1 (g bf16 [B,H/2,W/2,32]).  gw [C][K*K], gb [C] fp32, written.
+extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g_bf16, const uint8_t* pool_idx, int B,
+                                       int H, int W, float* gw, float* gb, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (kind == 0 || kind == 1), "thin_conv1c_wgrad: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(img && g_bf16 && gw, "thin_conv1c_wgrad: null pointer");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* g = (const __nv_bfloat16*)g_bf16;
+  cudaError_t ce;
+  if (kind == 0) {
+    LIVAE_CHECK_ARG(pool_idx, "thin_conv1c_wgrad: STN conv1 needs pool_idx");
+    if ((ce = cudaMemsetAsync(gw, 0, 16 * 25 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (gb && (ce = cudaMemsetAsync(gb, 0, 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    constexpr int RB = 256 / (5 * 4);
+    int bands = (H + RB - 1) / RB;
+    int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
+    conv1c_wgrad_kernel<16, 5, 1, true><<<dim3(bands, by), 256, 0, st>>>(img, g, pool_idx, B, H, W, H, W, 2, gw, gb);
+  } else {
+    if ((ce = cudaMemsetAsync(gw, 0, 32 * 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (gb && (ce = cudaMemsetAsync(gb, 0, 32 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    constexpr int RB = 256 / (4 * 8);
+    int bands = (H / 2 + RB - 1) / RB;
+    int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
+    conv1c_wgrad_kernel<32, 4, 2, false><<<dim3(bands, by), 256, 0, st>>>(img, g, nullptr, B, H, W, H / 2, W / 2, 1, gw, gb);
+  }
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// encoder c1 data gradient: g bf16 [B,H/2,W/2,32] -> gimg fp32 [B,H,W]
+extern "C" int livae_thin_conv1c_dgrad(const void* g_bf16, const float* w, int B, int H, int W, float* gimg,
+                                       livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0, "thin_conv1c_dgrad: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(g_bf16 && w && gimg, "thin_conv1c_dgrad: null pointer");
+  if (int e = require_sm100()) return e;
+  conv1c_dgrad_kernel<32, 4, 2><<<tgrid((int64_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g_bf16, w, B, H, W, H / 2, W / 2, 1, gimg);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// decoder d4 forward: x bf16 [B,H,W,32] (up-padded map) -> out fp32 [B,H-2,W-2], sigmoid
+extern "C" int livae_thin_convc1_fwd(const void* x_bf16, const float* w, const float* bias, int B, int H, int W,
+                                     int act, float* out, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 2 && W > 2, "thin_convc1_fwd: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(x_bf16 && w && out, "thin_convc1_fwd: null pointer");
+  if (int e = require_sm100()) return e;
+  convc1_fwd_kernel<32, 3><<<tgrid((int64_t)B * (H - 2) * (W - 2)), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_bf16, w, bias, B, H, W, H - 2, W - 2, act, out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// decoder d4 weight/bias gradient: gw [1][32][3][3], gb [1] (written); g fp32 [B,H-2,W-2] pre-activation
+extern "C" int livae_thin_convc1_wgrad(const void* x_bf16, const float* g, int B, int H, int W, float* gw, float* gb,
+                                       livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 2 && W > 2, "thin_convc1_wgrad: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(x_bf16 && g && gw, "thin_convc1_wgrad: null pointer");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(gw, 0, 32 * 9 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+  if (gb && (ce = cudaMemsetAsync(gb, 0, 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+  const int Ho = H - 2, Wo = W - 2;
+  int rows = 16;
+  while (rows * Wo * 4 > 40 * 1024 && rows > 1) rows >>= 1;
+  int bands = (Ho + rows - 1) / rows;
+  int by = (kNumSMs * 4 + bands - 1) / bands; if (by > B) by = B;
+  convc1_wgrad_kernel<32, 3><<<dim3(bands, by), 32 * 9, rows * Wo * 4, st>>>((const __nv_bfloat16*)x_bf16, g, B, H, W, Ho,
+                                                                            Wo, rows, gw, gb);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_sigmoid_bwd(const float* y, const float* g1, const float* g2, int64_t n, float* out,
+                                 livae_stream_t stream) {
+  LIVAE_CHECK_ARG(n >= 0, "sigmoid_bwd: bad size");
+  if (n == 0) return 0;
+  LIVAE_CHECK_ARG(y && g1 && out, "sigmoid_bwd: null pointer");
+  if (int e = require_sm100()) return e;
+  sigmoid_bwd_kernel<<<tgrid(n, 4), 256, 0, (cudaStream_t)stream>>>(y, g1, g2, n, out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_maxpool_bf16(const void* full, int B, int H, int W, int C, void* pooled, uint8_t* idx,
+                                  livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, "maxpool_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(full && pooled && idx, "maxpool_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  maxpool_bf16_kernel<<<tgrid((int64_t)B * (H / 2) * (W / 2) * C), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)full, B, H, W, C, (__nv_bfloat16*)pooled, idx);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_unpool_bf16(const void* g_pooled, const uint8_t* idx, int B, int H, int W, int C, void* g_full,
+                                 livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, "unpool_bf16: bad args");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(g_pooled && idx && g_full, "unpool_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  unpool_bf16_kernel<<<tgrid((int64_t)B * H * W * C, 2), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g_pooled, idx, B, H, W, C, (__nv_bfloat16*)g_full);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_relu_mask_cast_bf16(const float* g, const float* y, int64_t n, void* out_bf16,
+                                         livae_stream_t stream) {
+  LIVAE_CHECK_ARG(n >= 0, "relu_mask_cast_bf16: bad size");
+  if (n == 0) return 0;
+  LIVAE_CHECK_ARG(g && out_bf16, "relu_mask_cast_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  relu_mask_cast_kernel<<<tgrid(n, 4), 256, 0, (cudaStream_t)stream>>>(g, y, n, (__nv_bfloat16*)out_bf16);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}

@@ -3,7 +3,7 @@
 (include/livae_b200.h).  No CPU fallback: the ops raise if the CUDA library or device is missing.
 """
 from livae.loss import RVAELoss, VAELoss, cycle_consistency_loss
-from livae.model import RVAE, VAE, Decoder, Encoder, RotationSTN, VAEDecoder, VAEEncoder
+from livae.model import RVAE, VAE, Decoder, Encoder, RotationSTN, VAEDecoder, VAEEncoder, get_engine, set_engine
 from livae.train import (
     MetricLogger,
     compute_psnr,
@@ -21,5 +21,5 @@ __all__ = [
     "VAELoss", "RVAELoss", "cycle_consistency_loss",
     "VAE", "RVAE", "Encoder", "Decoder", "RotationSTN", "VAEEncoder", "VAEDecoder",
     "train_one_epoch", "train_rvae_one_epoch", "evaluate", "evaluate_rvae", "rotate_to_canonical",
-    "MetricLogger", "compute_psnr", "compute_ssim",
+    "MetricLogger", "compute_psnr", "compute_ssim", "set_engine", "get_engine",
 ]

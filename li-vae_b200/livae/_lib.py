@@ -53,7 +53,21 @@ _SIGS = {
     "livae_axpby_dev": "pppplps",
     "livae_conv_fwd": "d" + "p" * 6 + "s",
     "livae_conv_bwd": "d" + "p" * 8 + "s",
-    "livae_tc_pack_weights": "piiiiips",
+    "livae_tc_pack_weights": "piiiiiips",
+    "livae_permute_linear_grad": "piiips",
+    "livae_thin_conv1c_fwd": "ipppiiipps",
+    "livae_thin_conv1c_wgrad": "ipppiiipps",
+    "livae_thin_conv1c_dgrad": "ppiiips",
+    "livae_thin_convc1_fwd": "pppiiiips",
+    "livae_thin_convc1_wgrad": "ppiiipps",
+    "livae_sigmoid_bwd": "ppplps",
+    "livae_relu_mask_cast_bf16": "pplps",
+    "livae_maxpool_bf16": "piiiipps",
+    "livae_unpool_bf16": "ppiiiips",
+    "livae_upsample_pad_fwd_bf16": "piiiips",
+    "livae_upsample_pad_bwd_bf16": "piiiipps",
+    "livae_decfc_fwd_bf16": "pppiiiips",
+    "livae_decfc_bwd_bf16": "pppiiiippps",
     "livae_tc_conv": "t" + "p" * 5 + "s",
     "livae_tc_conv_dgrad": "t" + "p" * 5 + "s",
     "livae_tc_conv_wgrad": "t" + "p" * 5 + "s",

@@ -12,8 +12,23 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, tc
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+# Convolution engine: "tc" = tcgen05/TMA tensor cores with bf16 storage between layers (default;
+# parity class 1e-2, north_star "bf16 GEMM inputs"), "f32" = exact fp32 SIMT engine (1e-4).
+_ENGINE = "tc"
+
+
+def set_engine(name: str) -> None:
+    global _ENGINE
+    if name not in ("tc", "f32"):
+        raise ValueError(f"unknown engine {name!r} (expected 'tc' or 'f32')")
+    _ENGINE = name
+
+
+def get_engine() -> str:
+    return _ENGINE
 
 __all__ = ["VAEEncoder", "VAEDecoder", "VAE", "RotationSTN", "Encoder", "Decoder", "RVAE"]
 
@@ -179,6 +194,12 @@ class Encoder(nn.Module):
         self.fc_logvar = nn.Linear(flat_size, latent_dim)
 
     def forward(self, x):
+        if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, x.shape[1]):
+            loc, cl = self.rotation_stn.localization, self.conv_layers
+            return tc.EncoderTc.apply(x, loc[0].weight, loc[0].bias, loc[3].weight, loc[3].bias, loc[7].weight,
+                                      loc[7].bias, loc[9].weight, loc[9].bias, cl[0].weight, cl[0].bias,
+                                      cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight, cl[6].bias,
+                                      self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias)
         x_rotated, theta = self.rotation_stn(x)
         h = _run_encoder_convs(self.conv_layers, x_rotated)
         mu = ops.linear_nhwc(h, self.fc_mu.weight, self.fc_mu.bias)
@@ -207,6 +228,10 @@ class Decoder(nn.Module):
 
     def forward(self, z):
         q = self.patch_size // 16
+        if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, self.out_channels):
+            dl = self.deconv_layers
+            return tc.DecoderTc.apply(z, self.fc.weight, self.fc.bias, dl[2].weight, dl[2].bias, dl[6].weight,
+                                      dl[6].bias, dl[10].weight, dl[10].bias, dl[14].weight, dl[14].bias)
         h = ops.decoder_fc(z, self.fc.weight, self.fc.bias, 256, q)
         for n, i in enumerate((2, 6, 10, 14)):
             m = self.deconv_layers[i]

@@ -397,13 +397,18 @@ def cast(t, dtype):
     return out
 
 
-def tc_pack_weights(w, Cs, Cb, kh, kw, mode):
-    """torch-layout fp32 weight [Cs,Cb,kh,kw] -> bf16 [tap][Cs][Cb] (mode 0) / [flipped tap][Cb][Cs] (mode 1)"""
+def tc_pack_weights(w, Cs, Cb, kh, kw, mode, Cs_pad=None):
+    """torch-layout fp32 weight [Cs,Cb,kh,kw] -> bf16 packed for the tensor-core engine:
+    mode 0 [tap][Cs][Cb] (forward), 1 [flipped tap][Cb][Cs], 2 [tap][Cb][Cs] (data gradient),
+    3 [Cs_pad][tap][Cb] (Linear forward, K in (h,w,c) order), 4 [tap][Cb][Cs_pad] (Linear data gradient)"""
     w = _c(w)
     assert w.numel() == Cs * Cb * kh * kw and w.dtype == torch.float32 and w.is_cuda
-    shape = (kh * kw, Cs, Cb) if mode == 0 else (kh * kw, Cb, Cs)   # modes 1, 2: K axis = Cs
+    Cp = Cs if Cs_pad is None else Cs_pad
+    assert Cp >= Cs and (Cp == Cs or mode >= 3)
+    taps = kh * kw
+    shape = {0: (taps, Cp, Cb), 1: (taps, Cb, Cp), 2: (taps, Cb, Cp), 3: (Cp, taps, Cb), 4: (taps, Cb, Cp)}[mode]
     out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-    call("livae_tc_pack_weights", w, Cs, Cb, kh, kw, mode, out)
+    call("livae_tc_pack_weights", w, Cp, Cb, kh, kw, mode, Cs, out)
     return out
 
 

@@ -1,0 +1,237 @@
+"""Tensor-core path of the rVAE: the encoder (STN + conv stack + heads) and the decoder as TWO
+autograd Functions whose forward/backward are hand-scheduled sequences of C-ABI launches
+(reference model.py:237-262, 305-326, 375-388).
+
+Storage between layers is bf16 NHWC; parameters, their gradients, the 1-channel images, the
+latent heads and all loss arithmetic stay fp32.  The dense layers (STN conv2, encoder c2-c4,
+decoder d1-d3) and the three large Linear layers run on tcgen05 (csrc/conv_tc.cu,
+csrc/wgrad_tc.cu); the 1-channel ends run on the SIMT kernels in csrc/thin.cu.  Convention inside
+these Functions: a tensor handed from one layer's backward to the next is the PRE-activation
+gradient (the ReLU mask of a tensor is applied by whichever kernel produces its gradient).
+Parity class: 1e-2 relative (bf16 GEMM inputs), ELBO 1e-3 (north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, call
+
+BF = torch.bfloat16
+
+
+def supported(patch_size: int, latent_dim: int, in_channels: int) -> bool:
+    return in_channels == 1 and patch_size % 16 == 0 and patch_size >= 32 and 2 * latent_dim <= 256
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _linear_fwd(x2d, w, Cb, kh, kw, bias_pad, Npad, act, out_f32=True):
+    """nn.Linear over an NHWC-flattened map as a 1x1 tensor-core convolution; x2d bf16 [B, kh*kw*Cb]"""
+    B, K = x2d.shape
+    N = w.shape[0]
+    wp = ops.tc_pack_weights(w, N, Cb, kh, kw, 3, Cs_pad=Npad).view(1, Npad, K)
+    return ops.tc_conv(x2d.view(B, 1, 1, K), wp, bias_pad, 1, 1, 1, 0, act, out_f32=out_f32).view(B, Npad)
+
+
+def _linear_bwd(x2d, w, Cb, kh, kw, g_bf, Npad, relu_mask):
+    """-> (gw [N, Cb*kh*kw] in torch's (c,h,w) order, gb [N], gx bf16 [B, K] (masked by relu_mask > 0))"""
+    B, K = x2d.shape
+    N = w.shape[0]
+    gw_hwc, gb = ops.tc_conv_wgrad(x2d.view(B, 1, 1, K), g_bf.view(B, 1, 1, Npad), 1, 1, 1, 0)
+    gw = _empty((N, K), torch.float32, w.device)
+    call("livae_permute_linear_grad", gw_hwc, N, Cb, kh * kw, gw)
+    wp = ops.tc_pack_weights(w, N, Cb, kh, kw, 4, Cs_pad=Npad).view(1, K, Npad)
+    gx = ops.tc_conv(g_bf.view(B, 1, 1, Npad), wp, None, 1, 1, 1, 0, ACT_NONE, out_f32=False,
+                     relu_mask=relu_mask.view(B, 1, 1, K) if relu_mask is not None else None).view(B, K)
+    return gw, gb[:N].contiguous(), gx
+
+
+class EncoderTc(Function):
+    """(x, 20 parameters) -> (mu, logvar, theta); reference Encoder.forward, model.py:305-326"""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w3, b3, w7, b7, w9, b9, c0w, c0b, c2w, c2b, c4w, c4b, c6w, c6b, muw, mub, lvw, lvb):
+        ops.require_cuda(x)
+        x = x.contiguous()
+        B, _, P, _ = x.shape
+        dev = x.device
+        Ld = muw.shape[0]
+        h, q4, q16 = P // 2, P // 4, P // 16
+        # --- STN localisation (model.py:203-214)
+        a1 = _empty((B, h, h, 16), BF, dev); idx1 = _empty((B, h, h, 16), torch.uint8, dev)
+        call("livae_thin_conv1c_fwd", 0, x, w0, b0, B, P, P, a1, idx1)
+        a2f = ops.tc_conv(a1, ops.tc_pack_weights(w3, 32, 16, 5, 5, 0), b3, 5, 5, 1, 2, ACT_RELU)
+        a2 = _empty((B, q4, q4, 32), BF, dev); idx2 = _empty((B, q4, q4, 32), torch.uint8, dev)
+        call("livae_maxpool_bf16", a2f, B, h, h, 32, a2, idx2)
+        del a2f
+        f1 = _linear_fwd(a2.view(B, -1), w7, 32, q4, q4, b7, 32, ACT_RELU)           # fp32 [B,32]
+        d9 = L.ConvDesc(L.CONV, B, 1, 1, 32, 2, 1, 1, 1, 0, ACT_NONE, 0)
+        vec = _empty((B, 2), torch.float32, dev)
+        call("livae_conv_fwd", C.byref(d9), f1, w9, b9, vec, None, None)
+        cs = _empty((B, 2), torch.float32, dev); theta = _empty((B, 1), torch.float32, dev)
+        call("livae_stn_head_fwd", vec, B, cs, theta)
+        x_rot = torch.empty_like(x)
+        call("livae_rot_sample_fwd", x, cs, 1.0, B, 1, P, P, x_rot)
+        # --- encoder conv stack (model.py:289-298)
+        h1 = _empty((B, h, h, 32), BF, dev)
+        call("livae_thin_conv1c_fwd", 1, x_rot, c0w, c0b, B, P, P, h1, None)
+        h2 = ops.tc_conv(h1, ops.tc_pack_weights(c2w, 64, 32, 4, 4, 0), c2b, 4, 4, 2, 1, ACT_RELU)
+        h3 = ops.tc_conv(h2, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 0), c4b, 4, 4, 2, 1, ACT_RELU)
+        h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
+        # --- heads (model.py:302-303, 321-324): one GEMM for [fc_mu; fc_logvar]
+        Npad = _pad16(2 * Ld)
+        wcat = torch.cat([muw, lvw], 0)
+        bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
+        bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb
+        mulv = _linear_fwd(h4.view(B, -1), wcat, 256, q16, q16, bcat, Npad, ACT_NONE)
+        mu = mulv[:, :Ld].contiguous(); logvar = mulv[:, Ld:2 * Ld].contiguous()
+        ctx.save_for_backward(x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, wcat, a1, idx1, a2, idx2, f1, vec, cs, x_rot,
+                              h1, h2, h3, h4)
+        ctx.dims = (B, P, Ld, Npad)
+        ctx.set_materialize_grads(False)
+        return mu, logvar, theta
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mu, g_lv, g_theta):
+        (x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, wcat, a1, idx1, a2, idx2, f1, vec, cs, x_rot,
+         h1, h2, h3, h4) = ctx.saved_tensors
+        B, P, Ld, Npad = ctx.dims
+        dev = x.device
+        h, q4, q16 = P // 2, P // 4, P // 16
+        if g_mu is None and g_lv is None:
+            # only theta is consumed downstream (train.py:376-377, pretrain_stn.py:106-107): the
+            # gradient reaches the STN localisation only
+            if g_theta is None:
+                return (None,) * 21
+            return EncoderTc._backward_stn(ctx, None, g_theta)
+        # --- heads
+        g16 = torch.zeros((B, Npad), dtype=torch.float32, device=dev)
+        if g_mu is not None:
+            g16[:, :Ld] = g_mu
+        if g_lv is not None:
+            g16[:, Ld:2 * Ld] = g_lv
+        g16b = ops.cast(g16, BF)
+        gwcat, gbcat, gh4 = _linear_bwd(h4.view(B, -1), wcat, 256, q16, q16, g16b, Npad, h4.view(B, -1))
+        gh4 = gh4.view(B, q16, q16, 256)
+        # --- encoder convs c4, c3, c2 (tensor cores)
+        gw6, gb6 = ops.tc_conv_wgrad(h3, gh4, 4, 4, 2, 1)
+        gh3 = ops.tc_conv_dgrad(gh4, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 2), None, P // 8, P // 8, 4, 4, 2, 1,
+                                relu_mask=h3)
+        gw4, gb4 = ops.tc_conv_wgrad(h2, gh3, 4, 4, 2, 1)
+        gh2 = ops.tc_conv_dgrad(gh3, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 2), None, q4, q4, 4, 4, 2, 1,
+                                relu_mask=h2)
+        gw2, gb2 = ops.tc_conv_wgrad(h1, gh2, 4, 4, 2, 1)
+        gh1 = ops.tc_conv_dgrad(gh2, ops.tc_pack_weights(c2w, 64, 32, 4, 4, 2), None, h, h, 4, 4, 2, 1,
+                                relu_mask=h1)
+        # --- encoder c1 (thin) and the rotation
+        gc0w = torch.empty_like(c0w); gc0b = _empty((32,), torch.float32, dev)
+        call("livae_thin_conv1c_wgrad", 1, x_rot, gh1, None, B, P, P, gc0w, gc0b)
+        g_xrot = torch.empty_like(x)
+        call("livae_thin_conv1c_dgrad", gh1, c0w, B, P, P, g_xrot)
+        gcs = _empty((B, 2), torch.float32, dev)
+        call("livae_rot_sample_bwd", x, cs, 1.0, g_xrot, B, 1, P, P, None, gcs)
+        stn = EncoderTc._backward_stn(ctx, gcs, g_theta)
+        gmuw, glvw = gwcat[:Ld].contiguous(), gwcat[Ld:2 * Ld].contiguous()
+        gmub, glvb = gbcat[:Ld].contiguous(), gbcat[Ld:2 * Ld].contiguous()
+        return stn[:9] + (gc0w, gc0b, gw2, gb2, gw4, gb4, gw6, gb6, gmuw.view(Ld, -1), gmub, glvw.view(Ld, -1), glvb)
+
+    @staticmethod
+    def _backward_stn(ctx, gcs, g_theta):
+        """gradients of the 8 STN parameters from d/d(cos,sin) and d/dtheta (model.py:203-214, 245-261)"""
+        (x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, wcat, a1, idx1, a2, idx2, f1, vec, cs, x_rot,
+         h1, h2, h3, h4) = ctx.saved_tensors
+        B, P, Ld, Npad = ctx.dims
+        dev = x.device
+        h, q4 = P // 2, P // 4
+        gvec = _empty((B, 2), torch.float32, dev)
+        call("livae_stn_head_bwd", vec, gcs, g_theta.contiguous() if g_theta is not None else None, B, gvec)
+        # --- STN fc2 (fp32 engine), fc1, conv2 (tensor cores), conv1 (thin)
+        d9 = L.ConvDesc(L.CONV, B, 1, 1, 32, 2, 1, 1, 1, 0, ACT_NONE, 0)
+        gw9 = torch.empty_like(w9); gb9 = _empty((2,), torch.float32, dev); gf1 = torch.empty_like(f1)
+        call("livae_conv_bwd", C.byref(d9), f1, w9, vec, gvec, None, gw9, gb9, gf1)
+        gf1b = _empty((B, 32), BF, dev)
+        call("livae_relu_mask_cast_bf16", gf1, f1, gf1.numel(), gf1b)
+        gw7, gb7, ga2 = _linear_bwd(a2.view(B, -1), w7, 32, q4, q4, gf1b, 32, a2.view(B, -1))
+        g2full = _empty((B, h, h, 32), BF, dev)
+        call("livae_unpool_bf16", ga2, idx2, B, h, h, 32, g2full)
+        gw3, gb3 = ops.tc_conv_wgrad(a1, g2full, 5, 5, 1, 2)
+        ga1 = ops.tc_conv_dgrad(g2full, ops.tc_pack_weights(w3, 32, 16, 5, 5, 2), None, h, h, 5, 5, 1, 2,
+                                relu_mask=a1)
+        gw0 = torch.empty_like(w0); gb0 = _empty((16,), torch.float32, dev)
+        call("livae_thin_conv1c_wgrad", 0, x, ga1, idx1, B, P, P, gw0, gb0)
+        return (None, gw0, gb0, gw3, gb3, gw7.view_as(w7), gb7, gw9, gb9) + (None,) * 12
+
+
+class DecoderTc(Function):
+    """(z, 10 parameters) -> recon [B,1,P,P]; reference Decoder.forward, model.py:375-388"""
+
+    @staticmethod
+    def forward(ctx, z, fcw, fcb, d1w, d1b, d2w, d2b, d3w, d3b, d4w, d4b):
+        ops.require_cuda(z)
+        z = z.contiguous()
+        B, Ld = z.shape
+        dev = z.device
+        q = int(round((fcw.shape[0] // 256) ** 0.5))
+        y0 = _empty((B, q, q, 256), BF, dev)
+        call("livae_decfc_fwd_bf16", z, fcw, fcb, B, Ld, 256, q * q, y0)
+        ys, us = [y0], []
+        cur, hw = y0, q
+        for w, b, cin, cout in ((d1w, d1b, 256, 128), (d2w, d2b, 128, 64), (d3w, d3b, 64, 32)):
+            u = _empty((B, 2 * hw + 2, 2 * hw + 2, cin), BF, dev)
+            call("livae_upsample_pad_fwd_bf16", cur, B, hw, hw, cin, u)
+            cur = ops.tc_conv(u, ops.tc_pack_weights(w, cout, cin, 3, 3, 0), b, 3, 3, 1, 0, ACT_RELU)
+            us.append(u); ys.append(cur)
+            hw *= 2
+        u4 = _empty((B, 2 * hw + 2, 2 * hw + 2, 32), BF, dev)
+        call("livae_upsample_pad_fwd_bf16", cur, B, hw, hw, 32, u4)
+        P = 2 * hw
+        recon = _empty((B, 1, P, P), torch.float32, dev)
+        call("livae_thin_convc1_fwd", u4, d4w, d4b, B, P + 2, P + 2, ACT_SIGMOID, recon)
+        ctx.save_for_backward(z, fcw, d1w, d2w, d3w, d4w, recon, u4, *ys, *us)
+        ctx.dims = (B, Ld, q, P)
+        return recon
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_recon):
+        saved = ctx.saved_tensors
+        z, fcw, d1w, d2w, d3w, d4w, recon, u4 = saved[:8]
+        ys, us = saved[8:12], saved[12:15]
+        B, Ld, q, P = ctx.dims
+        dev = z.device
+        gpre4 = torch.empty_like(recon)
+        call("livae_sigmoid_bwd", recon, g_recon.contiguous(), None, recon.numel(), gpre4)
+        gd4w = torch.empty_like(d4w); gd4b = _empty((1,), torch.float32, dev)
+        call("livae_thin_convc1_wgrad", u4, gpre4, B, P + 2, P + 2, gd4w, gd4b)
+        gu = _empty((B, P + 2, P + 2, 32), BF, dev)
+        call("livae_thin_conv1c_fwd", 2, gpre4, d4w, None, B, P, P, gu, None)
+        grads = []
+        hw = P // 2
+        for i, (w, cin, cout) in zip((3, 2, 1), ((d3w, 64, 32), (d2w, 128, 64), (d1w, 256, 128))):
+            y, u = ys[i], us[i - 1]
+            gy = torch.empty_like(y)                              # pre-activation gradient of conv i
+            call("livae_upsample_pad_bwd_bf16", gu, B, hw, hw, cout, y, gy)
+            gw, gb = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0)
+            gu = ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, cout, cin, 3, 3, 2), None, hw + 2, hw + 2, 3, 3, 1, 0)
+            grads.append((gw, gb))
+            hw //= 2
+        gy0 = torch.empty_like(ys[0])
+        call("livae_upsample_pad_bwd_bf16", gu, B, q, q, 256, ys[0], gy0)
+        gfcw = torch.empty_like(fcw); gfcb = _empty((fcw.shape[0],), torch.float32, dev)
+        gz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        call("livae_decfc_bwd_bf16", z, fcw, gy0, B, Ld, 256, q * q, gfcw, gfcb, gz)
+        (g3w, g3b), (g2w, g2b), (g1w, g1b) = grads
+        return gz, gfcw, gfcb, g1w, g1b, g2w, g2b, g3w, g3b, gd4w, gd4b

@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "tc_engine: run the livae model on the tcgen05 engine (default for tests: f32)")
 
 
 def pytest_collection_modifyitems(config, items):
