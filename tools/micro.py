@@ -1,0 +1,52 @@
+"""micro-benchmark of individual C-ABI kernels at the C3 shapes (B=2048, P=128); used for ncu captures"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "li-vae_b200")]
+import torch
+from livae import ops
+
+B = int(os.environ.get("MB", "2048"))
+which = sys.argv[1:] or ["wgrad_stn2"]
+dev = "cuda"
+bf = torch.bfloat16
+
+
+def timeit(fn, n=3):
+    fn(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+for w in which:
+    if w == "wgrad_stn2":
+        x = torch.randn(B, 64, 64, 16, device=dev).to(bf); g = torch.randn(B, 64, 64, 32, device=dev).to(bf)
+        print(w, timeit(lambda: ops.tc_conv_wgrad(x, g, 5, 5, 1, 2)), "ms")
+    elif w == "wgrad_d3":
+        x = torch.randn(B, 66, 66, 64, device=dev).to(bf); g = torch.randn(B, 64, 64, 32, device=dev).to(bf)
+        print(w, timeit(lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)), "ms")
+    elif w == "wgrad_d1":
+        x = torch.randn(B, 18, 18, 256, device=dev).to(bf); g = torch.randn(B, 16, 16, 128, device=dev).to(bf)
+        print(w, timeit(lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)), "ms")
+    elif w == "fwd_d3":
+        x = torch.randn(B, 66, 66, 64, device=dev).to(bf); wt = torch.randn(32, 64, 3, 3, device=dev)
+        wp = ops.tc_pack_weights(wt, 32, 64, 3, 3, 0)
+        print(w, timeit(lambda: ops.tc_conv(x, wp, None, 3, 3, 1, 0, 1)), "ms")
+    elif w == "fwd_c4":
+        x = torch.randn(B, 16, 16, 128, device=dev).to(bf); wt = torch.randn(256, 128, 4, 4, device=dev)
+        wp = ops.tc_pack_weights(wt, 256, 128, 4, 4, 0)
+        print(w, timeit(lambda: ops.tc_conv(x, wp, None, 4, 4, 2, 1, 1)), "ms")
+    elif w == "thin_wgrad0":
+        img = torch.rand(B, 1, 128, 128, device=dev); g = torch.randn(B, 64, 64, 16, device=dev).to(bf)
+        idx = torch.randint(0, 4, (B, 64, 64, 16), device=dev, dtype=torch.uint8)
+        gw = torch.empty(16, 1, 5, 5, device=dev); gb = torch.empty(16, device=dev)
+        from livae._lib import call
+        print(w, timeit(lambda: call("livae_thin_conv1c_wgrad", 0, img, g, idx, B, 128, 128, gw, gb)), "ms")
+    elif w == "thin_wgrad_d4":
+        u = torch.randn(B, 130, 130, 32, device=dev).to(bf); g = torch.randn(B, 128, 128, device=dev)
+        gw = torch.empty(1, 32, 3, 3, device=dev); gb = torch.empty(1, device=dev)
+        from livae._lib import call
+        print(w, timeit(lambda: call("livae_thin_convc1_wgrad", u, g, B, 130, 130, gw, gb)), "ms")
