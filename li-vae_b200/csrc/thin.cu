@@ -100,8 +100,11 @@ __global__ void __launch_bounds__(256) conv1c_fwd_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // 1 -> C convolution weight (+bias) gradient: gw[c][tap] = sum img[b, oy*S-pad+ky, ox*S-pad+kx] * g[b,oy,ox,c]
 // g bf16: [B,Ho,Wo,C] pre-activation gradient, or (POOL) the pooled gradient [B,Ho/2,Wo/2,C] routed by idx.
-// Thread = (tap row ky, 4 channels, output row of the band); accumulators stay in registers over all
-// images the CTA walks, then shared-memory reduction and one global atomic per weight per CTA.
+// CTA = a band of RB output rows, walking over images.  Per image the band's zero-padded image rows
+// (fp32) and its gradient rows (bf16, pool routing resolved while staging) are staged in shared memory
+// with coalesced loads; thread = (tap row ky, 4 channels, output row) runs along x with K*4 register
+// accumulators (K + 1 shared loads per K*4 FMAs).  One shared reduction + one global atomic per
+// weight per CTA at the very end.
 template <int C, int K, int S, bool POOL>
 __global__ void __launch_bounds__(256) conv1c_wgrad_kernel(const float* __restrict__ img,
                                                            const __nv_bfloat16* __restrict__ g,
@@ -111,58 +114,78 @@ __global__ void __launch_bounds__(256) conv1c_wgrad_kernel(const float* __restri
   constexpr int CG = C / 4;
   constexpr int COMBOS = K * CG;
   constexpr int RB = 256 / COMBOS;          // output rows per band
+  constexpr int IR = (RB - 1) * S + K;      // staged image rows
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int IWp = (Wo - 1) * S + K;         // staged image row width (zero padded)
+  float* simg = reinterpret_cast<float*>(dsm);                                  // [IR][IWp]
+  __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(simg + ((IR * IWp + 3) & ~3));   // [RB][Wo][C]
   __shared__ float sacc[K * K][C];
   __shared__ float sbias[C];
   for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) (&sacc[0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < C; i += blockDim.x) sbias[i] = 0.f;
-  __syncthreads();
   const int t = threadIdx.x;
   const int ky = t % K, cg = (t / K) % CG, r = t / COMBOS;
-  const bool active = r < RB;
-  const int oy = blockIdx.x * RB + r;
+  const int oy0 = blockIdx.x * RB;
+  const int nrows = min(RB, Ho - oy0);
+  const bool active = r < nrows;
   float acc[K][4];
   float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < K; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  if (active && oy < Ho) {
-    const int iy = oy * S - pad + ky;
-    const bool row_ok = iy >= 0 && iy < H;
-    for (int b = blockIdx.y; b < B; b += gridDim.y) {
-      const float* im = img + ((int64_t)b * H + (row_ok ? iy : 0)) * W;
+  const int iy0 = oy0 * S - pad;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    __syncthreads();
+    // stage image rows [iy0, iy0+IR) x [-pad, -pad+IWp), zero outside
+    const float* im = img + (int64_t)b * H * W;
+    for (int i = t; i < IR * IWp; i += blockDim.x) {
+      const int rr = i / IWp, cc = i - rr * IWp;
+      const int iy = iy0 + rr, ix = cc - pad;
+      simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(im + iy * W + ix) : 0.f;
+    }
+    // stage gradient rows (4 channels = 8 bytes per item)
+    for (int i = t; i < nrows * Wo * CG; i += blockDim.x) {
+      const int c4 = i % CG; const int q = i / CG; const int ox = q % Wo; const int rr = q / Wo;
+      const int oy = oy0 + rr;
+      uint2 v;
+      if (POOL) {
+        const int64_t pi = ((((int64_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1)) + (ox >> 1)) * C + c4 * 4;
+        const int pos = ((oy & 1) << 1) | (ox & 1);
+        const uint32_t id4 = __ldg(reinterpret_cast<const uint32_t*>(idx + pi));
+        v = __ldg(reinterpret_cast<const uint2*>(g + pi));
+        if ((int)(id4 & 0xff) != pos) v.x &= 0xffff0000u;
+        if ((int)((id4 >> 8) & 0xff) != pos) v.x &= 0x0000ffffu;
+        if ((int)((id4 >> 16) & 0xff) != pos) v.y &= 0xffff0000u;
+        if ((int)((id4 >> 24) & 0xff) != pos) v.y &= 0x0000ffffu;
+      } else {
+        v = __ldg(reinterpret_cast<const uint2*>(g + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4));
+      }
+      *reinterpret_cast<uint2*>(sg + ((int64_t)(rr * Wo + ox)) * C + c4 * 4) = v;
+    }
+    __syncthreads();
+    if (active) {
+      const float* irow = simg + (r * S + ky) * IWp;
+      const __nv_bfloat16* grow = sg + (int64_t)r * Wo * C + cg * 4;
+#pragma unroll 2
       for (int ox = 0; ox < Wo; ++ox) {
-        float g4[4];
-        if (POOL) {
-          const int64_t pi = ((((int64_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1)) + (ox >> 1)) * C + cg * 4;
-          const int pos = ((oy & 1) << 1) | (ox & 1);
-          const uint32_t id4 = *reinterpret_cast<const uint32_t*>(idx + pi);
-          const uint2 gv = *reinterpret_cast<const uint2*>(g + pi);
-          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(&gv);
+        const uint2 gv = *reinterpret_cast<const uint2*>(grow + (int64_t)ox * C);
+        const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&gv);
+        const float2 g01 = __bfloat1622float2(gp[0]), g23 = __bfloat1622float2(gp[1]);
+        if (ky == 0) { accb[0] += g01.x; accb[1] += g01.y; accb[2] += g23.x; accb[3] += g23.y; }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) g4[j] = (int)((id4 >> (8 * j)) & 0xff) == pos ? bf(gp[j]) : 0.f;
-        } else {
-          const uint2 gv = *reinterpret_cast<const uint2*>(g + (((int64_t)b * Ho + oy) * Wo + ox) * C + cg * 4);
-          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(&gv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) g4[j] = bf(gp[j]);
-        }
-        if (ky == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) accb[j] += g4[j];
-        }
-        if (row_ok) {
-          const int ix0 = ox * S - pad;
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            const int ix = ix0 + kx;
-            const float v = (ix >= 0 && ix < W) ? __ldg(im + ix) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[kx][j] = fmaf(v, g4[j], acc[kx][j]);
-          }
+        for (int kx = 0; kx < K; ++kx) {
+          const float v = irow[ox * S + kx];
+          acc[kx][0] = fmaf(v, g01.x, acc[kx][0]);
+          acc[kx][1] = fmaf(v, g01.y, acc[kx][1]);
+          acc[kx][2] = fmaf(v, g23.x, acc[kx][2]);
+          acc[kx][3] = fmaf(v, g23.y, acc[kx][3]);
         }
       }
     }
+  }
+  __syncthreads();
+  if (active) {
 #pragma unroll
     for (int kx = 0; kx < K; ++kx)
 #pragma unroll
@@ -216,32 +239,51 @@ __global__ void __launch_bounds__(256) convc1_fwd_kernel(const __nv_bfloat16* __
 }
 
 // C -> 1 convolution weight (+bias) gradient: gw[c][tap] = sum x[b,oy+ky,ox+kx,c] * g[b,oy,ox]  (g fp32, pre-activation)
-// thread = (tap, c); CTA = a band of output rows, walking over images with register accumulators.
-template <int C, int K>
-__global__ void __launch_bounds__(C* K* K) convc1_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
-                                                               const float* __restrict__ g, int B, int H, int W,
-                                                               int Ho, int Wo, int rows_per_band,
-                                                               float* __restrict__ gw, float* __restrict__ gb) {
-  extern __shared__ float sg[];   // rows_per_band x Wo of g
+// CTA = a band of RWB output rows, walking over images; the band's (RWB+K-1) input rows (bf16, all C
+// channels) and gradient rows (fp32) are staged in shared memory with 16-byte coalesced loads.
+// thread = (tap, channel pair, row-slice): one bf16x2 shared load feeds two FMAs.
+template <int C, int K, int RWB>
+__global__ void __launch_bounds__(K* K*(C / 2) * 2) convc1_wgrad_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                        const float* __restrict__ g, int B, int H,
+                                                                        int W, int Ho, int Wo, float* __restrict__ gw,
+                                                                        float* __restrict__ gb) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  constexpr int NT = K * K * (C / 2) * 2;
+  __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(dsm);                 // [RWB+K-1][W][C]
+  float* sg = reinterpret_cast<float*>(sx + (size_t)(RWB + K - 1) * W * C);  // [RWB][Wo]
   const int t = threadIdx.x;
-  const int c = t % C, tap = t / C;
+  const int half = t & 1;
+  const int c2 = (t >> 1) % (C / 2);
+  const int tap = (t >> 1) / (C / 2);
   const int ky = tap / K, kx = tap % K;
-  const int oy0 = blockIdx.x * rows_per_band;
-  const int nrows = min(rows_per_band, Ho - oy0);
-  float acc = 0.f, accb = 0.f;
+  const int oy0 = blockIdx.x * RWB;
+  const int nrows = min(RWB, Ho - oy0);
+  float a0 = 0.f, a1 = 0.f, accb = 0.f;
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     __syncthreads();
-    for (int i = t; i < nrows * Wo; i += blockDim.x) sg[i] = g[((int64_t)b * Ho + oy0) * Wo + i];
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((int64_t)b * H + oy0) * W * C);
+    const int n16 = (nrows + K - 1) * W * C / 8;
+    for (int i = t; i < n16; i += NT) reinterpret_cast<uint4*>(sx)[i] = __ldg(src + i);
+    for (int i = t; i < nrows * Wo; i += NT) {
+      const float v = g[((int64_t)b * Ho + oy0) * Wo + i];
+      sg[i] = v;
+      accb += v;
+    }
     __syncthreads();
-    for (int r = 0; r < nrows; ++r) {
-      const __nv_bfloat16* xr = x + (((int64_t)b * H + oy0 + r + ky) * W + kx) * C + c;
+    for (int r = half; r < nrows; r += 2) {
+      const __nv_bfloat16* xr = sx + ((size_t)(r + ky) * W + kx) * C + 2 * c2;
       const float* gr = sg + r * Wo;
 #pragma unroll 4
-      for (int ox = 0; ox < Wo; ++ox) acc = fmaf(bf(xr[(int64_t)ox * C]), gr[ox], acc);
+      for (int ox = 0; ox < Wo; ++ox) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + (size_t)ox * C));
+        const float gg = gr[ox];
+        a0 = fmaf(v.x, gg, a0);
+        a1 = fmaf(v.y, gg, a1);
+      }
     }
-    for (int i = t; i < nrows * Wo; i += blockDim.x) accb += sg[i];
   }
-  atomicAdd(gw + c * K * K + tap, acc);
+  atomicAdd(gw + (2 * c2) * K * K + tap, a0);
+  atomicAdd(gw + (2 * c2 + 1) * K * K + tap, a1);
   if (gb) {
     accb = warp_sum(accb);
     if ((t & 31) == 0) atomicAdd(gb, accb);
@@ -387,17 +429,27 @@ extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g
     LIVAE_CHECK_ARG(pool_idx, "thin_conv1c_wgrad: STN conv1 needs pool_idx");
     if ((ce = cudaMemsetAsync(gw, 0, 16 * 25 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
     if (gb && (ce = cudaMemsetAsync(gb, 0, 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
-    constexpr int RB = 256 / (5 * 4);
+    constexpr int RB = 256 / (5 * 4), IR = (RB - 1) + 5;
+    const int IWp = (W - 1) + 5;
+    const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * W * 16 * 2;
+    LIVAE_CHECK_ARG(smem <= 200 * 1024, "thin_conv1c_wgrad: image too wide for the staged kernel");
+    static bool attr0 = false;
+    if (!attr0) { cudaFuncSetAttribute(conv1c_wgrad_kernel<16, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr0 = true; }
     int bands = (H + RB - 1) / RB;
     int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
-    conv1c_wgrad_kernel<16, 5, 1, true><<<dim3(bands, by), 256, 0, st>>>(img, g, pool_idx, B, H, W, H, W, 2, gw, gb);
+    conv1c_wgrad_kernel<16, 5, 1, true><<<dim3(bands, by), 256, smem, st>>>(img, g, pool_idx, B, H, W, H, W, 2, gw, gb);
   } else {
     if ((ce = cudaMemsetAsync(gw, 0, 32 * 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
     if (gb && (ce = cudaMemsetAsync(gb, 0, 32 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
-    constexpr int RB = 256 / (4 * 8);
+    constexpr int RB = 256 / (4 * 8), IR = (RB - 1) * 2 + 4;
+    const int IWp = (W / 2 - 1) * 2 + 4;
+    const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * (W / 2) * 32 * 2;
+    LIVAE_CHECK_ARG(smem <= 200 * 1024, "thin_conv1c_wgrad: image too wide for the staged kernel");
+    static bool attr1 = false;
+    if (!attr1) { cudaFuncSetAttribute(conv1c_wgrad_kernel<32, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
     int bands = (H / 2 + RB - 1) / RB;
     int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
-    conv1c_wgrad_kernel<32, 4, 2, false><<<dim3(bands, by), 256, 0, st>>>(img, g, nullptr, B, H, W, H / 2, W / 2, 1, gw, gb);
+    conv1c_wgrad_kernel<32, 4, 2, false><<<dim3(bands, by), 256, smem, st>>>(img, g, nullptr, B, H, W, H / 2, W / 2, 1, gw, gb);
   }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
@@ -441,12 +493,15 @@ extern "C" int livae_thin_convc1_wgrad(const void* x_bf16, const float* g, int B
   if ((ce = cudaMemsetAsync(gw, 0, 32 * 9 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
   if (gb && (ce = cudaMemsetAsync(gb, 0, 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
   const int Ho = H - 2, Wo = W - 2;
-  int rows = 16;
-  while (rows * Wo * 4 > 40 * 1024 && rows > 1) rows >>= 1;
-  int bands = (Ho + rows - 1) / rows;
+  constexpr int RWB = 4;
+  const size_t smem = (size_t)(RWB + 2) * W * 32 * 2 + (size_t)RWB * Wo * 4;
+  LIVAE_CHECK_ARG(smem <= 200 * 1024 && (W * 32) % 8 == 0, "thin_convc1_wgrad: map too wide for the staged kernel");
+  static bool attrd = false;
+  if (!attrd) { cudaFuncSetAttribute(convc1_wgrad_kernel<32, 3, RWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attrd = true; }
+  int bands = (Ho + RWB - 1) / RWB;
   int by = (kNumSMs * 4 + bands - 1) / bands; if (by > B) by = B;
-  convc1_wgrad_kernel<32, 3><<<dim3(bands, by), 32 * 9, rows * Wo * 4, st>>>((const __nv_bfloat16*)x_bf16, g, B, H, W, Ho,
-                                                                            Wo, rows, gw, gb);
+  convc1_wgrad_kernel<32, 3, RWB><<<dim3(bands, by), 9 * 16 * 2, smem, st>>>((const __nv_bfloat16*)x_bf16, g, B, H, W, Ho, Wo,
+                                                                           gw, gb);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
