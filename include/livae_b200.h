@@ -224,6 +224,9 @@ int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int 
 int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, int L, int C, int HW,
                          float* gw, float* gb, float* gz, livae_stream_t stream);
 
+/* tuning / test hook: 0 = fetch one TMA box per filter tap; 1 (default) = fetch one haloed box per tap
+ * group and address each tap as a row shift of it */
+void livae_tc_set_halo_mode(int mode);
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

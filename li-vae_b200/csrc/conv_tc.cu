@@ -68,6 +68,55 @@ struct ConvTcParams {
   const __nv_bfloat16* relu_mask;  // may be null: out *= (relu_mask > 0), same shape as out
 };
 
+// Epilogue of one accumulator row per thread: TMEM -> registers -> bias / activation / ReLU mask of the
+// consumer -> bf16 or fp32 NHWC row.  tcgen05.ld is warp-collective, so invalid rows still issue it.
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, int nbase, int N, int Ntot, bool valid, int64_t pix,
+                                              void* out, int out_f32, const float* __restrict__ bias, int act,
+                                              const __nv_bfloat16* __restrict__ relu_mask) {
+    for (int cc = 0; cc < N; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)cc, v);   // warp-collective: issued by all lanes, stores predicated
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int c0 = nbase + cc;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(v[i]);
+        if (bias) a += __ldg(bias + c0 + i);
+        if (act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
+        f[i] = a;
+      }
+      if (relu_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(relu_mask + pix * Ntot + c0);
+        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
+        const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!(__bfloat162float(mb0[i]) > 0.f)) f[i] = 0.f;
+          if (!(__bfloat162float(mb1[i]) > 0.f)) f[8 + i] = 0.f;
+        }
+      }
+      if (out_f32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * Ntot + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Ntot + c0);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+}
+
 static constexpr int kThreads = 192;
 
 template <int STAGES>
@@ -162,50 +211,156 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int nbase = (int)blockIdx.y * p.N;
-    for (int cc = 0; cc < p.N; cc += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)cc, v);   // warp-collective: issued by all lanes, stores predicated
-      tmem_ld_wait();
-      if (!valid) continue;
-      const int c0 = nbase + cc;
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(v[i]);
-        if (p.bias) a += __ldg(p.bias + c0 + i);
-        if (p.act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
-        else if (p.act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
-        f[i] = a;
-      }
-      if (p.relu_mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + pix * p.Ntot + c0);
-        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-        const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
-        const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!(__bfloat162float(mb0[i]) > 0.f)) f[i] = 0.f;
-          if (!(__bfloat162float(mb1[i]) > 0.f)) f[8 + i] = 0.f;
+    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32,
+                  p.bias, p.act, p.relu_mask);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// "Halo" variant: the taps of a convolution are row shifts of ONE input tile.  The CTA's output
+// tile is 8 rows x 16 columns of the output grid, stored as 128 consecutive shared-memory rows
+// (pixel-major); the input box [8 + hy rows] x [16 cols] x kc channels is fetched ONCE per
+// (tap group, channel chunk) and each tap's A operand is the same buffer addressed from row
+// (dy*16 + dx).  Columns x >= tw = 16 - hx read pixels of the next row and are discarded, so the
+// MMA runs at tw/16 efficiency but L2->shared traffic drops by the number of taps per group
+// (9x for 3x3, 25x for 5x5, 4x for the stride-2 4x4 layers, whose taps split into 4 parity groups).
+// Two independent mbarrier rings: A boxes (2 slots) and per-tap weight tiles (4 slots).
+struct HaloGroup { int16_t dy, dx, tap_begin, tap_end; };
+struct ConvTcHaloParams {
+  int tiles_x, tiles_y;
+  int tw;                 // valid output columns per tile (16 - max column shift)
+  int box_rows;           // rows of the input box (8 + max row shift)
+  int Hq, Wq, Ho, Wo, os, oy0, ox0, in_stride;
+  int ngroups;
+  HaloGroup grp[4];
+  int ntaps;
+  uint8_t tap_shift[kMaxTaps];   // shared-memory row offset of each tap inside its group's box
+  int8_t tap_w[kMaxTaps];
+  int kc, nkc, N, Ntot, B;
+  void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
+};
+
+static constexpr int kSA = 2, kSB = 4;
+
+__global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const ConvTcHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t fullA[kSA], emptyA[kSA], fullB[kSB], emptyB[kSB], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)p.kc * 2u;
+  const uint32_t a_bytes = (uint32_t)(p.box_rows * 16) * row_bytes;
+  const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
+  const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smemB = smem + kSA * a_slot;
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)p.N) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kSA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+  const int b = tile;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int x0 = tx * p.tw * p.in_stride, y0 = ty * 8 * p.in_stride;
+      int ia = 0, ib = 0;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const HaloGroup G = p.grp[g];
+        for (int c = 0; c < p.nkc; ++c) {
+          const int sa = ia % kSA;
+          mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+          tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
+          ++ia;
+          for (int t = G.tap_begin; t < G.tap_end; ++t) {
+            const int sb = ib % kSB;
+            mbar_wait(&emptyB[sb], ((uint32_t)(ib / kSB) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&fullB[sb], b_bytes);
+            tma_load_3d(smemB + (uint32_t)sb * b_slot, &tmB, &fullB[sb], c * p.kc, (int)blockIdx.y * p.N,
+                        (int)p.tap_w[t]);
+            ++ib;
+          }
         }
-      }
-      if (p.out_f32) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Ntot + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      } else {
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Ntot + c0);
-        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+      const uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+      const uint32_t sbo = 8u * row_bytes;
+      const int ksteps = p.kc / 16;
+      int ia = 0, ib = 0;
+      uint32_t first = 1u;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const HaloGroup G = p.grp[g];
+        for (int c = 0; c < p.nkc; ++c) {
+          const int sa = ia % kSA;
+          mbar_wait(&fullA[sa], (uint32_t)(ia / kSA) & 1u);
+          const uint32_t a_base = smem_u32(smem + (uint32_t)sa * a_slot);
+          for (int t = G.tap_begin; t < G.tap_end; ++t) {
+            const int sb = ib % kSB;
+            mbar_wait(&fullB[sb], (uint32_t)(ib / kSB) & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)p.tap_shift[t] * row_bytes;
+            const uint32_t b_addr = smem_u32(smemB + (uint32_t)sb * b_slot);
+            // The swizzle is a function of the absolute shared-memory address (measured: a start
+            // shifted by whole rows needs NO descriptor base offset), so TMA's write pattern and the
+            // MMA's read pattern agree for any row shift.
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+              const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+              umma_f16(tmem_base, ad, bd, idesc, first ? 0u : 1u);
+              first = 0u;
+            }
+            umma_commit(&emptyB[sb]);
+            ++ib;
+          }
+          umma_commit(&emptyA[sa]);
+          ++ia;
+        }
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int px = row & 15, py = row >> 4;
+    const int qy = ty * 8 + py, qx = tx * p.tw + px;
+    const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
+    const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32,
+                  p.bias, p.act, p.relu_mask);
     tc_fence_before();
   }
   __syncthreads();
@@ -282,12 +437,102 @@ static bool channels_ok(int Cin, int Cout) {
   return Cin == 16 || Cin == 32;
 }
 
+// 0 = one TMA box per tap (conv_tc_kernel); 1 = one haloed box per tap group (conv_tc_halo_kernel)
+static int g_halo_mode = 1;
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// returns 1 when the shape is not eligible for the halo kernel
+static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
+                               int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
+                               const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
+                               const float* bias, int act, const void* relu_mask, cudaStream_t st) {
+  ConvTcHaloParams p;
+  const int s = in_stride;
+  // group taps by the parity class of their input offset; inside a group taps are whole-row/col shifts
+  int gkey[4][2]; int ng = 0;
+  int order[kMaxTaps], gof[kMaxTaps], n = 0;
+  int gmin_y[4], gmin_x[4];
+  for (int t = 0; t < ntaps; ++t) {
+    int ry = ((tdy[t] % s) + s) % s, rx = ((tdx[t] % s) + s) % s;
+    int g = -1;
+    for (int i = 0; i < ng; ++i) if (gkey[i][0] == ry && gkey[i][1] == rx) g = i;
+    if (g < 0) { if (ng == 4) return 1; g = ng++; gkey[g][0] = ry; gkey[g][1] = rx; gmin_y[g] = tdy[t]; gmin_x[g] = tdx[t]; }
+    if (tdy[t] < gmin_y[g]) gmin_y[g] = tdy[t];
+    if (tdx[t] < gmin_x[g]) gmin_x[g] = tdx[t];
+    gof[t] = g;
+  }
+  int max_sy = 0, max_sx = 0;
+  for (int g = 0; g < ng; ++g) {
+    p.grp[g].tap_begin = (int16_t)n;
+    for (int t = 0; t < ntaps; ++t) {
+      if (gof[t] != g) continue;
+      int sy = (tdy[t] - gmin_y[g]) / s, sx = (tdx[t] - gmin_x[g]) / s;
+      if (sy > max_sy) max_sy = sy;
+      if (sx > max_sx) max_sx = sx;
+      order[n] = t;
+      p.tap_shift[n] = (uint8_t)(sy * 16 + sx);
+      p.tap_w[n] = (int8_t)tw_idx[t];
+      ++n;
+    }
+    p.grp[g].tap_end = (int16_t)n;
+    p.grp[g].dy = (int16_t)gmin_y[g]; p.grp[g].dx = (int16_t)gmin_x[g];
+  }
+  (void)order; (void)floordiv;
+  if (max_sx > 8 || max_sy * 16 + max_sx > 200) return 1;
+  p.ngroups = ng; p.ntaps = ntaps;
+  p.tw = 16 - max_sx;
+  p.box_rows = 8 + max_sy;
+  if ((p.box_rows * s) > 256 || 16 * s > 256) return 1;
+  p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + 7) / 8;
+  p.Hq = Hq; p.Wq = Wq; p.Ho = Ho; p.Wo = Wo; p.os = os; p.oy0 = oy0; p.ox0 = ox0; p.in_stride = s;
+  p.kc = Cin >= 64 ? 64 : Cin;
+  p.nkc = Cin / p.kc;
+  int nchunk = N;
+  if (N > 256) { nchunk = 256; while (N % nchunk != 0) nchunk -= 16; }
+  p.N = nchunk; p.Ntot = N; p.B = B;
+  p.out = out; p.out_f32 = out_f32; p.bias = bias; p.act = act; p.relu_mask = (const __nv_bfloat16*)relu_mask;
+  const int row_bytes = p.kc * 2;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(16 * s), (uint32_t)(p.box_rows * s), 1u};
+    uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+    if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)wtaps};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.N, 1};
+    if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
+  }
+  const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
+  const size_t smem = (size_t)kSA * a_slot + (size_t)kSB * b_slot + 1024;
+  if (smem > 200 * 1024) return 1;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * B;
+  conv_tc_halo_kernel<<<dim3(tiles, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 // One launch: out[b, q*os+o0, :, N] = epilogue( sum_taps in[b, q*in_stride + d(tap), :, Cin] * W[wtap][N][Cin] )
 static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
                           int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
                           const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
                           const float* bias, int act, const void* relu_mask, cudaStream_t st) {
   LIVAE_CHECK_ARG(ntaps >= 1 && ntaps <= kMaxTaps, "tc_conv: too many taps (%d)", ntaps);
+  if (g_halo_mode != 0 && ntaps > 1 && Wq >= 8 && Hq >= 4) {
+    int rc = launch_conv_tc_halo(in, B, Hin, Win, Cin, wpacked, wtaps, N, Hq, Wq, Ho, Wo, os, oy0, ox0, in_stride,
+                                 ntaps, tdy, tdx, tw_idx, out, out_f32, bias, act, relu_mask, st);
+    if (rc != 1) return rc;   // 1 = shape not eligible, fall through to the per-tap kernel
+  }
   ConvTcParams p;
   choose_tile(Hq, Wq, B, &p.tw, &p.th, &p.nb);
   LIVAE_CHECK_ARG(p.tw * in_stride <= 256 && p.th * in_stride <= 256, "tc_conv: TMA box too large");
@@ -443,3 +688,6 @@ extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, 
     }
   return 0;
 }
+
+// tuning / test hook: 0 = per-tap boxes only, 1 = halo kernel where eligible
+extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; }

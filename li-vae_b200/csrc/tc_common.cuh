@@ -103,9 +103,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   bits  0-13 start address >> 4      bits 16-29 leading-dim byte offset >> 4
 //   bits 32-45 stride-dim byte offset >> 4   bits 46-47 version (1 on sm_100)
 //   bits 61-63 swizzle: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
+//   bits 49-51 base offset: (start address >> 7) & 7 when the start is not aligned to the swizzle
+//   repeat (1024 B for 128B swizzle), e.g. a tile addressed from a shifted row
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
+                                                   uint32_t layout_type, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;

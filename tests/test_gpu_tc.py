@@ -34,6 +34,16 @@ TC_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["halo", "per_tap"], autouse=True)
+def halo_mode(request):
+    """every tensor-core convolution test runs on both kernels: haloed tile + row-shifted taps
+    (default) and one TMA box per tap"""
+    from livae import _lib
+    _lib.lib().livae_tc_set_halo_mode(request.param)
+    yield
+    _lib.lib().livae_tc_set_halo_mode(1)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 def test_tc_conv_forward(case):
     from livae import ops
