@@ -227,6 +227,7 @@ int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, 
 /* tuning / test hook: 0 = fetch one TMA box per filter tap; 1 (default) = fetch one haloed box per tap
  * group and address each tap as a row shift of it */
 void livae_tc_set_halo_mode(int mode);
+void livae_tc_set_wgrad_halo(int mode);   /* the same switch for the weight-gradient kernel */
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

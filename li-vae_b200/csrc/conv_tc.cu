@@ -244,16 +244,20 @@ struct ConvTcHaloParams {
   uint8_t tap_shift[kMaxTaps];   // shared-memory row offset of each tap inside its group's box
   int8_t tap_w[kMaxTaps];
   int kc, nkc, N, Ntot, B;
+  int b_resident;         // 1: all ntaps*nkc weight tiles stay in shared memory for the CTA's lifetime
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
 };
 
 static constexpr int kSA = 2, kSB = 4;
 
+// Persistent: grid.x CTAs walk the tile list round-robin.  The accumulator is double-buffered in
+// TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the
+// TMA + MMA main loop of tile i+1, and barrier/TMEM/tensor-map setup is paid once per CTA.
 __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t fullA[kSA], emptyA[kSA], fullB[kSB], emptyB[kSB], accum_bar;
+  __shared__ __align__(8) uint64_t fullA[kSA], emptyA[kSA], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,15 +268,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
   const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smemB = smem + kSA * a_slot;
-  uint32_t ncols = 32;
-  while (ncols < (uint32_t)p.N) ncols <<= 1;
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
+  const uint32_t ncols = 2u * acc_cols;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -283,31 +288,41 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-  const int b = tile;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.B;
 
   if (warp == 0) {
     if (lane == 0) {
-      const int x0 = tx * p.tw * p.in_stride, y0 = ty * 8 * p.in_stride;
       int ia = 0, ib = 0;
-      for (int g = 0; g < p.ngroups; ++g) {
-        const HaloGroup G = p.grp[g];
-        for (int c = 0; c < p.nkc; ++c) {
-          const int sa = ia % kSA;
-          mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-          tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
-          ++ia;
-          for (int t = G.tap_begin; t < G.tap_end; ++t) {
-            const int sb = ib % kSB;
-            mbar_wait(&emptyB[sb], ((uint32_t)(ib / kSB) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&fullB[sb], b_bytes);
-            tma_load_3d(smemB + (uint32_t)sb * b_slot, &tmB, &fullB[sb], c * p.kc, (int)blockIdx.y * p.N,
+      if (p.b_resident) {   // small filters: fetch every weight tile once
+        mbar_arrive_expect_tx(&fullB[0], b_bytes * (uint32_t)(p.ntaps * p.nkc));
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int c = 0; c < p.nkc; ++c)
+            tma_load_3d(smemB + (uint32_t)(t * p.nkc + c) * b_slot, &tmB, &fullB[0], c * p.kc, (int)blockIdx.y * p.N,
                         (int)p.tap_w[t]);
-            ++ib;
+      }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t3 = tile;
+        const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
+        const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
+        const int b = t3;
+        const int x0 = tx * p.tw * p.in_stride, y0 = ty * 8 * p.in_stride;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const HaloGroup G = p.grp[g];
+          for (int c = 0; c < p.nkc; ++c) {
+            const int sa = ia % kSA;
+            mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+            tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
+            ++ia;
+            if (p.b_resident) continue;
+            for (int t = G.tap_begin; t < G.tap_end; ++t) {
+              const int sb = ib % kSB;
+              mbar_wait(&emptyB[sb], ((uint32_t)(ib / kSB) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&fullB[sb], b_bytes);
+              tma_load_3d(smemB + (uint32_t)sb * b_slot, &tmB, &fullB[sb], c * p.kc, (int)blockIdx.y * p.N,
+                          (int)p.tap_w[t]);
+              ++ib;
+            }
           }
         }
       }
@@ -318,50 +333,69 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
       const uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
       const uint32_t sbo = 8u * row_bytes;
       const int ksteps = p.kc / 16;
-      int ia = 0, ib = 0;
-      uint32_t first = 1u;
-      for (int g = 0; g < p.ngroups; ++g) {
-        const HaloGroup G = p.grp[g];
-        for (int c = 0; c < p.nkc; ++c) {
-          const int sa = ia % kSA;
-          mbar_wait(&fullA[sa], (uint32_t)(ia / kSA) & 1u);
-          const uint32_t a_base = smem_u32(smem + (uint32_t)sa * a_slot);
-          for (int t = G.tap_begin; t < G.tap_end; ++t) {
-            const int sb = ib % kSB;
-            mbar_wait(&fullB[sb], (uint32_t)(ib / kSB) & 1u);
-            tc_fence_after();
-            const uint32_t a_addr = a_base + (uint32_t)p.tap_shift[t] * row_bytes;
-            const uint32_t b_addr = smem_u32(smemB + (uint32_t)sb * b_slot);
-            // The swizzle is a function of the absolute shared-memory address (measured: a start
-            // shifted by whole rows needs NO descriptor base offset), so TMA's write pattern and the
-            // MMA's read pattern agree for any row shift.
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-              const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-              umma_f16(tmem_base, ad, bd, idesc, first ? 0u : 1u);
-              first = 0u;
+      int ia = 0, ib = 0, it = 0;
+      if (p.b_resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)acc * acc_cols;
+        uint32_t first = 1u;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const HaloGroup G = p.grp[g];
+          for (int c = 0; c < p.nkc; ++c) {
+            const int sa = ia % kSA;
+            mbar_wait(&fullA[sa], (uint32_t)(ia / kSA) & 1u);
+            const uint32_t a_base = smem_u32(smem + (uint32_t)sa * a_slot);
+            if (p.b_resident) tc_fence_after();
+            for (int t = G.tap_begin; t < G.tap_end; ++t) {
+              const int sb = p.b_resident ? t * p.nkc + c : ib % kSB;
+              if (!p.b_resident) {
+                mbar_wait(&fullB[sb], (uint32_t)(ib / kSB) & 1u);
+                tc_fence_after();
+              }
+              const uint32_t a_addr = a_base + (uint32_t)p.tap_shift[t] * row_bytes;
+              const uint32_t b_addr = smem_u32(smemB + (uint32_t)sb * b_slot);
+              // The swizzle is a function of the absolute shared-memory address (measured: a start
+              // shifted by whole rows needs NO descriptor base offset), so TMA's write pattern and the
+              // MMA's read pattern agree for any row shift.
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+                const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+                umma_f16(d_addr, ad, bd, idesc, first ? 0u : 1u);
+                first = 0u;
+              }
+              if (!p.b_resident) { umma_commit(&emptyB[sb]); ++ib; }
             }
-            umma_commit(&emptyB[sb]);
-            ++ib;
+            umma_commit(&emptyA[sa]);
+            ++ia;
           }
-          umma_commit(&emptyA[sa]);
-          ++ia;
         }
+        umma_commit(&tfull[acc]);
       }
-      umma_commit(&accum_bar);
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int px = row & 15, py = row >> 4;
-    const int qy = ty * 8 + py, qx = tx * p.tw + px;
-    const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
-    const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32,
-                  p.bias, p.act, p.relu_mask);
-    tc_fence_before();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int t3 = tile;
+      const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
+      const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
+      const int b = t3;
+      const int acc = it & 1;
+      const int qy = ty * 8 + py, qx = tx * p.tw + px;
+      const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
+      const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
+      mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols, (int)blockIdx.y * p.N, p.N, p.Ntot,
+                    valid, pix, p.out, p.out_f32, p.bias, p.act, p.relu_mask);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -509,7 +543,8 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   }
   const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
-  const size_t smem = (size_t)kSA * a_slot + (size_t)kSB * b_slot + 1024;
+  p.b_resident = ((size_t)ntaps * p.nkc * b_slot <= 32 * 1024) ? 1 : 0;
+  const size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
   static bool attr_done = false;
   if (!attr_done) {
@@ -517,7 +552,17 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
     attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * B;
-  conv_tc_halo_kernel<<<dim3(tiles, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  // persistent grid: as many CTAs per SM as shared memory and the 512 TMEM columns allow
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  int per_sm_tmem = (int)(512 / (2 * acc_cols));
+  if (per_sm > per_sm_tmem) per_sm = per_sm_tmem;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int gx = kNumSMs * per_sm;
+  if (gx > tiles) gx = tiles;
+  conv_tc_halo_kernel<<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -172,6 +172,161 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo variant of the weight gradient.  Per pipeline stage ONE haloed input box per (stride-parity
+// class, channel chunk) and one gy tile [TH rows x TW cols] are fetched; every filter tap is then a
+// ROW-SHIFTED view of the same input box (MN-major descriptors take an arbitrary 16-byte-aligned
+// start, and the swizzle is a function of the absolute shared address), so the input tile is read
+// once instead of once per tap (9x / 25x less L2->shared traffic).
+//   K step j = gy row j (16 pixels; TW = 8: two 8-pixel rows, K-atom stride = one input row)
+//   A' start  = box + ((j + sy) * Wx + sx) * row_bytes          B' start = gy + j * 16 * row_bytes
+// Row groups: 128 accumulator rows = 128/kcb "atoms" of kcb channels, LBO apart.  kcb = 64: the two
+// atoms are two channel chunks of one tap, or two taps (LBO = difference of their shifts).
+// kcb = 32/16: atoms are consecutive-column taps of one filter row (LBO = one pixel row); atoms
+// past the end of the filter row compute garbage rows that the epilogue skips.
+static constexpr int kMaxGroups = 32;
+static constexpr int kMaxTapsW = 32;
+struct WgGroup { uint32_t base_off, lbo; int16_t atom[8]; };   // atom: tap * 8 + chunk, or -1
+struct WgradHaloParams {
+  int TH, TW, Wx;              // gy tile, input box row width (pixels)
+  int tiles_x, tiles_y, B, tiles_per_cta;
+  int stride;
+  int nbox; int16_t box_dy[16], box_dx[16], box_c[16];   // input boxes: origin offset and channel chunk
+  uint32_t box_slot;           // bytes per input box slot (1024-aligned)
+  uint32_t xbox_bytes;         // bytes one input box delivers (Hbox * Wx * kcb * 2)
+  int Cb, Cs, kcb, kcs, ntaps;
+  int ngroups, G;
+  WgGroup grp[kMaxGroups];
+  float* gw_acc;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                const __grid_constant__ CUtensorMap tmG,
+                                                                const WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rbx = (uint32_t)p.kcb * 2u, rbg = (uint32_t)p.kcs * 2u;
+  const int nboxg = p.Cs / p.kcs;
+  const uint32_t gbox_bytes = (uint32_t)(p.TH * p.TW) * rbg;
+  const uint32_t gbox_slot = (gbox_bytes + 1023u) & ~1023u;
+  const uint32_t a_region = (uint32_t)p.nbox * p.box_slot;
+  const uint32_t stage_bytes = a_region + (uint32_t)nboxg * gbox_slot;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(p.G * p.Cs)) ncols <<= 1;
+
+  const int g0 = blockIdx.x * p.G;
+  const int ng = min(p.G, p.ngroups - g0);
+  const int total_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int t_beg = blockIdx.y * p.tiles_per_cta;
+  const int t_end = min(total_tiles, t_beg + p.tiles_per_cta);
+  const int nt = t_end - t_beg;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (nt > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t tx_bytes = (uint32_t)p.nbox * p.xbox_bytes + (uint32_t)nboxg * gbox_bytes;
+        for (int it = 0; it < nt; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          int tile = t_beg + it;
+          const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+          const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+          const int b = tile;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          uint8_t* st = smem + (uint32_t)s * stage_bytes;
+          for (int c = 0; c < nboxg; ++c)
+            tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], c * p.kcs, tx * p.TW, ty * p.TH, b);
+          for (int i = 0; i < p.nbox; ++i)
+            tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], p.box_c[i] * p.kcb,
+                        tx * p.TW * p.stride + p.box_dx[i], ty * p.TH * p.stride + p.box_dy[i], b);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, p.Cs, 1, 1);
+        const uint32_t ltx = rbx == 128 ? 2u : rbx == 64 ? 4u : 6u;
+        const uint32_t ltg = rbg == 128 ? 2u : rbg == 64 ? 4u : 6u;
+        // K atom = 8 pixels: TW = 16 -> consecutive rows; TW = 8 -> the next gy row, i.e. one input row down
+        const uint32_t sbox = (p.TW == 16 ? 8u : (uint32_t)p.Wx) * rbx;
+        const uint32_t sbog = 8u * rbg;
+        const int ksteps = p.TH * p.TW / 16;
+        const int rows_per_kstep = 16 / p.TW;   // gy rows covered by one K step
+        for (int it = 0; it < nt; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (uint32_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_region;
+          for (int g = 0; g < ng; ++g) {
+            const WgGroup G = p.grp[g0 + g];
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t xo = (uint32_t)(k * rows_per_kstep * p.Wx) * rbx;
+              const uint64_t ad = make_smem_desc(a_addr + G.base_off + xo, G.lbo, sbox, ltx);
+              const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 16u * rbg, gbox_slot, sbog, ltg);
+              umma_f16(tmem_base + (uint32_t)(g * p.Cs), ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&accum_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      mbar_wait(&accum_bar, 0);
+      tc_fence_after();
+      for (int g = 0; g < ng; ++g) {
+        const int a = p.grp[g0 + g].atom[row / p.kcb];
+        const bool valid = a >= 0;
+        const int tap = a >> 3, ch = a & 7;
+        const int cb = ch * p.kcb + row % p.kcb;
+        float* dst = p.gw_acc + ((int64_t)tap * p.Cb + cb) * p.Cs;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cs);
+        for (int c0 = 0; c0 < p.Cs; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) red_add_f32(dst + c0 + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
 // gw_acc fp32 [tap][cb][cs] -> torch layout gw[cs][cb][tap] (written)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, int Cs, int Cb, int taps, float* __restrict__ gw) {
   int n = Cs * Cb * taps;
@@ -210,6 +365,169 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 
 using namespace livae;
 using namespace livae::tc;
+
+
+static int g_wgrad_halo = 1;
+
+// returns 0 = launched, 1 = shape not eligible (caller falls back to the per-tap kernel)
+static int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho,
+                             int Wo, cudaStream_t st) {
+  const int s = d->stride, kh = d->kh, kw = d->kw, pad = d->pad;
+  if (Wo < 8 || Ho < 2 || kh * kw < 2) return 1;
+  WgradHaloParams p;
+  p.Cb = d->Cin; p.Cs = d->Cout; p.ntaps = kh * kw; p.stride = s; p.B = d->B;
+  p.kcb = p.Cb >= 64 ? 64 : p.Cb;
+  p.kcs = p.Cs >= 64 ? 64 : p.Cs;
+  const int nchunk = p.Cb / p.kcb;
+  if (nchunk > 8) return 1;
+  const int apg = 128 / p.kcb;
+  const uint32_t rbx = (uint32_t)p.kcb * 2u;
+  p.TW = Wo >= 16 ? 16 : 8;
+  // parity classes of the tap offsets (dy = ky - pad, in input pixels)
+  struct Tap { int par, sy, sx, idx; };
+  Tap taps[kMaxTapsW];
+  int npar = 0, par_key[4][2], par_min[4][2];
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      int dy = ky - pad, dx = kx - pad;
+      int ry = ((dy % s) + s) % s, rx = ((dx % s) + s) % s;
+      int g = -1;
+      for (int i = 0; i < npar; ++i) if (par_key[i][0] == ry && par_key[i][1] == rx) g = i;
+      if (g < 0) { if (npar == 4) return 1; g = npar++; par_key[g][0] = ry; par_key[g][1] = rx; par_min[g][0] = dy; par_min[g][1] = dx; }
+      if (dy < par_min[g][0]) par_min[g][0] = dy;
+      if (dx < par_min[g][1]) par_min[g][1] = dx;
+      taps[ky * kw + kx] = Tap{g, dy, dx, ky * kw + kx};
+    }
+  int max_sy = 0, max_sx = 0;
+  for (int t = 0; t < p.ntaps; ++t) {
+    taps[t].sy = (taps[t].sy - par_min[taps[t].par][0]) / s;
+    taps[t].sx = (taps[t].sx - par_min[taps[t].par][1]) / s;
+    if (taps[t].sy > max_sy) max_sy = taps[t].sy;
+    if (taps[t].sx > max_sx) max_sx = taps[t].sx;
+  }
+  p.Wx = p.TW + max_sx;
+  // rows of the gy tile: keep a stage around <= 80 KB
+  const int per_row_bytes = p.Wx * p.Cb * 2 * npar + p.TW * p.Cs * 2;
+  int TH = 8;
+  while (TH > 2 && (TH + max_sy) * per_row_bytes > 80 * 1024) TH >>= 1;
+  if (TH * p.TW < 16) return 1;
+  if (TH > Ho) { TH = Ho; if ((TH * p.TW) % 16 != 0) return 1; }
+  p.TH = TH;
+  const int Hbox = TH + max_sy;
+  if (Hbox * s > 256 || p.Wx * s > 256) return 1;
+  p.xbox_bytes = (uint32_t)(Hbox * p.Wx) * rbx;
+  p.box_slot = (p.xbox_bytes + 2048u + 1023u) & ~1023u;   // slack: garbage atoms read past the box
+  p.nbox = npar * nchunk;
+  if (p.nbox > 16) return 1;
+  for (int g = 0; g < npar; ++g)
+    for (int c = 0; c < nchunk; ++c) {
+      p.box_dy[g * nchunk + c] = (int16_t)par_min[g][0];
+      p.box_dx[g * nchunk + c] = (int16_t)par_min[g][1];
+      p.box_c[g * nchunk + c] = (int16_t)c;
+    }
+  auto tap_off = [&](const Tap& t, int c) -> uint32_t {
+    return (uint32_t)(t.par * nchunk + c) * p.box_slot + (uint32_t)(t.sy * p.Wx + t.sx) * rbx;
+  };
+  // row groups
+  int ng = 0;
+  auto new_group = [&]() -> WgGroup* {
+    if (ng == kMaxGroups) return nullptr;
+    WgGroup* g = &p.grp[ng++];
+    for (int i = 0; i < 8; ++i) g->atom[i] = -1;
+    g->lbo = rbx;
+    return g;
+  };
+  if (apg == 2 && nchunk >= 2) {
+    for (int t = 0; t < p.ntaps; ++t)
+      for (int c = 0; c < nchunk; c += 2) {
+        WgGroup* g = new_group(); if (!g) return 1;
+        g->base_off = tap_off(taps[t], c); g->lbo = p.box_slot;
+        g->atom[0] = (int16_t)(taps[t].idx * 8 + c); g->atom[1] = (int16_t)(taps[t].idx * 8 + c + 1);
+      }
+  } else if (apg == 2) {   // one chunk: pair taps of the same parity class (ascending shift)
+    for (int par = 0; par < npar; ++par) {
+      int prev = -1;
+      for (int t = 0; t < p.ntaps; ++t) {
+        if (taps[t].par != par) continue;
+        if (prev < 0) { prev = t; continue; }
+        WgGroup* g = new_group(); if (!g) return 1;
+        g->base_off = tap_off(taps[prev], 0); g->lbo = tap_off(taps[t], 0) - tap_off(taps[prev], 0);
+        g->atom[0] = (int16_t)(taps[prev].idx * 8); g->atom[1] = (int16_t)(taps[t].idx * 8);
+        prev = -1;
+      }
+      if (prev >= 0) {
+        WgGroup* g = new_group(); if (!g) return 1;
+        g->base_off = tap_off(taps[prev], 0); g->lbo = rbx;
+        g->atom[0] = (int16_t)(taps[prev].idx * 8);
+      }
+    }
+  } else {   // kcb = 32 / 16: atoms = consecutive-column taps of one (parity, row shift)
+    for (int par = 0; par < npar; ++par)
+      for (int sy = 0; sy <= max_sy; ++sy) {
+        int cnt = 0; WgGroup* g = nullptr;
+        for (int sx = 0; sx <= max_sx; ++sx) {
+          int found = -1;
+          for (int t = 0; t < p.ntaps; ++t) if (taps[t].par == par && taps[t].sy == sy && taps[t].sx == sx) found = t;
+          if (found < 0) continue;
+          if (!g || cnt == apg) {
+            g = new_group(); if (!g) return 1;
+            g->base_off = tap_off(taps[found], 0); g->lbo = rbx; cnt = 0;
+          }
+          // atoms are LBO = one pixel row apart: column shifts must be consecutive inside a group
+          int a = (int)((tap_off(taps[found], 0) - g->base_off) / rbx);
+          if (a >= apg) { g = new_group(); if (!g) return 1; g->base_off = tap_off(taps[found], 0); g->lbo = rbx; a = 0; }
+          g->atom[a] = (int16_t)(taps[found].idx * 8);
+          cnt = a + 1;
+        }
+      }
+  }
+  p.ngroups = ng;
+  int G = 512 / p.Cs;
+  if (G > 8) G = 8;
+  if (G > ng) G = ng;
+  p.G = G;
+  const int gsets = (ng + G - 1) / G;
+  p.tiles_x = (Wo + p.TW - 1) / p.TW; p.tiles_y = (Ho + TH - 1) / TH;
+  const int total_tiles = p.tiles_x * p.tiles_y * d->B;
+  int splits = (kNumSMs + gsets - 1) / gsets;
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (total_tiles + splits - 1) / splits;
+  splits = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.gw_acc = gw_acc;
+  const int nboxg = p.Cs / p.kcs;
+  const uint32_t gbox_slot = ((uint32_t)(TH * p.TW * p.kcs * 2) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)p.nbox * p.box_slot + (uint32_t)nboxg * gbox_slot;
+  if (2u * stage_bytes + 1024u > 200u * 1024u) return 1;
+
+  CUtensorMap tmX, tmG;
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->Win * d->Cin * 2, (uint64_t)d->Hin * d->Win * d->Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kcb, (uint32_t)(p.Wx * s), (uint32_t)(Hbox * s), 1u};
+    uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+    if (int e = make_tmap_bf16(&tmX, x, 4, dims, str, box, es, p.kcb * 2)) return e;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->B};
+    uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)Wo * d->Cout * 2, (uint64_t)Ho * Wo * d->Cout * 2};
+    uint32_t box[4] = {(uint32_t)p.kcs, (uint32_t)p.TW, (uint32_t)TH, 1u};
+    if (int e = make_tmap_bf16(&tmG, gy, 4, dims, str, box, nullptr, p.kcs * 2)) return e;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wgrad_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  dim3 grid(gsets, splits);
+  if (4u * stage_bytes + 1024u <= 200u * 1024u)
+    wgrad_halo_kernel<4><<<grid, kWgThreads, 4 * stage_bytes + 1024, st>>>(tmX, tmG, p);
+  else
+    wgrad_halo_kernel<2><<<grid, kWgThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d) {
   if (!d) return 0;
@@ -279,6 +597,10 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   cudaError_t ce = cudaMemsetAsync(ws, 0, (size_t)livae_tc_wgrad_ws_bytes(d), st);
   if (ce != cudaSuccess) { set_error("tc_conv_wgrad memset: %s", cudaGetErrorString(ce)); return (int)ce; }
 
+  int halo_rc = g_wgrad_halo ? launch_wgrad_halo(d, x, gy, (float*)ws, Ho, Wo, st) : 1;
+  if (halo_rc != 0 && halo_rc != 1) return halo_rc;
+  if (halo_rc == 1) {
+
   const uint32_t a_bytes = (uint32_t)G * 128u * kPK * 2u;
   const uint32_t b_bytes = (uint32_t)kPK * p.Cs * 2u;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
@@ -294,6 +616,7 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   else
     wgrad_tc_kernel<2><<<grid, kWgThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   LIVAE_CUDA_LAUNCH_CHECK();
+  }
   const int n = p.Cs * p.Cb * p.ntaps;
   unpack_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.gw_acc, p.Cs, p.Cb, p.ntaps, gw);
   LIVAE_CUDA_LAUNCH_CHECK();
@@ -308,3 +631,5 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   }
   return 0;
 }
+
+extern "C" void livae_tc_set_wgrad_halo(int mode) { g_wgrad_halo = mode ? 1 : 0; }

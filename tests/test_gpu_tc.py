@@ -40,8 +40,10 @@ def halo_mode(request):
     (default) and one TMA box per tap"""
     from livae import _lib
     _lib.lib().livae_tc_set_halo_mode(request.param)
+    _lib.lib().livae_tc_set_wgrad_halo(request.param)
     yield
     _lib.lib().livae_tc_set_halo_mode(1)
+    _lib.lib().livae_tc_set_wgrad_halo(1)
 
 
 @pytest.mark.parametrize("case", TC_CASES)

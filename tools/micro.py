@@ -35,6 +35,10 @@ for w in which:
         x = torch.randn(B, 66, 66, 64, device=dev).to(bf); wt = torch.randn(32, 64, 3, 3, device=dev)
         wp = ops.tc_pack_weights(wt, 32, 64, 3, 3, 0)
         print(w, timeit(lambda: ops.tc_conv(x, wp, None, 3, 3, 1, 0, 1)), "ms")
+    elif w == "fwd_stn2":
+        x = torch.randn(B, 64, 64, 16, device=dev).to(bf); wt = torch.randn(32, 16, 5, 5, device=dev)
+        wp = ops.tc_pack_weights(wt, 32, 16, 5, 5, 0)
+        print(w, timeit(lambda: ops.tc_conv(x, wp, None, 5, 5, 1, 2, 1)), "ms")
     elif w == "fwd_c4":
         x = torch.randn(B, 16, 16, 128, device=dev).to(bf); wt = torch.randn(256, 128, 4, 4, device=dev)
         wp = ops.tc_pack_weights(wt, 256, 128, 4, 4, 0)
