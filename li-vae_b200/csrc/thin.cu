@@ -374,6 +374,55 @@ __global__ void __launch_bounds__(256) unpool_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// 8 channels (one 16-byte vector) per thread
+__global__ void __launch_bounds__(256) maxpool_bf16v_kernel(const uint4* __restrict__ full, int B, int H, int W, int C8,
+                                                            uint4* __restrict__ pooled, uint2* __restrict__ idx) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int64_t n = (int64_t)B * Hp * Wp * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8); int64_t q = i / C8; const int px = (int)(q % Wp); q /= Wp; const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    const uint4* s = full + (((int64_t)b * H + 2 * py) * W + 2 * px) * C8 + c;
+    uint4 v[4] = {__ldg(s), __ldg(s + C8), __ldg(s + (int64_t)W * C8), __ldg(s + (int64_t)W * C8 + C8)};
+    uint4 o; uint8_t id[8];
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float best = bf(reinterpret_cast<const __nv_bfloat16*>(&v[0])[j]); int bi = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        float t = bf(reinterpret_cast<const __nv_bfloat16*>(&v[k])[j]);
+        if (t > best) { best = t; bi = k; }
+      }
+      ob[j] = __float2bfloat16_rn(best);
+      id[j] = (uint8_t)bi;
+    }
+    pooled[i] = o;
+    idx[i] = *reinterpret_cast<uint2*>(id);
+  }
+}
+__global__ void __launch_bounds__(256) unpool_bf16v_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx,
+                                                           int B, int H, int W, int C8, uint4* __restrict__ full) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int64_t n = (int64_t)B * Hp * Wp * C8;   // one thread per pooled vector, writes its 2x2 window
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8); int64_t q = i / C8; const int px = (int)(q % Wp); q /= Wp; const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    const uint4 gv = __ldg(g + i);
+    const uint2 iv = __ldg(idx + i);
+    const uint8_t* id = reinterpret_cast<const uint8_t*>(&iv);
+    const uint16_t* gs = reinterpret_cast<const uint16_t*>(&gv);
+    uint4* d = full + (((int64_t)b * H + 2 * py) * W + 2 * px) * C8 + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 o; uint16_t* os = reinterpret_cast<uint16_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) os[j] = id[j] == k ? gs[j] : (uint16_t)0;
+      d[(int64_t)(k >> 1) * W * C8 + (k & 1) * C8] = o;
+    }
+  }
+}
+
 static inline int tgrid(int64_t n, int per = 1) {
   int64_t blocks = (n + 256LL * per - 1) / (256LL * per);
   if (blocks < 1) blocks = 1;
@@ -523,8 +572,12 @@ extern "C" int livae_maxpool_bf16(const void* full, int B, int H, int W, int C, 
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(full && pooled && idx, "maxpool_bf16: null pointer");
   if (int e = require_sm100()) return e;
-  maxpool_bf16_kernel<<<tgrid((int64_t)B * (H / 2) * (W / 2) * C), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)full, B, H, W, C, (__nv_bfloat16*)pooled, idx);
+  if ((C & 7) == 0 && (((uintptr_t)full | (uintptr_t)pooled) & 15) == 0 && ((uintptr_t)idx & 7) == 0)
+    maxpool_bf16v_kernel<<<tgrid((int64_t)B * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)full, B, H, W, C / 8, (uint4*)pooled, (uint2*)idx);
+  else
+    maxpool_bf16_kernel<<<tgrid((int64_t)B * (H / 2) * (W / 2) * C), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)full, B, H, W, C, (__nv_bfloat16*)pooled, idx);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -535,8 +588,12 @@ extern "C" int livae_unpool_bf16(const void* g_pooled, const uint8_t* idx, int B
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(g_pooled && idx && g_full, "unpool_bf16: null pointer");
   if (int e = require_sm100()) return e;
-  unpool_bf16_kernel<<<tgrid((int64_t)B * H * W * C, 2), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g_pooled, idx, B, H, W, C, (__nv_bfloat16*)g_full);
+  if ((C & 7) == 0 && (((uintptr_t)g_pooled | (uintptr_t)g_full) & 15) == 0 && ((uintptr_t)idx & 7) == 0)
+    unpool_bf16v_kernel<<<tgrid((int64_t)B * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)g_pooled, (const uint2*)idx, B, H, W, C / 8, (uint4*)g_full);
+  else
+    unpool_bf16_kernel<<<tgrid((int64_t)B * H * W * C, 2), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)g_pooled, idx, B, H, W, C, (__nv_bfloat16*)g_full);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
