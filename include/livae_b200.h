@@ -228,6 +228,9 @@ int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, 
  * group and address each tap as a row shift of it */
 void livae_tc_set_halo_mode(int mode);
 void livae_tc_set_wgrad_halo(int mode);   /* the same switch for the weight-gradient kernel */
+/* 1 (default): the thin 1-channel layers run on tcgen05 (thread-built im2col / col2im operands,
+ * csrc/thin_tc.cu) where the shape is eligible; 0: SIMT kernels only */
+void livae_thin_set_tc(int mode);
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

@@ -42,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -56,6 +62,17 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
       : "memory");
+}
+
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma, TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Byte offset of 16-byte chunk `chunk` of row `row` inside a K-major tile whose rows are `rb` = 32 / 64 /
+// 128 bytes and hardware-swizzled (CU_TENSOR_MAP_SWIZZLE_32B/64B/128B: address bits [4, 4+n) ^= bits
+// [7, 7+n)); the tile base must be 1024-byte aligned.  Threads that build an operand tile themselves
+// write through this map so the tile is byte-identical to what TMA would have delivered.
+__device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk, uint32_t rb) {
+  const uint32_t off = row * rb + chunk * 16u;
+  return off ^ (((off >> 7) & ((rb >> 4) - 1u)) << 4);
 }
 
 // ---- tcgen05 -------------------------------------------------------------------------------

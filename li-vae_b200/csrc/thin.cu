@@ -7,6 +7,7 @@
 // storage on the wide side, fp32 images on the 1-channel side.  Gradient conventions follow the
 // tensor-core engine: tensors handed between layers are PRE-activation gradients.
 #include "common.cuh"
+#include "thin_tc.cuh"
 
 namespace livae {
 
@@ -434,6 +435,10 @@ static inline int tgrid(int64_t n, int per = 1) {
 
 using namespace livae;
 
+// 1 (default): tensor-core versions (thin_tc.cu) where the shape is eligible; 0: SIMT kernels only
+static int g_thin_tc = 1;
+extern "C" void livae_thin_set_tc(int mode) { g_thin_tc = mode ? 1 : 0; }
+
 // kind: 0 = STN conv1 (C=16,K=5,S=1,+ReLU+pool), 1 = encoder c1 (C=32,K=4,S=2,+ReLU),
 //       2 = decoder d4 data gradient (C=32,K=3,S=1, flipped taps, no activation)
 extern "C" int livae_thin_conv1c_fwd(int kind, const float* img, const float* w, const float* bias, int B, int H,
@@ -444,6 +449,11 @@ extern "C" int livae_thin_conv1c_fwd(int kind, const float* img, const float* w,
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+  LIVAE_CHECK_ARG(kind != 0 || pool_idx, "thin_conv1c_fwd: STN conv1 needs pool_idx");
+  if (g_thin_tc) {
+    int rc = tc::thin_tc_conv1c_fwd(kind, img, w, bias, B, H, W, out_bf16, pool_idx, st);
+    if (rc != 1) return rc;
+  }
   if (kind == 0) {
     LIVAE_CHECK_ARG(pool_idx && (H % 2) == 0 && (W % 2) == 0, "thin_conv1c_fwd: STN conv1 needs pool_idx and even size");
     int quads = (H / 2) * (W / 2);
@@ -478,6 +488,10 @@ extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g
     LIVAE_CHECK_ARG(pool_idx, "thin_conv1c_wgrad: STN conv1 needs pool_idx");
     if ((ce = cudaMemsetAsync(gw, 0, 16 * 25 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
     if (gb && (ce = cudaMemsetAsync(gb, 0, 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (g_thin_tc) {
+      int rc = tc::thin_tc_wgrad(0, img, g_bf16, pool_idx, B, H, W, gw, gb, st);
+      if (rc != 1) return rc;
+    }
     constexpr int RB = 256 / (5 * 4), IR = (RB - 1) + 5;
     const int IWp = (W - 1) + 5;
     const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * W * 16 * 2;
@@ -490,6 +504,10 @@ extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g
   } else {
     if ((ce = cudaMemsetAsync(gw, 0, 32 * 16 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
     if (gb && (ce = cudaMemsetAsync(gb, 0, 32 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
+    if (g_thin_tc) {
+      int rc = tc::thin_tc_wgrad(1, img, g_bf16, nullptr, B, H, W, gw, gb, st);
+      if (rc != 1) return rc;
+    }
     constexpr int RB = 256 / (4 * 8), IR = (RB - 1) * 2 + 4;
     const int IWp = (W / 2 - 1) * 2 + 4;
     const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * (W / 2) * 32 * 2;
@@ -511,6 +529,10 @@ extern "C" int livae_thin_conv1c_dgrad(const void* g_bf16, const float* w, int B
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(g_bf16 && w && gimg, "thin_conv1c_dgrad: null pointer");
   if (int e = require_sm100()) return e;
+  if (g_thin_tc) {
+    int rc = tc::thin_tc_col2im(1, g_bf16, w, nullptr, B, H / 2, W / 2, LIVAE_ACT_NONE, gimg, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   conv1c_dgrad_kernel<32, 4, 2><<<tgrid((int64_t)B * H * W), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)g_bf16, w, B, H, W, H / 2, W / 2, 1, gimg);
   LIVAE_CUDA_LAUNCH_CHECK();
@@ -524,6 +546,10 @@ extern "C" int livae_thin_convc1_fwd(const void* x_bf16, const float* w, const f
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(x_bf16 && w && out, "thin_convc1_fwd: null pointer");
   if (int e = require_sm100()) return e;
+  if (g_thin_tc) {
+    int rc = tc::thin_tc_col2im(0, x_bf16, w, bias, B, H, W, act, out, (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   convc1_fwd_kernel<32, 3><<<tgrid((int64_t)B * (H - 2) * (W - 2)), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_bf16, w, bias, B, H, W, H - 2, W - 2, act, out);
   LIVAE_CUDA_LAUNCH_CHECK();
@@ -542,6 +568,10 @@ extern "C" int livae_thin_convc1_wgrad(const void* x_bf16, const float* g, int B
   if ((ce = cudaMemsetAsync(gw, 0, 32 * 9 * 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
   if (gb && (ce = cudaMemsetAsync(gb, 0, 4, st)) != cudaSuccess) { set_error("memset"); return (int)ce; }
   const int Ho = H - 2, Wo = W - 2;
+  if (g_thin_tc) {
+    int rc = tc::thin_tc_wgrad(2, g, x_bf16, nullptr, B, Ho, Wo, gw, gb, st);
+    if (rc != 1) return rc;
+  }
   constexpr int RWB = 4;
   const size_t smem = (size_t)(RWB + 2) * W * 32 * 2 + (size_t)RWB * Wo * 4;
   LIVAE_CHECK_ARG(smem <= 200 * 1024 && (W * 32) % 8 == 0, "thin_convc1_wgrad: map too wide for the staged kernel");

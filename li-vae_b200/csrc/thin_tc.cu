@@ -1,0 +1,848 @@
+// Thin 1-channel layers of the rVAE on tcgen05 tensor cores.
+//
+// The three layers that touch a 1-channel image (STN conv1 1->16 5x5 +ReLU +pool, model.py:204-206;
+// encoder c1 1->32 4x4 s2 +ReLU, model.py:290; decoder d4 32->1 3x3 +sigmoid, model.py:371-372) have
+// GEMM shapes with K <= 25 or N = 1.  As SIMT kernels they are bound by FMA/LDS issue (one shared load
+// per FMA), 5-10x above their HBM time.  Here every one of their forward / data-gradient /
+// weight-gradient passes is a 128-row UMMA whose *thin* operand is assembled in shared memory by the
+// CTA's threads (written through the hardware swizzle map, fence.proxy.async, then tcgen05.mma) while
+// the *wide* bf16 NHWC tensor streams through TMA untouched:
+//
+//   A. conv1c_tc_kernel   1 -> C forward (STN conv1 + pool, encoder c1, d4 data gradient):
+//        D[128 px, C] = im2col(img)[128 px, K=taps] * W[C, taps]^T, A rows gathered from a bf16 copy of
+//        the zero-padded image held in shared memory (32-bit loads + funnel shifts, no per-tap loop).
+//   B. col2im_tc_kernel   C -> 1 (d4 forward, encoder c1 data gradient):
+//        P[128 px, taps] = X[128 px, C] * W[taps, C]^T with X = 128 consecutive NHWC pixels (one TMA
+//        box), then out[o] = sum_taps P[o + shift(tap)][tap] from a ring buffer of P rows in shared
+//        memory (col2im).  Weights are split hi + lo bf16 (two column groups), so results are fp32-exact
+//        in the weights.
+//   C. tap_wgrad_tc_kernel  weight gradients of all three layers:
+//        D[tap, C] += A[tap, 64 px] * G[64 px, C] with A = tap-shifted copies of the 1-channel image
+//        (hi and lo bf16 rows -> fp32-exact), G = the wide tensor as an MN-major TMA box; the
+//        accumulator stays in TMEM for the CTA's whole life, one atomicAdd per weight per CTA at the end.
+//        A row of ones gives the bias gradient for free.
+#include "tc_common.cuh"
+#include "thin_tc.cuh"
+#include <string.h>
+
+namespace livae {
+namespace tc {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+// {hi | lo << 16}: v ~= bf16(hi) + bf16(lo), relative error ~2^-17
+__device__ __forceinline__ uint32_t split_hi_lo(float v) {
+  const uint32_t h = bf16_bits(v);
+  const uint32_t l = bf16_bits(v - bf16_bits_to_float(h));
+  return h | (l << 16);
+}
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
+}
+
+// =============================================================================================
+// A. 1 -> C forward
+// =============================================================================================
+template <int KIND> struct FwdCfg;
+// STN conv1: 5x5 p2, ReLU, 2x2 max-pool.  K order (ky, kx padded to 6): 30 -> 32
+template <> struct FwdCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, KW2 = 6, KPAD = 32, POOL = 1, FLIP = 0, RELU = 1 }; };
+// encoder c1: 4x4 s2 p1, ReLU.  K = 16
+template <> struct FwdCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 0, RELU = 1 }; };
+// data gradient of decoder d4 (3x3 p0): full correlation with the flipped filter, pad 2.  K (ky, kx padded to 4): 12 -> 16
+template <> struct FwdCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 1, RELU = 0 }; };
+
+struct FwdParams {
+  const float* img; const float* w; const float* bias;
+  int B, H, W;          // image
+  int Ho, Wo;           // convolution output grid
+  int Hs, pitch;        // staged (zero padded) image: rows, bf16 elements per row (even)
+  void* out; uint8_t* idx;
+};
+
+// Warp roles (288 threads): warp 0 = MMA issuer, warps 1-4 = builders (one A row per thread), warps 5-8 =
+// epilogue.  NS {A tile, TMEM accumulator} slots with full/empty mbarriers keep the three roles on
+// different tiles at once: a tile's latency chain (gather -> fence -> MMA -> tcgen05.ld -> stores) is
+// long compared with its work, so throughput comes from overlapping tiles, not from any single step.
+static constexpr int kFwdThreads = 288;
+
+template <int KIND>
+__global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1c_tc_kernel(const FwdParams p) {
+  using Cfg = FwdCfg<KIND>;
+  constexpr int C = Cfg::C, KS = Cfg::KS, PAD = Cfg::PAD, KW2 = Cfg::KW2, KPAD = Cfg::KPAD;
+  constexpr bool POOL = Cfg::POOL != 0;
+  constexpr uint32_t RB = KPAD * 2;                 // bytes per A / W row (64 or 32)
+  constexpr int NSUB = POOL ? 4 : 1;
+  constexpr int NCOL = NSUB * C;                    // TMEM columns per accumulator
+  constexpr uint32_t A_SUB = 128u * RB;
+  constexpr uint32_t A_BUF = NSUB * A_SUB;
+  constexpr int NS = POOL ? 2 : 4;                  // pipeline slots
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], t_full[NS], t_empty[NS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[32];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + NS * A_BUF;
+  uint32_t* simg32 = reinterpret_cast<uint32_t*>(sW + 2048);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pitch2 = p.pitch >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, NS * NCOL); tmem_relinquish(); }
+  // weight tile W[c][k], k = ky * KW2 + kx, zero in the padding slots
+  for (int i = tid; i < C * KPAD; i += kFwdThreads) {
+    const int c = i / KPAD, k = i % KPAD;
+    const int ky = k / KW2, kx = k % KW2;
+    float v = 0.f;
+    if (ky < KS && kx < KS) {
+      const int t = ky * KS + kx;
+      v = p.w[c * KS * KS + (Cfg::FLIP ? KS * KS - 1 - t : t)];
+    }
+    *reinterpret_cast<uint16_t*>(sW + swz_off((uint32_t)c, (uint32_t)k >> 3, RB) + (k & 7) * 2) = bf16_bits(v);
+  }
+  if (tid < 32) sbias[tid] = (p.bias && tid < C) ? p.bias[tid] : 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int Wg = POOL ? (p.Wo >> 1) : p.Wo;            // grid the 128-row tiles walk over
+  const int npx = POOL ? (p.Ho >> 1) * Wg : p.Ho * Wg;
+  const int ntiles = (npx + 127) >> 7;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
+      const uint32_t lt = RB == 64 ? 4u : 6u;
+      const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 8u * RB, lt);
+      const uint64_t bd0 = make_smem_desc(smem_u32(sW), 16u, 8u * RB, lt);
+      uint32_t it = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+        for (int tile = 0; tile < ntiles; ++tile, ++it) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1u;
+          mbar_wait(&t_empty[s], ph ^ 1u);
+          mbar_wait(&a_full[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+            for (int ks = 0; ks < KPAD / 16; ++ks)
+              umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
+                       bd0 + ((ks * 32u) >> 4), idesc, ks > 0 ? 1u : 0u);
+          umma_commit(&a_empty[s]);
+          umma_commit(&t_full[s]);
+        }
+    }
+  } else if (warp <= 4) {
+    // ------------------------------------------------------------------ builders
+    const int bt = tid - 32;
+    uint32_t it = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // every builder is done reading the previous image
+      const float* im = p.img + (int64_t)img * p.H * p.W;
+      {
+        // 4 words (8 pixels) per thread per batch: all loads are issued before the first use
+        const int nw = p.Hs * pitch2;
+        for (int i0 = bt; i0 < nw; i0 += 128 * 4) {
+          float v0[4], v1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * 128, nw - 1);
+            const int r = i / pitch2, c = (i - r * pitch2) * 2;
+            const int iy = r - PAD, ix = c - PAD;
+            const int iyc = min(max(iy, 0), p.H - 1);
+            const float a = __ldg(im + iyc * p.W + min(max(ix, 0), p.W - 1));
+            const float b = __ldg(im + iyc * p.W + min(max(ix + 1, 0), p.W - 1));
+            const bool oky = iy >= 0 && iy < p.H;
+            v0[u] = (oky && ix >= 0 && ix < p.W) ? a : 0.f;
+            v1[u] = (oky && ix + 1 >= 0 && ix + 1 < p.W) ? b : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u * 128 < nw) simg32[i0 + u * 128] = pack_bf16x2(v0[u], v1[u]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      int pp = bt;                                        // this thread's pixel of the current tile
+      for (int tile = 0; tile < ntiles; ++tile, ++it, pp += 128) {
+        const uint32_t s = it % NS;
+        uint8_t* a_buf = sA + s * A_BUF;
+        const int pc = pp < npx ? pp : npx - 1;           // rows past the end: any finite data
+        const int gy = pc / Wg, gx = pc - gy * Wg;
+        if (KIND == 0) {
+          uint32_t wd[6][3];
+          const uint32_t* base = simg32 + (2 * gy) * pitch2 + gx;
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) wd[i][j] = base[i * pitch2 + j];
+          mbar_wait(&a_empty[s], ((it / NS) & 1u) ^ 1u);
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) {
+            const int dy = sb >> 1, dx = sb & 1;
+            uint32_t k[16];
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+              const uint32_t r0 = wd[dy + ky][0], r1 = wd[dy + ky][1], r2 = wd[dy + ky][2];
+              if (dx == 0) { k[ky * 3] = r0; k[ky * 3 + 1] = r1; k[ky * 3 + 2] = r2; }
+              else { k[ky * 3] = __funnelshift_r(r0, r1, 16); k[ky * 3 + 1] = __funnelshift_r(r1, r2, 16); k[ky * 3 + 2] = r2 >> 16; }
+            }
+            k[15] = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(a_buf + sb * A_SUB + swz_off((uint32_t)bt, (uint32_t)j, RB)) =
+                  make_uint4(k[4 * j], k[4 * j + 1], k[4 * j + 2], k[4 * j + 3]);
+          }
+        } else if (KIND == 1) {
+          const uint32_t* base = simg32 + (2 * gy) * pitch2 + gx;
+          uint32_t k[8];
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky) { k[2 * ky] = base[ky * pitch2]; k[2 * ky + 1] = base[ky * pitch2 + 1]; }
+          mbar_wait(&a_empty[s], ((it / NS) & 1u) ^ 1u);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)bt, (uint32_t)j, RB)) =
+                make_uint4(k[4 * j], k[4 * j + 1], k[4 * j + 2], k[4 * j + 3]);
+        } else {
+          const uint32_t* base = simg32 + gy * pitch2 + (gx >> 1);
+          const uint32_t sh = (uint32_t)(gx & 1) * 16u;
+          uint32_t k[8];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t l0 = base[ky * pitch2], l1 = base[ky * pitch2 + 1], l2 = base[ky * pitch2 + 2];
+            k[2 * ky] = __funnelshift_r(l0, l1, sh);
+            k[2 * ky + 1] = __funnelshift_r(l1, l2, sh);
+          }
+          k[6] = 0u; k[7] = 0u;
+          mbar_wait(&a_empty[s], ((it / NS) & 1u) ^ 1u);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)bt, (uint32_t)j, RB)) =
+                make_uint4(k[4 * j], k[4 * j + 1], k[4 * j + 2], k[4 * j + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    float bias_r[16];                                     // pooled layer only (the others read sbias)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) bias_r[c] = sbias[c];
+    uint32_t it = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+      for (int tile = 0; tile < ntiles; ++tile, ++it) {
+        const uint32_t s = it % NS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * NCOL;
+        const int pp = tile * 128 + row;
+        const bool valid = pp < npx;
+        mbar_wait(&t_full[s], (it / NS) & 1u);
+        tc_fence_after();
+        if (POOL) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) tmem_ld16(taddr + (uint32_t)(sb * 16), v[sb]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[s]);
+          if (valid) {
+            uint32_t ow[8]; uint32_t iw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              float best[2]; uint32_t bi[2];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const float b = bias_r[c + j];
+                best[j] = fmaxf(__uint_as_float(v[0][c + j]) + b, 0.f); bi[j] = 0u;
+#pragma unroll
+                for (int sb = 1; sb < 4; ++sb) {
+                  const float a = fmaxf(__uint_as_float(v[sb][c + j]) + b, 0.f);
+                  if (a > best[j]) { best[j] = a; bi[j] = (uint32_t)sb; }
+                }
+              }
+              ow[c >> 1] = pack_bf16x2(best[0], best[1]);
+              iw[c >> 2] |= (bi[0] << ((c & 3) * 8)) | (bi[1] << (((c & 3) + 1) * 8));
+            }
+            const int64_t o = (int64_t)img * npx + pp;
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o * 16);
+            op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            op[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            *reinterpret_cast<uint4*>(p.idx + o * 16) = make_uint4(iw[0], iw[1], iw[2], iw[3]);
+          }
+        } else {
+          uint32_t v[2][16];
+          tmem_ld16(taddr, v[0]);
+          tmem_ld16(taddr + 16u, v[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[s]);
+          if (valid) {
+            uint32_t ow[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              float a0 = __uint_as_float(v[c >> 4][c & 15]) + sbias[c];
+              float a1 = __uint_as_float(v[c >> 4][(c & 15) + 1]) + sbias[c + 1];
+              if (Cfg::RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              ow[c >> 1] = pack_bf16x2(a0, a1);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)img * npx + pp) * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_uint4(ow[4 * j], ow[4 * j + 1], ow[4 * j + 2], ow[4 * j + 3]);
+          }
+        }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, NS * NCOL); }
+}
+
+template <int KIND>
+static int launch_fwd(const float* img, const float* w, const float* bias, int B, int H, int W, int Ho, int Wo,
+                      void* out, uint8_t* idx, cudaStream_t st) {
+  using Cfg = FwdCfg<KIND>;
+  FwdParams p;
+  p.img = img; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo;
+  p.Hs = (Ho - 1) * Cfg::S + Cfg::KS;
+  p.pitch = ((Wo - 1) * Cfg::S + Cfg::KW2 + 2 + 1) & ~1;
+  p.out = out; p.idx = idx;
+  const int ns = Cfg::POOL ? 2 : 4;
+  const size_t a_buf = (size_t)(Cfg::POOL ? 4 : 1) * 128 * Cfg::KPAD * 2;
+  const size_t smem = 1024 + ns * a_buf + 2048 + (size_t)p.Hs * p.pitch * 2;
+  if (smem > 110 * 1024) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(conv1c_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); attr = true; }
+  int occ = (int)((227 * 1024) / (smem + 1024));
+  const int occ_tmem = 512 / (ns * (Cfg::POOL ? 4 : 1) * Cfg::C);
+  if (occ > occ_tmem) occ = occ_tmem;
+  if (occ > (Cfg::POOL ? 2 : 3)) occ = Cfg::POOL ? 2 : 3;
+  if (occ < 1) occ = 1;
+  int grid = kNumSMs * occ;
+  if (grid > B) grid = B;
+  conv1c_tc_kernel<KIND><<<grid, kFwdThreads, smem, st>>>(p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+int thin_tc_conv1c_fwd(int kind, const float* img, const float* w, const float* bias, int B, int H, int W,
+                       void* out_bf16, uint8_t* pool_idx, cudaStream_t st) {
+  if ((H & 1) || (W & 1) || H < 4 || W < 4) return 1;
+  if ((((uintptr_t)out_bf16 | (uintptr_t)pool_idx) & 15) != 0) return 1;
+  if (kind == 0) return launch_fwd<0>(img, w, bias, B, H, W, H, W, out_bf16, pool_idx, st);
+  if (kind == 1) return launch_fwd<1>(img, w, bias, B, H, W, H / 2, W / 2, out_bf16, nullptr, st);
+  return launch_fwd<2>(img, w, nullptr, B, H, W, H + 2, W + 2, out_bf16, nullptr, st);
+}
+
+// =============================================================================================
+// B. C -> 1 through GEMM + col2im
+// =============================================================================================
+struct C2iParams {
+  int B, Hin, Win, npx, ntiles;
+  int Ho, Wo;
+  int ring;             // power of two
+  int act;
+  const float* w; const float* bias; float* out;
+};
+
+static constexpr int kC2iStages = 4;
+
+// KIND 0: decoder d4 forward, out[oy,ox] = act(bias + sum_{ky,kx,c} x[oy+ky, ox+kx, c] w[c][ky][kx]), 3x3
+// KIND 1: encoder c1 data gradient, gimg[iy,ix] = sum_{ky,kx,c} g[(iy+1-ky)/2, (ix+1-kx)/2, c] w[c][ky][kx], 4x4 s2 p1
+template <int KIND>
+__global__ void __launch_bounds__(192) col2im_tc_kernel(const __grid_constant__ CUtensorMap tmX, const C2iParams p) {
+  constexpr int T = KIND == 0 ? 9 : 16;
+  constexpr uint32_t A_BYTES = 128u * 64u;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t fullA[kC2iStages], emptyA[kC2iStages], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kC2iStages * A_BYTES;            // [32 rows: 16 hi taps, 16 lo taps][32 ch] bf16, 64-byte rows
+  float* ring = reinterpret_cast<float*>(sW + 2048);    // [T][ring]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RING = p.ring, RM = p.ring - 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < kC2iStages; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 64); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 32 * 32; i += 192) {
+    const int n = i >> 5, c = i & 31, t = n & 15;
+    const float wv = t < T ? p.w[c * T + t] : 0.f;
+    const uint32_t hl = split_hi_lo(wv);
+    *reinterpret_cast<uint16_t*>(sW + swz_off((uint32_t)n, (uint32_t)c >> 3, 64u) + (c & 7) * 2) =
+        (uint16_t)(n < 16 ? (hl & 0xffffu) : (hl >> 16));
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+        for (int tile = 0; tile < p.ntiles; ++tile, ++it) {
+          const uint32_t s = it % kC2iStages;
+          mbar_wait(&emptyA[s], ((it / kC2iStages) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&fullA[s], A_BYTES);
+          tma_load_2d(sA + s * A_BYTES, &tmX, &fullA[s], 0, img * p.npx + tile * 128);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
+      const uint32_t w_addr = smem_u32(sW);
+      uint32_t it = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+        for (int tile = 0; tile < p.ntiles; ++tile, ++it) {
+          const uint32_t s = it % kC2iStages, acc = it & 1u;
+          mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);
+          mbar_wait(&fullA[s], (it / kC2iStages) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = make_smem_desc(a_addr + ks * 32u, 16u, 512u, 4u);
+            const uint64_t bd = make_smem_desc(w_addr + ks * 32u, 16u, 512u, 4u);
+            umma_f16(tmem_base + acc * 32u, ad, bd, idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&emptyA[s]);
+          umma_commit(&tfull[acc]);
+        }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const float b0 = p.bias ? p.bias[0] : 0.f;
+    uint32_t it = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      int lim_prev = 0;
+      for (int tile = 0; tile < p.ntiles; ++tile, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(&tfull[acc], (it >> 1) & 1u);
+        tc_fence_after();
+        uint32_t v0[16], v1[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32u;
+        tmem_ld16(taddr, v0);
+        tmem_ld16(taddr + 16u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        const int pin = tile * 128 + r;
+        if (pin < p.npx) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) ring[t * RING + (pin & RM)] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (KIND == 0) {
+          const int D = 2 * p.Win + 2;
+          const int qo = tile * 128 - D + r;
+          if (qo >= 0) {
+            const int oy = qo / p.Win, ox = qo - oy * p.Win;
+            if (oy < p.Ho && ox < p.Wo) {
+              float a = b0;
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) a += ring[(ky * 3 + kx) * RING + ((qo + ky * p.Win + kx) & RM)];
+              if (p.act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
+              else if (p.act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
+              p.out[((int64_t)img * p.Ho + oy) * p.Wo + ox] = a;
+            }
+          }
+        } else {
+          // input rows complete after this tile -> output rows that can be finished
+          int rc = (tile + 1) * 128 / p.Win;
+          if (tile == p.ntiles - 1 || rc > p.Hin) rc = p.Hin;
+          int lim = rc >= p.Hin ? p.Ho : (2 * rc - 1 > 0 ? 2 * rc - 1 : 0);
+          const int nout = (lim - lim_prev) * p.Wo;
+          for (int j = r; j < nout; j += 128) {
+            const int dy = j / p.Wo;
+            const int iy = lim_prev + dy, ix = j - dy * p.Wo;
+            float a = 0.f;
+#pragma unroll
+            for (int ay = 0; ay < 2; ++ay) {
+              const int ky = ((iy + 1) & 1) + 2 * ay;
+              const int ty = iy + 1 - ky;
+              if (ty < 0 || (ty >> 1) >= p.Hin) continue;
+#pragma unroll
+              for (int ax = 0; ax < 2; ++ax) {
+                const int kx = ((ix + 1) & 1) + 2 * ax;
+                const int tx = ix + 1 - kx;
+                if (tx < 0 || (tx >> 1) >= p.Win) continue;
+                a += ring[(ky * 4 + kx) * RING + (((ty >> 1) * p.Win + (tx >> 1)) & RM)];
+              }
+            }
+            p.out[((int64_t)img * p.Ho + iy) * p.Wo + ix] = a;
+          }
+          lim_prev = lim;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");    // ring reads of this image done before the next one writes
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+int thin_tc_col2im(int kind, const void* x, const float* w, const float* bias, int B, int Hin, int Win, int act,
+                   float* out, cudaStream_t st) {
+  if (((uintptr_t)x & 15) != 0) return 1;
+  C2iParams p;
+  p.B = B; p.Hin = Hin; p.Win = Win; p.npx = Hin * Win; p.ntiles = (p.npx + 127) / 128;
+  if (kind == 0) { p.Ho = Hin - 2; p.Wo = Win - 2; } else { p.Ho = 2 * Hin; p.Wo = 2 * Win; }
+  if ((int64_t)B * p.npx >= (1ll << 31)) return 1;
+  int ring = 256;
+  while (ring < 256 + 3 * Win + 2) ring <<= 1;
+  p.ring = ring; p.act = act; p.w = w; p.bias = bias; p.out = out;
+  const int T = kind == 0 ? 9 : 16;
+  const size_t smem = 1024 + (size_t)kC2iStages * 128 * 64 + 2048 + (size_t)T * ring * 4;
+  if (smem > 110 * 1024) return 1;
+  CUtensorMap tmX;
+  {
+    uint64_t dims[2] = {32, (uint64_t)B * p.npx};
+    uint64_t str[1] = {64};
+    uint32_t box[2] = {32, 128};
+    if (int e = make_tmap_bf16(&tmX, x, 2, dims, str, box, nullptr, 64)) return e;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(col2im_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(col2im_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    attr = true;
+  }
+  int occ = (int)((227 * 1024) / (smem + 1024));
+  if (occ > 4) occ = 4;
+  if (occ < 1) occ = 1;
+  int grid = kNumSMs * occ;
+  if (grid > B) grid = B;
+  if (kind == 0) col2im_tc_kernel<0><<<grid, 192, smem, st>>>(tmX, p);
+  else col2im_tc_kernel<1><<<grid, 192, smem, st>>>(tmX, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// C. weight gradients
+// =============================================================================================
+template <int KIND> struct WgCfg;
+// STN conv1: gw[c][ky][kx] = sum img[y+ky-2, x+kx-2] * gfull[y,x,c]; gfull = pooled gradient routed by idx
+template <> struct WgCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, FLIP = 0, BTMA = 0, ONES = 1 }; };
+// encoder c1: gw[c][ky][kx] = sum img[2oy-1+ky, 2ox-1+kx] * g[oy,ox,c]
+template <> struct WgCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, FLIP = 0, BTMA = 1, ONES = 1 }; };
+// decoder d4: gw[c][ky][kx] = sum_{iy,ix} x[iy,ix,c] * gpre[iy-ky, ix-kx]   (src = gpre, wide = x)
+template <> struct WgCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, FLIP = 1, BTMA = 1, ONES = 0 }; };
+
+struct WgParams {
+  const float* src;     // 1-channel fp32 [B][H][W]
+  int B, H, W;
+  int Hg, Wg, npx, nst; // reduction grid, pixels and 64-pixel stages per image
+  int Hs, pitch;        // staged source (zero padded): rows, 32-bit words per row
+  const void* gp; const uint8_t* idx;   // KIND 0: pooled gradient bf16 [B][H/2][W/2][16] and argmax
+  float* gw; float* gb;
+};
+
+static constexpr int kWgA = 4, kWgB = 10, kWgThreadsT = 320;
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (size and addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One CTA per SM, 320 threads: warp 0 = producer of the wide operand (TMA boxes / bulk copies, kWgB slots
+// = 40 KB in flight: with one CTA per SM the bytes in flight decide the HBM throughput), warp 1 = MMA
+// issuer (4 UMMAs of K = 16 pixels per 64-pixel stage, descriptors precomputed), warps 2-9 = builders of
+// the tap rows (and, for the STN layer, of the un-pooled gradient tile).  Roles meet only at mbarriers.
+template <int KIND>
+__global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+  using Cfg = WgCfg<KIND>;
+  constexpr int C = Cfg::C, KS = Cfg::KS, S = Cfg::S, PAD = Cfg::PAD, T = KS * KS;
+  constexpr bool BTMA = Cfg::BTMA != 0;
+  constexpr uint32_t RBB = C * 2;                       // bytes per pixel row of the wide operand
+  constexpr uint32_t A_BYTES = 128u * 128u;             // [128 rows][64 px] bf16, 128-byte swizzled rows
+  constexpr uint32_t B_BYTES = 64u * RBB;               // MN-major tile the MMA reads
+  constexpr uint32_t R_SLOT = BTMA ? 4096u : 2048u;     // ring slot: the TMA box itself, or pooled gradient (1 KB) + argmax (512 B)
+  constexpr uint32_t U_SLOT = 2048u;                    // KIND 0: un-pooled tile, one per A slot
+  constexpr int NBUILD = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kWgA], a_empty[kWgA], b_full[kWgB], b_empty[kWgB], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sR = smem + kWgA * A_BYTES;
+  uint8_t* sU = sR + kWgB * R_SLOT;
+  uint32_t* simg = reinterpret_cast<uint32_t*>(sU + (BTMA ? 0u : kWgA * U_SLOT));   // {hi | lo << 16} per pixel
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    if (BTMA) prefetch_tmap(&tmB);
+    for (int s = 0; s < kWgA; ++s) { mbar_init(&a_full[s], NBUILD / 32); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWgB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], BTMA ? 1 : NBUILD / 32); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 32); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int Wp = p.Wg >> 1;
+  const int pool_cnt = p.Wg >= 64 ? 32 : 16;              // KIND 0: pooled pixels under one 64-pixel stage
+
+  int nimg = 0;
+  for (int img = blockIdx.x; img < p.B; img += gridDim.x) ++nimg;
+  const uint32_t total = (uint32_t)nimg * (uint32_t)p.nst;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer of the wide operand
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+        for (int stg = 0; stg < p.nst; ++stg, ++g) {
+          const uint32_t b = g % kWgB;
+          mbar_wait(&b_empty[b], ((g / kWgB) & 1u) ^ 1u);
+          if (BTMA) {
+            mbar_arrive_expect_tx(&b_full[b], B_BYTES);
+            tma_load_2d(sR + b * R_SLOT, &tmB, &b_full[b], 0, img * p.npx + stg * 64);
+          } else {
+            const int p0 = stg * 64;
+            const int y0 = p0 / p.Wg, x0 = p0 - y0 * p.Wg;
+            const int64_t ps = (int64_t)img * (p.Hg >> 1) * Wp + (y0 >> 1) * Wp + (x0 >> 1);
+            mbar_arrive_expect_tx(&b_full[b], (uint32_t)pool_cnt * 48u);
+            bulk_load_1d(sR + b * R_SLOT, reinterpret_cast<const __nv_bfloat16*>(p.gp) + ps * 16, (uint32_t)pool_cnt * 32u, &b_full[b]);
+            bulk_load_1d(sR + b * R_SLOT + 1024, p.idx + ps * 16, (uint32_t)pool_cnt * 16u, &b_full[b]);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A K-major, B MN-major
+      const uint32_t ltb = RBB == 64 ? 4u : 6u;
+      const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 1024u, 2u);
+      const uint64_t bd0 = make_smem_desc(smem_u32(BTMA ? sR : sU), B_BYTES, 8u * RBB, ltb);
+      for (uint32_t g = 0; g < total; ++g) {
+        const uint32_t a = g % kWgA, b = g % kWgB;
+        mbar_wait(&a_full[a], (g / kWgA) & 1u);
+        if (BTMA) mbar_wait(&b_full[b], (g / kWgB) & 1u);
+        tc_fence_after();
+        const uint64_t ad = ad0 + ((a * A_BYTES) >> 4);
+        const uint64_t bd = bd0 + ((BTMA ? b * R_SLOT : a * U_SLOT) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base, ad + ((ks * 32u) >> 4), bd + ((ks * 16u * RBB) >> 4), idesc, (g | (uint32_t)ks) != 0u ? 1u : 0u);
+        umma_commit(&a_empty[a]);
+        if (BTMA) umma_commit(&b_empty[b]);
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ builders
+    const int bt = tid - 64;
+    uint32_t g = 0;
+    float bias_acc = 0.f;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // every builder is done reading the previous image
+      const float* im = p.src + (int64_t)img * p.H * p.W;
+      {
+        const int n = p.Hs * p.pitch;
+        for (int i0 = bt; i0 < n; i0 += NBUILD * 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = min(i0 + u * NBUILD, n - 1);
+            const int r = i / p.pitch, c = i - r * p.pitch;
+            const int iy = r - PAD, ix = c - PAD;
+            const float a = __ldg(im + min(max(iy, 0), p.H - 1) * p.W + min(max(ix, 0), p.W - 1));
+            v[u] = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? a : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i0 + u * NBUILD < n) {
+              if (KIND == 2) bias_acc += v[u];
+              simg[i0 + u * NBUILD] = split_hi_lo(v[u]);
+            }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int stg = 0; stg < p.nst; ++stg, ++g) {
+        const uint32_t a = g % kWgA, b = g % kWgB;
+        uint8_t* a_buf = sA + a * A_BYTES;
+        const int p0 = stg * 64;
+        mbar_wait(&a_empty[a], ((g / kWgA) & 1u) ^ 1u);   // MMAs of stage g - kWgA have finished reading this slot
+        // ---- A: rows t (hi), 32 + t (lo), 64 (ones); 8 chunks of 8 pixels each
+        for (int task = bt; task < (T + Cfg::ONES) * 8; task += NBUILD) {
+          const int t = task >> 3, ch = task & 7;
+          const int pbeg = p0 + ch * 8;
+          if (t == T) {                                     // ones row: bias gradient
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = (pbeg + 2 * e < p.npx ? 0x3F80u : 0u) | (pbeg + 2 * e + 1 < p.npx ? 0x3F800000u : 0u);
+            *reinterpret_cast<uint4*>(a_buf + swz_off(64u, (uint32_t)ch, 128u)) = make_uint4(o[0], o[1], o[2], o[3]);
+            continue;
+          }
+          const int ky = t / KS, kx = t - ky * KS;
+          const int dy = Cfg::FLIP ? (KS - 1 - ky) : ky, dx = Cfg::FLIP ? (KS - 1 - kx) : kx;
+          const int y = pbeg / p.Wg, x = pbeg - y * p.Wg;
+          uint32_t e8[8];
+          if (KIND != 2) {                                  // Wg % 8 == 0: the chunk stays inside one row
+            const uint32_t* src = simg + (y * S + dy) * p.pitch + x * S + dx;
+            const bool ok = pbeg < p.npx;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) e8[e] = ok ? src[e * S] : 0u;
+          } else {                                          // the chunk may wrap once into the next row
+            const uint32_t* src = simg + (y + dy) * p.pitch + x + dx;
+            const int wrap = p.Wg - x;                      // elements e >= wrap belong to row y + 1
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              e8[e] = (pbeg + e < p.npx) ? src[e >= wrap ? e - p.Wg + p.pitch : e] : 0u;
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x5410);
+            lo[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x7632);
+          }
+          *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)t, (uint32_t)ch, 128u)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)(32 + t), (uint32_t)ch, 128u)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        // ---- B (KIND 0): un-pool the gradient into the MN-major tile [64 px][16 ch], 32-byte rows
+        if (KIND == 0) {
+          mbar_wait(&b_full[b], (g / kWgB) & 1u);
+          if (bt >= 128) {                                  // warps 6-9 (the ones with a single A task)
+            const int j = (bt - 128) >> 1, h = bt & 1;
+            const int pp = p0 + j;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (pp < p.npx) {
+              const int y = pp / p.Wg, x = pp - y * p.Wg;
+              const int y0 = p0 / p.Wg, x0 = p0 - y0 * p.Wg;
+              const int local = (((y >> 1) - (y0 >> 1)) * Wp + ((x - x0) >> 1)) * 2 + h;   // 16-byte units of the pooled slot
+              const uint4 pg = *reinterpret_cast<const uint4*>(sR + b * R_SLOT + local * 16);
+              const uint2 pi = *reinterpret_cast<const uint2*>(sR + b * R_SLOT + 1024 + local * 8);
+              const uint32_t pos = (uint32_t)(((y & 1) << 1) | (x & 1));
+              const uint32_t gv[4] = {pg.x, pg.y, pg.z, pg.w};
+              uint32_t ov[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t iw = e < 2 ? pi.x : pi.y;
+                const uint32_t i0 = (iw >> ((e & 1) * 16)) & 0xffu, i1 = (iw >> ((e & 1) * 16 + 8)) & 0xffu;
+                ov[e] = (i0 == pos ? (gv[e] & 0xffffu) : 0u) | (i1 == pos ? (gv[e] & 0xffff0000u) : 0u);
+              }
+              o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+            }
+            *reinterpret_cast<uint4*>(sU + a * U_SLOT + swz_off((uint32_t)j, (uint32_t)h, 32u)) = o;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[a]);
+          if (KIND == 0) mbar_arrive(&b_empty[b]);          // pooled slot consumed (read into registers above)
+        }
+      }
+    }
+    if (KIND == 2 && p.gb) {
+      const float sacc = warp_sum(bias_acc);
+      if (lane == 0) atomicAdd(p.gb, sacc);
+    }
+    if (warp < 6) {   // warps 2-5 cover the four TMEM lane quadrants
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      mbar_wait(&accum_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      uint32_t v[2][16];
+      tmem_ld16(taddr, v[0]);
+      if (C == 32) tmem_ld16(taddr + 16u, v[1]);
+      tmem_ld_wait();
+      const int t = r < 32 ? r : r - 32;
+      if (r < 64 && t < T) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) atomicAdd(p.gw + c * T + t, __uint_as_float(v[c >> 4][c & 15]));
+      } else if (Cfg::ONES && r == 64 && p.gb) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) atomicAdd(p.gb + c, __uint_as_float(v[c >> 4][c & 15]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+}
+
+template <int KIND>
+static int launch_wg(const float* src, const void* big, const uint8_t* idx, int B, int H, int W, int Hg, int Wg,
+                     float* gw, float* gb, cudaStream_t st) {
+  using Cfg = WgCfg<KIND>;
+  WgParams p;
+  p.src = src; p.B = B; p.H = H; p.W = W; p.Hg = Hg; p.Wg = Wg; p.npx = Hg * Wg; p.nst = (p.npx + 63) / 64;
+  p.Hs = (Hg - 1) * Cfg::S + Cfg::KS; p.pitch = (Wg - 1) * Cfg::S + Cfg::KS;
+  p.gp = big; p.idx = idx; p.gw = gw; p.gb = gb;
+  if ((int64_t)B * p.npx >= (1ll << 31)) return 1;
+  const size_t ring = Cfg::BTMA ? (size_t)kWgB * 4096 : (size_t)kWgB * 2048 + (size_t)kWgA * 2048;
+  const size_t smem = 1024 + (size_t)kWgA * 128 * 128 + ring + (size_t)p.Hs * p.pitch * 4;
+  if (smem > 220 * 1024) return 1;
+  CUtensorMap tmB;
+  if (Cfg::BTMA) {
+    uint64_t dims[2] = {(uint64_t)Cfg::C, (uint64_t)B * p.npx};
+    uint64_t str[1] = {(uint64_t)Cfg::C * 2};
+    uint32_t box[2] = {(uint32_t)Cfg::C, 64};
+    if (int e = make_tmap_bf16(&tmB, big, 2, dims, str, box, nullptr, Cfg::C * 2)) return e;
+  } else {
+    memset(&tmB, 0, sizeof(tmB));
+  }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tap_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  int grid = kNumSMs;
+  if (grid > B) grid = B;
+  tap_wgrad_tc_kernel<KIND><<<grid, kWgThreadsT, smem, st>>>(tmB, p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+// kind 0: STN conv1 (src = img [B,H,W], big = pooled gradient, idx); kind 1: encoder c1 (big = g [B,H/2,W/2,32]);
+// kind 2: decoder d4 (src = gpre [B,H,W], big = x [B,H+2,W+2,32]).  gw / gb must be zeroed by the caller.
+int thin_tc_wgrad(int kind, const float* src, const void* big, const uint8_t* idx, int B, int H, int W, float* gw,
+                  float* gb, cudaStream_t st) {
+  if (((uintptr_t)big & 15) != 0) return 1;
+  if (kind == 0) {
+    // a 64-pixel stage must cover whole pooled rows or half of one: W a multiple of 64, or 16 / 32
+    if (!((W % 64) == 0 || W == 32 || W == 16) || (H & 3) || ((uintptr_t)idx & 15)) return 1;
+    return launch_wg<0>(src, big, idx, B, H, W, H, W, gw, gb, st);
+  }
+  if (kind == 1) {
+    if ((W & 15) || (H & 1)) return 1;
+    return launch_wg<1>(src, big, nullptr, B, H, W, H / 2, W / 2, gw, gb, st);
+  }
+  return launch_wg<2>(src, big, nullptr, B, H, W, H + 2, W + 2, gw, gb, st);
+}
+
+}  // namespace tc
+}  // namespace livae
+

@@ -41,9 +41,15 @@ def test_stn_conv1_fwd_and_wgrad(B, P):
     g = _bf(torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32))) * (y.detach() > 0)
     (y * g).sum().backward()
     gw = torch.empty(16, 1, 5, 5, device="cuda"); gb = torch.empty(16, device="cuda")
-    _call("livae_thin_conv1c_wgrad", 0, x.cuda(), _nhwc(g).cuda().to(BF), idx, B, P, P, gw, gb)
-    assert rel_l2(gw.cpu(), w.grad) < 2e-3      # argmax may differ where bf16 rounding ties the pool
-    assert rel_l2(gb.cpu(), b.grad) < 2e-3
+    # route by the REFERENCE argmax (position 0..3 inside the 2x2 window): the kernel's own argmax may
+    # differ wherever bf16 rounding of image / weights ties the pool, which is not the wgrad's business
+    iy, ix = ind // P, ind % P
+    ref_idx = _nhwc(((iy % 2) * 2 + (ix % 2)).to(torch.uint8)).cuda()
+    agree = (ref_idx == idx).float().mean().item()
+    assert agree > 0.97, agree
+    _call("livae_thin_conv1c_wgrad", 0, x.cuda(), _nhwc(g).cuda().to(BF), ref_idx, B, P, P, gw, gb)
+    assert rel_l2(gw.cpu(), w.grad) < 1e-4
+    assert rel_l2(gb.cpu(), b.grad) < 1e-4
 
 
 @pytest.mark.parametrize("B,P", [(3, 32), (2, 128)])
@@ -77,7 +83,7 @@ def test_decoder_d4_fwd_bwd(B, P):
     ud = _nhwc(u.detach()).cuda().to(BF)
     r = torch.empty(B, 1, P, P, device="cuda")
     _call("livae_thin_convc1_fwd", ud, w.detach().cuda(), b.detach().cuda(), B, P + 2, P + 2, 2, r)
-    assert rel_l2(r.cpu(), y.detach()) < 1e-5
+    assert rel_l2(r.cpu(), y.detach()) < 2e-5
     g1 = torch.tensor(rng.standard_normal((B, 1, P, P)).astype(np.float32))
     g2 = torch.tensor(rng.standard_normal((B, 1, P, P)).astype(np.float32))
     (y * (g1 + g2)).sum().backward()
