@@ -140,6 +140,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with fp16 A and B (format code 0): 11-bit mantissa for operands of known small range
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
 
 inline uint32_t swizzle_layout_type(int row_bytes) {  // UMMA layout_type for a K-major row pitch
   return row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : row_bytes == 32 ? 6u : 0u;

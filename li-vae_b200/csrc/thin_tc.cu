@@ -43,6 +43,16 @@ __device__ __forceinline__ uint32_t split_hi_lo(float v) {
   const uint32_t l = bf16_bits(v - bf16_bits_to_float(h));
   return h | (l << 16);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 variant of split_hi_lo
+__device__ __forceinline__ uint32_t split_hi_lo_f16(float v) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+}
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
 }
@@ -52,11 +62,14 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // =============================================================================================
 template <int KIND> struct FwdCfg;
 // STN conv1: 5x5 p2, ReLU, 2x2 max-pool.  K order (ky, kx padded to 6): 30 -> 32
-template <> struct FwdCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, KW2 = 6, KPAD = 32, POOL = 1, FLIP = 0, RELU = 1 }; };
+// F16: operands in fp16 instead of bf16 -- the image is in [0, 1] (min-max normalised patches, data.py:553-558)
+// and the filter weights are O(1), so fp16's 11-bit mantissa costs nothing in range and rounds the image 8x finer.
+template <> struct FwdCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, KW2 = 6, KPAD = 32, POOL = 1, FLIP = 0, RELU = 1, F16 = 1 }; };
 // encoder c1: 4x4 s2 p1, ReLU.  K = 16
-template <> struct FwdCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 0, RELU = 1 }; };
+template <> struct FwdCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 0, RELU = 1, F16 = 1 }; };
 // data gradient of decoder d4 (3x3 p0): full correlation with the flipped filter, pad 2.  K (ky, kx padded to 4): 12 -> 16
-template <> struct FwdCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 1, RELU = 0 }; };
+// (bf16: the image here is a gradient of arbitrary scale)
+template <> struct FwdCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 1, RELU = 0, F16 = 0 }; };
 
 struct FwdParams {
   const float* img; const float* w; const float* bias;
@@ -89,8 +102,8 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
   __shared__ float sbias[32];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + NS * A_BUF;
-  uint32_t* simg32 = reinterpret_cast<uint32_t*>(sW + 2048);
+  uint8_t* sW = smem + NS * A_BUF;                    // two weight tiles: bf16 hi part, bf16 lo part (w ~= hi + lo)
+  uint32_t* simg32 = reinterpret_cast<uint32_t*>(sW + 4096);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pitch2 = p.pitch >> 1;
 
@@ -108,7 +121,10 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
       const int t = ky * KS + kx;
       v = p.w[c * KS * KS + (Cfg::FLIP ? KS * KS - 1 - t : t)];
     }
-    *reinterpret_cast<uint16_t*>(sW + swz_off((uint32_t)c, (uint32_t)k >> 3, RB) + (k & 7) * 2) = bf16_bits(v);
+    const uint32_t hl = Cfg::F16 ? split_hi_lo_f16(v) : split_hi_lo(v);
+    const uint32_t o = swz_off((uint32_t)c, (uint32_t)k >> 3, RB) + (k & 7) * 2;
+    *reinterpret_cast<uint16_t*>(sW + o) = (uint16_t)(hl & 0xffffu);
+    *reinterpret_cast<uint16_t*>(sW + 2048 + o) = (uint16_t)(hl >> 16);
   }
   if (tid < 32) sbias[tid] = (p.bias && tid < C) ? p.bias[tid] : 0.f;
   fence_proxy_async();
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
   if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
+      const uint32_t idesc = Cfg::F16 ? make_idesc_f16(128, C, 0, 0) : make_idesc_bf16(128, C, 0, 0);
       const uint32_t lt = RB == 64 ? 4u : 6u;
       const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 8u * RB, lt);
       const uint64_t bd0 = make_smem_desc(smem_u32(sW), 16u, 8u * RB, lt);
@@ -138,9 +154,11 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub)
 #pragma unroll
-            for (int ks = 0; ks < KPAD / 16; ++ks)
-              umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
-                       bd0 + ((ks * 32u) >> 4), idesc, ks > 0 ? 1u : 0u);
+            for (int hl = 0; hl < 2; ++hl)                 // D = A * Whi^T + A * Wlo^T: weights exact to ~2^-17
+#pragma unroll
+              for (int ks = 0; ks < KPAD / 16; ++ks)
+                umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
+                         bd0 + ((hl * 2048u + ks * 32u) >> 4), idesc, (ks | hl) > 0 ? 1u : 0u);
           umma_commit(&a_empty[s]);
           umma_commit(&t_full[s]);
         }
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (i0 + u * 128 < nw) simg32[i0 + u * 128] = pack_bf16x2(v0[u], v1[u]);
+            if (i0 + u * 128 < nw) simg32[i0 + u * 128] = Cfg::F16 ? pack_f16x2(v0[u], v1[u]) : pack_bf16x2(v0[u], v1[u]);
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -325,7 +343,7 @@ static int launch_fwd(const float* img, const float* w, const float* bias, int B
   p.out = out; p.idx = idx;
   const int ns = Cfg::POOL ? 2 : 4;
   const size_t a_buf = (size_t)(Cfg::POOL ? 4 : 1) * 128 * Cfg::KPAD * 2;
-  const size_t smem = 1024 + ns * a_buf + 2048 + (size_t)p.Hs * p.pitch * 2;
+  const size_t smem = 1024 + ns * a_buf + 4096 + (size_t)p.Hs * p.pitch * 2;
   if (smem > 110 * 1024) return 1;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv1c_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); attr = true; }
@@ -565,7 +583,22 @@ struct WgParams {
   float* gw; float* gb;
 };
 
-static constexpr int kWgA = 4, kWgB = 10, kWgThreadsT = 320;
+// Ring geometry.  Every mbarrier is waited on by ONE owner that visits its phases in order (a parity
+// wait two phases ahead of the barrier would pass spuriously), so the owners' strides divide the ring
+// sizes: issuer = g % 3 owns A slots {i, i+3} and B slots {i, i+3, i+6, i+9}; team = g % NTEAMS (2 or 3)
+// owns A slots of the same residue.
+static constexpr int kWgA = 6, kWgB = 12, kWgIssuers = 3;
+template <int KIND> struct WgLayout {
+  using Cfg = WgCfg<KIND>;
+  static constexpr int TASKS = (Cfg::KS * Cfg::KS + Cfg::ONES) * 8;
+  static constexpr int NAW = (TASKS + 31) / 32;           // A-builder warps per team
+  static constexpr int NBWT = Cfg::BTMA ? 0 : 4;          // un-pool warps per team
+  static constexpr int TEAMW = NAW + NBWT;
+  static constexpr int NTEAMS = KIND == 0 ? 2 : 3;
+  static constexpr int BUILDW = NTEAMS * TEAMW;           // 22 / 15 / 9 builder warps
+  static constexpr int FIRSTB = 1 + kWgIssuers;           // first builder warp
+  static constexpr int THREADS = 32 * (FIRSTB + BUILDW);
+};
 
 // 1-D bulk copy global -> shared, completion on an mbarrier (size and addresses multiples of 16 bytes)
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -574,12 +607,17 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-// One CTA per SM, 320 threads: warp 0 = producer of the wide operand (TMA boxes / bulk copies, kWgB slots
-// = 40 KB in flight: with one CTA per SM the bytes in flight decide the HBM throughput), warp 1 = MMA
-// issuer (4 UMMAs of K = 16 pixels per 64-pixel stage, descriptors precomputed), warps 2-9 = builders of
-// the tap rows (and, for the STN layer, of the un-pooled gradient tile).  Roles meet only at mbarriers.
+// One CTA per SM: warp 0 = producer of the wide operand (TMA boxes / bulk copies, kWgB slots = 40 KB in
+// flight: with one CTA per SM the bytes in flight decide the HBM throughput), warps 1-3 = MMA issuers
+// (stage g belongs to issuer g % 3, each with its own TMEM accumulator: waiting on two mbarriers, issuing 4
+// UMMAs and committing costs one thread ~800 cycles of pure latency per 64-pixel stage, three of them keep
+// the tensor pipe busy), the remaining warps = builders.  A stage's tap
+// rows are (T + 1) * 8 independent 16-byte chunk tasks, i.e. only 3-7 warps of work and a long latency
+// chain (shared loads -> byte permutes -> swizzled stores -> proxy fence -> mbarrier), so the builder
+// warps form TEAMS that work on different stages concurrently; every thread owns one fixed (tap, chunk)
+// task and walks its pixel coordinates incrementally (no divisions in the stage loop).
 template <int KIND>
-__global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+__global__ void __launch_bounds__(WgLayout<KIND>::THREADS, 1) tap_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmB, const WgParams p) {
   using Cfg = WgCfg<KIND>;
   constexpr int C = Cfg::C, KS = Cfg::KS, S = Cfg::S, PAD = Cfg::PAD, T = KS * KS;
   constexpr bool BTMA = Cfg::BTMA != 0;
@@ -588,7 +626,10 @@ __global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_
   constexpr uint32_t B_BYTES = 64u * RBB;               // MN-major tile the MMA reads
   constexpr uint32_t R_SLOT = BTMA ? 4096u : 2048u;     // ring slot: the TMA box itself, or pooled gradient (1 KB) + argmax (512 B)
   constexpr uint32_t U_SLOT = 2048u;                    // KIND 0: un-pooled tile, one per A slot
-  constexpr int NBUILD = 256;
+  using Lay = WgLayout<KIND>;
+  constexpr int TASKS = Lay::TASKS, NAW = Lay::NAW, NBWT = Lay::NBWT, TEAMW = Lay::TEAMW, NTEAMS = Lay::NTEAMS;
+  constexpr int NBUILD = 32 * Lay::BUILDW, FIRSTB = Lay::FIRSTB;
+  static_assert(kWgA % NTEAMS == 0 && kWgA % kWgIssuers == 0 && kWgB % kWgIssuers == 0, "ring ownership");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kWgA], a_empty[kWgA], b_full[kWgB], b_empty[kWgB], accum_bar;
   __shared__ uint32_t tmem_base_s;
@@ -601,12 +642,12 @@ __global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_
 
   if (tid == 0) {
     if (BTMA) prefetch_tmap(&tmB);
-    for (int s = 0; s < kWgA; ++s) { mbar_init(&a_full[s], NBUILD / 32); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < kWgB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], BTMA ? 1 : NBUILD / 32); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < kWgA; ++s) { mbar_init(&a_full[s], TEAMW); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kWgB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], BTMA ? 1 : NBWT); }
+    mbar_init(&accum_bar, kWgIssuers);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&tmem_base_s, 32); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -622,7 +663,8 @@ __global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_
     // ------------------------------------------------------------------ producer of the wide operand
     if (lane == 0) {
       uint32_t g = 0;
-      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+        int y0 = 0, x0 = 0;                               // KIND 0: first pixel of the stage
         for (int stg = 0; stg < p.nst; ++stg, ++g) {
           const uint32_t b = g % kWgB;
           mbar_wait(&b_empty[b], ((g / kWgB) & 1u) ^ 1u);
@@ -630,44 +672,63 @@ __global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_
             mbar_arrive_expect_tx(&b_full[b], B_BYTES);
             tma_load_2d(sR + b * R_SLOT, &tmB, &b_full[b], 0, img * p.npx + stg * 64);
           } else {
-            const int p0 = stg * 64;
-            const int y0 = p0 / p.Wg, x0 = p0 - y0 * p.Wg;
             const int64_t ps = (int64_t)img * (p.Hg >> 1) * Wp + (y0 >> 1) * Wp + (x0 >> 1);
             mbar_arrive_expect_tx(&b_full[b], (uint32_t)pool_cnt * 48u);
             bulk_load_1d(sR + b * R_SLOT, reinterpret_cast<const __nv_bfloat16*>(p.gp) + ps * 16, (uint32_t)pool_cnt * 32u, &b_full[b]);
             bulk_load_1d(sR + b * R_SLOT + 1024, p.idx + ps * 16, (uint32_t)pool_cnt * 16u, &b_full[b]);
+            x0 += 64;
+            while (x0 >= p.Wg) { x0 -= p.Wg; ++y0; }
           }
         }
+      }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp < FIRSTB) {
+    // ------------------------------------------------------------------ MMA issuers
     if (lane == 0) {
+      const uint32_t wi = (uint32_t)(warp - 1);
       const uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A K-major, B MN-major
       const uint32_t ltb = RBB == 64 ? 4u : 6u;
       const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 1024u, 2u);
       const uint64_t bd0 = make_smem_desc(smem_u32(BTMA ? sR : sU), B_BYTES, 8u * RBB, ltb);
-      for (uint32_t g = 0; g < total; ++g) {
-        const uint32_t a = g % kWgA, b = g % kWgB;
-        mbar_wait(&a_full[a], (g / kWgA) & 1u);
-        if (BTMA) mbar_wait(&b_full[b], (g / kWgB) & 1u);
+      const uint32_t d_addr = tmem_base + wi * 32u;
+      uint32_t a = wi % kWgA, b = wi % kWgB, pa = 0u, pb = 0u, first = 1u;   // slots / phase parities of stage g
+      for (uint32_t g = wi; g < total; g += kWgIssuers) {
+        mbar_wait(&a_full[a], pa);
+        if (BTMA) mbar_wait(&b_full[b], pb);
         tc_fence_after();
         const uint64_t ad = ad0 + ((a * A_BYTES) >> 4);
         const uint64_t bd = bd0 + ((BTMA ? b * R_SLOT : a * U_SLOT) >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base, ad + ((ks * 32u) >> 4), bd + ((ks * 16u * RBB) >> 4), idesc, (g | (uint32_t)ks) != 0u ? 1u : 0u);
+          umma_f16(d_addr, ad + ((ks * 32u) >> 4), bd + ((ks * 16u * RBB) >> 4), idesc, (ks > 0 || !first) ? 1u : 0u);
+        first = 0u;
         umma_commit(&a_empty[a]);
         if (BTMA) umma_commit(&b_empty[b]);
+        a += kWgIssuers; if (a >= kWgA) { a -= kWgA; pa ^= 1u; }
+        b += kWgIssuers; if (b >= kWgB) { b -= kWgB; pb ^= 1u; }
       }
       umma_commit(&accum_bar);
     }
   } else {
     // ------------------------------------------------------------------ builders
-    const int bt = tid - 64;
-    uint32_t g = 0;
+    const int bw = warp - FIRSTB, bt = tid - 32 * FIRSTB;
+    const int team = bw / TEAMW, rw = bw - team * TEAMW;
+    const bool in_team = team < NTEAMS;
+    const bool a_role = in_team && rw < NAW;
+    const int task = rw * 32 + lane;                      // a_role: fixed (tap, chunk) of this thread
+    const bool a_task = a_role && task < TASKS;
+    const int t = task >> 3, ch = task & 7;
+    const int ky = t / KS, kx = t - ky * KS;
+    const int dy = Cfg::FLIP ? (KS - 1 - ky) : ky, dx = Cfg::FLIP ? (KS - 1 - kx) : kx;
+    const uint32_t off_hi = swz_off((uint32_t)(t < T ? t : 64), (uint32_t)ch, 128u);
+    const uint32_t off_lo = swz_off((uint32_t)(32 + (t < T ? t : 0)), (uint32_t)ch, 128u);
+    const int ub = (rw - NAW) * 32 + lane;                // un-pool role: (pixel j, channel half h)
+    const int uj = ub >> 1, uh = ub & 1;
+    const uint32_t off_u = swz_off((uint32_t)uj, (uint32_t)uh, 32u);
+    uint32_t gbase = 0;
     float bias_acc = 0.f;
-    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // every builder is done reading the previous image
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, gbase += (uint32_t)p.nst) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");     // every builder is done reading the previous image
       const float* im = p.src + (int64_t)img * p.H * p.W;
       {
         const int n = p.Hs * p.pitch;
@@ -689,111 +750,122 @@ __global__ void __launch_bounds__(kWgThreadsT) tap_wgrad_tc_kernel(const __grid_
             }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int stg = 0; stg < p.nst; ++stg, ++g) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");
+      if (!in_team) continue;
+      // this team's stages of the image: those with global index g = gbase + stg congruent to team
+      const int stg0 = (team + NTEAMS - (int)(gbase % NTEAMS)) % NTEAMS;
+      // pixel coordinates of this thread's chunk (a_role) or pixel (un-pool role) and of the stage start
+      int pbeg = stg0 * 64 + (a_role ? ch * 8 : uj);
+      int y = pbeg / p.Wg, x = pbeg - y * p.Wg;
+      int y0 = (stg0 * 64) / p.Wg, x0 = stg0 * 64 - y0 * p.Wg;
+      for (int stg = stg0; stg < p.nst; stg += NTEAMS) {
+        const uint32_t g = gbase + (uint32_t)stg;
         const uint32_t a = g % kWgA, b = g % kWgB;
         uint8_t* a_buf = sA + a * A_BYTES;
-        const int p0 = stg * 64;
-        mbar_wait(&a_empty[a], ((g / kWgA) & 1u) ^ 1u);   // MMAs of stage g - kWgA have finished reading this slot
-        // ---- A: rows t (hi), 32 + t (lo), 64 (ones); 8 chunks of 8 pixels each
-        for (int task = bt; task < (T + Cfg::ONES) * 8; task += NBUILD) {
-          const int t = task >> 3, ch = task & 7;
-          const int pbeg = p0 + ch * 8;
-          if (t == T) {                                     // ones row: bias gradient
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] = (pbeg + 2 * e < p.npx ? 0x3F80u : 0u) | (pbeg + 2 * e + 1 < p.npx ? 0x3F800000u : 0u);
-            *reinterpret_cast<uint4*>(a_buf + swz_off(64u, (uint32_t)ch, 128u)) = make_uint4(o[0], o[1], o[2], o[3]);
-            continue;
-          }
-          const int ky = t / KS, kx = t - ky * KS;
-          const int dy = Cfg::FLIP ? (KS - 1 - ky) : ky, dx = Cfg::FLIP ? (KS - 1 - kx) : kx;
-          const int y = pbeg / p.Wg, x = pbeg - y * p.Wg;
+        if (a_role) {
+          // ---- A: rows t (hi), 32 + t (lo), 64 (ones)
           uint32_t e8[8];
-          if (KIND != 2) {                                  // Wg % 8 == 0: the chunk stays inside one row
-            const uint32_t* src = simg + (y * S + dy) * p.pitch + x * S + dx;
-            const bool ok = pbeg < p.npx;
+          if (a_task && t < T) {
+            if (KIND != 2) {                                // Wg % 8 == 0: the chunk stays inside one row
+              const uint32_t* src = simg + (y * S + dy) * p.pitch + x * S + dx;
+              const bool ok = pbeg < p.npx;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) e8[e] = ok ? src[e * S] : 0u;
-          } else {                                          // the chunk may wrap once into the next row
-            const uint32_t* src = simg + (y + dy) * p.pitch + x + dx;
-            const int wrap = p.Wg - x;                      // elements e >= wrap belong to row y + 1
+              for (int e = 0; e < 8; ++e) e8[e] = ok ? src[e * S] : 0u;
+            } else {                                        // the chunk may wrap once into the next row
+              const uint32_t* src = simg + (y + dy) * p.pitch + x + dx;
+              const int wrap = p.Wg - x;                    // elements e >= wrap belong to row y + 1
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              e8[e] = (pbeg + e < p.npx) ? src[e >= wrap ? e - p.Wg + p.pitch : e] : 0u;
+              for (int e = 0; e < 8; ++e)
+                e8[e] = (pbeg + e < p.npx) ? src[e >= wrap ? e - p.Wg + p.pitch : e] : 0u;
+            }
           }
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x5410);
-            lo[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x7632);
-          }
-          *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)t, (uint32_t)ch, 128u)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)(32 + t), (uint32_t)ch, 128u)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        // ---- B (KIND 0): un-pool the gradient into the MN-major tile [64 px][16 ch], 32-byte rows
-        if (KIND == 0) {
-          mbar_wait(&b_full[b], (g / kWgB) & 1u);
-          if (bt >= 128) {                                  // warps 6-9 (the ones with a single A task)
-            const int j = (bt - 128) >> 1, h = bt & 1;
-            const int pp = p0 + j;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (pp < p.npx) {
-              const int y = pp / p.Wg, x = pp - y * p.Wg;
-              const int y0 = p0 / p.Wg, x0 = p0 - y0 * p.Wg;
-              const int local = (((y >> 1) - (y0 >> 1)) * Wp + ((x - x0) >> 1)) * 2 + h;   // 16-byte units of the pooled slot
-              const uint4 pg = *reinterpret_cast<const uint4*>(sR + b * R_SLOT + local * 16);
-              const uint2 pi = *reinterpret_cast<const uint2*>(sR + b * R_SLOT + 1024 + local * 8);
-              const uint32_t pos = (uint32_t)(((y & 1) << 1) | (x & 1));
-              const uint32_t gv[4] = {pg.x, pg.y, pg.z, pg.w};
-              uint32_t ov[4];
+          mbar_wait(&a_empty[a], ((g / kWgA) & 1u) ^ 1u);   // MMAs of stage g - kWgA have finished reading this slot
+          if (a_task) {
+            if (t < T) {
+              uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const uint32_t iw = e < 2 ? pi.x : pi.y;
-                const uint32_t i0 = (iw >> ((e & 1) * 16)) & 0xffu, i1 = (iw >> ((e & 1) * 16 + 8)) & 0xffu;
-                ov[e] = (i0 == pos ? (gv[e] & 0xffffu) : 0u) | (i1 == pos ? (gv[e] & 0xffff0000u) : 0u);
+                hi[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x5410);
+                lo[e] = __byte_perm(e8[2 * e], e8[2 * e + 1], 0x7632);
               }
-              o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+              *reinterpret_cast<uint4*>(a_buf + off_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(a_buf + off_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            } else {                                        // ones row: bias gradient
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = (pbeg + 2 * e < p.npx ? 0x3F80u : 0u) | (pbeg + 2 * e + 1 < p.npx ? 0x3F800000u : 0u);
+              *reinterpret_cast<uint4*>(a_buf + off_hi) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<uint4*>(sU + a * U_SLOT + swz_off((uint32_t)j, (uint32_t)h, 32u)) = o;
           }
+        } else {
+          // ---- B (KIND 0): un-pool the gradient into the MN-major tile [64 px][16 ch], 32-byte rows
+          mbar_wait(&b_full[b], (g / kWgB) & 1u);
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (pbeg < p.npx) {
+            const int local = (((y >> 1) - (y0 >> 1)) * Wp + ((x - x0) >> 1)) * 2 + uh;   // 16-byte units of the pooled slot
+            const uint4 pg = *reinterpret_cast<const uint4*>(sR + b * R_SLOT + local * 16);
+            const uint2 pi = *reinterpret_cast<const uint2*>(sR + b * R_SLOT + 1024 + local * 8);
+            const uint32_t pos = (uint32_t)(((y & 1) << 1) | (x & 1));
+            const uint32_t gv[4] = {pg.x, pg.y, pg.z, pg.w};
+            uint32_t ov[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t iw = e < 2 ? pi.x : pi.y;
+              const uint32_t i0 = (iw >> ((e & 1) * 16)) & 0xffu, i1 = (iw >> ((e & 1) * 16 + 8)) & 0xffu;
+              ov[e] = (i0 == pos ? (gv[e] & 0xffffu) : 0u) | (i1 == pos ? (gv[e] & 0xffff0000u) : 0u);
+            }
+            o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+          }
+          mbar_wait(&a_empty[a], ((g / kWgA) & 1u) ^ 1u);   // the un-pooled tile shares the A slot's lifetime
+          *reinterpret_cast<uint4*>(sU + a * U_SLOT + off_u) = o;
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&a_full[a]);
-          if (KIND == 0) mbar_arrive(&b_empty[b]);          // pooled slot consumed (read into registers above)
+          if (!a_role) mbar_arrive(&b_empty[b]);            // pooled slot consumed
         }
+        // advance this thread's pixel by NTEAMS stages
+        pbeg += 64 * NTEAMS;
+        x += 64 * NTEAMS; while (x >= p.Wg) { x -= p.Wg; ++y; }
+        x0 += 64 * NTEAMS; while (x0 >= p.Wg) { x0 -= p.Wg; ++y0; }
       }
     }
     if (KIND == 2 && p.gb) {
       const float sacc = warp_sum(bias_acc);
       if (lane == 0) atomicAdd(p.gb, sacc);
     }
-    if (warp < 6) {   // warps 2-5 cover the four TMEM lane quadrants
+    if (bw < 4) {   // four builder warps cover the four TMEM lane quadrants
       const int q = warp & 3;
       const int r = q * 32 + lane;
       mbar_wait(&accum_bar, 0);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      uint32_t v[2][16];
-      tmem_ld16(taddr, v[0]);
-      if (C == 32) tmem_ld16(taddr + 16u, v[1]);
-      tmem_ld_wait();
-      const int t = r < 32 ? r : r - 32;
-      if (r < 64 && t < T) {
+      float acc[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) atomicAdd(p.gw + c * T + t, __uint_as_float(v[c >> 4][c & 15]));
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+      for (uint32_t wi = 0; wi < (uint32_t)kWgIssuers && wi < total; ++wi) {   // issuers that never ran left garbage
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wi * 32u;
+        uint32_t v[2][16];
+        tmem_ld16(taddr, v[0]);
+        if (C == 32) tmem_ld16(taddr + 16u, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += __uint_as_float(v[c >> 4][c & 15]);
+      }
+      const int tt = r < 32 ? r : r - 32;
+      if (r < 64 && tt < T) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) atomicAdd(p.gw + c * T + tt, acc[c]);
       } else if (Cfg::ONES && r == 64 && p.gb) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) atomicAdd(p.gb + c, __uint_as_float(v[c >> 4][c & 15]));
+        for (int c = 0; c < C; ++c) atomicAdd(p.gb + c, acc[c]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 template <int KIND>
@@ -821,7 +893,7 @@ static int launch_wg(const float* src, const void* big, const uint8_t* idx, int 
   if (!attr) { cudaFuncSetAttribute(tap_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
   int grid = kNumSMs;
   if (grid > B) grid = B;
-  tap_wgrad_tc_kernel<KIND><<<grid, kWgThreadsT, smem, st>>>(tmB, p);
+  tap_wgrad_tc_kernel<KIND><<<grid, WgLayout<KIND>::THREADS, smem, st>>>(tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
