@@ -54,3 +54,12 @@ for w in which:
         gw = torch.empty(1, 32, 3, 3, device=dev); gb = torch.empty(1, device=dev)
         from livae._lib import call
         print(w, timeit(lambda: call("livae_thin_convc1_wgrad", u, g, B, 130, 130, gw, gb)), "ms")
+    elif w == "upsample":
+        from livae._lib import call
+        for hw, c in ((8, 256), (16, 128), (32, 64), (64, 32)):
+            x = torch.randn(B, hw, hw, c, device=dev).to(bf); u = torch.empty(B, 2 * hw + 2, 2 * hw + 2, c, device=dev, dtype=bf)
+            gx = torch.empty_like(x)
+            nb = (x.numel() + u.numel()) * 2
+            tf = timeit(lambda: call("livae_upsample_pad_fwd_bf16", x, B, hw, hw, c, u))
+            tb = timeit(lambda: call("livae_upsample_pad_bwd_bf16", u, B, hw, hw, c, x, gx))
+            print(f"upsample {hw}x{hw}x{c}: fwd {tf:.3f} ms ({nb / tf / 1e6:.0f} GB/s)  bwd {tb:.3f} ms ({(nb + x.numel() * 2) / tb / 1e6:.0f} GB/s)")
