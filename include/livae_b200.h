@@ -231,6 +231,9 @@ void livae_tc_set_wgrad_halo(int mode);   /* the same switch for the weight-grad
 /* 1 (default): the thin 1-channel layers run on tcgen05 (thread-built im2col / col2im operands,
  * csrc/thin_tc.cu) where the shape is eligible; 0: SIMT kernels only */
 void livae_thin_set_tc(int mode);
+/* pipeline tracing: device buffer of 4 x 1024 int64 that CTA 0 of a traced kernel fills with
+ * (slot << 56 | clock64) records per warp role (tools/probe.py prints the timeline); NULL = off */
+void livae_set_probe(void* dev_ptr);
 /* dtype conversion between LIVAE_F32 and LIVAE_BF16, n elements */
 int livae_cast(const void* src, int dt_src, void* dst, int dt_dst, int64_t n, livae_stream_t stream);
 

@@ -16,6 +16,8 @@
 namespace livae {
 namespace tc {
 
+long long* g_probe = nullptr;
+
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
@@ -246,22 +248,90 @@ struct ConvTcHaloParams {
   int kc, nkc, N, Ntot, B;
   int b_resident;         // 1: all ntaps*nkc weight tiles stay in shared memory for the CTA's lifetime
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
+  long long* probe;
 };
 
 static constexpr int kSA = 2, kSB = 4;
 
+// Epilogue of one accumulator row per thread, 32 columns per pass: both tcgen05.ld and the ReLU-mask loads
+// of the pass are in flight before the first use; bias comes from shared memory.
+__device__ __forceinline__ void epilogue_rows32(uint32_t taddr, int nbase, int N, int Ntot, bool valid, int64_t pix,
+                                                void* out, int out_f32, const float* __restrict__ sbias, int act,
+                                                const __nv_bfloat16* __restrict__ relu_mask) {
+  for (int cc = 0; cc < N; cc += 32) {
+    const bool two = cc + 16 < N;                 // N is a multiple of 16: the last pass may be half
+    uint32_t v[32];
+    tmem_ld16(taddr + (uint32_t)cc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    if (two) tmem_ld16(taddr + (uint32_t)cc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+    uint4 m[4];
+    const int c0 = nbase + cc;
+    if (relu_mask && valid) {
+      const uint4* mp = reinterpret_cast<const uint4*>(relu_mask + pix * Ntot + c0);
+      m[0] = __ldg(mp); m[1] = __ldg(mp + 1);
+      if (two) { m[2] = __ldg(mp + 2); m[3] = __ldg(mp + 3); }
+    }
+    tmem_ld_wait();
+    if (!valid) continue;
+    const int nh = two ? 2 : 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h >= nh) break;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(v[h * 16 + i]) + sbias[cc + h * 16 + i];
+        if (act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
+        f[i] = a;
+      }
+      if (relu_mask) {
+        const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m[2 * h]);
+        const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m[2 * h + 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!(__bfloat162float(mb0[i]) > 0.f)) f[i] = 0.f;
+          if (!(__bfloat162float(mb1[i]) > 0.f)) f[8 + i] = 0.f;
+        }
+      }
+      if (out_f32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * Ntot + c0 + h * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Ntot + c0 + h * 16);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+}
+
 // Persistent: grid.x CTAs walk the tile list round-robin.  The accumulator is double-buffered in
 // TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the
 // TMA + MMA main loop of tile i+1, and barrier/TMEM/tensor-map setup is paid once per CTA.
+// The MMA issuer is ONE thread and every instruction of its loop is a dependent-latency step (measured
+// with livae_set_probe: descriptor construction from kernel parameters cost ~450 cycles per MMA, 10x the
+// MMA itself), so the loop is reduced to: one shared-memory load (tap offset, precomputed in descriptor
+// units) + two 64-bit adds per tap, K steps unrolled at compile time.
+template <int KSTEPS>
 __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t fullA[kSA], emptyA[kSA], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_tapoff[kMaxTaps];        // row shift of each tap in descriptor address units (16 B)
+  __shared__ int s_grp[4][2];                    // tap_begin, tap_end of each group
+  __shared__ float s_bias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row_bytes = (uint32_t)p.kc * 2u;
+  constexpr uint32_t row_bytes = KSTEPS * 32u;
   const uint32_t a_bytes = (uint32_t)(p.box_rows * 16) * row_bytes;
   const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
@@ -284,6 +354,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
     tmem_alloc(&tmem_base_s, ncols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.ntaps; i += kThreads) s_tapoff[i] = ((uint32_t)p.tap_shift[i] * row_bytes) >> 4;
+  for (int i = threadIdx.x; i < p.ngroups; i += kThreads) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
+  for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -292,7 +365,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      int ia = 0, ib = 0;
+      int ia = 0, ib = 0, pn = 0;
       if (p.b_resident) {   // small filters: fetch every weight tile once
         mbar_arrive_expect_tx(&fullB[0], b_bytes * (uint32_t)(p.ntaps * p.nkc));
         for (int t = 0; t < p.ntaps; ++t)
@@ -310,7 +383,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
           const HaloGroup G = p.grp[g];
           for (int c = 0; c < p.nkc; ++c) {
             const int sa = ia % kSA;
+            probe_rec(p.probe, 0, 0, pn);
             mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
+            probe_rec(p.probe, 0, 1, pn);
             mbar_arrive_expect_tx(&fullA[sa], a_bytes);
             tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
             ++ia;
@@ -330,55 +405,71 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
-      const uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
-      const uint32_t sbo = 8u * row_bytes;
-      const int ksteps = p.kc / 16;
-      int ia = 0, ib = 0, it = 0;
-      if (p.b_resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
+      constexpr uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+      constexpr uint32_t sbo = 8u * row_bytes;
+      // The swizzle is a function of the absolute shared-memory address (measured: a start shifted by
+      // whole rows needs NO descriptor base offset), so TMA's write pattern and the MMA's read pattern
+      // agree for any row shift: a tap is "the A descriptor + its row shift".
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem), 16u, sbo, lt);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smemB), 16u, sbo, lt);
+      const uint32_t a_slot16 = a_slot >> 4, b_slot16 = b_slot >> 4;
+      const int ngroups = p.ngroups, nkc = p.nkc;
+      const bool resident = p.b_resident != 0;
+      uint32_t ia = 0, ib = 0, it = 0;
+      int pn = 0;
+      if (resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        const uint32_t acc = it & 1u;
+        probe_rec(p.probe, 1, 0, pn);
+        mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        probe_rec(p.probe, 1, 1, pn);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)acc * acc_cols;
-        uint32_t first = 1u;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const HaloGroup G = p.grp[g];
-          for (int c = 0; c < p.nkc; ++c) {
-            const int sa = ia % kSA;
-            mbar_wait(&fullA[sa], (uint32_t)(ia / kSA) & 1u);
-            const uint32_t a_base = smem_u32(smem + (uint32_t)sa * a_slot);
-            if (p.b_resident) tc_fence_after();
-            for (int t = G.tap_begin; t < G.tap_end; ++t) {
-              const int sb = p.b_resident ? t * p.nkc + c : ib % kSB;
-              if (!p.b_resident) {
-                mbar_wait(&fullB[sb], (uint32_t)(ib / kSB) & 1u);
+        const uint32_t d_addr = tmem_base + acc * acc_cols;
+        uint32_t accum = 0u;
+        for (int g = 0; g < ngroups; ++g) {
+          const int tb = s_grp[g][0], te = s_grp[g][1];
+          for (int c = 0; c < nkc; ++c) {
+            const uint32_t sa = ia & (kSA - 1);
+            mbar_wait(&fullA[sa], (ia / kSA) & 1u);
+            probe_rec(p.probe, 1, 2, pn);
+            tc_fence_after();
+            const uint64_t ad_s = adesc0 + sa * a_slot16;
+            if (resident) {
+              uint64_t bd = bdesc0 + (uint32_t)(tb * nkc + c) * b_slot16;
+              const uint32_t bstep = (uint32_t)nkc * b_slot16;
+              for (int t = tb; t < te; ++t, bd += bstep) {
+                const uint64_t ad = ad_s + s_tapoff[t];
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) { umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
+              }
+            } else {
+              for (int t = tb; t < te; ++t) {
+                const uint32_t sb = ib & (kSB - 1);
+                mbar_wait(&fullB[sb], (ib / kSB) & 1u);
                 tc_fence_after();
+                const uint64_t ad = ad_s + s_tapoff[t];
+                const uint64_t bd = bdesc0 + sb * b_slot16;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) { umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
+                umma_commit(&emptyB[sb]);
+                ++ib;
               }
-              const uint32_t a_addr = a_base + (uint32_t)p.tap_shift[t] * row_bytes;
-              const uint32_t b_addr = smem_u32(smemB + (uint32_t)sb * b_slot);
-              // The swizzle is a function of the absolute shared-memory address (measured: a start
-              // shifted by whole rows needs NO descriptor base offset), so TMA's write pattern and the
-              // MMA's read pattern agree for any row shift.
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-                const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-                umma_f16(d_addr, ad, bd, idesc, first ? 0u : 1u);
-                first = 0u;
-              }
-              if (!p.b_resident) { umma_commit(&emptyB[sb]); ++ib; }
             }
+            probe_rec(p.probe, 1, 3, pn);
             umma_commit(&emptyA[sa]);
             ++ia;
           }
         }
         umma_commit(&tfull[acc]);
+        probe_rec(p.probe, 1, 4, pn);
       }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int px = row & 15, py = row >> 4;
-    int it = 0;
+    int it = 0, pn = 0;
+    long long* pb = (warp == 2 && lane == 0) ? p.probe : nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int t3 = tile;
       const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
@@ -388,10 +479,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
       const int qy = ty * 8 + py, qx = tx * p.tw + px;
       const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
       const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
+      probe_rec(pb, 2, 0, pn);
       mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+      probe_rec(pb, 2, 1, pn);
       tc_fence_after();
-      epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols, (int)blockIdx.y * p.N, p.N, p.Ntot,
-                    valid, pix, p.out, p.out_f32, p.bias, p.act, p.relu_mask);
+      epilogue_rows32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols, (int)blockIdx.y * p.N, p.N, p.Ntot,
+                      valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
+      probe_rec(pb, 2, 2, pn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -526,6 +620,7 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   if (N > 256) { nchunk = 256; while (N % nchunk != 0) nchunk -= 16; }
   p.N = nchunk; p.Ntot = N; p.B = B;
   p.out = out; p.out_f32 = out_f32; p.bias = bias; p.act = act; p.relu_mask = (const __nv_bfloat16*)relu_mask;
+  p.probe = g_probe;
   const int row_bytes = p.kc * 2;
   CUtensorMap tmA, tmB;
   {
@@ -543,12 +638,14 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   }
   const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
-  p.b_resident = ((size_t)ntaps * p.nkc * b_slot <= 32 * 1024) ? 1 : 0;
+  p.b_resident = ((size_t)ntaps * p.nkc * b_slot <= 72 * 1024) ? 1 : 0;
   const size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * B;
@@ -562,7 +659,9 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   if (per_sm < 1) per_sm = 1;
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
-  conv_tc_halo_kernel<<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  if (p.kc == 64) conv_tc_halo_kernel<4><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 32) conv_tc_halo_kernel<2><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  else conv_tc_halo_kernel<1><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -733,6 +832,9 @@ extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, 
     }
   return 0;
 }
+
+// tracing hook (tc_common.cuh): device buffer of 4 x 1024 int64, or NULL to switch tracing off
+extern "C" void livae_set_probe(void* dev_ptr) { g_probe = (long long*)dev_ptr; }
 
 // tuning / test hook: 0 = per-tap boxes only, 1 = halo kernel where eligible
 extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; }

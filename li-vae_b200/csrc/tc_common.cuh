@@ -150,6 +150,16 @@ inline uint32_t swizzle_layout_type(int row_bytes) {  // UMMA layout_type for a 
   return row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : row_bytes == 32 ? 6u : 0u;
 }
 
+// ---- pipeline tracing ------------------------------------------------------------------------
+// livae_set_probe(dev_ptr) hands the kernels a device buffer of int64; CTA 0 of a traced kernel appends
+// (role << 60 | slot << 56 | clock64) records at its pipeline points (role-private regions of 1024
+// records), which tools/probe.py prints as a timeline.  nullptr (default) = no tracing.
+extern long long* g_probe;
+__device__ __forceinline__ void probe_rec(long long* buf, int role, int slot, int& n) {
+  if (buf && blockIdx.x == 0 && blockIdx.y == 0 && n < 1024)
+    buf[role * 1024 + n++] = ((long long)slot << 56) | (clock64() & 0xffffffffffffffll);
+}
+
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

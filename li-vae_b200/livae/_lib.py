@@ -107,6 +107,8 @@ def lib():
     L.livae_tc_set_halo_mode.argtypes = [C.c_int]
     L.livae_tc_set_wgrad_halo.restype = None
     L.livae_tc_set_wgrad_halo.argtypes = [C.c_int]
+    L.livae_set_probe.restype = None
+    L.livae_set_probe.argtypes = [C.c_void_p]
     L.livae_thin_set_tc.restype = None
     L.livae_thin_set_tc.argtypes = [C.c_int]
     L.livae_tc_conv_supported.restype = C.c_int
@@ -125,7 +127,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
 
 
 def ptr(t):

@@ -1,0 +1,38 @@
+"""Pipeline timeline of one traced kernel launch (livae_set_probe): per warp role, the clock64 deltas
+between its pipeline points for CTA 0.  usage: python tools/probe.py <case> [first_record]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "li-vae_b200")]
+import torch
+from livae import _lib, ops
+L = _lib.lib()
+B, dev, bf = int(os.environ.get("MB", "2048")), "cuda", torch.bfloat16
+case = sys.argv[1]
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+if case == "fwd_stn2":
+    x = torch.randn(B, 64, 64, 16, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(32, 16, 5, 5, device=dev), 32, 16, 5, 5, 0)
+    run = lambda: ops.tc_conv(x, wp, None, 5, 5, 1, 2, 1)
+elif case == "fwd_d3":
+    x = torch.randn(B, 66, 66, 64, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(32, 64, 3, 3, device=dev), 32, 64, 3, 3, 0)
+    run = lambda: ops.tc_conv(x, wp, None, 3, 3, 1, 0, 1)
+elif case == "fwd_d1":
+    x = torch.randn(B, 18, 18, 256, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(128, 256, 3, 3, device=dev), 128, 256, 3, 3, 0)
+    run = lambda: ops.tc_conv(x, wp, None, 3, 3, 1, 0, 1)
+elif case == "fwd_c3":
+    x = torch.randn(B, 32, 32, 64, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(128, 64, 4, 4, device=dev), 128, 64, 4, 4, 0)
+    run = lambda: ops.tc_conv(x, wp, None, 4, 4, 2, 1, 1)
+run(); torch.cuda.synchronize()
+buf = torch.zeros(4096, dtype=torch.int64, device=dev)
+L.livae_set_probe(buf.data_ptr())
+run(); torch.cuda.synchronize()
+L.livae_set_probe(None)
+r = buf.cpu().tolist()
+for role, name in enumerate(("producer", "mma", "epilogue", "other")):
+    recs = [(v >> 56, v & ((1 << 56) - 1)) for v in r[role * 1024:(role + 1) * 1024] if v != 0]
+    if not recs:
+        continue
+    print(f"--- {case} {name}: {len(recs)} records; showing from #{first}")
+    prev = recs[first - 1][1] if first > 0 and len(recs) > first else recs[0][1]
+    for i, (s, t) in enumerate(recs[first:first + 24]):
+        print(f"  slot {s}  dt={t - prev:6d}")
+        prev = t
