@@ -183,6 +183,24 @@ int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, const void*
 int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d);
 int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw, float* gb,
                         void* ws, livae_stream_t stream);
+/* ---- conv 5x5 p2 + ReLU + MaxPool2 (STN conv2, model.py:207-209) in space-to-depth form (csrc/conv_s2d.cu):
+ * a 3x3 convolution over 2x2 pixel blocks with 4*Ci -> 4*Co channels; the pooling is the epilogue.
+ *   pack   mode 0: bf16 [9][4*Co][4*Ci] (forward), mode 1: bf16 [9][4*Ci][4*Co] (data gradient), w fp32 [Co][Ci][5][5]
+ *   fwd    x bf16 [B,H,W,Ci] -> y bf16 [B,H/2,W/2,Co] + idx (argmax position 0..3, torch scan order)
+ *   unpool_s2d: pooled PRE-activation gradient + idx -> g_s2d bf16 [B,H/2,W/2,4*Co]
+ *   dgrad  g_s2d -> gx bf16 [B,H,W,Ci], masked by relu_mask (same layout as gx) > 0
+ *   wgrad  gw fp32 [Co][Ci][5][5], gb fp32 [Co] (may be NULL); ws: livae_tc_conv5pool_wgrad_ws_bytes */
+int livae_tc_conv5pool_supported(int B, int H, int W, int Ci, int Co);
+int livae_tc_conv5pool_pack(const float* w, int Co, int Ci, int mode, void* out_bf16, livae_stream_t stream);
+int livae_tc_conv5pool_fwd(const void* x, const void* wpacked0, const float* bias, int B, int H, int W, int Ci, int Co,
+                           void* y, uint8_t* idx, livae_stream_t stream);
+int livae_unpool_s2d_bf16(const void* g_pooled, const uint8_t* idx, int B, int Hp, int Wp, int Co, void* g_s2d,
+                          livae_stream_t stream);
+int livae_tc_conv5pool_dgrad(const void* g_s2d, const void* wpacked1, const void* relu_mask, int B, int H, int W, int Ci,
+                             int Co, void* gx, livae_stream_t stream);
+int64_t livae_tc_conv5pool_wgrad_ws_bytes(int Ci, int Co);
+int livae_tc_conv5pool_wgrad(const void* x, const void* g_s2d, int B, int H, int W, int Ci, int Co, float* gw, float* gb,
+                             void* ws, livae_stream_t stream);
 /* Linear weight gradient: tensor-core layout [N][(h,w,c)] -> torch [N][(c,h,w)] */
 int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float* dst_chw, livae_stream_t stream);
 

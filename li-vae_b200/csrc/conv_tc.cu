@@ -249,6 +249,7 @@ struct ConvTcHaloParams {
   int b_resident;         // 1: all ntaps*nkc weight tiles stay in shared memory for the CTA's lifetime
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
   long long* probe;
+  int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
 };
 
 static constexpr int kSA = 2, kSB = 4;
@@ -312,6 +313,80 @@ __device__ __forceinline__ void epilogue_rows32(uint32_t taddr, int nbase, int N
   }
 }
 
+// epi_mode 1: the N = 4*Co accumulator columns of a row are the 2x2 output pixels (phase = dy*2+dx, torch's
+// max-pool scan order) of one block: bias + ReLU + max / argmax over the four phases.
+__device__ __forceinline__ void epilogue_pool4(uint32_t taddr, int N, bool valid, int64_t pix, void* out,
+                                               uint8_t* __restrict__ idx, const float* __restrict__ sbias) {
+  const int Co = N >> 2;
+  for (int cc = 0; cc < Co; cc += 16) {
+    uint32_t v[4][16];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) tmem_ld16(taddr + (uint32_t)(ph * Co + cc), v[ph]);
+    tmem_ld_wait();
+    if (!valid) continue;
+    uint32_t ow[8], iw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+      float best[2]; uint32_t bi[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float b = sbias[cc + c + j];
+        best[j] = fmaxf(__uint_as_float(v[0][c + j]) + b, 0.f); bi[j] = 0u;
+#pragma unroll
+        for (int ph = 1; ph < 4; ++ph) {
+          const float a = fmaxf(__uint_as_float(v[ph][c + j]) + b, 0.f);
+          if (a > best[j]) { best[j] = a; bi[j] = (uint32_t)ph; }
+        }
+      }
+      __nv_bfloat162 hh = __floats2bfloat162_rn(best[0], best[1]);
+      ow[c >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+      iw[c >> 2] |= (bi[0] << ((c & 3) * 8)) | (bi[1] << (((c & 3) + 1) * 8));
+    }
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Co + cc);
+    op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    op[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    *reinterpret_cast<uint4*>(idx + pix * Co + cc) = make_uint4(iw[0], iw[1], iw[2], iw[3]);
+  }
+}
+
+// epi_mode 2: the N = 4*Ci columns of block (qy,qx) go back to the four pixels of a plain NHWC tensor
+// [B, 2*Hq, 2*Wq, Ci] (bf16), each masked by relu_mask (same layout) > 0.
+__device__ __forceinline__ void epilogue_unblock(uint32_t taddr, int N, bool valid, int b, int qy, int qx, int Hq, int Wq,
+                                                 void* out, const __nv_bfloat16* __restrict__ relu_mask) {
+  const int Ci = N >> 2;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int64_t pix = ((int64_t)b * 2 * Hq + 2 * qy + (ph >> 1)) * (2 * Wq) + 2 * qx + (ph & 1);
+    for (int cc = 0; cc < Ci; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)(ph * Ci + cc), v);
+      uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+      if (relu_mask && valid) {
+        const uint4* mp = reinterpret_cast<const uint4*>(relu_mask + pix * Ci + cc);
+        m0 = __ldg(mp); m1 = __ldg(mp + 1);
+      }
+      tmem_ld_wait();
+      if (!valid) continue;
+      const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
+      const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float f0 = __uint_as_float(v[2 * i]), f1 = __uint_as_float(v[2 * i + 1]);
+        if (relu_mask) {
+          const __nv_bfloat16* mb = i < 4 ? mb0 : mb1;
+          if (!(__bfloat162float(mb[(2 * i) & 7]) > 0.f)) f0 = 0.f;
+          if (!(__bfloat162float(mb[(2 * i + 1) & 7]) > 0.f)) f1 = 0.f;
+        }
+        __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+        w[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Ci + cc);
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  }
+}
+
 // Persistent: grid.x CTAs walk the tile list round-robin.  The accumulator is double-buffered in
 // TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the
 // TMA + MMA main loop of tile i+1, and barrier/TMEM/tensor-map setup is paid once per CTA.
@@ -356,7 +431,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
   }
   for (int i = threadIdx.x; i < p.ntaps; i += kThreads) s_tapoff[i] = ((uint32_t)p.tap_shift[i] * row_bytes) >> 4;
   for (int i = threadIdx.x; i < p.ngroups; i += kThreads) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
-  for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
+  if (p.epi_mode == 1) {
+    for (int i = threadIdx.x; i < (p.N >> 2); i += kThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  } else {
+    for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -387,7 +466,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
             mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
             probe_rec(p.probe, 0, 1, pn);
             mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
+            if (p.a_s2d) tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], 0, x0 + G.dx, 2 * (y0 + G.dy) + c, b);
+            else tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
             ++ia;
             if (p.b_resident) continue;
             for (int t = G.tap_begin; t < G.tap_end; ++t) {
@@ -483,8 +563,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
       mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
       probe_rec(pb, 2, 1, pn);
       tc_fence_after();
-      epilogue_rows32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols, (int)blockIdx.y * p.N, p.N, p.Ntot,
-                      valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
+      if (p.epi_mode == 0)
+        epilogue_rows32(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
+      else if (p.epi_mode == 1)
+        epilogue_pool4(taddr, p.N, valid, ((int64_t)b * p.Hq + qy) * p.Wq + qx, p.out, p.pool_idx, s_bias);
+      else
+        epilogue_unblock(taddr, p.N, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
       probe_rec(pb, 2, 2, pn);
       tc_fence_before();
       __syncwarp();
@@ -571,11 +656,14 @@ static int g_halo_mode = 1;
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // returns 1 when the shape is not eligible for the halo kernel
-static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
-                               int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
-                               const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
-                               const float* bias, int act, const void* relu_mask, cudaStream_t st) {
+int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
+                        int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
+                        const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
+                        const float* bias, int act, const void* relu_mask, cudaStream_t st, HaloOpts opts) {
   ConvTcHaloParams p;
+  p.a_s2d = opts.a_s2d; p.epi_mode = opts.epi_mode; p.pool_idx = opts.pool_idx;
+  if (opts.a_s2d && (Cin != 64 || in_stride != 1)) return 1;
+  if (opts.epi_mode != 0 && (N > 256 || (N & 63))) return 1;
   const int s = in_stride;
   // group taps by the parity class of their input offset; inside a group taps are whole-row/col shifts
   int gkey[4][2]; int ng = 0;
@@ -615,6 +703,7 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + 7) / 8;
   p.Hq = Hq; p.Wq = Wq; p.Ho = Ho; p.Wo = Wo; p.os = os; p.oy0 = oy0; p.ox0 = ox0; p.in_stride = s;
   p.kc = Cin >= 64 ? 64 : Cin;
+  if (opts.a_s2d) p.kc = Cin / 2;          // one K chunk per pixel row of the 2x2 block (see the tensor map below)
   p.nkc = Cin / p.kc;
   int nchunk = N;
   if (N > 256) { nchunk = 256; while (N % nchunk != 0) nchunk -= 16; }
@@ -623,7 +712,19 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   p.probe = g_probe;
   const int row_bytes = p.kc * 2;
   CUtensorMap tmA, tmB;
-  {
+  if (opts.a_s2d) {
+    // Plain NHWC [B, 2*Hin, 2*Win, C] (C = Cin / 4) read block-wise.  K chunk ey (= pixel row inside the
+    // block) is a box over {(ex, c): 2C contiguous elements, X: stride 2C, pixel row r = 2*Y + ey walked
+    // with element stride 2, B}.  (A single 5-D box {2C, ey, X, Y, B} does NOT work: with a swizzled map
+    // TMA lays every innermost-dimension run on its own 128-byte shared-memory row -- measured -- so the two
+    // halves of a block would not be contiguous.)
+    const uint64_t C = (uint64_t)Cin / 4, Wf = 2 * (uint64_t)Win, Hf = 2 * (uint64_t)Hin;
+    uint64_t dims[4] = {2 * C, (uint64_t)Win, Hf, (uint64_t)B};
+    uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
+    uint32_t box[4] = {(uint32_t)(2 * C), 16u, (uint32_t)(2 * p.box_rows), 1u};
+    uint32_t es[4] = {1, 1, 2, 1};
+    if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
+  } else {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(16 * s), (uint32_t)(p.box_rows * s), 1u};
@@ -638,7 +739,9 @@ static int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin,
   }
   const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
-  p.b_resident = ((size_t)ntaps * p.nkc * b_slot <= 72 * 1024) ? 1 : 0;
+  // keep every weight tile in shared memory for the CTA's lifetime whenever they fit next to the two A slots
+  // (even at one CTA per SM: streaming them costs an mbarrier wait + a commit per tap, more than the tap's MMAs)
+  p.b_resident = ((size_t)ntaps * p.nkc * b_slot + (size_t)kSA * a_slot + 1024 <= 200 * 1024) ? 1 : 0;
   const size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
   static bool attr_done = false;
@@ -674,7 +777,7 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
   LIVAE_CHECK_ARG(ntaps >= 1 && ntaps <= kMaxTaps, "tc_conv: too many taps (%d)", ntaps);
   if (g_halo_mode != 0 && ntaps > 1 && Wq >= 8 && Hq >= 4) {
     int rc = launch_conv_tc_halo(in, B, Hin, Win, Cin, wpacked, wtaps, N, Hq, Wq, Ho, Wo, os, oy0, ox0, in_stride,
-                                 ntaps, tdy, tdx, tw_idx, out, out_f32, bias, act, relu_mask, st);
+                                 ntaps, tdy, tdx, tw_idx, out, out_f32, bias, act, relu_mask, st, HaloOpts{0, 0, nullptr});
     if (rc != 1) return rc;   // 1 = shape not eligible, fall through to the per-tap kernel
   }
   ConvTcParams p;

@@ -30,15 +30,21 @@ __device__ __forceinline__ SrcCoord src_coord(float g, int n) {
   float u = ((g + 1.f) * fn - 1.f) * 0.5f;
   float mult = fn * 0.5f;
   float v = u + 0.5f;
-  if (v < 0.f) { v = -v; mult = -mult; }
-  float flips = floorf(v / fn);
-  float extra = fmodf(v, fn);
   float r;
-  if (((int)flips & 1) == 0) {
-    r = extra - 0.5f;
+  if (v >= 0.f && v < fn) {
+    // inside the image (all but the corner pixels of a rotated patch): flips = 0 and fmodf(v, fn) = v
+    // exactly, so this is bit-identical to the general path below without its division and fmodf
+    r = v - 0.5f;
   } else {
-    r = fn - extra - 0.5f;
-    mult = -mult;
+    if (v < 0.f) { v = -v; mult = -mult; }
+    float flips = floorf(v / fn);
+    float extra = fmodf(v, fn);
+    if (((int)flips & 1) == 0) {
+      r = extra - 0.5f;
+    } else {
+      r = fn - extra - 0.5f;
+      mult = -mult;
+    }
   }
   if (r <= 0.f) { r = 0.f; mult = 0.f; }
   else if (r >= fn - 1.f) { r = fn - 1.f; mult = 0.f; }
@@ -100,13 +106,17 @@ __global__ void __launch_bounds__(256) rot_sample_fwd_kernel(
 }
 
 // kSmemGrad: accumulate grad_input in a shared tile; otherwise (image too large for shared
-// memory) fall back to global atomics on a pre-zeroed buffer.
-template <bool kSmemGrad>
+// memory) fall back to global atomics on a pre-zeroed buffer.  kSmemImg: the source image is staged in
+// shared memory as in the forward kernel (the four taps of a pixel are gathers; from global memory they
+// miss L1, which the gradient tile has squeezed to a few KB, on every pixel).
+template <bool kSmemGrad, bool kSmemImg>
 __global__ void __launch_bounds__(512) rot_sample_bwd_kernel(
     const float* __restrict__ img, const float* __restrict__ cs, float sgn,
     const float* __restrict__ gout, int C, int H, int W, float* __restrict__ gimg,
     float* __restrict__ gcs) {
-  extern __shared__ __align__(16) float s_g[];
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_img = s_dyn;                                   // [H*W] when kSmemImg
+  float* s_g = s_dyn + (kSmemImg ? H * W : 0);            // [H*W] when kSmemGrad && gimg
   __shared__ float red[2][32];
   int b = blockIdx.x;
   int n = H * W;
@@ -117,10 +127,17 @@ __global__ void __launch_bounds__(512) rot_sample_bwd_kernel(
     const float* src = img + ((int64_t)b * C + ch) * n;
     const float* go = gout + ((int64_t)b * C + ch) * n;
     float* gi = gimg ? gimg + ((int64_t)b * C + ch) * n : nullptr;
-    if (kSmemGrad && gi) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) s_g[i] = 0.f;
+    if (kSmemImg) {
       __syncthreads();
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(s_img);
+      for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+      for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) s_img[i] = __ldg(src + i);
     }
+    if (kSmemGrad && gi)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s_g[i] = 0.f;
+    if (kSmemImg || (kSmemGrad && gi)) __syncthreads();
+    const float* tap = kSmemImg ? s_img : src;
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
       int i = p / W, j = p - i * W;
       float ys = (2.f * i + 1.f) * invH - 1.f;
@@ -132,11 +149,11 @@ __global__ void __launch_bounds__(512) rot_sample_bwd_kernel(
       float fx = cx.v - fx0, fy = cy.v - fy0;
       bool x1ok = x0 + 1 < W, y1ok = y0 + 1 < H;
       int x1 = x1ok ? x0 + 1 : x0, y1 = y1ok ? y0 + 1 : y0;
-      float g = go[p];
-      float v00 = __ldg(src + y0 * W + x0);
-      float v01 = x1ok ? __ldg(src + y0 * W + x1) : 0.f;
-      float v10 = y1ok ? __ldg(src + y1 * W + x0) : 0.f;
-      float v11 = (x1ok && y1ok) ? __ldg(src + y1 * W + x1) : 0.f;
+      float g = __ldg(go + p);
+      float v00 = tap[y0 * W + x0];
+      float v01 = x1ok ? tap[y0 * W + x1] : 0.f;
+      float v10 = y1ok ? tap[y1 * W + x0] : 0.f;
+      float v11 = (x1ok && y1ok) ? tap[y1 * W + x1] : 0.f;
       if (gi) {
         float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy);
         float w10 = (1.f - fx) * fy, w11 = fx * fy;
@@ -220,18 +237,26 @@ extern "C" int livae_rot_sample_bwd(const float* img, const float* cs, float sgn
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
   size_t bytes = (size_t)H * W * sizeof(float);
-  if (!gimg || bytes <= (size_t)kMaxSmemImage) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(rot_sample_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kMaxSmemImage);
-      attr_done = true;
-    }
-    rot_sample_bwd_kernel<true><<<B, 512, gimg ? bytes : 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(rot_sample_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
+    cudaFuncSetAttribute(rot_sample_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
+    attr_done = true;
+  }
+  const bool aligned = ((uintptr_t)img & 15) == 0;
+  if (!gimg) {
+    if (aligned && bytes <= (size_t)kMaxSmemImage)
+      rot_sample_bwd_kernel<true, true><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+    else
+      rot_sample_bwd_kernel<true, false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+  } else if (aligned && 2 * bytes <= (size_t)kMaxSmemImage) {
+    rot_sample_bwd_kernel<true, true><<<B, 512, 2 * bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+  } else if (bytes <= (size_t)kMaxSmemImage) {
+    rot_sample_bwd_kernel<true, false><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   } else {
     cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)B * C * bytes, st);
     if (e != cudaSuccess) { set_error("rot_sample_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
-    rot_sample_bwd_kernel<false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+    rot_sample_bwd_kernel<false, false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;

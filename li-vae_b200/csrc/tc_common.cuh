@@ -64,6 +64,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma, TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // Byte offset of 16-byte chunk `chunk` of row `row` inside a K-major tile whose rows are `rb` = 32 / 64 /
@@ -169,6 +177,23 @@ EncodeTiledFn get_encode_tiled();
 // bf16 tensor map: dims/strides innermost first; strides in BYTES for dims 1..rank-1
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides, int inner_bytes);
+
+// ---- halo-kernel launchers shared between translation units (conv_tc.cu, wgrad_tc.cu, conv_s2d.cu) ----
+// a_s2d: the input operand is read in SPACE-TO-DEPTH form: `in` is a plain NHWC tensor [B, 2*Hin, 2*Win, Cin/4]
+//        and a strided tensor map delivers each 2x2 pixel block as 4*C channels (order (ey, ex, c)), one K
+//        chunk per pixel row of the block -- no data movement, the re-blocking is done by the TMA strides.
+// epi_mode 0: plain NHWC store; 1: N = 4*Co columns are the four pixels of a 2x2 block -> bias + ReLU +
+//        max-pool over them, pooled bf16 [B,Hq,Wq,Co] + argmax (pool_idx); 2: N = 4*Ci columns are written
+//        back as the four pixels of the block of a plain NHWC tensor [B,2*Hq,2*Wq,Ci] (relu_mask in that layout)
+struct HaloOpts { int a_s2d; int epi_mode; uint8_t* pool_idx; };
+int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
+                        int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
+                        const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
+                        const float* bias, int act, const void* relu_mask, cudaStream_t st, HaloOpts opts);
+// returns 0 = launched, 1 = shape not eligible
+int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho, int Wo,
+                      cudaStream_t st, int x_s2d);
+void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st);   // gb must be zeroed
 
 }  // namespace tc
 }  // namespace livae

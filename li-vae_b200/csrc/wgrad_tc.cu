@@ -198,6 +198,8 @@ struct WgradHaloParams {
   int ngroups, G;
   WgGroup grp[kMaxGroups];
   float* gw_acc;
+  long long* probe;
+  int x_s2d;                   // input operand read in space-to-depth form through a 5-D tensor map (tc_common.cuh)
 };
 
 template <int STAGES>
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmG,
                                                                 const WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_gdesc[8];     // A descriptor of each row group of this CTA, stage 0
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
     if (warp == 0) {
       if (lane == 0) {
         const uint32_t tx_bytes = (uint32_t)p.nbox * p.xbox_bytes + (uint32_t)nboxg * gbox_bytes;
+        int pn = 0;
         for (int it = 0; it < nt; ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -255,18 +259,28 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
           const int tx = tile % p.tiles_x; tile /= p.tiles_x;
           const int ty = tile % p.tiles_y; tile /= p.tiles_y;
           const int b = tile;
+          probe_rec(p.probe, 0, 0, pn);
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          probe_rec(p.probe, 0, 1, pn);
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           uint8_t* st = smem + (uint32_t)s * stage_bytes;
           for (int c = 0; c < nboxg; ++c)
             tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], c * p.kcs, tx * p.TW, ty * p.TH, b);
-          for (int i = 0; i < p.nbox; ++i)
-            tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], p.box_c[i] * p.kcb,
-                        tx * p.TW * p.stride + p.box_dx[i], ty * p.TH * p.stride + p.box_dy[i], b);
+          for (int i = 0; i < p.nbox; ++i) {
+            if (p.x_s2d)   // chunk = pixel row inside the 2x2 block (HaloOpts in tc_common.cuh)
+              tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], 0, tx * p.TW + p.box_dx[i],
+                          2 * (ty * p.TH + p.box_dy[i]) + p.box_c[i], b);
+            else
+              tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], p.box_c[i] * p.kcb,
+                          tx * p.TW * p.stride + p.box_dx[i], ty * p.TH * p.stride + p.box_dy[i], b);
+          }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
+        // single-thread issue loop: every descriptor is "precomputed constant + stage base + K-step
+        // increment" (two 64-bit adds per MMA; building descriptors from kernel parameters inside the
+        // loop cost several hundred cycles of dependent latency per MMA)
         const uint32_t idesc = make_idesc_bf16(128, p.Cs, 1, 1);
         const uint32_t ltx = rbx == 128 ? 2u : rbx == 64 ? 4u : 6u;
         const uint32_t ltg = rbg == 128 ? 2u : rbg == 64 ? 4u : 6u;
@@ -275,22 +289,33 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
         const uint32_t sbog = 8u * rbg;
         const int ksteps = p.TH * p.TW / 16;
         const int rows_per_kstep = 16 / p.TW;   // gy rows covered by one K step
+        const uint32_t a_kstep16 = ((uint32_t)(rows_per_kstep * p.Wx) * rbx) >> 4;
+        const uint32_t b_kstep16 = (16u * rbg) >> 4;
+        const uint64_t bd0 = make_smem_desc(smem_u32(smem) + a_region, gbox_slot, sbog, ltg);
+        const uint32_t stage16 = stage_bytes >> 4;
+        for (int g = 0; g < ng; ++g) {
+          const WgGroup G = p.grp[g0 + g];
+          s_gdesc[g] = make_smem_desc(smem_u32(smem) + G.base_off, G.lbo, sbox, ltx);
+        }
+        uint32_t accum = 0u;
+        int pn = 0;
         for (int it = 0; it < nt; ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          probe_rec(p.probe, 1, 0, pn);
           mbar_wait(&full_bar[s], ph);
+          probe_rec(p.probe, 1, 1, pn);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (uint32_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + a_region;
+          const uint32_t so = (uint32_t)s * stage16;
           for (int g = 0; g < ng; ++g) {
-            const WgGroup G = p.grp[g0 + g];
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t xo = (uint32_t)(k * rows_per_kstep * p.Wx) * rbx;
-              const uint64_t ad = make_smem_desc(a_addr + G.base_off + xo, G.lbo, sbox, ltx);
-              const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 16u * rbg, gbox_slot, sbog, ltg);
-              umma_f16(tmem_base + (uint32_t)(g * p.Cs), ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-            }
+            uint64_t ad = s_gdesc[g] + so;
+            uint64_t bd = bd0 + so;
+            const uint32_t d_addr = tmem_base + (uint32_t)(g * p.Cs);
+            for (int k = 0; k < ksteps; ++k, ad += a_kstep16, bd += b_kstep16)
+              umma_f16(d_addr, ad, bd, idesc, accum | (uint32_t)(k > 0));
           }
+          accum = 1u;
+          probe_rec(p.probe, 1, 2, pn);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&accum_bar);
@@ -370,13 +395,15 @@ using namespace livae::tc;
 static int g_wgrad_halo = 1;
 
 // returns 0 = launched, 1 = shape not eligible (caller falls back to the per-tap kernel)
-static int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho,
-                             int Wo, cudaStream_t st) {
+namespace livae { namespace tc {
+int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho,
+                      int Wo, cudaStream_t st, int x_s2d) {
   const int s = d->stride, kh = d->kh, kw = d->kw, pad = d->pad;
   if (Wo < 8 || Ho < 2 || kh * kw < 2) return 1;
   WgradHaloParams p;
   p.Cb = d->Cin; p.Cs = d->Cout; p.ntaps = kh * kw; p.stride = s; p.B = d->B;
   p.kcb = p.Cb >= 64 ? 64 : p.Cb;
+  if (x_s2d) p.kcb = p.Cb / 2;
   p.kcs = p.Cs >= 64 ? 64 : p.Cs;
   const int nchunk = p.Cb / p.kcb;
   if (nchunk > 8) return 1;
@@ -461,25 +488,26 @@ static int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const v
         g->atom[0] = (int16_t)(taps[prev].idx * 8);
       }
     }
-  } else {   // kcb = 32 / 16: atoms = consecutive-column taps of one (parity, row shift)
-    for (int par = 0; par < npar; ++par)
-      for (int sy = 0; sy <= max_sy; ++sy) {
-        int cnt = 0; WgGroup* g = nullptr;
-        for (int sx = 0; sx <= max_sx; ++sx) {
-          int found = -1;
-          for (int t = 0; t < p.ntaps; ++t) if (taps[t].par == par && taps[t].sy == sy && taps[t].sx == sx) found = t;
-          if (found < 0) continue;
-          if (!g || cnt == apg) {
-            g = new_group(); if (!g) return 1;
-            g->base_off = tap_off(taps[found], 0); g->lbo = rbx; cnt = 0;
+  } else {   // kcb = 32 / 16: atoms = consecutive-column taps of one (parity, row shift, channel chunk)
+    for (int c = 0; c < nchunk; ++c)
+      for (int par = 0; par < npar; ++par)
+        for (int sy = 0; sy <= max_sy; ++sy) {
+          int cnt = 0; WgGroup* g = nullptr;
+          for (int sx = 0; sx <= max_sx; ++sx) {
+            int found = -1;
+            for (int t = 0; t < p.ntaps; ++t) if (taps[t].par == par && taps[t].sy == sy && taps[t].sx == sx) found = t;
+            if (found < 0) continue;
+            if (!g || cnt == apg) {
+              g = new_group(); if (!g) return 1;
+              g->base_off = tap_off(taps[found], c); g->lbo = rbx; cnt = 0;
+            }
+            // atoms are LBO = one pixel row apart: column shifts must be consecutive inside a group
+            int a = (int)((tap_off(taps[found], c) - g->base_off) / rbx);
+            if (a >= apg) { g = new_group(); if (!g) return 1; g->base_off = tap_off(taps[found], c); g->lbo = rbx; a = 0; }
+            g->atom[a] = (int16_t)(taps[found].idx * 8 + c);
+            cnt = a + 1;
           }
-          // atoms are LBO = one pixel row apart: column shifts must be consecutive inside a group
-          int a = (int)((tap_off(taps[found], 0) - g->base_off) / rbx);
-          if (a >= apg) { g = new_group(); if (!g) return 1; g->base_off = tap_off(taps[found], 0); g->lbo = rbx; a = 0; }
-          g->atom[a] = (int16_t)(taps[found].idx * 8);
-          cnt = a + 1;
         }
-      }
   }
   p.ngroups = ng;
   int G = 512 / p.Cs;
@@ -495,13 +523,23 @@ static int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const v
   p.tiles_per_cta = (total_tiles + splits - 1) / splits;
   splits = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.gw_acc = gw_acc;
+  p.probe = g_probe;
+  p.x_s2d = x_s2d;
+  if (x_s2d && (d->Cin != 64 || s != 1)) return 1;
   const int nboxg = p.Cs / p.kcs;
   const uint32_t gbox_slot = ((uint32_t)(TH * p.TW * p.kcs * 2) + 1023u) & ~1023u;
   const uint32_t stage_bytes = (uint32_t)p.nbox * p.box_slot + (uint32_t)nboxg * gbox_slot;
   if (2u * stage_bytes + 1024u > 200u * 1024u) return 1;
 
   CUtensorMap tmX, tmG;
-  {
+  if (x_s2d) {
+    const uint64_t C = (uint64_t)d->Cin / 4, Wf = 2 * (uint64_t)d->Win, Hf = 2 * (uint64_t)d->Hin;
+    uint64_t dims[4] = {2 * C, (uint64_t)d->Win, Hf, (uint64_t)d->B};
+    uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
+    uint32_t box[4] = {(uint32_t)(2 * C), (uint32_t)p.Wx, (uint32_t)(2 * Hbox), 1u};
+    uint32_t es[4] = {1, 1, 2, 1};
+    if (int e = make_tmap_bf16(&tmX, x, 4, dims, str, box, es, p.kcb * 2)) return e;
+  } else {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->Win * d->Cin * 2, (uint64_t)d->Hin * d->Win * d->Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kcb, (uint32_t)(p.Wx * s), (uint32_t)(Hbox * s), 1u};
@@ -528,6 +566,14 @@ static int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const v
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
+
+void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st) {
+  int64_t rows = (R + kNumSMs * 4 - 1) / (kNumSMs * 4);
+  if (rows < 64) rows = 64;
+  colsum_bf16_kernel<<<(int)((R + rows - 1) / rows), 256, 0, st>>>((const __nv_bfloat16*)g, R, C, gb, rows);
+  count_launch(1);
+}
+}}  // namespace livae::tc
 
 extern "C" int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d) {
   if (!d) return 0;
@@ -597,7 +643,7 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   cudaError_t ce = cudaMemsetAsync(ws, 0, (size_t)livae_tc_wgrad_ws_bytes(d), st);
   if (ce != cudaSuccess) { set_error("tc_conv_wgrad memset: %s", cudaGetErrorString(ce)); return (int)ce; }
 
-  int halo_rc = g_wgrad_halo ? launch_wgrad_halo(d, x, gy, (float*)ws, Ho, Wo, st) : 1;
+  int halo_rc = g_wgrad_halo ? launch_wgrad_halo(d, x, gy, (float*)ws, Ho, Wo, st, 0) : 1;
   if (halo_rc != 0 && halo_rc != 1) return halo_rc;
   if (halo_rc == 1) {
 

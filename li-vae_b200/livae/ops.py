@@ -460,3 +460,44 @@ def tc_conv_wgrad(x, gy, kh, kw, stride, pad, want_bias=True):
     ws = torch.empty(L.lib().livae_tc_wgrad_ws_bytes(C.byref(d)) // 4, dtype=torch.float32, device=x.device)
     call("livae_tc_conv_wgrad", C.byref(d), x, gy, gw, gb, ws)
     return gw, gb
+
+
+# ---- conv 5x5 p2 + ReLU + MaxPool2 in space-to-depth form (csrc/conv_s2d.cu; STN conv2, model.py:207-209)
+def conv5pool_supported(B, H, W, Ci, Co):
+    return bool(L.lib().livae_tc_conv5pool_supported(B, H, W, Ci, Co))
+
+
+def conv5pool_pack(w, mode):
+    Co, Ci = w.shape[0], w.shape[1]
+    shape = (9, 4 * Co, 4 * Ci) if mode == 0 else (9, 4 * Ci, 4 * Co)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    call("livae_tc_conv5pool_pack", _c(w), Co, Ci, mode, out)
+    return out
+
+
+def conv5pool_fwd(x, w, bias):
+    """x bf16 [B,H,W,Ci], w fp32 [Co,Ci,5,5] -> (pooled bf16 [B,H/2,W/2,Co], idx uint8)"""
+    B, H, W, Ci = x.shape
+    Co = w.shape[0]
+    y = torch.empty((B, H // 2, W // 2, Co), dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty((B, H // 2, W // 2, Co), dtype=torch.uint8, device=x.device)
+    call("livae_tc_conv5pool_fwd", x, conv5pool_pack(w, 0), bias, B, H, W, Ci, Co, y, idx)
+    return y, idx
+
+
+def conv5pool_bwd(x, w, g_pooled, idx, want_dgrad=True):
+    """x bf16 [B,H,W,Ci] (the layer input = ReLU output of the layer below, used as its mask), g_pooled bf16
+    PRE-activation gradient [B,H/2,W/2,Co] -> (gw fp32 [Co,Ci,5,5], gb fp32 [Co], gx bf16 [B,H,W,Ci] masked by x > 0)"""
+    B, H, W, Ci = x.shape
+    Co = w.shape[0]
+    g4 = torch.empty((B, H // 2, W // 2, 4 * Co), dtype=torch.bfloat16, device=x.device)
+    call("livae_unpool_s2d_bf16", g_pooled, idx, B, H // 2, W // 2, Co, g4)
+    gw = torch.empty_like(w)
+    gb = torch.empty(Co, dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.lib().livae_tc_conv5pool_wgrad_ws_bytes(Ci, Co) // 4, dtype=torch.float32, device=x.device)
+    call("livae_tc_conv5pool_wgrad", x, g4, B, H, W, Ci, Co, gw, gb, ws)
+    gx = None
+    if want_dgrad:
+        gx = torch.empty_like(x)
+        call("livae_tc_conv5pool_dgrad", g4, conv5pool_pack(w, 1), x, B, H, W, Ci, Co, gx)
+    return gw, gb, gx

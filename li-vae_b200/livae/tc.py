@@ -72,10 +72,13 @@ class EncoderTc(Function):
         # --- STN localisation (model.py:203-214)
         a1 = _empty((B, h, h, 16), BF, dev); idx1 = _empty((B, h, h, 16), torch.uint8, dev)
         call("livae_thin_conv1c_fwd", 0, x, w0, b0, B, P, P, a1, idx1)
-        a2f = ops.tc_conv(a1, ops.tc_pack_weights(w3, 32, 16, 5, 5, 0), b3, 5, 5, 1, 2, ACT_RELU)
-        a2 = _empty((B, q4, q4, 32), BF, dev); idx2 = _empty((B, q4, q4, 32), torch.uint8, dev)
-        call("livae_maxpool_bf16", a2f, B, h, h, 32, a2, idx2)
-        del a2f
+        if ops.conv5pool_supported(B, h, h, 16, 32):     # space-to-depth form, pooling in the epilogue
+            a2, idx2 = ops.conv5pool_fwd(a1, w3, b3)
+        else:
+            a2f = ops.tc_conv(a1, ops.tc_pack_weights(w3, 32, 16, 5, 5, 0), b3, 5, 5, 1, 2, ACT_RELU)
+            a2 = _empty((B, q4, q4, 32), BF, dev); idx2 = _empty((B, q4, q4, 32), torch.uint8, dev)
+            call("livae_maxpool_bf16", a2f, B, h, h, 32, a2, idx2)
+            del a2f
         f1 = _linear_fwd(a2.view(B, -1), w7, 32, q4, q4, b7, 32, ACT_RELU)           # fp32 [B,32]
         d9 = L.ConvDesc(L.CONV, B, 1, 1, 32, 2, 1, 1, 1, 0, ACT_NONE, 0)
         vec = _empty((B, 2), torch.float32, dev)
@@ -165,11 +168,14 @@ class EncoderTc(Function):
         gf1b = _empty((B, 32), BF, dev)
         call("livae_relu_mask_cast_bf16", gf1, f1, gf1.numel(), gf1b)
         gw7, gb7, ga2 = _linear_bwd(a2.view(B, -1), w7, 32, q4, q4, gf1b, 32, a2.view(B, -1))
-        g2full = _empty((B, h, h, 32), BF, dev)
-        call("livae_unpool_bf16", ga2, idx2, B, h, h, 32, g2full)
-        gw3, gb3 = ops.tc_conv_wgrad(a1, g2full, 5, 5, 1, 2)
-        ga1 = ops.tc_conv_dgrad(g2full, ops.tc_pack_weights(w3, 32, 16, 5, 5, 2), None, h, h, 5, 5, 1, 2,
-                                relu_mask=a1)
+        if ops.conv5pool_supported(B, h, h, 16, 32):
+            gw3, gb3, ga1 = ops.conv5pool_bwd(a1, w3, ga2.contiguous(), idx2)
+        else:
+            g2full = _empty((B, h, h, 32), BF, dev)
+            call("livae_unpool_bf16", ga2, idx2, B, h, h, 32, g2full)
+            gw3, gb3 = ops.tc_conv_wgrad(a1, g2full, 5, 5, 1, 2)
+            ga1 = ops.tc_conv_dgrad(g2full, ops.tc_pack_weights(w3, 32, 16, 5, 5, 2), None, h, h, 5, 5, 1, 2,
+                                    relu_mask=a1)
         gw0 = torch.empty_like(w0); gb0 = _empty((16,), torch.float32, dev)
         call("livae_thin_conv1c_wgrad", 0, x, ga1, idx1, B, P, P, gw0, gb0)
         return (None, gw0, gb0, gw3, gb3, gw7.view_as(w7), gb7, gw9, gb9) + (None,) * 12

@@ -150,3 +150,33 @@ def test_cast_roundtrip():
     b = ops.cast(x, torch.bfloat16)
     assert torch.equal(b, x.to(torch.bfloat16))
     assert torch.equal(ops.cast(b, torch.float32), b.float())
+
+
+@pytest.mark.parametrize("B,H", [(3, 16), (2, 64), (5, 32)])
+def test_conv5pool_space_to_depth(B, H):
+    """STN conv2 (model.py:207-209) as a 3x3 convolution over 2x2 pixel blocks with the max-pool in the
+    epilogue (csrc/conv_s2d.cu) against conv2d + relu + max_pool2d on the same bf16-rounded operands"""
+    import torch.nn.functional as F
+    from livae import ops
+    rng = np.random.default_rng(B * H)
+    bfr = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    x = bfr(torch.tensor(rng.random((B, 16, H, H)).astype(np.float32))).requires_grad_(True)
+    w = bfr(torch.tensor((rng.standard_normal((32, 16, 5, 5)) * 0.08).astype(np.float32))).requires_grad_(True)
+    b = torch.tensor((rng.standard_normal(32) * 0.1).astype(np.float32), requires_grad=True)
+    full = torch.relu(F.conv2d(x, w, b, padding=2))
+    y, ind = F.max_pool2d(full, 2, 2, return_indices=True)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    xd = nhwc(x.detach()).cuda().to(torch.bfloat16)
+    got, idx = ops.conv5pool_fwd(xd, w.detach().cuda(), b.detach().cuda())
+    assert rel_l2(got.float().cpu(), nhwc(y.detach())) < 5e-3
+    ref_idx = nhwc((((ind // H) % 2) * 2 + (ind % H) % 2).to(torch.uint8))
+    agree = (idx.cpu() == ref_idx).float().mean().item()
+    assert agree > 0.97, agree
+    # backward with the REFERENCE routing
+    g = bfr(torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32))) * (y.detach() > 0)
+    (y * g).sum().backward()
+    gw, gb, gx = ops.conv5pool_bwd(xd, w.detach().cuda(), nhwc(g).cuda().to(torch.bfloat16), ref_idx.cuda())
+    assert rel_l2(gw.cpu(), w.grad) < 1e-3, rel_l2(gw.cpu(), w.grad)
+    assert rel_l2(gb.cpu(), b.grad) < 1e-3
+    want_gx = nhwc(x.grad) * (nhwc(x.detach()) > 0)
+    assert rel_l2(gx.float().cpu(), want_gx) < 5e-3, rel_l2(gx.float().cpu(), want_gx)

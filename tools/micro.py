@@ -63,3 +63,13 @@ for w in which:
             tf = timeit(lambda: call("livae_upsample_pad_fwd_bf16", x, B, hw, hw, c, u))
             tb = timeit(lambda: call("livae_upsample_pad_bwd_bf16", u, B, hw, hw, c, x, gx))
             print(f"upsample {hw}x{hw}x{c}: fwd {tf:.3f} ms ({nb / tf / 1e6:.0f} GB/s)  bwd {tb:.3f} ms ({(nb + x.numel() * 2) / tb / 1e6:.0f} GB/s)")
+    elif w == "rot":
+        from livae._lib import call
+        x = torch.rand(B, 1, 128, 128, device=dev); g = torch.randn(B, 1, 128, 128, device=dev)
+        ang = torch.rand(B, device=dev) * 6.28
+        cs = torch.stack([ang.cos(), ang.sin()], 1).contiguous()
+        out = torch.empty_like(x); gi = torch.empty_like(x); gcs = torch.empty(B, 2, device=dev)
+        nb = B * 128 * 128 * 4
+        t = timeit(lambda: call("livae_rot_sample_fwd", x, cs, 1.0, B, 1, 128, 128, out)); print(f"rot fwd {t:.3f} ms {2 * nb / t / 1e6:.0f} GB/s")
+        t = timeit(lambda: call("livae_rot_sample_bwd", x, cs, 1.0, g, B, 1, 128, 128, gi, gcs)); print(f"rot bwd full {t:.3f} ms {3 * nb / t / 1e6:.0f} GB/s")
+        t = timeit(lambda: call("livae_rot_sample_bwd", x, cs, 1.0, g, B, 1, 128, 128, None, gcs)); print(f"rot bwd grid-only {t:.3f} ms {2 * nb / t / 1e6:.0f} GB/s")

@@ -21,6 +21,15 @@ elif case == "fwd_d1":
 elif case == "fwd_c3":
     x = torch.randn(B, 32, 32, 64, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(128, 64, 4, 4, device=dev), 128, 64, 4, 4, 0)
     run = lambda: ops.tc_conv(x, wp, None, 4, 4, 2, 1, 1)
+if case == "wgrad_stn2":
+    x = torch.randn(B, 64, 64, 16, device=dev).to(bf); g = torch.randn(B, 64, 64, 32, device=dev).to(bf)
+    run = lambda: ops.tc_conv_wgrad(x, g, 5, 5, 1, 2)
+elif case == "wgrad_d3":
+    x = torch.randn(B, 66, 66, 64, device=dev).to(bf); g = torch.randn(B, 64, 64, 32, device=dev).to(bf)
+    run = lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)
+elif case == "wgrad_d1":
+    x = torch.randn(B, 18, 18, 256, device=dev).to(bf); g = torch.randn(B, 16, 16, 128, device=dev).to(bf)
+    run = lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)
 run(); torch.cuda.synchronize()
 buf = torch.zeros(4096, dtype=torch.int64, device=dev)
 L.livae_set_probe(buf.data_ptr())
