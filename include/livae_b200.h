@@ -201,6 +201,12 @@ int livae_tc_conv5pool_dgrad(const void* g_s2d, const void* wpacked1, const void
 int64_t livae_tc_conv5pool_wgrad_ws_bytes(int Ci, int Co);
 int livae_tc_conv5pool_wgrad(const void* x, const void* g_s2d, int B, int H, int W, int Ci, int Co, float* gw, float* gb,
                              void* ws, livae_stream_t stream);
+/* data gradient of a 4x4 stride-2 pad-1 convolution as one 3x3 convolution over the gy grid that writes whole
+ * 2x2 blocks of gx (csrc/conv_s2d.cu); wblk = livae_tc_dgrad_s2blk_pack(w fp32 [Cout][Cin][4][4]) bf16 [9][4*Cin][Cout] */
+int livae_tc_dgrad_s2blk_supported(int Hin, int Win, int Cin, int Cout);
+int livae_tc_dgrad_s2blk_pack(const float* w, int Cout, int Cin, void* out_bf16, livae_stream_t stream);
+int livae_tc_dgrad_s2blk(const void* gy, const void* wblk, const void* relu_mask, int B, int Hin, int Win, int Cin,
+                         int Cout, void* gx, livae_stream_t stream);
 /* Linear weight gradient: tensor-core layout [N][(h,w,c)] -> torch [N][(c,h,w)] */
 int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float* dst_chw, livae_stream_t stream);
 

@@ -303,6 +303,43 @@ __global__ void __launch_bounds__(256) decfc_fwd_kernel(const float* __restrict_
   }
 }
 
+// Weight-stationary bf16 variant: a thread owns 8 consecutive channels of one pixel (its 8 x L weights and
+// biases live in registers), walks a slice of the batch and writes one 16-byte vector per sample --
+// coalesced stores, no per-element index arithmetic, weights read once.  L <= 8.
+template <int LMAX>
+__global__ void __launch_bounds__(256) decfc_fwd_ws_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, int B, int L, int C8, int HW,
+                                                           uint4* __restrict__ out) {
+  const int v = blockIdx.x * 256 + threadIdx.x;         // vector index inside one sample: p * C8 + c8
+  const int nv = HW * C8;
+  if (v >= nv) return;
+  const int p = v / C8, c0 = (v - p * C8) * 8;
+  float wr[8][LMAX], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int row = (c0 + j) * HW + p;
+    br[j] = bias[row];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) wr[j][l] = l < L ? w[(int64_t)row * L + l] : 0.f;
+  }
+  const int bchunk = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  for (int b = b0; b < b1; ++b) {
+    float zl[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) zl[l] = l < L ? __ldg(z + b * L + l) : 0.f;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = br[j];
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) a = fmaf(zl[l], wr[j][l], a);
+      o[j] = fmaxf(a, 0.f);
+    }
+    out[(int64_t)b * nv + v] = f_to_bf8(o);
+  }
+}
+
 // gz[b,l] = sum_n gpre[b,n] w[n,l]; one CTA per sample
 // y == nullptr: gy is already the pre-activation gradient (tensor-core path convention)
 template <typename T>
@@ -548,8 +585,16 @@ extern "C" int livae_decfc_fwd_bf16(const float* z, const float* w, const float*
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(z && w && bias && out, "decfc_fwd_bf16: null pointer");
   if (int e = require_sm100()) return e;
-  decfc_fwd_kernel<__nv_bfloat16><<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(
-      z, w, bias, B, L, C, HW, (__nv_bfloat16*)out);
+  if (L <= 4 && (C & 7) == 0 && ((uintptr_t)out & 15) == 0) {
+    const int nv = HW * (C / 8);
+    const int gx = (nv + 255) / 256;
+    int gy = (kNumSMs * 8 + gx - 1) / gx;
+    if (gy > B) gy = B;
+    decfc_fwd_ws_kernel<4><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C / 8, HW, (uint4*)out);
+  } else {
+    decfc_fwd_kernel<__nv_bfloat16><<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(
+        z, w, bias, B, L, C, HW, (__nv_bfloat16*)out);
+  }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

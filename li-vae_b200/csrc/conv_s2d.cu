@@ -8,7 +8,7 @@
 // outside the 5x5 window: 69 % dense), i.e. 36 MMAs of N = 128 per 512 pixels -- 2.3x fewer tensor-pipe
 // cycles per pixel forward, 3-4x fewer for the gradients -- and the 2x2 max-pool becomes a max over four
 // column groups of the accumulator row, done in the epilogue: the un-pooled activation never exists.
-// The re-blocking costs nothing: a 5-D TMA tensor map reads the plain NHWC tensor block-wise (HaloOpts).
+// The re-blocking costs nothing: a strided TMA tensor map reads the plain NHWC tensor block-wise (HaloOpts).
 //
 //   forward : x [B,H,W,16] --s2d--> [B,H/2,W/2,64] * W'[9][128][64] -> pooled y [B,H/2,W/2,32] + argmax
 //   dgrad   : g (pooled, routed by argmax) --unpool_s2d--> [B,H/2,W/2,128] * W''[9][64][128] -> gx [B,H,W,16]
@@ -80,6 +80,24 @@ __global__ void fold_s2d_wgrad_kernel(const float* __restrict__ acc, const float
   }
   if (gb && blockIdx.x == 0)
     for (int co = threadIdx.x; co < Co; co += blockDim.x) gb[co] = gb4[co] + gb4[Co + co] + gb4[2 * Co + co] + gb4[3 * Co + co];
+}
+
+// Data gradient of a 4x4 stride-2 pad-1 convolution (encoder c2-c4, model.py:292-296) as ONE 3x3
+// convolution over the gy grid that produces whole 2x2 blocks of gx:
+//   out[tap = (DY+1)*3 + DX+1][n = (ey,ex,ci)][k = co] = w[co][ci][ky][kx],  ky = ey + 1 - 2*DY, kx = ex + 1 - 2*DX
+// (zero outside the 4x4 filter: 4 of 9 taps per output phase).  Compared with the four per-parity launches
+// this reads gy once, writes gx in full 128-byte lines and has N = 4*Cin instead of Cin.
+__global__ void pack_s2blk_kernel(const float* __restrict__ w, int Co, int Ci, __nv_bfloat16* __restrict__ out) {
+  const int N = 4 * Ci, total = 9 * N * Co;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Co; int t = i / Co; const int n = t % N; const int tap = t / N;
+    const int DY = tap / 3 - 1, DX = tap % 3 - 1;
+    const int ph = n / Ci, ci = n % Ci;
+    const int ky = (ph >> 1) + 1 - 2 * DY, kx = (ph & 1) + 1 - 2 * DX;
+    float v = 0.f;
+    if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) v = w[((co * Ci + ci) * 4 + ky) * 4 + kx];
+    out[i] = __float2bfloat16_rn(v);
+  }
 }
 
 static void block_taps(int* tdy, int* tdx, int* tw) {
@@ -184,4 +202,35 @@ extern "C" int livae_tc_conv5pool_wgrad(const void* x, const void* g_s2d, int B,
   fold_s2d_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, gb4, Co, Ci, gw, gb);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
+}
+
+// ---- 4x4 stride-2 pad-1 data gradient in block form (see pack_s2blk_kernel) ----
+extern "C" int livae_tc_dgrad_s2blk_supported(int Hin, int Win, int Cin, int Cout) {
+  return ((Hin | Win) & 1) == 0 && Hin >= 16 && Win >= 16 && (Cin == 16 || Cin == 32 || Cin == 64) &&
+         (Cout == 32 || (Cout % 64) == 0) ? 1 : 0;
+}
+// w fp32 [Cout][Cin][4][4] -> bf16 [9][4*Cin][Cout]
+extern "C" int livae_tc_dgrad_s2blk_pack(const float* w, int Cout, int Cin, void* out_bf16, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(w && out_bf16 && Cout > 0 && Cin > 0, "tc_dgrad_s2blk_pack: bad args");
+  if (int e = require_sm100()) return e;
+  const int n = 9 * 4 * Cin * Cout;
+  pack_s2blk_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__nv_bfloat16*)out_bf16);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+// gx bf16 [B,Hin,Win,Cin] = data gradient of conv(Cin->Cout, 4x4, s2, p1) at gy bf16 [B,Hin/2,Win/2,Cout], times (relu_mask > 0)
+extern "C" int livae_tc_dgrad_s2blk(const void* gy, const void* wblk, const void* relu_mask, int B, int Hin, int Win, int Cin,
+                                    int Cout, void* gx, livae_stream_t stream) {
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(livae_tc_dgrad_s2blk_supported(Hin, Win, Cin, Cout), "tc_dgrad_s2blk: shape not supported");
+  LIVAE_CHECK_ARG(gy && wblk && gx, "tc_dgrad_s2blk: null pointer");
+  LIVAE_CHECK_ARG((((uintptr_t)gy | (uintptr_t)wblk | (uintptr_t)gx | (uintptr_t)relu_mask) & 15) == 0, "tc_dgrad_s2blk: alignment");
+  if (int e = require_sm100()) return e;
+  int tdy[9], tdx[9], tw[9];
+  block_taps(tdy, tdx, tw);
+  const int Ho = Hin / 2, Wo = Win / 2;
+  int rc = launch_conv_tc_halo(gy, B, Ho, Wo, Cout, wblk, 9, 4 * Cin, Ho, Wo, Ho, Wo, 1, 0, 0, 1, 9, tdy, tdx, tw, gx, 0,
+                               nullptr, LIVAE_ACT_NONE, relu_mask, (cudaStream_t)stream, HaloOpts{0, 2, nullptr});
+  if (rc == 1) { set_error("tc_dgrad_s2blk: shape rejected by the halo kernel"); return -1; }
+  return rc;
 }

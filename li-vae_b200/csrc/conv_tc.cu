@@ -350,40 +350,52 @@ __device__ __forceinline__ void epilogue_pool4(uint32_t taddr, int N, bool valid
 }
 
 // epi_mode 2: the N = 4*Ci columns of block (qy,qx) go back to the four pixels of a plain NHWC tensor
-// [B, 2*Hq, 2*Wq, Ci] (bf16), each masked by relu_mask (same layout) > 0.
-__device__ __forceinline__ void epilogue_unblock(uint32_t taddr, int N, bool valid, int b, int qy, int qx, int Hq, int Wq,
+// [B, 2*Hq, 2*Wq, Ci] (bf16), each masked by relu_mask (same layout) > 0.  The mask vectors of phase p+1 are
+// requested before phase p is processed (a global-load latency per 16 columns made this epilogue slower than
+// the tile's MMAs).  CI16 = Ci / 16 (1, 2 or 4).
+template <int CI16>
+__device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int b, int qy, int qx, int Hq, int Wq,
                                                  void* out, const __nv_bfloat16* __restrict__ relu_mask) {
-  const int Ci = N >> 2;
-  for (int ph = 0; ph < 4; ++ph) {
-    const int64_t pix = ((int64_t)b * 2 * Hq + 2 * qy + (ph >> 1)) * (2 * Wq) + 2 * qx + (ph & 1);
-    for (int cc = 0; cc < Ci; cc += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)(ph * Ci + cc), v);
-      uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-      if (relu_mask && valid) {
-        const uint4* mp = reinterpret_cast<const uint4*>(relu_mask + pix * Ci + cc);
-        m0 = __ldg(mp); m1 = __ldg(mp + 1);
-      }
-      tmem_ld_wait();
-      if (!valid) continue;
-      const __nv_bfloat16* mb0 = reinterpret_cast<const __nv_bfloat16*>(&m0);
-      const __nv_bfloat16* mb1 = reinterpret_cast<const __nv_bfloat16*>(&m1);
-      uint32_t w[8];
+  constexpr int Ci = CI16 * 16;
+  const bool use_mask = relu_mask != nullptr && valid;
+  uint4 mnext[2 * CI16];
+  auto pix_of = [&](int ph) { return ((int64_t)b * 2 * Hq + 2 * qy + (ph >> 1)) * (2 * Wq) + 2 * qx + (ph & 1); };
+  auto load_mask = [&](int ph) {
+    const uint4* mp = reinterpret_cast<const uint4*>(relu_mask + pix_of(ph) * Ci);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float f0 = __uint_as_float(v[2 * i]), f1 = __uint_as_float(v[2 * i + 1]);
-        if (relu_mask) {
-          const __nv_bfloat16* mb = i < 4 ? mb0 : mb1;
-          if (!(__bfloat162float(mb[(2 * i) & 7]) > 0.f)) f0 = 0.f;
-          if (!(__bfloat162float(mb[(2 * i + 1) & 7]) > 0.f)) f1 = 0.f;
+    for (int i = 0; i < 2 * CI16; ++i) mnext[i] = __ldg(mp + i);
+  };
+  if (use_mask) load_mask(0);
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph) {
+    uint32_t v[CI16][16];
+#pragma unroll
+    for (int c = 0; c < CI16; ++c) tmem_ld16(taddr + (uint32_t)(ph * Ci + c * 16), v[c]);
+    uint4 m[2 * CI16];
+#pragma unroll
+    for (int i = 0; i < 2 * CI16; ++i) m[i] = mnext[i];
+    if (use_mask && ph < 3) load_mask(ph + 1);
+    tmem_ld_wait();
+    if (!valid) continue;
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix_of(ph) * Ci);
+#pragma unroll
+    for (int c = 0; c < CI16; ++c)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m[2 * c + h]);
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float f0 = __uint_as_float(v[c][h * 8 + 2 * i]), f1 = __uint_as_float(v[c][h * 8 + 2 * i + 1]);
+          if (relu_mask) {
+            if (!(__bfloat162float(mb[2 * i]) > 0.f)) f0 = 0.f;
+            if (!(__bfloat162float(mb[2 * i + 1]) > 0.f)) f1 = 0.f;
+          }
+          __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+          w[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
-        w[i] = *reinterpret_cast<uint32_t*>(&hh);
+        o[2 * c + h] = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Ci + cc);
-      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    }
   }
 }
 
@@ -394,8 +406,10 @@ __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, int N, bool val
 // with livae_set_probe: descriptor construction from kernel parameters cost ~450 cycles per MMA, 10x the
 // MMA itself), so the loop is reduced to: one shared-memory load (tap offset, precomputed in descriptor
 // units) + two 64-bit adds per tap, K steps unrolled at compile time.
-template <int KSTEPS>
-__global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+// EPI = epilogue mode (HaloOpts): a template parameter so that the register-hungry pooled / un-blocking
+// epilogues do not cost the plain convolutions their occupancy.
+template <int KSTEPS, int EPI>
+__global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
   }
   for (int i = threadIdx.x; i < p.ntaps; i += kThreads) s_tapoff[i] = ((uint32_t)p.tap_shift[i] * row_bytes) >> 4;
   for (int i = threadIdx.x; i < p.ngroups; i += kThreads) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
-  if (p.epi_mode == 1) {
+  if (EPI == 1) {
     for (int i = threadIdx.x; i < (p.N >> 2); i += kThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   } else {
     for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
@@ -564,12 +578,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_halo_kernel(const __grid_con
       probe_rec(pb, 2, 1, pn);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
-      if (p.epi_mode == 0)
+      if (EPI == 0)
         epilogue_rows32(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
-      else if (p.epi_mode == 1)
+      else if (EPI == 1)
         epilogue_pool4(taddr, p.N, valid, ((int64_t)b * p.Hq + qy) * p.Wq + qx, p.out, p.pool_idx, s_bias);
+      else if (p.N == 64)
+        epilogue_unblock<1>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
+      else if (p.N == 128)
+        epilogue_unblock<2>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
       else
-        epilogue_unblock(taddr, p.N, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
+        epilogue_unblock<4>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
       probe_rec(pb, 2, 2, pn);
       tc_fence_before();
       __syncwarp();
@@ -663,7 +681,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   ConvTcHaloParams p;
   p.a_s2d = opts.a_s2d; p.epi_mode = opts.epi_mode; p.pool_idx = opts.pool_idx;
   if (opts.a_s2d && (Cin != 64 || in_stride != 1)) return 1;
-  if (opts.epi_mode != 0 && (N > 256 || (N & 63))) return 1;
+  if (opts.epi_mode != 0 && N != 64 && N != 128 && N != 256) return 1;
   const int s = in_stride;
   // group taps by the parity class of their input offset; inside a group taps are whole-row/col shifts
   int gkey[4][2]; int ng = 0;
@@ -746,9 +764,11 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   if (smem > 200 * 1024) return 1;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * B;
@@ -762,9 +782,16 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   if (per_sm < 1) per_sm = 1;
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
-  if (p.kc == 64) conv_tc_halo_kernel<4><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
-  else if (p.kc == 32) conv_tc_halo_kernel<2><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
-  else conv_tc_halo_kernel<1><<<dim3(gx, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
+  const dim3 grid(gx, N / p.N);
+  if (opts.epi_mode == 1) {
+    if (p.kc != 32) return 1;
+    conv_tc_halo_kernel<2, 1><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else if (opts.epi_mode == 2) {
+    if (p.kc != 64) return 1;
+    conv_tc_halo_kernel<4, 2><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else if (p.kc == 64) conv_tc_halo_kernel<4, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 32) conv_tc_halo_kernel<2, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  else conv_tc_halo_kernel<1, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

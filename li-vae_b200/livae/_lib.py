@@ -72,6 +72,8 @@ _SIGS = {
     "livae_tc_conv_dgrad": "t" + "p" * 5 + "s",
     "livae_tc_conv_wgrad": "t" + "p" * 5 + "s",
     "livae_cast": "pipils",
+    "livae_tc_dgrad_s2blk_pack": "piips",
+    "livae_tc_dgrad_s2blk": "pppiiiiips",
     "livae_tc_conv5pool_pack": "piiips",
     "livae_tc_conv5pool_fwd": "pppiiiiipps",
     "livae_unpool_s2d_bf16": "ppiiiips",
@@ -116,6 +118,8 @@ def lib():
     L.livae_set_probe.argtypes = [C.c_void_p]
     L.livae_thin_set_tc.restype = None
     L.livae_thin_set_tc.argtypes = [C.c_int]
+    L.livae_tc_dgrad_s2blk_supported.restype = C.c_int
+    L.livae_tc_dgrad_s2blk_supported.argtypes = [C.c_int] * 4
     L.livae_tc_conv5pool_supported.restype = C.c_int
     L.livae_tc_conv5pool_supported.argtypes = [C.c_int] * 5
     L.livae_tc_conv5pool_wgrad_ws_bytes.restype = C.c_int64
@@ -136,7 +140,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
 
 
 def ptr(t):

@@ -501,3 +501,19 @@ def conv5pool_bwd(x, w, g_pooled, idx, want_dgrad=True):
         gx = torch.empty_like(x)
         call("livae_tc_conv5pool_dgrad", g4, conv5pool_pack(w, 1), x, B, H, W, Ci, Co, gx)
     return gw, gb, gx
+
+
+def dgrad_s2blk_supported(Hin, Win, Cin, Cout):
+    return bool(L.lib().livae_tc_dgrad_s2blk_supported(Hin, Win, Cin, Cout))
+
+
+def dgrad_s2blk(gy, w, Hin, Win, relu_mask=None):
+    """data gradient of conv(Cin->Cout, 4x4, stride 2, pad 1): gy bf16 [B,Hin/2,Win/2,Cout], w fp32 [Cout,Cin,4,4]
+    -> gx bf16 [B,Hin,Win,Cin] (times relu_mask > 0); one launch in block form (csrc/conv_s2d.cu)"""
+    B = gy.shape[0]
+    Cout, Cin = w.shape[0], w.shape[1]
+    wblk = torch.empty((9, 4 * Cin, Cout), dtype=torch.bfloat16, device=gy.device)
+    call("livae_tc_dgrad_s2blk_pack", _c(w), Cout, Cin, wblk)
+    gx = torch.empty((B, Hin, Win, Cin), dtype=torch.bfloat16, device=gy.device)
+    call("livae_tc_dgrad_s2blk", gy, wblk, relu_mask, B, Hin, Win, Cin, Cout, gx)
+    return gx

@@ -58,6 +58,13 @@ def _linear_bwd(x2d, w, Cb, kh, kw, g_bf, Npad, relu_mask):
     return gw, gb[:N].contiguous(), gx
 
 
+def _dgrad_s2(gy, w, Cout, Cin, hin, mask):
+    """data gradient of an encoder 4x4 stride-2 convolution, masked by the ReLU of the layer below"""
+    if ops.dgrad_s2blk_supported(hin, hin, Cin, Cout):
+        return ops.dgrad_s2blk(gy, w, hin, hin, relu_mask=mask)
+    return ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, Cout, Cin, 4, 4, 2), None, hin, hin, 4, 4, 2, 1, relu_mask=mask)
+
+
 class EncoderTc(Function):
     """(x, 20 parameters) -> (mu, logvar, theta); reference Encoder.forward, model.py:305-326"""
 
@@ -131,14 +138,11 @@ class EncoderTc(Function):
         gh4 = gh4.view(B, q16, q16, 256)
         # --- encoder convs c4, c3, c2 (tensor cores)
         gw6, gb6 = ops.tc_conv_wgrad(h3, gh4, 4, 4, 2, 1)
-        gh3 = ops.tc_conv_dgrad(gh4, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 2), None, P // 8, P // 8, 4, 4, 2, 1,
-                                relu_mask=h3)
+        gh3 = _dgrad_s2(gh4, c6w, 256, 128, P // 8, h3)
         gw4, gb4 = ops.tc_conv_wgrad(h2, gh3, 4, 4, 2, 1)
-        gh2 = ops.tc_conv_dgrad(gh3, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 2), None, q4, q4, 4, 4, 2, 1,
-                                relu_mask=h2)
+        gh2 = _dgrad_s2(gh3, c4w, 128, 64, q4, h2)
         gw2, gb2 = ops.tc_conv_wgrad(h1, gh2, 4, 4, 2, 1)
-        gh1 = ops.tc_conv_dgrad(gh2, ops.tc_pack_weights(c2w, 64, 32, 4, 4, 2), None, h, h, 4, 4, 2, 1,
-                                relu_mask=h1)
+        gh1 = _dgrad_s2(gh2, c2w, 64, 32, h, h1)
         # --- encoder c1 (thin) and the rotation
         gc0w = torch.empty_like(c0w); gc0b = _empty((32,), torch.float32, dev)
         call("livae_thin_conv1c_wgrad", 1, x_rot, gh1, None, B, P, P, gc0w, gc0b)

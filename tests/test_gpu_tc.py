@@ -180,3 +180,24 @@ def test_conv5pool_space_to_depth(B, H):
     assert rel_l2(gb.cpu(), b.grad) < 1e-3
     want_gx = nhwc(x.grad) * (nhwc(x.detach()) > 0)
     assert rel_l2(gx.float().cpu(), want_gx) < 5e-3, rel_l2(gx.float().cpu(), want_gx)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(3, 32, 32, 64), (2, 16, 64, 128), (4, 64, 32, 64)])
+def test_dgrad_stride2_block_form(B, H, Cin, Cout):
+    """data gradient of conv 4x4 s2 p1 as one 3x3 block convolution (csrc/conv_s2d.cu) vs autograd"""
+    import torch.nn.functional as F
+    from livae import ops
+    if not ops.dgrad_s2blk_supported(H, H, Cin, Cout):
+        pytest.skip("shape not eligible")
+    rng = np.random.default_rng(B + H + Cin)
+    bfr = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    x = torch.tensor(rng.standard_normal((B, Cin, H, H)).astype(np.float32), requires_grad=True)
+    w = bfr(torch.tensor((rng.standard_normal((Cout, Cin, 4, 4)) / np.sqrt(16 * Cin)).astype(np.float32)))
+    y = F.conv2d(x, w, None, stride=2, padding=1)
+    g = bfr(torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32)))
+    (y * g).sum().backward()
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    mask = torch.tensor(rng.standard_normal((B, H, H, Cin)).astype(np.float32)).cuda().to(torch.bfloat16)
+    gx = ops.dgrad_s2blk(nhwc(g).cuda().to(torch.bfloat16), w.cuda(), H, H, relu_mask=mask)
+    want = nhwc(x.grad) * (mask.float().cpu() > 0)
+    assert rel_l2(gx.float().cpu(), want) < 5e-3, rel_l2(gx.float().cpu(), want)
