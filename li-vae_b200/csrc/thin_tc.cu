@@ -898,6 +898,235 @@ static int launch_wg(const float* src, const void* big, const uint8_t* idx, int 
   return 0;
 }
 
+// =============================================================================================
+// C'. STN conv1 weight gradient, pixel-phase folded (W = 128)
+// =============================================================================================
+// gw[c][ky][kx] = sum_{b,y,x} imgpad[y+ky][x+kx] * G[y][x][c]  (G = un-pooled gradient, 16 channels).
+// Writing x = 8*xg + ph turns one image ROW into a single K = 16 UMMA:
+//     D[(ph, c)][(ky, j)] += sum_xg  G[y][8*xg + ph][c] * imgpad[y + ky][8*xg + j],      j = ph + kx in [0, 12)
+//   A (MN-major, M = 8 phases x 16 channels = 128): the un-pooled gradient row exactly as it lies in memory,
+//     assembled by the builder warps from the pooled gradient + argmax (bulk-copied ring);
+//   B (K-major, 32-byte rows): R[r*12 + j][xg] = imgpad[r][8*xg + j], built ONCE per image for all 132 rows;
+//     the operand of image row y is the 64-row window starting at row 12*y (rows 60..63 = garbage columns);
+//     hi and lo bf16 copies (two MMAs into the same accumulator) keep the image exact to ~2^-17.
+// 256 MMAs per image instead of 1024, every one with all 128 accumulator rows useful, and an eighth of the
+// thread-side operand assembly of the tap-row formulation above.  gw[c][ky][kx] = sum_ph D[(ph,c)][(ky, ph+kx)].
+static int g_fold = 1;
+static constexpr int kFoldA = 6, kFoldP = 8, kFoldIssuers = 3, kFoldTeams = 2, kFoldTeamW = 8;
+static constexpr int kFoldFirstB = 1 + kFoldIssuers;
+static constexpr int kFoldThreads = 32 * (kFoldFirstB + kFoldTeams * kFoldTeamW);
+static constexpr uint32_t kFoldBRows = 1600;          // 132 * 12 = 1584 rows + the tail the last window reads
+
+struct FoldParams {
+  const float* img; const void* gp; const uint8_t* idx;
+  int B;
+  float* gw; float* gb;
+};
+
+__global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const FoldParams p) {
+  constexpr int H = 128, W = 128, Hp = 64, Wp = 64;
+  constexpr uint32_t A_BYTES = 4096, P_SLOT = 4096, B_ARR = kFoldBRows * 32u;
+  constexpr int NBUILD = 32 * kFoldTeams * kFoldTeamW;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kFoldA], a_empty[kFoldA], p_full[kFoldP], p_empty[kFoldP], b_free, accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_gb[16];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sBhi = smem;
+  uint8_t* sBlo = sBhi + B_ARR;
+  uint8_t* sA = sBlo + B_ARR;
+  uint8_t* sP = sA + kFoldA * A_BYTES;
+  float* sD = reinterpret_cast<float*>(sA);            // epilogue scratch [128][65], after the pipeline drained (33 KB: A + P rings)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kFoldA; ++s) { mbar_init(&a_full[s], kFoldTeamW); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kFoldP; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], kFoldTeams * kFoldTeamW); }
+    mbar_init(&b_free, kFoldIssuers);
+    mbar_init(&accum_bar, kFoldIssuers);
+    fence_barrier_init();
+  }
+  if (tid < 16) s_gb[tid] = 0.f;
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  int nimg = 0;
+  for (int img = blockIdx.x; img < p.B; img += gridDim.x) ++nimg;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: pooled gradient rows + argmax
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+        for (int py = 0; py < Hp; ++py, ++g) {
+          const uint32_t s = g % kFoldP;
+          mbar_wait(&p_empty[s], ((g / kFoldP) & 1u) ^ 1u);
+          const int64_t ps = ((int64_t)img * Hp + py) * Wp;
+          mbar_arrive_expect_tx(&p_full[s], Wp * 48u);
+          bulk_load_1d(sP + s * P_SLOT, reinterpret_cast<const __nv_bfloat16*>(p.gp) + ps * 16, Wp * 32u, &p_full[s]);
+          bulk_load_1d(sP + s * P_SLOT + 2048, p.idx + ps * 16, Wp * 16u, &p_full[s]);
+        }
+    }
+  } else if (warp < kFoldFirstB) {
+    // ------------------------------------------------------------------ MMA issuers (row g -> issuer g % 3)
+    if (lane == 0) {
+      const uint32_t wi = (uint32_t)(warp - 1);
+      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 0);    // A MN-major, B K-major
+      // A: two M atoms of 64 (LBO = 2048 B), K atoms of 8 rows 1024 B apart; B: 32-byte rows, 8-row groups 256 B apart
+      const uint64_t ad0 = make_smem_desc(smem_u32(sA), 2048u, 1024u, 2u);
+      const uint64_t bh0 = make_smem_desc(smem_u32(sBhi), 16u, 256u, 6u);
+      const uint64_t bl0 = make_smem_desc(smem_u32(sBlo), 16u, 256u, 6u);
+      const uint32_t d_addr = tmem_base + wi * 64u;
+      const uint32_t total = (uint32_t)nimg * H;
+      uint32_t a = wi % kFoldA, pa = 0u, first = 1u;
+      for (uint32_t g = wi; g < total; g += kFoldIssuers) {
+        const uint32_t y = g % H;
+        mbar_wait(&a_full[a], pa);
+        tc_fence_after();
+        const uint64_t ad = ad0 + ((a * A_BYTES) >> 4);
+        const uint32_t boff = (y * 12u * 32u) >> 4;
+        umma_f16(d_addr, ad, bh0 + boff, idesc, first ? 0u : 1u);
+        umma_f16(d_addr, ad, bl0 + boff, idesc, 1u);
+        first = 0u;
+        umma_commit(&a_empty[a]);
+        // last row of an image handled by this issuer: the B arrays may be rebuilt once these MMAs are done
+        if (y + kFoldIssuers >= (uint32_t)H) umma_commit(&b_free);
+        a += kFoldIssuers; if (a >= kFoldA) { a -= kFoldA; pa ^= 1u; }
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ builders
+    const int bw = warp - kFoldFirstB, bt = tid - 32 * kFoldFirstB;
+    const int team = bw / kFoldTeamW;
+    const int task = (bw - team * kFoldTeamW) * 32 + lane;        // (pixel x, channel half h) of the image row
+    const int x = task >> 1, h = task & 1;
+    const int xg = x >> 3, ph = x & 7;
+    // MN-major, 128-byte swizzled: M atom (ph / 4) * 2048 + K atom (xg / 8) * 1024 + K row (xg % 8) * 128 + 16-byte chunk
+    const uint32_t a_off = (uint32_t)(ph >> 2) * 2048u + (uint32_t)(xg >> 3) * 1024u + (uint32_t)(xg & 7) * 128u +
+                           ((((uint32_t)(ph & 3) * 2u + (uint32_t)h) ^ (uint32_t)(xg & 7)) << 4);
+    float gsum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
+    uint32_t gbase = 0, ii = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, gbase += H, ++ii) {
+      // ---- B arrays of this image: R[r*12 + j][xg] = imgpad[r][8*xg + j] (hi and lo)
+      if (ii > 0) mbar_wait(&b_free, (ii - 1) & 1u);             // the previous image's MMAs are done reading them
+      const float* im = p.img + (int64_t)img * H * W;
+      for (int c = bt; c < 132 * 12 * 2; c += NBUILD) {           // chunk = (row n, 8 consecutive xg)
+        const int n = c >> 1, kh = c & 1;
+        const int r = n / 12, j = n - r * 12;
+        const int iy = r - 2;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ix = 8 * (kh * 8 + e) + j - 2;
+          v[e] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(im + iy * W + ix) : 0.f;
+        }
+        uint32_t hl[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hl[e] = split_hi_lo(v[e]);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { hi[e] = __byte_perm(hl[2 * e], hl[2 * e + 1], 0x5410); lo[e] = __byte_perm(hl[2 * e], hl[2 * e + 1], 0x7632); }
+        const uint32_t o = swz_off((uint32_t)n, (uint32_t)kh, 32u);
+        *reinterpret_cast<uint4*>(sBhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sBlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");
+      // ---- one A tile per image row: un-pool the gradient row y
+      for (int y = team; y < H; y += kFoldTeams) {
+        const uint32_t g = gbase + (uint32_t)y;
+        const uint32_t a = g % kFoldA;
+        const uint32_t gp_ = (gbase >> 1) + (uint32_t)(y >> 1);   // global pooled-row counter
+        const uint32_t ps = gp_ % kFoldP;
+        mbar_wait(&p_full[ps], (gp_ / kFoldP) & 1u);
+        const int local = (x >> 1) * 2 + h;                       // 16-byte units of the pooled slot
+        const uint4 pg = *reinterpret_cast<const uint4*>(sP + ps * P_SLOT + local * 16);
+        const uint2 pi = *reinterpret_cast<const uint2*>(sP + ps * P_SLOT + 2048 + local * 8);
+        const uint32_t pos = (uint32_t)(((y & 1) << 1) | (x & 1));
+        const uint32_t gv[4] = {pg.x, pg.y, pg.z, pg.w};
+        uint32_t ov[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t iw = e < 2 ? pi.x : pi.y;
+          const uint32_t i0 = (iw >> ((e & 1) * 16)) & 0xffu, i1 = (iw >> ((e & 1) * 16 + 8)) & 0xffu;
+          ov[e] = (i0 == pos ? (gv[e] & 0xffffu) : 0u) | (i1 == pos ? (gv[e] & 0xffff0000u) : 0u);
+          gsum[2 * e] += __uint_as_float(ov[e] << 16);
+          gsum[2 * e + 1] += __uint_as_float(ov[e] & 0xffff0000u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[ps]);                // pooled slot consumed (it is in registers)
+        mbar_wait(&a_empty[a], ((g / kFoldA) & 1u) ^ 1u);
+        *reinterpret_cast<uint4*>(sA + a * A_BYTES + a_off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[a]);
+      }
+    }
+    // ---- bias gradient: channel (h*8 + e) summed over this thread's pixels, then over the CTA
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = gsum[e];
+      // lanes with equal h: xor-shuffle over the x bits of the lane index (bits 1..4)
+#pragma unroll
+      for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((lane >> 1) == 0) atomicAdd(&s_gb[h * 8 + e], v);
+    }
+    // ---- epilogue: D[(ph,c)][(ky,j)] summed over the issuers' accumulators -> gw[c][ky][kx] += D[..][(ky, ph+kx)]
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");       // every builder is past the rings: reuse them as scratch
+    if (bw < 4) {
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      float acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+      for (uint32_t wi = 0; wi < (uint32_t)kFoldIssuers && wi < (uint32_t)nimg * H; ++wi) {
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + wi * 64u + (uint32_t)cc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[cc + c] += __uint_as_float(v[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) sD[m * 65 + c] = acc[c];
+      __syncwarp();
+      const int mph = m >> 4, mc = m & 15;
+      for (int t = 0; t < 25; ++t) {
+        const int ky = t / 5, kx = t - ky * 5;
+        atomicAdd(p.gw + mc * 25 + t, sD[m * 65 + ky * 12 + mph + kx]);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");
+    if (p.gb && bt < 16) atomicAdd(p.gb + bt, s_gb[bt]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+static int launch_conv1_wgrad_fold(const float* img, const void* gp, const uint8_t* idx, int B, float* gw, float* gb,
+                                   cudaStream_t st) {
+  FoldParams p;
+  p.img = img; p.gp = gp; p.idx = idx; p.B = B; p.gw = gw; p.gb = gb;
+  const size_t smem = 1024 + 2 * (size_t)kFoldBRows * 32 + (size_t)kFoldA * 4096 + (size_t)kFoldP * 4096;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(conv1_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  int grid = kNumSMs;
+  if (grid > B) grid = B;
+  conv1_wgrad_fold_kernel<<<grid, kFoldThreads, smem, st>>>(p);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 // kind 0: STN conv1 (src = img [B,H,W], big = pooled gradient, idx); kind 1: encoder c1 (big = g [B,H/2,W/2,32]);
 // kind 2: decoder d4 (src = gpre [B,H,W], big = x [B,H+2,W+2,32]).  gw / gb must be zeroed by the caller.
 int thin_tc_wgrad(int kind, const float* src, const void* big, const uint8_t* idx, int B, int H, int W, float* gw,
@@ -906,6 +1135,7 @@ int thin_tc_wgrad(int kind, const float* src, const void* big, const uint8_t* id
   if (kind == 0) {
     // a 64-pixel stage must cover whole pooled rows or half of one: W a multiple of 64, or 16 / 32
     if (!((W % 64) == 0 || W == 32 || W == 16) || (H & 3) || ((uintptr_t)idx & 15)) return 1;
+    if (H == 128 && W == 128 && g_fold) return launch_conv1_wgrad_fold(src, big, idx, B, gw, gb, st);
     return launch_wg<0>(src, big, idx, B, H, W, H, W, gw, gb, st);
   }
   if (kind == 1) {
