@@ -186,97 +186,206 @@ __global__ void __launch_bounds__(256) upsample_pad_bwd_bf16v_kernel(const uint4
   }
 }
 
-// ---- row-wise variants (C/8 a power of two): one CTA per output row, so the only index arithmetic in
-// the element loop is a shift and a mask (the flat kernels above spend ~5 64-bit divisions per 16-byte
-// vector and are instruction-bound at ~2 TB/s), and the adjoint is separable: vertical taps straight
-// from global memory into an fp32 row in shared memory, horizontal taps from there.
-static constexpr int kUpRows = 1;   // output rows per CTA (more rows per CTA measured slower: less parallelism)
+// ---- column-walk variants (C/8 a power of two).  The flat kernels above spend ~5 64-bit divisions per
+// 16-byte vector and are instruction-bound at ~2 TB/s; one-row-per-CTA kernels were launch/latency-bound at
+// 2-3 TB/s.  Here a thread owns one (column, 8-channel) slot and walks down a chunk of rows: all column taps
+// and weights are computed once, vertical neighbours are carried in registers, and every step issues several
+// independent 16-byte loads.
+//
+// Forward, "dual grid": block (r, s), r in [-1, H-1], s in [-1, W-1], is the 2x2 group of upsampled pixels
+// (2r+1..2r+2, 2s+1..2s+2); all four interpolate between the same source rows {rA, rB} and columns {cA, cB}
+// (up_src gives i0 = rA, i1 = rB for both), so a step loads one new source row (2 vectors) and stores 4
+// (plus the reflected border copies).
+static constexpr int kUpChunk = 16;      // block rows / source rows per CTA
 
-__global__ void __launch_bounds__(256) upsample_pad_fwd_row_kernel(const uint4* __restrict__ x, int H, int W, int logc8,
-                                                                   uint4* __restrict__ out) {
+// packed fp32 pairs (FFMA2 on sm_100): halves the instruction count of these conversion-heavy kernels
+struct F8 { float2 v[4]; };
+__device__ __forceinline__ F8 bf8_to_f2(const uint4& u) {
+  F8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ uint4 f2_to_bf8(const F8& f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __float22bfloat162_rn(f.v[i]);
+  return u;
+}
+// (1-f)*a + f*b with ATen's association: both products, then the sum (here: mul, then fma)
+__device__ __forceinline__ F8 lerp8(const F8& a, const F8& b, float f) {
+  F8 r;
+  const float2 w0 = make_float2(1.f - f, 1.f - f), w1 = make_float2(f, f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __ffma2_rn(w1, b.v[i], __fmul2_rn(w0, a.v[i]));
+  return r;
+}
+
+__global__ void __launch_bounds__(288, 3) upsample_pad_fwd_walk_kernel(const uint4* __restrict__ x, int H, int W, int logc8,
+                                                                       int rows_per_cta, uint4* __restrict__ out) {
   const int Ho = 2 * H + 2, Wo = 2 * W + 2, C8 = 1 << logc8;
   const int b = blockIdx.y;
-  const int nv = Wo * C8;
-  for (int Y = blockIdx.x * kUpRows; Y < min(Ho, (int)(blockIdx.x + 1) * kUpRows); ++Y) {
-    const Up1D ty = up1d(Y, H);
-    const uint4* r0 = x + ((int64_t)b * H + ty.i0) * W * C8;
-    const uint4* r1 = x + ((int64_t)b * H + ty.i1) * W * C8;
-    uint4* o = out + ((int64_t)b * Ho + Y) * nv;
-    const float wy1 = ty.f, wy0 = 1.f - ty.f;
-    for (int t = threadIdx.x; t < nv; t += 256) {
-      const int X = t >> logc8, c = t & (C8 - 1);
-      const Up1D tx = up1d(X, W);
-      float v00[8], v01[8], v10[8], v11[8], r[8];
-      bf8_to_f(__ldg(r0 + tx.i0 * C8 + c), v00);
-      bf8_to_f(__ldg(r0 + tx.i1 * C8 + c), v01);
-      bf8_to_f(__ldg(r1 + tx.i0 * C8 + c), v10);
-      bf8_to_f(__ldg(r1 + tx.i1 * C8 + c), v11);
-      const float wx1 = tx.f, wx0 = 1.f - tx.f;
+  const int r_begin = (int)blockIdx.x * rows_per_cta - 1, r_end = min(H, r_begin + rows_per_cta);   // block rows [r_begin, r_end)
+  const uint4* xb = x + (int64_t)b * H * W * C8;
+  uint4* ob = out + (int64_t)b * Ho * Wo * C8;
+  for (int t = threadIdx.x; t < (W + 1) * C8; t += blockDim.x) {
+    const int s = (t >> logc8) - 1, c = t & (C8 - 1);
+    const int cA = max(s, 0), cB = min(cA + 1, W - 1);
+    // the two upsampled columns of this block, their lerp weights and padded positions
+    const int v0 = 2 * s + 1, v1 = 2 * s + 2;
+    const bool c0ok = v0 >= 0, c1ok = v1 < 2 * W;
+    float fx0 = 0.f, fx1 = 0.f;
+    { int i0, i1; if (c0ok) up_src(v0, W, &i0, &i1, &fx0); if (c1ok) up_src(v1, W, &i0, &i1, &fx1); }
+    const int X0 = v0 + 1, X1 = v1 + 1;
+    const int X0dup = v0 == 1 ? 0 : (v0 == 2 * W - 2 ? 2 * W + 1 : -1);
+    const int X1dup = v1 == 1 ? 0 : (v1 == 2 * W - 2 ? 2 * W + 1 : -1);
+    const uint4* xa = xb + (int64_t)cA * C8 + c;
+    const uint4* xq = xb + (int64_t)cB * C8 + c;
+    // horizontal lerps of the two source rows of the block (ATen's inner parentheses), carried down the walk
+    F8 lo0, lo1, hi0, hi1;
+    int prev_rB = -1;
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; ++r) {
+      const int rA = max(r, 0), rB = min(rA + 1, H - 1);
+      if (rA == prev_rB) { lo0 = hi0; lo1 = hi1; }
+      else {
+        const F8 a = bf8_to_f2(__ldg(xa + (int64_t)rA * W * C8)), q = bf8_to_f2(__ldg(xq + (int64_t)rA * W * C8));
+        lo0 = lerp8(a, q, fx0); lo1 = lerp8(a, q, fx1);
+      }
+      if (rB != rA) {
+        const F8 a = bf8_to_f2(__ldg(xa + (int64_t)rB * W * C8)), q = bf8_to_f2(__ldg(xq + (int64_t)rB * W * C8));
+        hi0 = lerp8(a, q, fx0); hi1 = lerp8(a, q, fx1);
+      } else { hi0 = lo0; hi1 = lo1; }
+      prev_rB = rB;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = wy0 * (wx0 * v00[j] + wx1 * v01[j]) + wy1 * (wx0 * v10[j] + wx1 * v11[j]);
-      o[t] = f_to_bf8(r);
+      for (int k = 0; k < 2; ++k) {
+        const int u = 2 * r + 1 + k;
+        if (u < 0 || u >= 2 * H) continue;
+        int i0, i1; float fy;
+        up_src(u, H, &i0, &i1, &fy);
+        uint4* o0 = ob + (int64_t)(u + 1) * Wo * C8 + c;
+        const int Ydup = u == 1 ? 0 : (u == 2 * H - 2 ? 2 * H + 1 : -1);
+        uint4* o1 = ob + (int64_t)Ydup * Wo * C8 + c;
+        if (c0ok) {
+          const uint4 q = f2_to_bf8(lerp8(lo0, hi0, fy));
+          o0[X0 * C8] = q;
+          if (X0dup >= 0) o0[X0dup * C8] = q;
+          if (Ydup >= 0) {
+            o1[X0 * C8] = q;
+            if (X0dup >= 0) o1[X0dup * C8] = q;
+          }
+        }
+        if (c1ok) {
+          const uint4 q = f2_to_bf8(lerp8(lo1, hi1, fy));
+          o0[X1 * C8] = q;
+          if (X1dup >= 0) o0[X1dup * C8] = q;
+          if (Ydup >= 0) {
+            o1[X1 * C8] = q;
+            if (X1dup >= 0) o1[X1dup * C8] = q;
+          }
+        }
+      }
     }
   }
 }
 
-static constexpr int kUpBwdRows = 1;   // low-res rows per CTA
-
-__global__ void __launch_bounds__(256) upsample_pad_bwd_row_kernel(const uint4* __restrict__ g, int H, int W, int logc8,
-                                                                   const uint4* __restrict__ mask_y,
-                                                                   uint4* __restrict__ gx) {
-  extern __shared__ __align__(16) float srow[];     // [Wo][C] fp32: vertical taps already applied
+// weight of upsampled row u on source row i (0 outside [0, 2n))
+__device__ __forceinline__ float up_w(int u, int i, int n) {
+  if (u < 0 || u >= 2 * n) return 0.f;
+  int i0, i1; float f;
+  up_src(u, n, &i0, &i1, &f);
+  return (i0 == i ? 1.f - f : 0.f) + (i1 == i ? f : 0.f);
+}
+// Adjoint, separable with register carry: E[u] = horizontal adjoint of the gradient row(s) that read upsampled
+// row u (padded row u+1, plus the reflected copy for u = 1 and u = 2H-2); source row i needs E[2i-1..2i+2], of
+// which the first two were the "new" rows of step i-1.  Thread = (source column j, 8 channels).  The column
+// taps of j are the padded columns 2j..2j+3 plus, for j = 1 / j = W-2, the reflected border column; they live
+// in registers (static indices only -- a dynamically built tap list went to local memory).
+struct UpTaps { int X[6]; float w[6]; };
+__device__ __forceinline__ UpTaps up_col_taps(int j, int W) {
+  UpTaps t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int X = 2 * j + k;
+    t.X[k] = X;
+    t.w[k] = up_w(unpad(X, 2 * W), j, W);      // X = 0 and X = 2W+1 are copies of upsampled columns 1 and 2W-2
+  }
+  t.X[4] = 0;         t.w[4] = j == 1 ? up_w(1, j, W) : 0.f;
+  t.X[5] = 2 * W + 1; t.w[5] = j == W - 2 ? up_w(2 * W - 2, j, W) : 0.f;
+  return t;
+}
+__device__ __forceinline__ void up_adj_hrow(const uint4* __restrict__ grow, const UpTaps& ax, int C8, F8& h) {
+  uint4 q[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (ax.w[k] != 0.f) q[k] = __ldg(grow + (int64_t)ax.X[k] * C8);
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (ax.w[k] != 0.f) {
+      const F8 v = bf8_to_f2(q[k]);
+      const float2 w = make_float2(ax.w[k], ax.w[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h.v[e] = __ffma2_rn(w, v.v[e], h.v[e]);
+    }
+}
+__global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uint4* __restrict__ g, int H, int W, int logc8,
+                                                                    int rows_per_cta, const uint4* __restrict__ mask_y,
+                                                                    uint4* __restrict__ gx) {
   const int Ho = 2 * H + 2, Wo = 2 * W + 2, C8 = 1 << logc8;
   const int b = blockIdx.y;
-  const uint4* gb = g + (int64_t)b * Ho * Wo * C8;
-  for (int i = blockIdx.x * kUpBwdRows; i < min(H, (int)(blockIdx.x + 1) * kUpBwdRows); ++i) {
-    const Adj1D ay = adj1d(i, H);
-    __syncthreads();                                  // the previous row's horizontal pass is done with srow
-    for (int t = threadIdx.x; t < Wo * C8; t += 256) {
-      uint4 q[6];
+  const int i_begin = (int)blockIdx.x * rows_per_cta, i_end = min(H, i_begin + rows_per_cta);
+  for (int t = threadIdx.x; t < W * C8; t += blockDim.x) {
+    const int j = t >> logc8, c = t & (C8 - 1);
+    const UpTaps ax = up_col_taps(j, W);
+    const uint4* gcol = g + (int64_t)b * Ho * Wo * C8 + c;    // (row Y, column X) at gcol[(Y*Wo + X)*C8]
+    // walk the upsampled rows u that touch source rows [i_begin, i_end): row u adds (1-f) E[u] to source row
+    // i0(u) and f E[u] to i1(u); acc0 / acc1 are the running sums of source rows a and a+1
+    F8 acc0, acc1;
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
-        if (a < ay.n) q[a] = __ldg(gb + (int64_t)ay.Y[a] * Wo * C8 + t);
-      float acc[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-        if (a < ay.n) {
-          float v[8];
-          bf8_to_f(q[a], v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(ay.w[a], v[e], acc[e]);
-        }
-      float4* d = reinterpret_cast<float4*>(srow + (size_t)t * 8);
-      d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    __syncthreads();
-    const int64_t obase = ((int64_t)b * H + i) * W * C8;
-    for (int t = threadIdx.x; t < W * C8; t += 256) {
-      const int j = t >> logc8, c = t & (C8 - 1);
-      uint4 mk = make_uint4(0, 0, 0, 0);
-      if (mask_y) mk = __ldg(mask_y + obase + t);
-      const Adj1D ax = adj1d(j, W);
-      float acc[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      for (int d = 0; d < ax.n; ++d) {
-        const float4* sp = reinterpret_cast<const float4*>(srow + ((size_t)ax.Y[d] * C8 + c) * 8);
-        const float4 v0 = sp[0], v1 = sp[1];
-        const float w = ax.w[d];
-        acc[0] = fmaf(w, v0.x, acc[0]); acc[1] = fmaf(w, v0.y, acc[1]); acc[2] = fmaf(w, v0.z, acc[2]); acc[3] = fmaf(w, v0.w, acc[3]);
-        acc[4] = fmaf(w, v1.x, acc[4]); acc[5] = fmaf(w, v1.y, acc[5]); acc[6] = fmaf(w, v1.z, acc[6]); acc[7] = fmaf(w, v1.w, acc[7]);
-      }
+    for (int e = 0; e < 4; ++e) { acc0.v[e] = make_float2(0.f, 0.f); acc1.v[e] = make_float2(0.f, 0.f); }
+    int a = i_begin - 1;
+    auto emit = [&]() {
+      if (a < i_begin || a >= i_end) return;
+      const int64_t o = (((int64_t)b * H + a) * W + j) * C8 + c;
       if (mask_y) {
-        float m[8];
-        bf8_to_f(mk, m);
+        const F8 m = bf8_to_f2(__ldg(mask_y + o));
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (!(m[e] > 0.f)) acc[e] = 0.f;
+        for (int e = 0; e < 4; ++e) {
+          if (!(m.v[e].x > 0.f)) acc0.v[e].x = 0.f;
+          if (!(m.v[e].y > 0.f)) acc0.v[e].y = 0.f;
+        }
       }
-      gx[obase + t] = f_to_bf8(acc);
+      gx[o] = f2_to_bf8(acc0);
+    };
+    const int u_lo = max(0, 2 * i_begin - 1), u_hi = min(2 * H - 1, 2 * i_end);
+#pragma unroll 1
+    for (int u = u_lo; u <= u_hi; ++u) {
+      int i0, i1; float f;
+      up_src(u, H, &i0, &i1, &f);
+      if (i0 > a) {
+        emit();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc0.v[e] = acc1.v[e]; acc1.v[e] = make_float2(0.f, 0.f); }
+        ++a;
+      }
+      F8 E;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) E.v[e] = make_float2(0.f, 0.f);
+      const int Ydup = u == 1 ? 0 : (u == 2 * H - 2 ? 2 * H + 1 : -1);
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const int Y = rep ? Ydup : u + 1;
+        if (Y < 0) break;
+        up_adj_hrow(gcol + (int64_t)Y * Wo * C8, ax, C8, E);
+      }
+      const float w0 = i1 == i0 ? 1.f : 1.f - f, w1 = i1 == i0 ? 0.f : f;
+      const float2 w02 = make_float2(w0, w0), w12 = make_float2(w1, w1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc0.v[e] = __ffma2_rn(w02, E.v[e], acc0.v[e]); acc1.v[e] = __ffma2_rn(w12, E.v[e], acc1.v[e]); }
     }
+    emit();
   }
 }
 
@@ -546,7 +655,12 @@ extern "C" int livae_upsample_pad_fwd_bf16(const void* x, int B, int H, int W, i
   int64_t n = (int64_t)B * (2 * H + 2) * (2 * W + 2) * C;
   const int logc8 = (C & 7) == 0 ? log2_exact(C / 8) : -1;
   if (logc8 >= 0 && B <= 65535 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0)
-    upsample_pad_fwd_row_kernel<<<dim3((2 * H + 2 + kUpRows - 1) / kUpRows, B), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, H, W, logc8, (uint4*)out);
+  {
+    const int nchunk = (H + 1 + kUpChunk - 1) / kUpChunk, rows = (H + 1 + nchunk - 1) / nchunk;
+    int threads = (((W + 1) << logc8) + 31) & ~31;
+    if (threads > 288) threads = 288;
+    upsample_pad_fwd_walk_kernel<<<dim3(nchunk, B), threads, 0, (cudaStream_t)stream>>>((const uint4*)x, H, W, logc8, rows, (uint4*)out);
+  }
   else if ((C & 7) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0)
     upsample_pad_fwd_bf16v_kernel<<<sgrid(n / 8, 1), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, B, H, W, C / 8,
                                                                                    (uint4*)out);
@@ -565,10 +679,13 @@ extern "C" int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, i
   if (int e = require_sm100()) return e;
   int64_t n = (int64_t)B * H * W * C;
   const int logc8 = (C & 7) == 0 ? log2_exact(C / 8) : -1;
-  const size_t row_smem = (size_t)(2 * W + 2) * C * 4;
-  if (logc8 >= 0 && B <= 65535 && row_smem <= 48 * 1024 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0)
-    upsample_pad_bwd_row_kernel<<<dim3((H + kUpBwdRows - 1) / kUpBwdRows, B), 256, row_smem, (cudaStream_t)stream>>>((const uint4*)g, H, W, logc8,
-                                                                                     (const uint4*)relu_mask_y, (uint4*)gx);
+  if (logc8 >= 0 && B <= 65535 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0) {
+    const int nchunk = (H + kUpChunk - 1) / kUpChunk, rows = (H + nchunk - 1) / nchunk;
+    int threads = ((W << logc8) + 31) & ~31;
+    if (threads > 256) threads = 256;
+    upsample_pad_bwd_walk_kernel<<<dim3(nchunk, B), threads, 0, (cudaStream_t)stream>>>((const uint4*)g, H, W, logc8, rows,
+                                                                                       (const uint4*)relu_mask_y, (uint4*)gx);
+  }
   else if ((C & 7) == 0 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0)
     upsample_pad_bwd_bf16v_kernel<<<sgrid(n / 8, 1), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)g, B, H, W, C / 8, (const uint4*)relu_mask_y, (uint4*)gx);

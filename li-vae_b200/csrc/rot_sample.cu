@@ -25,26 +25,28 @@ struct SrcCoord {
 
 // ATen grid_sampler: unnormalise (align_corners=False), reflect about [-0.5, n-0.5], clip to
 // [0, n-1] (gradient zero where clipped, clip_coordinates_set_grad uses <= / >=).
+// two or more reflections (never for a rotation about the centre, whose coordinates stay within 1.21 n):
+// kept out of line so the pixel loops carry no fmodf / division code
+__device__ __noinline__ float2 reflect_general(float v, float fn, float mult) {
+  const float flips = floorf(v / fn);
+  const float extra = fmodf(v, fn);
+  if (((int)flips & 1) == 0) return make_float2(extra - 0.5f, mult);
+  return make_float2(fn - extra - 0.5f, -mult);
+}
 __device__ __forceinline__ SrcCoord src_coord(float g, int n) {
-  float fn = (float)n;
-  float u = ((g + 1.f) * fn - 1.f) * 0.5f;
+  const float fn = (float)n;
+  const float u = ((g + 1.f) * fn - 1.f) * 0.5f;
   float mult = fn * 0.5f;
   float v = u + 0.5f;
-  float r;
-  if (v >= 0.f && v < fn) {
-    // inside the image (all but the corner pixels of a rotated patch): flips = 0 and fmodf(v, fn) = v
-    // exactly, so this is bit-identical to the general path below without its division and fmodf
-    r = v - 0.5f;
-  } else {
-    if (v < 0.f) { v = -v; mult = -mult; }
-    float flips = floorf(v / fn);
-    float extra = fmodf(v, fn);
-    if (((int)flips & 1) == 0) {
-      r = extra - 0.5f;
-    } else {
-      r = fn - extra - 0.5f;
-      mult = -mult;
-    }
+  mult = v < 0.f ? -mult : mult;
+  v = fabsf(v);
+  // flips = 0: fmodf(v, fn) = v; flips = 1: fmodf(v, fn) = v - fn, exact (Sterbenz) -- branch-free selects
+  const bool flip1 = v >= fn;
+  float r = flip1 ? fn - (v - fn) - 0.5f : v - 0.5f;
+  mult = flip1 ? -mult : mult;
+  if (v >= 2.f * fn) {
+    const float2 q = reflect_general(v, fn, flip1 ? -mult : mult);
+    r = q.x; mult = q.y;
   }
   if (r <= 0.f) { r = 0.f; mult = 0.f; }
   else if (r >= fn - 1.f) { r = fn - 1.f; mult = 0.f; }
@@ -52,155 +54,255 @@ __device__ __forceinline__ SrcCoord src_coord(float g, int n) {
   return o;
 }
 
+// Shared-memory tile: (H+1) rows of odd pitch >= W+1 floats, the extra column / row zero-filled.  Source
+// coordinates are clipped to [0, n-1], so a +1 tap can only fall outside when its weight is exactly 0 (x0 = W-1,
+// fx = 0): with the zero border all four taps are unpredicated loads.  The odd pitch makes bank = (x + y) mod 32,
+// so neither near-horizontal nor near-vertical source lines (rotations near 0 / 90 degrees) serialise.
+// The kernels are instruction-bound, not gather-bound (measured: the bank layout alone changed nothing), so the
+// pixel loop is kept lean: 4 consecutive pixels per thread (one float4 store), no integer divisions, per-row
+// terms hoisted, reflection resolved without fmodf for up to one flip.
+__device__ __host__ __forceinline__ int tile_pitch(int W) { return (W + 1) | 1; }
+
+__device__ __forceinline__ void stage_image(const float* __restrict__ src, float* __restrict__ tile, int H, int W) {
+  const int pitch = tile_pitch(W);
+  if ((W & 3) == 0) {
+    const int wq = W >> 2;
+    int y = threadIdx.x / wq, x4 = threadIdx.x - y * wq;
+    const int dy = blockDim.x / wq, dx = blockDim.x - dy * wq;
+    for (int i = threadIdx.x; i < H * wq; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      float* d = tile + y * pitch + 4 * x4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      y += dy; x4 += dx;
+      if (x4 >= wq) { x4 -= wq; ++y; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+      const int y = i / W;
+      tile[y * pitch + (i - y * W)] = __ldg(src + i);
+    }
+  }
+  for (int y = threadIdx.x; y < H; y += blockDim.x)
+    for (int x = W; x < pitch; ++x) tile[y * pitch + x] = 0.f;
+  for (int x = threadIdx.x; x < pitch; x += blockDim.x) tile[H * pitch + x] = 0.f;
+}
+
+// (float)k for 0 <= k < 2^23 without the conversion pipe (F2I / I2F / FRND run at a quarter of the FMA rate and
+// five of them per pixel made that pipe a co-limiter): k | 0x4B000000 is the float 2^23 + k
+__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(k | 0x4B000000) - 8388608.f; }
+
+// bilinear taps of one output pixel (ATen grid_sampler_2d, reflection padding, align_corners=False)
+struct Taps {
+  int o00;                  // tile offset of the (y0, x0) tap; the others are +1, +pitch, +pitch+1
+  bool x1ok, y1ok;
+  float fx, fy, multx, multy;
+};
+// gxr = -s*ys, gyr = c*ys: the row terms of the rotated grid coordinate (same products as c*xs - s*ys, s*xs + c*ys)
+__device__ __forceinline__ Taps make_taps(float xs, float gxr, float gyr, float c, float s, int H, int W, int pitch) {
+  Taps t;
+  const SrcCoord cx = src_coord(fmaf(c, xs, gxr), W);
+  const SrcCoord cy = src_coord(fmaf(s, xs, gyr), H);
+  const int x0 = __float2int_rd(cx.v), y0 = __float2int_rd(cy.v);     // 0 <= v <= n-1 after the clip
+  t.fx = cx.v - small_int_to_float(x0); t.fy = cy.v - small_int_to_float(y0);
+  t.multx = cx.mult; t.multy = cy.mult;
+  t.x1ok = x0 + 1 < W; t.y1ok = y0 + 1 < H;
+  t.o00 = y0 * pitch + x0;
+  return t;
+}
+template <bool kPadded>
+__device__ __forceinline__ void fetch_taps(const float* __restrict__ tap, const Taps& t, int pitch, float& v00, float& v01,
+                                           float& v10, float& v11) {
+  v00 = tap[t.o00];
+  if (kPadded) {
+    v01 = tap[t.o00 + 1]; v10 = tap[t.o00 + pitch]; v11 = tap[t.o00 + pitch + 1];
+  } else {
+    v01 = t.x1ok ? tap[t.o00 + 1] : 0.f;
+    v10 = t.y1ok ? tap[t.o00 + pitch] : 0.f;
+    v11 = (t.x1ok && t.y1ok) ? tap[t.o00 + pitch + 1] : 0.f;
+  }
+}
+
+// Walks the image in 32x4-pixel warp blocks (lane = 4 consecutive pixels of one row), warps round-robin.
+struct BlockWalk {
+  int bx, by, bw, bh, nwarps;
+  __device__ __forceinline__ BlockWalk(int H, int W) {
+    bw = (W + 31) >> 5; bh = (H + 3) >> 2; nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    by = warp / bw; bx = warp - by * bw;
+  }
+  __device__ __forceinline__ bool valid() const { return by < bh; }
+  __device__ __forceinline__ void next() {
+    bx += nwarps;
+    while (bx >= bw) { bx -= bw; ++by; }
+  }
+};
+
 template <bool kSmem>
 __global__ void __launch_bounds__(256) rot_sample_fwd_kernel(
     const float* __restrict__ img, const float* __restrict__ cs, float sgn, int C, int H, int W,
     float* __restrict__ out) {
   extern __shared__ __align__(16) float s_img[];
-  int bc = blockIdx.x;
-  int b = bc / C;
+  const int bc = blockIdx.x;
+  const int b = bc / C;
   const float* src = img + (int64_t)bc * H * W;
   float* dst = out + (int64_t)bc * H * W;
-  int n = H * W;
   if (kSmem) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(s_img);
-    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
-    for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) s_img[i] = __ldg(src + i);
+    stage_image(src, s_img, H, W);
     __syncthreads();
   }
   const float* tap = kSmem ? s_img : src;
-  float c = cs[2 * b], s = sgn * cs[2 * b + 1];
-  float invW = 1.f / (float)W, invH = 1.f / (float)H;
-  int wq = (W + 3) / 4;
-  for (int q = threadIdx.x; q < H * wq; q += blockDim.x) {
-    int i = q / wq, j0 = (q - i * wq) * 4;
-    float ys = (2.f * i + 1.f) * invH - 1.f;
+  const int pitch = kSmem ? tile_pitch(W) : W;
+  const float c = cs[2 * b], s = sgn * cs[2 * b + 1];
+  const float invW = 1.f / (float)W, invH = 1.f / (float)H;
+  const int lane = threadIdx.x & 31;
+  const int lx = lane & 7, ly = lane >> 3;
+  const bool vec_ok = (W & 3) == 0 && (((uintptr_t)dst) & 15) == 0;
+  for (BlockWalk w(H, W); w.valid(); w.next()) {
+    const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+    if (i >= H || j0 >= W) continue;
+    const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
+    const float gxr = -(s * ys), gyr = c * ys;
     float o[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int j = j0 + t;
-      float xs = (2.f * j + 1.f) * invW - 1.f;
-      SrcCoord cx = src_coord(c * xs - s * ys, W);
-      SrcCoord cy = src_coord(s * xs + c * ys, H);
-      float fx0 = floorf(cx.v), fy0 = floorf(cy.v);
-      int x0 = (int)fx0, y0 = (int)fy0;
-      float fx = cx.v - fx0, fy = cy.v - fy0;
-      // coordinates are clipped to [0,n-1]: only the +1 taps can fall outside
-      bool x1ok = x0 + 1 < W, y1ok = y0 + 1 < H;
-      int x1 = x1ok ? x0 + 1 : x0, y1 = y1ok ? y0 + 1 : y0;
-      float v00 = tap[y0 * W + x0];
-      float v01 = x1ok ? tap[y0 * W + x1] : 0.f;
-      float v10 = y1ok ? tap[y1 * W + x0] : 0.f;
-      float v11 = (x1ok && y1ok) ? tap[y1 * W + x1] : 0.f;
+    for (int k = 0; k < 4; ++k) {
+      const float xs = (2.f * small_int_to_float(j0 + k) + 1.f) * invW - 1.f;
+      const Taps t = make_taps(xs, gxr, gyr, c, s, H, W, pitch);
+      float v00, v01, v10, v11;
+      fetch_taps<kSmem>(tap, t, pitch, v00, v01, v10, v11);
       // same association as ATen: nw*(1-fx)(1-fy) + ne*fx(1-fy) + sw*(1-fx)fy + se*fx*fy
-      o[t] = v00 * ((1.f - fx) * (1.f - fy)) + v01 * (fx * (1.f - fy)) +
-             v10 * ((1.f - fx) * fy) + v11 * (fx * fy);
+      o[k] = v00 * ((1.f - t.fx) * (1.f - t.fy)) + v01 * (t.fx * (1.f - t.fy)) +
+             v10 * ((1.f - t.fx) * t.fy) + v11 * (t.fx * t.fy);
     }
-    if ((W & 3) == 0) {
+    if (vec_ok) {
       *reinterpret_cast<float4*>(dst + i * W + j0) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
-      for (int t = 0; t < 4 && j0 + t < W; ++t) dst[i * W + j0 + t] = o[t];
+      for (int k = 0; k < 4 && j0 + k < W; ++k) dst[i * W + j0 + k] = o[k];
     }
   }
 }
 
-// kSmemGrad: accumulate grad_input in a shared tile; otherwise (image too large for shared
-// memory) fall back to global atomics on a pre-zeroed buffer.  kSmemImg: the source image is staged in
-// shared memory as in the forward kernel (the four taps of a pixel are gathers; from global memory they
-// miss L1, which the gradient tile has squeezed to a few KB, on every pixel).
-template <bool kSmemGrad, bool kSmemImg>
-__global__ void __launch_bounds__(512) rot_sample_bwd_kernel(
+// Backward, one CTA per sample, ONE shared tile used twice: phase A stages the image and gathers the four taps
+// for dL/d(cos), dL/d(sin) (warp shuffles + one shared exchange); phase B (only when grad_input is wanted)
+// re-uses the tile as the grad_input accumulator -- shared atomics, no HBM traffic, one coalesced float4 write
+// of the tile.  One 66 KB tile instead of image + accumulator side by side keeps 3 CTAs per SM resident.
+// kSmem = false (image larger than shared memory): taps from global memory, global atomics on a pre-zeroed gimg.
+template <bool kSmem>
+__global__ void __launch_bounds__(256) rot_sample_bwd_kernel(
     const float* __restrict__ img, const float* __restrict__ cs, float sgn,
     const float* __restrict__ gout, int C, int H, int W, float* __restrict__ gimg,
     float* __restrict__ gcs) {
-  extern __shared__ __align__(16) float s_dyn[];
-  float* s_img = s_dyn;                                   // [H*W] when kSmemImg
-  float* s_g = s_dyn + (kSmemImg ? H * W : 0);            // [H*W] when kSmemGrad && gimg
+  extern __shared__ __align__(16) float s_tile[];
   __shared__ float red[2][32];
-  int b = blockIdx.x;
-  int n = H * W;
-  float c = cs[2 * b], s = sgn * cs[2 * b + 1];
-  float invW = 1.f / (float)W, invH = 1.f / (float)H;
+  const int b = blockIdx.x;
+  const int n = H * W;
+  const float c = cs[2 * b], s = sgn * cs[2 * b + 1];
+  const float invW = 1.f / (float)W, invH = 1.f / (float)H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lx = lane & 7, ly = lane >> 3;
+  const int pitch = kSmem ? tile_pitch(W) : W;
   float acc_c = 0.f, acc_s = 0.f;
   for (int ch = 0; ch < C; ++ch) {
     const float* src = img + ((int64_t)b * C + ch) * n;
     const float* go = gout + ((int64_t)b * C + ch) * n;
     float* gi = gimg ? gimg + ((int64_t)b * C + ch) * n : nullptr;
-    if (kSmemImg) {
-      __syncthreads();
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(s_img);
-      for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
-      for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) s_img[i] = __ldg(src + i);
-    }
-    if (kSmemGrad && gi)
-      for (int i = threadIdx.x; i < n; i += blockDim.x) s_g[i] = 0.f;
-    if (kSmemImg || (kSmemGrad && gi)) __syncthreads();
-    const float* tap = kSmemImg ? s_img : src;
-    for (int p = threadIdx.x; p < n; p += blockDim.x) {
-      int i = p / W, j = p - i * W;
-      float ys = (2.f * i + 1.f) * invH - 1.f;
-      float xs = (2.f * j + 1.f) * invW - 1.f;
-      SrcCoord cx = src_coord(c * xs - s * ys, W);
-      SrcCoord cy = src_coord(s * xs + c * ys, H);
-      float fx0 = floorf(cx.v), fy0 = floorf(cy.v);
-      int x0 = (int)fx0, y0 = (int)fy0;
-      float fx = cx.v - fx0, fy = cy.v - fy0;
-      bool x1ok = x0 + 1 < W, y1ok = y0 + 1 < H;
-      int x1 = x1ok ? x0 + 1 : x0, y1 = y1ok ? y0 + 1 : y0;
-      float g = __ldg(go + p);
-      float v00 = tap[y0 * W + x0];
-      float v01 = x1ok ? tap[y0 * W + x1] : 0.f;
-      float v10 = y1ok ? tap[y1 * W + x0] : 0.f;
-      float v11 = (x1ok && y1ok) ? tap[y1 * W + x1] : 0.f;
-      if (gi) {
-        float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy);
-        float w10 = (1.f - fx) * fy, w11 = fx * fy;
-        float* t = kSmemGrad ? s_g : gi;
-        atomicAdd(t + y0 * W + x0, w00 * g);
-        if (x1ok) atomicAdd(t + y0 * W + x1, w01 * g);
-        if (y1ok) atomicAdd(t + y1 * W + x0, w10 * g);
-        if (x1ok && y1ok) atomicAdd(t + y1 * W + x1, w11 * g);
+    const bool vec_ok = (W & 3) == 0 && (((uintptr_t)go) & 15) == 0;
+    if (gcs) {
+      if (kSmem) {
+        __syncthreads();
+        stage_image(src, s_tile, H, W);
+        __syncthreads();
       }
-      // d(out)/d(ix), d(out)/d(iy)
-      float gix = (-(1.f - fy) * v00 + (1.f - fy) * v01 - fy * v10 + fy * v11) * g;
-      float giy = (-(1.f - fx) * v00 - fx * v01 + (1.f - fx) * v10 + fx * v11) * g;
-      float ggx = gix * cx.mult, ggy = giy * cy.mult;
-      // affine_grid backward: base_grid^T @ grad_grid for [[c,-s],[s,c]]
-      acc_c += ggx * xs + ggy * ys;
-      acc_s += -ggx * ys + ggy * xs;
-    }
-    if (kSmemGrad && gi) {
-      __syncthreads();
-      if ((n & 3) == 0) {
-        float4* d4 = reinterpret_cast<float4*>(gi);
-        const float4* s4 = reinterpret_cast<const float4*>(s_g);
-        for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = s4[i];
-      } else {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) gi[i] = s_g[i];
+      const float* tap = kSmem ? s_tile : src;
+      for (BlockWalk w(H, W); w.valid(); w.next()) {
+        const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+        if (i >= H || j0 >= W) continue;
+        const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
+        const float gxr = -(s * ys), gyr = c * ys;
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4*>(go + i * W + j0)); g4[0] = q.x; g4[1] = q.y; g4[2] = q.z; g4[3] = q.w; }
+        else for (int k = 0; k < 4 && j0 + k < W; ++k) g4[k] = __ldg(go + i * W + j0 + k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (j0 + k >= W) break;
+          const float xs = (2.f * small_int_to_float(j0 + k) + 1.f) * invW - 1.f;
+          const Taps t = make_taps(xs, gxr, gyr, c, s, H, W, pitch);
+          float v00, v01, v10, v11;
+          fetch_taps<kSmem>(tap, t, pitch, v00, v01, v10, v11);
+          const float g = g4[k];
+          // d(out)/d(ix), d(out)/d(iy)
+          const float gix = (-(1.f - t.fy) * v00 + (1.f - t.fy) * v01 - t.fy * v10 + t.fy * v11) * g;
+          const float giy = (-(1.f - t.fx) * v00 - t.fx * v01 + (1.f - t.fx) * v10 + t.fx * v11) * g;
+          const float ggx = gix * t.multx, ggy = giy * t.multy;
+          // affine_grid backward: base_grid^T @ grad_grid for [[c,-s],[s,c]]
+          acc_c += ggx * xs + ggy * ys;
+          acc_s += -ggx * ys + ggy * xs;
+        }
       }
-      __syncthreads();
+    }
+    if (gi) {
+      float* acc = kSmem ? s_tile : gi;
+      if (kSmem) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < (H + 1) * pitch; k += blockDim.x) s_tile[k] = 0.f;
+        __syncthreads();
+      }
+      for (BlockWalk w(H, W); w.valid(); w.next()) {
+        const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+        if (i >= H || j0 >= W) continue;
+        const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
+        const float gxr = -(s * ys), gyr = c * ys;
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4*>(go + i * W + j0)); g4[0] = q.x; g4[1] = q.y; g4[2] = q.z; g4[3] = q.w; }
+        else for (int k = 0; k < 4 && j0 + k < W; ++k) g4[k] = __ldg(go + i * W + j0 + k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (j0 + k >= W) break;
+          const float xs = (2.f * small_int_to_float(j0 + k) + 1.f) * invW - 1.f;
+          const Taps t = make_taps(xs, gxr, gyr, c, s, H, W, pitch);
+          const float g = g4[k];
+          atomicAdd(acc + t.o00, (1.f - t.fx) * (1.f - t.fy) * g);
+          if (t.x1ok) atomicAdd(acc + t.o00 + 1, t.fx * (1.f - t.fy) * g);
+          if (t.y1ok) atomicAdd(acc + t.o00 + pitch, (1.f - t.fx) * t.fy * g);
+          if (t.x1ok && t.y1ok) atomicAdd(acc + t.o00 + pitch + 1, t.fx * t.fy * g);
+        }
+      }
+      if (kSmem) {
+        __syncthreads();
+        if ((W & 3) == 0 && (((uintptr_t)gi) & 15) == 0) {
+          const int wq = W >> 2;
+          int y = threadIdx.x / wq, x4 = threadIdx.x - y * wq;
+          const int dy = blockDim.x / wq, dx = blockDim.x - dy * wq;
+          for (int k = threadIdx.x; k < H * wq; k += blockDim.x) {
+            const float* sp = s_tile + y * pitch + 4 * x4;
+            reinterpret_cast<float4*>(gi)[k] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            y += dy; x4 += dx;
+            if (x4 >= wq) { x4 -= wq; ++y; }
+          }
+        } else {
+          for (int k = threadIdx.x; k < n; k += blockDim.x) { const int y = k / W; gi[k] = s_tile[y * pitch + (k - y * W)]; }
+        }
+      }
     }
   }
+  if (!gcs) return;
   acc_c = warp_sum(acc_c);
   acc_s = warp_sum(acc_s);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { red[0][w] = acc_c; red[1][w] = acc_s; }
+  if (lane == 0) { red[0][warp] = acc_c; red[1][warp] = acc_s; }
   __syncthreads();
-  if (w == 0) {
-    int nw = blockDim.x >> 5;
-    float a = lane < nw ? red[0][lane] : 0.f;
-    float d = lane < nw ? red[1][lane] : 0.f;
+  if (warp == 0) {
+    float a = lane < nwarps ? red[0][lane] : 0.f;
+    float d = lane < nwarps ? red[1][lane] : 0.f;
     a = warp_sum(a);
     d = warp_sum(d);
-    if (lane == 0 && gcs) { gcs[2 * b] = a; gcs[2 * b + 1] = sgn * d; }
+    if (lane == 0) { gcs[2 * b] = a; gcs[2 * b + 1] = sgn * d; }
   }
 }
 
 static constexpr int kMaxSmemImage = 200 * 1024;  // bytes of one staged image / gradient tile
 
 }  // namespace livae
+
+static size_t tile_bytes(int H, int W) { return (size_t)(H + 1) * livae::tile_pitch(W) * sizeof(float); }
 
 extern "C" int livae_rot_sample_fwd(const float* img, const float* cs, float sgn, int B, int C, int H,
                                     int W, float* out, livae_stream_t stream) {
@@ -210,7 +312,7 @@ extern "C" int livae_rot_sample_fwd(const float* img, const float* cs, float sgn
   LIVAE_CHECK_ARG(img && cs && out, "rot_sample_fwd: null pointer");
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t bytes = (size_t)H * W * sizeof(float);
+  const size_t bytes = tile_bytes(H, W);
   if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -236,27 +338,20 @@ extern "C" int livae_rot_sample_bwd(const float* img, const float* cs, float sgn
   LIVAE_CHECK_ARG(gimg || gcs, "rot_sample_bwd: nothing to compute");
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t bytes = (size_t)H * W * sizeof(float);
+  const size_t bytes = tile_bytes(H, W);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(rot_sample_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
-    cudaFuncSetAttribute(rot_sample_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
+    cudaFuncSetAttribute(rot_sample_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
     attr_done = true;
   }
-  const bool aligned = ((uintptr_t)img & 15) == 0;
-  if (!gimg) {
-    if (aligned && bytes <= (size_t)kMaxSmemImage)
-      rot_sample_bwd_kernel<true, true><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
-    else
-      rot_sample_bwd_kernel<true, false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
-  } else if (aligned && 2 * bytes <= (size_t)kMaxSmemImage) {
-    rot_sample_bwd_kernel<true, true><<<B, 512, 2 * bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
-  } else if (bytes <= (size_t)kMaxSmemImage) {
-    rot_sample_bwd_kernel<true, false><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+  if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
+    rot_sample_bwd_kernel<true><<<B, 256, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   } else {
-    cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)B * C * bytes, st);
-    if (e != cudaSuccess) { set_error("rot_sample_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
-    rot_sample_bwd_kernel<false, false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+    if (gimg) {
+      cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)B * C * H * W * sizeof(float), st);
+      if (e != cudaSuccess) { set_error("rot_sample_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    rot_sample_bwd_kernel<false><<<B, 256, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;

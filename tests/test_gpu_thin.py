@@ -145,6 +145,26 @@ def test_pool_unpool_upsample_decfc_bf16():
     assert rel_l2(gw.cpu(), w.grad) < 1e-5 and rel_l2(gb.cpu(), b.grad) < 1e-5 and rel_l2(gz.cpu(), z.grad) < 1e-5
 
 
+@pytest.mark.parametrize("B,Cc,H,W", [(2, 256, 8, 8), (2, 32, 64, 64), (1, 64, 37, 21), (3, 8, 2, 2), (1, 24, 5, 7)])
+def test_upsample_pad_bf16_shapes(B, Cc, H, W):
+    """Upsample(x2, bilinear) + ReflectionPad2d(1) (model.py:357-370) and its adjoint at the decoder's shapes,
+    across row-chunk boundaries (H > 16), ragged sizes and a channel count that takes the flat kernel (24)."""
+    rng = np.random.default_rng(B * Cc + H)
+    x = _bf(torch.tensor(rng.standard_normal((B, Cc, H, W)).astype(np.float32))).requires_grad_(True)
+    up = F.pad(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
+    gy = _bf(torch.tensor(rng.standard_normal(tuple(up.shape)).astype(np.float32)))
+    (up * gy).sum().backward()
+    xd = _nhwc(x.detach()).cuda().to(BF)
+    out = torch.full((B, 2 * H + 2, 2 * W + 2, Cc), float("nan"), dtype=BF, device="cuda")
+    _call("livae_upsample_pad_fwd_bf16", xd, B, H, W, Cc, out)
+    assert torch.equal(out.float().cpu(), _nhwc(up.detach()).to(BF).float())      # same fp32 formula, one rounding
+    for mask in (None, torch.tensor(rng.standard_normal((B, H, W, Cc)).astype(np.float32)).cuda().to(BF)):
+        gx = torch.full((B, H, W, Cc), float("nan"), dtype=BF, device="cuda")
+        _call("livae_upsample_pad_bwd_bf16", _nhwc(gy).cuda().to(BF), B, H, W, Cc, mask, gx)
+        want = _nhwc(x.grad) if mask is None else _nhwc(x.grad) * (mask.float().cpu() > 0)
+        assert rel_l2(gx.float().cpu(), want) < 5e-3
+
+
 @pytest.mark.parametrize("B,Cc,hw,N", [(5, 32, 8, 32), (130, 256, 2, 4), (64, 32, 32, 32)])
 def test_linear_as_tensor_core_gemm(B, Cc, hw, N):
     """nn.Linear over an NHWC-flattened map (model.py:210-213, 321-324) via livae.tc._linear_fwd/_linear_bwd"""
