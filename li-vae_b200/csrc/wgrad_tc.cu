@@ -15,6 +15,8 @@ namespace livae {
 namespace tc {
 
 static constexpr int kWgThreads = 192;
+static constexpr int kWgHaloThreads = 192;
+static constexpr int kWgIssuers = 5;         // halo kernel: lane 0 of warps 1-5 each issue the MMAs of their own row groups
 static constexpr int kPK = 64;   // pixels per pipeline stage (UMMA K = 16 -> 4 MMAs per group per stage)
 
 struct WgradParams {
@@ -203,7 +205,7 @@ struct WgradHaloParams {
 };
 
 template <int STAGES>
-__global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                 const __grid_constant__ CUtensorMap tmG,
                                                                 const WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmG);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kWgIssuers); }
+    mbar_init(&accum_bar, kWgIssuers);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -276,9 +278,15 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
           }
         }
       }
-    } else if (warp == 1) {
+    } else {
       if (lane == 0) {
-        // single-thread issue loop: every descriptor is "precomputed constant + stage base + K-step
+        // FIVE issuing threads (lane 0 of warps 1-5; warps 2-5 are idle until the epilogue anyway), row groups
+        // dealt round-robin: one thread sustains one tcgen05.mma per ~50-85 cycles (tools/umma_rate.cu and the
+        // probe of this loop), but an M=128 MMA with N <= 64 only occupies the pipe for (128+N)/4 = 36..48
+        // cycles (shared-memory operand read), so a single issuer left the tensor pipe idle half the time on
+        // the narrow layers.  All wait on the same full barrier and all commit to the stage's empty barrier.
+        const int iw = warp - 1;
+        // per-thread issue loop: every descriptor is "precomputed constant + stage base + K-step
         // increment" (two 64-bit adds per MMA; building descriptors from kernel parameters inside the
         // loop cost several hundred cycles of dependent latency per MMA)
         const uint32_t idesc = make_idesc_bf16(128, p.Cs, 1, 1);
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
         const uint32_t b_kstep16 = (16u * rbg) >> 4;
         const uint64_t bd0 = make_smem_desc(smem_u32(smem) + a_region, gbox_slot, sbog, ltg);
         const uint32_t stage16 = stage_bytes >> 4;
-        for (int g = 0; g < ng; ++g) {
+        for (int g = iw; g < ng; g += kWgIssuers) {
           const WgGroup G = p.grp[g0 + g];
           s_gdesc[g] = make_smem_desc(smem_u32(smem) + G.base_off, G.lbo, sbox, ltx);
         }
@@ -302,12 +310,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
         for (int it = 0; it < nt; ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          probe_rec(p.probe, 1, 0, pn);
+          if (iw == 0) probe_rec(p.probe, 1, 0, pn);
           mbar_wait(&full_bar[s], ph);
-          probe_rec(p.probe, 1, 1, pn);
+          if (iw == 0) probe_rec(p.probe, 1, 1, pn);
           tc_fence_after();
           const uint32_t so = (uint32_t)s * stage16;
-          for (int g = 0; g < ng; ++g) {
+          for (int g = iw; g < ng; g += kWgIssuers) {
             uint64_t ad = s_gdesc[g] + so;
             uint64_t bd = bd0 + so;
             const uint32_t d_addr = tmem_base + (uint32_t)(g * p.Cs);
@@ -315,12 +323,13 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
               umma_f16(d_addr, ad, bd, idesc, accum | (uint32_t)(k > 0));
           }
           accum = 1u;
-          probe_rec(p.probe, 1, 2, pn);
+          if (iw == 0) probe_rec(p.probe, 1, 2, pn);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&accum_bar);
       }
-    } else {
+      __syncwarp();
+      if (warp >= 2) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
       mbar_wait(&accum_bar, 0);
@@ -343,6 +352,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_halo_kernel(const __grid_con
         }
       }
       tc_fence_before();
+      }
     }
   }
   __syncthreads();
@@ -560,9 +570,9 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   }
   dim3 grid(gsets, splits);
   if (4u * stage_bytes + 1024u <= 200u * 1024u)
-    wgrad_halo_kernel<4><<<grid, kWgThreads, 4 * stage_bytes + 1024, st>>>(tmX, tmG, p);
+    wgrad_halo_kernel<4><<<grid, kWgHaloThreads, 4 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   else
-    wgrad_halo_kernel<2><<<grid, kWgThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
+    wgrad_halo_kernel<2><<<grid, kWgHaloThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
