@@ -188,12 +188,12 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
 // past the end of the filter row compute garbage rows that the epilogue skips.
 static constexpr int kMaxGroups = 32;
 static constexpr int kMaxTapsW = 32;
-struct WgGroup { uint32_t base_off, lbo; int16_t atom[8]; };   // atom: tap * 8 + chunk, or -1
+struct WgGroup { uint32_t base_off, lbo; int16_t atom[8]; uint32_t boxmask; };   // atom: tap * 8 + chunk, or -1; boxmask: input boxes read
 struct WgradHaloParams {
   int TH, TW, Wx;              // gy tile, input box row width (pixels)
   int tiles_x, tiles_y, B, tiles_per_cta;
   int stride;
-  int nbox; int16_t box_dy[16], box_dx[16], box_c[16];   // input boxes: origin offset and channel chunk
+  int nbox, nbox_cta; int16_t box_dy[16], box_dx[16], box_c[16];   // input boxes: origin offset and channel chunk
   uint32_t box_slot;           // bytes per input box slot (1024-aligned)
   uint32_t xbox_bytes;         // bytes one input box delivers (Hbox * Wx * kcb * 2)
   int Cb, Cs, kcb, kcs, ntaps;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
   const int nboxg = p.Cs / p.kcs;
   const uint32_t gbox_bytes = (uint32_t)(p.TH * p.TW) * rbg;
   const uint32_t gbox_slot = (gbox_bytes + 1023u) & ~1023u;
-  const uint32_t a_region = (uint32_t)p.nbox * p.box_slot;
+  const uint32_t a_region = (uint32_t)p.nbox_cta * p.box_slot;
   const uint32_t stage_bytes = a_region + (uint32_t)nboxg * gbox_slot;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint32_t ncols = 32;
@@ -232,6 +232,10 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
   const int t_beg = blockIdx.y * p.tiles_per_cta;
   const int t_end = min(total_tiles, t_beg + p.tiles_per_cta);
   const int nt = t_end - t_beg;
+  // only the input boxes (parity class x channel chunk) that this CTA's row groups read; slot = box id - first
+  uint32_t need = 0u;
+  for (int g = 0; g < ng; ++g) need |= p.grp[g0 + g].boxmask;
+  const int box_lo = need ? __ffs(need) - 1 : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
   if (nt > 0) {
     if (warp == 0) {
       if (lane == 0) {
-        const uint32_t tx_bytes = (uint32_t)p.nbox * p.xbox_bytes + (uint32_t)nboxg * gbox_bytes;
+        const uint32_t tx_bytes = (uint32_t)__popc(need) * p.xbox_bytes + (uint32_t)nboxg * gbox_bytes;
         int pn = 0;
         for (int it = 0; it < nt; ++it) {
           const int s = it % STAGES;
@@ -269,11 +273,12 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
           for (int c = 0; c < nboxg; ++c)
             tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], c * p.kcs, tx * p.TW, ty * p.TH, b);
           for (int i = 0; i < p.nbox; ++i) {
+            if (!((need >> i) & 1u)) continue;
             if (p.x_s2d)   // chunk = pixel row inside the 2x2 block (HaloOpts in tc_common.cuh)
-              tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], 0, tx * p.TW + p.box_dx[i],
+              tma_load_4d(st + (uint32_t)(i - box_lo) * p.box_slot, &tmX, &full_bar[s], 0, tx * p.TW + p.box_dx[i],
                           2 * (ty * p.TH + p.box_dy[i]) + p.box_c[i], b);
             else
-              tma_load_4d(st + (uint32_t)i * p.box_slot, &tmX, &full_bar[s], p.box_c[i] * p.kcb,
+              tma_load_4d(st + (uint32_t)(i - box_lo) * p.box_slot, &tmX, &full_bar[s], p.box_c[i] * p.kcb,
                           tx * p.TW * p.stride + p.box_dx[i], ty * p.TH * p.stride + p.box_dy[i], b);
           }
         }
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
         const uint32_t stage16 = stage_bytes >> 4;
         for (int g = iw; g < ng; g += kWgIssuers) {
           const WgGroup G = p.grp[g0 + g];
-          s_gdesc[g] = make_smem_desc(smem_u32(smem) + G.base_off, G.lbo, sbox, ltx);
+          s_gdesc[g] = make_smem_desc(smem_u32(smem) + G.base_off - (uint32_t)box_lo * p.box_slot, G.lbo, sbox, ltx);
         }
         uint32_t accum = 0u;
         int pn = 0;
@@ -443,10 +448,10 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
     if (taps[t].sx > max_sx) max_sx = taps[t].sx;
   }
   p.Wx = p.TW + max_sx;
-  // rows of the gy tile: keep a stage around <= 80 KB
-  const int per_row_bytes = p.Wx * p.Cb * 2 * npar + p.TW * p.Cs * 2;
-  int TH = 8;
-  while (TH > 2 && (TH + max_sy) * per_row_bytes > 80 * 1024) TH >>= 1;
+  // plan(TH): row groups, their input boxes and the stage size for a gy tile of TH rows; 0 = fits (>= 2 stages)
+  int gsets = 1, splits = 1, total_tiles = 0;
+  uint32_t stage_bytes = 0;
+  auto plan = [&](int TH) -> int {
   if (TH * p.TW < 16) return 1;
   if (TH > Ho) { TH = Ho; if ((TH * p.TW) % 16 != 0) return 1; }
   p.TH = TH;
@@ -472,15 +477,21 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
     WgGroup* g = &p.grp[ng++];
     for (int i = 0; i < 8; ++i) g->atom[i] = -1;
     g->lbo = rbx;
+    g->boxmask = 0u;
     return g;
   };
+  auto box_of = [&](const Tap& t, int c) -> uint32_t { return 1u << (t.par * nchunk + c); };
   if (apg == 2 && nchunk >= 2) {
-    for (int t = 0; t < p.ntaps; ++t)
-      for (int c = 0; c < nchunk; c += 2) {
-        WgGroup* g = new_group(); if (!g) return 1;
-        g->base_off = tap_off(taps[t], c); g->lbo = p.box_slot;
-        g->atom[0] = (int16_t)(taps[t].idx * 8 + c); g->atom[1] = (int16_t)(taps[t].idx * 8 + c + 1);
-      }
+    // parity class outermost: the groups of one CTA then share their input boxes
+    for (int par = 0; par < npar; ++par)
+      for (int c = 0; c < nchunk; c += 2)
+        for (int t = 0; t < p.ntaps; ++t) {
+          if (taps[t].par != par) continue;
+          WgGroup* g = new_group(); if (!g) return 1;
+          g->base_off = tap_off(taps[t], c); g->lbo = p.box_slot;
+          g->atom[0] = (int16_t)(taps[t].idx * 8 + c); g->atom[1] = (int16_t)(taps[t].idx * 8 + c + 1);
+          g->boxmask = box_of(taps[t], c) | box_of(taps[t], c + 1);
+        }
   } else if (apg == 2) {   // one chunk: pair taps of the same parity class (ascending shift)
     for (int par = 0; par < npar; ++par) {
       int prev = -1;
@@ -490,12 +501,14 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
         WgGroup* g = new_group(); if (!g) return 1;
         g->base_off = tap_off(taps[prev], 0); g->lbo = tap_off(taps[t], 0) - tap_off(taps[prev], 0);
         g->atom[0] = (int16_t)(taps[prev].idx * 8); g->atom[1] = (int16_t)(taps[t].idx * 8);
+        g->boxmask = box_of(taps[prev], 0);
         prev = -1;
       }
       if (prev >= 0) {
         WgGroup* g = new_group(); if (!g) return 1;
         g->base_off = tap_off(taps[prev], 0); g->lbo = rbx;
         g->atom[0] = (int16_t)(taps[prev].idx * 8);
+        g->boxmask = box_of(taps[prev], 0);
       }
     }
   } else {   // kcb = 32 / 16: atoms = consecutive-column taps of one (parity, row shift, channel chunk)
@@ -515,6 +528,7 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
             int a = (int)((tap_off(taps[found], c) - g->base_off) / rbx);
             if (a >= apg) { g = new_group(); if (!g) return 1; g->base_off = tap_off(taps[found], c); g->lbo = rbx; a = 0; }
             g->atom[a] = (int16_t)(taps[found].idx * 8 + c);
+            g->boxmask |= box_of(taps[found], c);
             cnt = a + 1;
           }
         }
@@ -523,11 +537,13 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   int G = 512 / p.Cs;
   if (G > 8) G = 8;
   if (G > ng) G = ng;
+  gsets = (ng + G - 1) / G;
+  G = (ng + gsets - 1) / gsets;          // balance the row groups over the sets
+  gsets = (ng + G - 1) / G;
   p.G = G;
-  const int gsets = (ng + G - 1) / G;
   p.tiles_x = (Wo + p.TW - 1) / p.TW; p.tiles_y = (Ho + TH - 1) / TH;
-  const int total_tiles = p.tiles_x * p.tiles_y * d->B;
-  int splits = (kNumSMs + gsets - 1) / gsets;
+  total_tiles = p.tiles_x * p.tiles_y * d->B;
+  splits = (kNumSMs + gsets - 1) / gsets;
   if (splits > total_tiles) splits = total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (total_tiles + splits - 1) / splits;
@@ -538,8 +554,30 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   if (x_s2d && (d->Cin != 64 || s != 1)) return 1;
   const int nboxg = p.Cs / p.kcs;
   const uint32_t gbox_slot = ((uint32_t)(TH * p.TW * p.kcs * 2) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (uint32_t)p.nbox * p.box_slot + (uint32_t)nboxg * gbox_slot;
-  if (2u * stage_bytes + 1024u > 200u * 1024u) return 1;
+  // a CTA keeps only the boxes its row groups read (a contiguous range of box ids: groups are ordered
+  // parity class / channel chunk outermost), in slots numbered from the first one
+  p.nbox_cta = 1;
+  for (int gs = 0; gs < gsets; ++gs) {
+    uint32_t need = 0u;
+    for (int g = gs * G; g < ng && g < (gs + 1) * G; ++g) need |= p.grp[g].boxmask;
+    int lo = 0, hi = 0;
+    while (!((need >> lo) & 1u)) ++lo;
+    for (int i = 0; i < 16; ++i) if ((need >> i) & 1u) hi = i;
+    if (hi - lo + 1 > p.nbox_cta) p.nbox_cta = hi - lo + 1;
+  }
+  stage_bytes = (uint32_t)p.nbox_cta * p.box_slot + (uint32_t)nboxg * gbox_slot;
+  return (2u * stage_bytes + 1024u > 200u * 1024u) ? 2 : 0;
+  };
+  {
+    int rc = 1;
+    for (int TH = 8; TH >= 2; TH >>= 1) {
+      rc = plan(TH);
+      if (rc == 0) break;          // the largest tile that leaves room for two stages
+      if (rc == 1) return 1;
+    }
+    if (rc != 0) { rc = plan(2); if (rc != 0) return 1; }
+  }
+  const int TH = p.TH, Hbox = TH + max_sy;
 
   CUtensorMap tmX, tmG;
   if (x_s2d) {

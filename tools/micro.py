@@ -31,6 +31,22 @@ for w in which:
     elif w == "wgrad_d1":
         x = torch.randn(B, 18, 18, 256, device=dev).to(bf); g = torch.randn(B, 16, 16, 128, device=dev).to(bf)
         print(w, timeit(lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)), "ms")
+    elif w.startswith("wg_") or w.startswith("fw_") or w.startswith("dg_"):
+        # generic: wg_/fw_/dg_<Cin>_<Cout>_<k>_<stride>_<pad>_<Hin>
+        _, ci, co, k, st, pd, hin = w.split("_"); ci, co, k, st, pd, hin = map(int, (ci, co, k, st, pd, hin))
+        ho = (hin + 2 * pd - k) // st + 1
+        x = torch.randn(B, hin, hin, ci, device=dev).to(bf); g = torch.randn(B, ho, ho, co, device=dev).to(bf)
+        wt = torch.randn(co, ci, k, k, device=dev)
+        fl = 2.0 * B * ho * ho * ci * co * k * k
+        if w.startswith("wg_"):
+            t = timeit(lambda: ops.tc_conv_wgrad(x, g, k, k, st, pd))
+        elif w.startswith("fw_"):
+            wp = ops.tc_pack_weights(wt, co, ci, k, k, 0)
+            t = timeit(lambda: ops.tc_conv(x, wp, None, k, k, st, pd, 1))
+        else:
+            wp = ops.tc_pack_weights(wt, co, ci, k, k, 2)
+            t = timeit(lambda: ops.tc_conv_dgrad(g, wp, None, hin, hin, k, k, st, pd))
+        print(f"{w}: {t:.3f} ms  {fl / t / 1e9:.0f} TF/s")
     elif w == "fwd_d3":
         x = torch.randn(B, 66, 66, 64, device=dev).to(bf); wt = torch.randn(32, 64, 3, 3, device=dev)
         wp = ops.tc_pack_weights(wt, 32, 64, 3, 3, 0)
