@@ -87,6 +87,11 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 8))
     warm = max(1, min(args.warmup, 2))
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     rate, ms, sb = cpu_reference_step_rate(steps, warm)
     cores = torch.get_num_threads()
     line = {
@@ -270,7 +275,7 @@ def main():
 
     import livae
     from livae import _lib, optim
-    from livae.train import train_rvae_step
+    from livae.train import train_rvae_step, DevicePrefetcher
     livae.set_engine(args.engine)
 
     torch.manual_seed(1234)
@@ -303,8 +308,13 @@ def main():
         barrier()
         e0.record()
         last = None
-        for i in range(args.steps):
-            out = step(batch_src[i % len(batch_src)])
+        feed = (batch_src[i % len(batch_src)] for i in range(args.steps))
+        if read_loss:
+            # e2e: host batches through the trainer's own prefetcher (livae.train.DevicePrefetcher, the loop
+            # train_rvae_one_epoch runs): batch i+1 is copied from pinned memory while step i computes
+            feed = DevicePrefetcher(feed, device)
+        for batch in feed:
+            out = step(batch)
             if read_loss:
                 last = out[1].item()        # device -> host read of the step's loss, every step
         e1.record()
@@ -338,7 +348,9 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        fam, calls_per_step = profile_families(step, batches)
+        # per-kernel accounting runs on rank 0 alone: no collective inside it (the other ranks wait at the barrier)
+        local_step = lambda batch: train_rvae_step(model, opt, crit, batch, device, CANON_W, MAX_NORM, None)
+        fam, calls_per_step = profile_families(local_step, batches)
         tot = sum(f["ms"] for f in fam.values())
         top_key, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = top["ms"] / top["calls"]

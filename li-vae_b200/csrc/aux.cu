@@ -243,6 +243,10 @@ __global__ void __launch_bounds__(288, 3) upsample_pad_fwd_walk_kernel(const uin
     const int X1dup = v1 == 1 ? 0 : (v1 == 2 * W - 2 ? 2 * W + 1 : -1);
     const uint4* xa = xb + (int64_t)cA * C8 + c;
     const uint4* xq = xb + (int64_t)cB * C8 + c;
+    uint4* oc = ob + c;
+    // 32-bit offsets inside one image (index arithmetic was 80% of this kernel's instructions)
+    const int rowx = W * C8, rowo = Wo * C8;
+    const int X0c = X0 * C8, X1c = X1 * C8, X0dc = X0dup * C8, X1dc = X1dup * C8;
     // horizontal lerps of the two source rows of the block (ATen's inner parentheses), carried down the walk
     F8 lo0, lo1, hi0, hi1;
     int prev_rB = -1;
@@ -251,11 +255,11 @@ __global__ void __launch_bounds__(288, 3) upsample_pad_fwd_walk_kernel(const uin
       const int rA = max(r, 0), rB = min(rA + 1, H - 1);
       if (rA == prev_rB) { lo0 = hi0; lo1 = hi1; }
       else {
-        const F8 a = bf8_to_f2(__ldg(xa + (int64_t)rA * W * C8)), q = bf8_to_f2(__ldg(xq + (int64_t)rA * W * C8));
+        const F8 a = bf8_to_f2(__ldg(xa + rA * rowx)), q = bf8_to_f2(__ldg(xq + rA * rowx));
         lo0 = lerp8(a, q, fx0); lo1 = lerp8(a, q, fx1);
       }
       if (rB != rA) {
-        const F8 a = bf8_to_f2(__ldg(xa + (int64_t)rB * W * C8)), q = bf8_to_f2(__ldg(xq + (int64_t)rB * W * C8));
+        const F8 a = bf8_to_f2(__ldg(xa + rB * rowx)), q = bf8_to_f2(__ldg(xq + rB * rowx));
         hi0 = lerp8(a, q, fx0); hi1 = lerp8(a, q, fx1);
       } else { hi0 = lo0; hi1 = lo1; }
       prev_rB = rB;
@@ -263,27 +267,26 @@ __global__ void __launch_bounds__(288, 3) upsample_pad_fwd_walk_kernel(const uin
       for (int k = 0; k < 2; ++k) {
         const int u = 2 * r + 1 + k;
         if (u < 0 || u >= 2 * H) continue;
-        int i0, i1; float fy;
-        up_src(u, H, &i0, &i1, &fy);
-        uint4* o0 = ob + (int64_t)(u + 1) * Wo * C8 + c;
-        const int Ydup = u == 1 ? 0 : (u == 2 * H - 2 ? 2 * H + 1 : -1);
-        uint4* o1 = ob + (int64_t)Ydup * Wo * C8 + c;
+        // up_src(u): rows 2r+1 / 2r+2 sit at r + 0.25 / r + 0.75 (row 0 is clamped to the first source row)
+        const float fy = k == 0 ? 0.25f : (r < 0 ? 0.f : 0.75f);
+        const int offY = (u + 1) * rowo;
+        const int offD = u == 1 ? 0 : (u == 2 * H - 2 ? (2 * H + 1) * rowo : -1);
         if (c0ok) {
           const uint4 q = f2_to_bf8(lerp8(lo0, hi0, fy));
-          o0[X0 * C8] = q;
-          if (X0dup >= 0) o0[X0dup * C8] = q;
-          if (Ydup >= 0) {
-            o1[X0 * C8] = q;
-            if (X0dup >= 0) o1[X0dup * C8] = q;
+          oc[offY + X0c] = q;
+          if (X0dup >= 0) oc[offY + X0dc] = q;
+          if (offD >= 0) {
+            oc[offD + X0c] = q;
+            if (X0dup >= 0) oc[offD + X0dc] = q;
           }
         }
         if (c1ok) {
           const uint4 q = f2_to_bf8(lerp8(lo1, hi1, fy));
-          o0[X1 * C8] = q;
-          if (X1dup >= 0) o0[X1dup * C8] = q;
-          if (Ydup >= 0) {
-            o1[X1 * C8] = q;
-            if (X1dup >= 0) o1[X1dup * C8] = q;
+          oc[offY + X1c] = q;
+          if (X1dup >= 0) oc[offY + X1dc] = q;
+          if (offD >= 0) {
+            oc[offD + X1c] = q;
+            if (X1dup >= 0) oc[offD + X1dc] = q;
           }
         }
       }
@@ -316,11 +319,18 @@ __device__ __forceinline__ UpTaps up_col_taps(int j, int W) {
   t.X[5] = 2 * W + 1; t.w[5] = j == W - 2 ? up_w(2 * W - 2, j, W) : 0.f;
   return t;
 }
-__device__ __forceinline__ void up_adj_hrow(const uint4* __restrict__ grow, const UpTaps& ax, int C8, F8& h) {
+// the same with X premultiplied by the vectors per pixel (C8): 32-bit offsets inside a gradient row
+__device__ __forceinline__ UpTaps up_col_taps_scaled(int j, int W, int C8) {
+  UpTaps t = up_col_taps(j, W);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) t.X[k] *= C8;
+  return t;
+}
+__device__ __forceinline__ void up_adj_hrow(const uint4* __restrict__ grow, const UpTaps& ax, F8& h) {
   uint4 q[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k)
-    if (ax.w[k] != 0.f) q[k] = __ldg(grow + (int64_t)ax.X[k] * C8);
+    if (ax.w[k] != 0.f) q[k] = __ldg(grow + ax.X[k]);
 #pragma unroll
   for (int k = 0; k < 6; ++k)
     if (ax.w[k] != 0.f) {
@@ -338,7 +348,8 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
   const int i_begin = (int)blockIdx.x * rows_per_cta, i_end = min(H, i_begin + rows_per_cta);
   for (int t = threadIdx.x; t < W * C8; t += blockDim.x) {
     const int j = t >> logc8, c = t & (C8 - 1);
-    const UpTaps ax = up_col_taps(j, W);
+    const UpTaps ax = up_col_taps_scaled(j, W, C8);
+    const int rowg = Wo * C8;
     const uint4* gcol = g + (int64_t)b * Ho * Wo * C8 + c;    // (row Y, column X) at gcol[(Y*Wo + X)*C8]
     // walk the upsampled rows u that touch source rows [i_begin, i_end): row u adds (1-f) E[u] to source row
     // i0(u) and f E[u] to i1(u); acc0 / acc1 are the running sums of source rows a and a+1
@@ -362,8 +373,9 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
     const int u_lo = max(0, 2 * i_begin - 1), u_hi = min(2 * H - 1, 2 * i_end);
 #pragma unroll 1
     for (int u = u_lo; u <= u_hi; ++u) {
-      int i0, i1; float f;
-      up_src(u, H, &i0, &i1, &f);
+      // up_src(u): row u sits at (u-1)/2 + 0.25 / 0.75; row 0 is clamped to source row 0
+      const int i0 = u == 0 ? 0 : (u - 1) >> 1, i1 = min(i0 + 1, H - 1);
+      const float f = u == 0 ? 0.f : ((u & 1) ? 0.25f : 0.75f);
       if (i0 > a) {
         emit();
 #pragma unroll
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
       for (int rep = 0; rep < 2; ++rep) {
         const int Y = rep ? Ydup : u + 1;
         if (Y < 0) break;
-        up_adj_hrow(gcol + (int64_t)Y * Wo * C8, ax, C8, E);
+        up_adj_hrow(gcol + Y * rowg, ax, E);
       }
       const float w0 = i1 == i0 ? 1.f : 1.f - f, w1 = i1 == i0 ? 0.f : f;
       const float2 w02 = make_float2(w0, w0), w12 = make_float2(w1, w1);

@@ -308,3 +308,19 @@ def test_train_rvae_one_epoch_tensor_core_learns():
         livae.train_rvae_one_epoch(m, loader, opt, crit, log, torch.device("cuda"))
     losses = log.metrics["train_loss"]
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def test_device_prefetcher_order_and_values():
+    """livae.train.DevicePrefetcher (double-buffered host->device staging used by the training loops and by
+    bench.py's e2e arm): batches arrive in order, bit-equal, with nested tuples and non-tensor items kept."""
+    from livae.train import DevicePrefetcher
+    dev = torch.device("cuda")
+    host = [(torch.full((4, 1, 8, 8), float(i)).pin_memory(), torch.arange(4.0) + i, 0.5 * i) for i in range(7)]
+    seen = 0
+    for i, (x, a, f) in enumerate(DevicePrefetcher(host, dev)):
+        y = x * 2.0                                     # consume on the compute stream, as a step would
+        assert x.device.type == "cuda" and a.device.type == "cuda" and f == 0.5 * i
+        assert torch.equal(y.cpu(), host[i][0] * 2.0) and torch.equal(a.cpu(), host[i][1])
+        seen += 1
+    assert seen == 7 and len(DevicePrefetcher(host, dev)) == 7
+    assert list(DevicePrefetcher([], dev)) == []
