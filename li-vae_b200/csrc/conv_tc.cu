@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();      // whole-warp loop, one lane issues (tc_common.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
       constexpr uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
       constexpr uint32_t sbo = 8u * row_bytes;
@@ -514,9 +515,9 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
       if (resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
-        probe_rec(p.probe, 1, 0, pn);
+        if (leader) probe_rec(p.probe, 1, 0, pn);
         mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
-        probe_rec(p.probe, 1, 1, pn);
+        if (leader) probe_rec(p.probe, 1, 1, pn);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + acc * acc_cols;
         uint32_t accum = 0u;
@@ -525,37 +526,37 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
           for (int c = 0; c < nkc; ++c) {
             const uint32_t sa = ia & (kSA - 1);
             mbar_wait(&fullA[sa], (ia / kSA) & 1u);
-            probe_rec(p.probe, 1, 2, pn);
+            if (leader) probe_rec(p.probe, 1, 2, pn);
             tc_fence_after();
             const uint64_t ad_s = adesc0 + sa * a_slot16;
             if (resident) {
               uint64_t bd = bdesc0 + (uint32_t)(tb * nkc + c) * b_slot16;
               const uint32_t bstep = (uint32_t)nkc * b_slot16;
               for (int t = tb; t < te; ++t, bd += bstep) {
-                const uint64_t ad = ad_s + s_tapoff[t];
+                const uint64_t ad = ad_s + (((uint32_t)p.tap_shift[t] * row_bytes) >> 4);   // kernel parameter: stays uniform
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) { umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
+                for (int k = 0; k < KSTEPS; ++k) { if (leader) umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
               }
             } else {
               for (int t = tb; t < te; ++t) {
                 const uint32_t sb = ib & (kSB - 1);
                 mbar_wait(&fullB[sb], (ib / kSB) & 1u);
                 tc_fence_after();
-                const uint64_t ad = ad_s + s_tapoff[t];
+                const uint64_t ad = ad_s + (((uint32_t)p.tap_shift[t] * row_bytes) >> 4);   // kernel parameter: stays uniform
                 const uint64_t bd = bdesc0 + sb * b_slot16;
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) { umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
-                umma_commit(&emptyB[sb]);
+                for (int k = 0; k < KSTEPS; ++k) { if (leader) umma_f16(d_addr, ad + 2u * k, bd + 2u * k, idesc, accum); accum = 1u; }
+                if (leader) umma_commit(&emptyB[sb]);
                 ++ib;
               }
             }
-            probe_rec(p.probe, 1, 3, pn);
-            umma_commit(&emptyA[sa]);
+            if (leader) probe_rec(p.probe, 1, 3, pn);
+            if (leader) umma_commit(&emptyA[sa]);
             ++ia;
           }
         }
-        umma_commit(&tfull[acc]);
-        probe_rec(p.probe, 1, 4, pn);
+        if (leader) umma_commit(&tfull[acc]);
+        if (leader) probe_rec(p.probe, 1, 4, pn);
       }
     }
   } else {

@@ -83,6 +83,16 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk, uint32
   return off ^ (((off >> 7) & ((rb >> 4) - 1u)) << 4);
 }
 
+// One lane of a converged warp.  MMA-issuing warps run their loops as a WHOLE warp and guard only the
+// tcgen05.mma / tcgen05.commit with this predicate: in a warp-uniform loop the descriptor arithmetic stays on
+// the uniform datapath, and one warp then issues an N <= 64 MMA every 39-48 cycles (the shared-memory operand
+// bound); the same loop under `if (lane == 0)` is divergent code and manages one per ~68 (tools/umma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
                                                                 const __grid_constant__ CUtensorMap tmG,
                                                                 const WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_gdesc[8];     // A descriptor of each row group of this CTA, stage 0
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
@@ -284,8 +283,9 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
         }
       }
     } else {
-      if (lane == 0) {
-        // FIVE issuing threads (lane 0 of warps 1-5; warps 2-5 are idle until the epilogue anyway), row groups
+      {
+        const bool leader = elect_one();      // whole-warp loop, one lane issues (tc_common.cuh)
+        // FIVE issuing warps (1-5; warps 2-5 are idle until the epilogue anyway), row groups
         // dealt round-robin: one thread sustains one tcgen05.mma per ~50-85 cycles (tools/umma_rate.cu and the
         // probe of this loop), but an M=128 MMA with N <= 64 only occupies the pipe for (128+N)/4 = 36..48
         // cycles (shared-memory operand read), so a single issuer left the tensor pipe idle half the time on
@@ -306,32 +306,38 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
         const uint32_t b_kstep16 = (16u * rbg) >> 4;
         const uint64_t bd0 = make_smem_desc(smem_u32(smem) + a_region, gbox_slot, sbog, ltg);
         const uint32_t stage16 = stage_bytes >> 4;
-        for (int g = iw; g < ng; g += kWgIssuers) {
-          const WgGroup G = p.grp[g0 + g];
-          s_gdesc[g] = make_smem_desc(smem_u32(smem) + G.base_off - (uint32_t)box_lo * p.box_slot, G.lbo, sbox, ltx);
-        }
+        // this warp's row groups (G <= 8, five issuers: at most two), descriptors in registers
+        const int gA = iw, gB = iw + kWgIssuers;
+        const bool hasA = gA < ng, hasB = gB < ng;
+        const uint32_t tile_base = smem_u32(smem) - (uint32_t)box_lo * p.box_slot;
+        const uint64_t dA = hasA ? make_smem_desc(tile_base + p.grp[g0 + gA].base_off, p.grp[g0 + gA].lbo, sbox, ltx) : 0ull;
+        const uint64_t dB = hasB ? make_smem_desc(tile_base + p.grp[g0 + gB].base_off, p.grp[g0 + gB].lbo, sbox, ltx) : 0ull;
+        const uint32_t tA = tmem_base + (uint32_t)(gA * p.Cs), tB = tmem_base + (uint32_t)(gB * p.Cs);
         uint32_t accum = 0u;
         int pn = 0;
         for (int it = 0; it < nt; ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          if (iw == 0) probe_rec(p.probe, 1, 0, pn);
+          if (iw == 0 && leader) probe_rec(p.probe, 1, 0, pn);
           mbar_wait(&full_bar[s], ph);
-          if (iw == 0) probe_rec(p.probe, 1, 1, pn);
+          if (iw == 0 && leader) probe_rec(p.probe, 1, 1, pn);
           tc_fence_after();
           const uint32_t so = (uint32_t)s * stage16;
-          for (int g = iw; g < ng; g += kWgIssuers) {
-            uint64_t ad = s_gdesc[g] + so;
-            uint64_t bd = bd0 + so;
-            const uint32_t d_addr = tmem_base + (uint32_t)(g * p.Cs);
+          if (hasA) {
+            uint64_t ad = dA + so, bd = bd0 + so;
             for (int k = 0; k < ksteps; ++k, ad += a_kstep16, bd += b_kstep16)
-              umma_f16(d_addr, ad, bd, idesc, accum | (uint32_t)(k > 0));
+              if (leader) umma_f16(tA, ad, bd, idesc, accum | (uint32_t)(k > 0));
+          }
+          if (hasB) {
+            uint64_t ad = dB + so, bd = bd0 + so;
+            for (int k = 0; k < ksteps; ++k, ad += a_kstep16, bd += b_kstep16)
+              if (leader) umma_f16(tB, ad, bd, idesc, accum | (uint32_t)(k > 0));
           }
           accum = 1u;
-          if (iw == 0) probe_rec(p.probe, 1, 2, pn);
-          umma_commit(&empty_bar[s]);
+          if (iw == 0 && leader) probe_rec(p.probe, 1, 2, pn);
+          if (leader) umma_commit(&empty_bar[s]);
         }
-        umma_commit(&accum_bar);
+        if (leader) umma_commit(&accum_bar);
       }
       __syncwarp();
       if (warp >= 2) {

@@ -21,6 +21,15 @@ elif case == "fwd_d1":
 elif case == "fwd_c3":
     x = torch.randn(B, 32, 32, 64, device=dev).to(bf); wp = ops.tc_pack_weights(torch.randn(128, 64, 4, 4, device=dev), 128, 64, 4, 4, 0)
     run = lambda: ops.tc_conv(x, wp, None, 4, 4, 2, 1, 1)
+if case == "c5p_fwd":
+    x = torch.randn(B, 64, 64, 16, device=dev).to(bf); w = torch.randn(32, 16, 5, 5, device=dev); bb = torch.randn(32, device=dev)
+    run = lambda: ops.conv5pool_fwd(x, w, bb)
+elif case == "s2blk_c2":
+    g = torch.randn(B, 32, 32, 64, device=dev).to(bf); w = torch.randn(64, 32, 4, 4, device=dev)
+    run = lambda: ops.dgrad_s2blk(g, w, 64, 64)
+elif case == "s2blk_c3":
+    g = torch.randn(B, 16, 16, 128, device=dev).to(bf); w = torch.randn(128, 64, 4, 4, device=dev)
+    run = lambda: ops.dgrad_s2blk(g, w, 32, 32)
 if case == "wgrad_stn2":
     x = torch.randn(B, 64, 64, 16, device=dev).to(bf); g = torch.randn(B, 64, 64, 32, device=dev).to(bf)
     run = lambda: ops.tc_conv_wgrad(x, g, 5, 5, 1, 2)

@@ -7,6 +7,13 @@
 #include "tc_common.cuh"
 using namespace livae::tc;
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <bool UNIFORM>
 __global__ void __launch_bounds__(192) rate_kernel(int N, int a_mn, int b_mn, int reps, int issuers, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar[4];
@@ -21,7 +28,9 @@ __global__ void __launch_bounds__(192) rate_kernel(int N, int a_mn, int b_mn, in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  if (warp >= 1 && warp <= issuers && lane == 0) {
+  if (warp >= 1 && warp <= issuers && (UNIFORM || lane == 0)) {
+    // UNIFORM: the whole warp runs the loop (descriptor arithmetic stays warp-uniform), one elected lane issues
+    const bool leader = UNIFORM ? elect_one() : true;
     const int w = warp - 1;
     const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
     const uint32_t a0 = smem_u32(smem) + (uint32_t)w * 8192u, b0 = smem_u32(smem) + 48 * 1024 + (uint32_t)w * 8192u;
@@ -32,8 +41,8 @@ __global__ void __launch_bounds__(192) rate_kernel(int N, int a_mn, int b_mn, in
     uint64_t bd = b_mn ? make_smem_desc(b0, 64u * rbg, 8u * rbg, rbg == 128 ? 2u : 4u) : make_smem_desc(b0, 16u, 1024u, 2u);
     // warm-up
     const uint32_t d0 = tmem_base + (uint32_t)w * 128u;
-    for (int i = 0; i < 8; ++i) umma_f16(d0, ad, bd, idesc, 1u);
-    umma_commit(&bar[w]);
+    for (int i = 0; i < 8; ++i) if (leader) umma_f16(d0, ad, bd, idesc, 1u);
+    if (leader) umma_commit(&bar[w]);
     mbar_wait(&bar[w], 0);
     tc_fence_after();
     const long long t0 = clock64();
@@ -42,15 +51,15 @@ __global__ void __launch_bounds__(192) rate_kernel(int N, int a_mn, int b_mn, in
     for (int i = 0; i < reps; i += 8) {
       // +32 bytes per K step, as in a real K loop; two accumulators alternate
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(d0, ad + 2u * k, bd + 2u * k, idesc, 1u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_f16(d0, ad + 2u * k, bd + 2u * k, idesc, 1u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(d1, ad + 2u * k, bd + 2u * k, idesc, 1u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_f16(d1, ad + 2u * k, bd + 2u * k, idesc, 1u);
     }
     const long long t1 = clock64();
-    umma_commit(&bar[w]);
+    if (leader) umma_commit(&bar[w]);
     mbar_wait(&bar[w], 1);
     const long long t2 = clock64();
-    if (blockIdx.x == 0 && w == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (blockIdx.x == 0 && w == 0 && leader) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
   tc_fence_before();
   __syncthreads();
@@ -59,19 +68,22 @@ __global__ void __launch_bounds__(192) rate_kernel(int N, int a_mn, int b_mn, in
 
 int main(int argc, char** argv) {
   long long* d; cudaMalloc(&d, 16);
-  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int reps = 2048;
   printf("cycles per tcgen05.mma (M=128, K=16, bf16, SS), %d back-to-back MMAs, 148 CTAs; ideal = N/2\n", reps);
-  for (int issuers : {1, 2, 3, 4})
-    for (int maj : {0, 3}) {
+  for (int uni = 0; uni < 2; ++uni)
+  for (int issuers : {1, 2})
+    for (int maj : {0}) {
       const int a_mn = maj & 1, b_mn = maj >> 1;
       for (int N : {16, 32, 64, 128}) {
         if (issuers > 1 && N > 128) continue;
-        rate_kernel<<<148, 192, 100 * 1024>>>(N, a_mn, b_mn, reps, issuers, d);
+        if (uni) rate_kernel<true><<<148, 192, 100 * 1024>>>(N, a_mn, b_mn, reps, issuers, d);
+        else rate_kernel<false><<<148, 192, 100 * 1024>>>(N, a_mn, b_mn, reps, issuers, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
         long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("issuers %d  A %s  B %s  N=%3d : issue %.1f  complete %.1f cyc per MMA per SM (ideal %.0f)\n", issuers, a_mn ? "MN" : "K ", b_mn ? "MN" : "K ",
+        printf("%s issuers %d  A %s  B %s  N=%3d : issue %.1f  complete %.1f cyc per MMA per SM (ideal %.0f)\n", uni ? "warp-uniform loop" : "lane-0 loop      ", issuers, a_mn ? "MN" : "K ", b_mn ? "MN" : "K ",
                N, (double)h[0] / reps / issuers, (double)h[1] / reps / issuers, N / 2.0);
       }
     }
