@@ -364,6 +364,15 @@ def main():
             roof = {"bound": "hbm", "kernel": top_key, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                     "share_of_step": top["ms"] / tot, "avg_launch_ms": per_launch_ms}
+        # measured DRAM traffic of that kernel (ncu --set full capture committed under profiles/), else null
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top_key)
+            if tr:
+                roof["traffic"] = tr["bytes_per_launch"]
+                roof["traffic_source"] = tr["source"]
+                roof["algorithmic_bytes_per_launch"] = top["bytes"] / top["calls"]
+        except Exception:
+            pass
         t_step = ms / args.steps / 1e3
         t_roof = max(FLOP_PER_PATCH * args.batch / (pk["tf_sust"] * 1e12),
                      BYTES_PER_PATCH_FP32 * args.batch / (pk["hbm"] * 1e9))

@@ -246,13 +246,14 @@ struct ConvTcHaloParams {
   uint8_t tap_shift[kMaxTaps];   // shared-memory row offset of each tap inside its group's box
   int8_t tap_w[kMaxTaps];
   int kc, nkc, N, Ntot, B;
+  int nsa;                // slots of the A ring
   int b_resident;         // 1: all ntaps*nkc weight tiles stay in shared memory for the CTA's lifetime
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
   long long* probe;
   int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
 };
 
-static constexpr int kSA = 2, kSB = 4;
+static constexpr int kSA = 2, kSAmax = 4, kSB = 4;   // A ring: kSA..kSAmax slots (p.nsa), as many as fit without costing a resident CTA
 
 // Epilogue of one accumulator row per thread, 32 columns per pass: both tcgen05.ld and the ReLU-mask loads
 // of the pass are in flight before the first use; bias comes from shared memory.
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t fullA[kSA], emptyA[kSA], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
+  __shared__ __align__(8) uint64_t fullA[kSAmax], emptyA[kSAmax], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_tapoff[kMaxTaps];        // row shift of each tap in descriptor address units (16 B)
   __shared__ int s_grp[4][2];                    // tap_begin, tap_end of each group
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
   const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
   const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smemB = smem + kSA * a_slot;
+  uint8_t* smemB = smem + (uint32_t)p.nsa * a_slot;
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
   const uint32_t ncols = 2u * acc_cols;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < kSA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < kSAmax; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     fence_barrier_init();
@@ -458,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
 
   if (warp == 0) {
     if (lane == 0) {
-      int ia = 0, ib = 0, pn = 0;
+      int sa = 0, ib = 0, pn = 0;
+      uint32_t pha = 0u;
       if (p.b_resident) {   // small filters: fetch every weight tile once
         mbar_arrive_expect_tx(&fullB[0], b_bytes * (uint32_t)(p.ntaps * p.nkc));
         for (int t = 0; t < p.ntaps; ++t)
@@ -475,14 +477,13 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
         for (int g = 0; g < p.ngroups; ++g) {
           const HaloGroup G = p.grp[g];
           for (int c = 0; c < p.nkc; ++c) {
-            const int sa = ia % kSA;
             probe_rec(p.probe, 0, 0, pn);
-            mbar_wait(&emptyA[sa], ((uint32_t)(ia / kSA) & 1u) ^ 1u);
+            mbar_wait(&emptyA[sa], pha ^ 1u);
             probe_rec(p.probe, 0, 1, pn);
             mbar_arrive_expect_tx(&fullA[sa], a_bytes);
             if (p.a_s2d) tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], 0, x0 + G.dx, 2 * (y0 + G.dy) + c, b);
             else tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
-            ++ia;
+            if (++sa == p.nsa) { sa = 0; pha ^= 1u; }
             if (p.b_resident) continue;
             for (int t = G.tap_begin; t < G.tap_end; ++t) {
               const int sb = ib % kSB;
@@ -510,7 +511,8 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
       const uint32_t a_slot16 = a_slot >> 4, b_slot16 = b_slot >> 4;
       const int ngroups = p.ngroups, nkc = p.nkc;
       const bool resident = p.b_resident != 0;
-      uint32_t ia = 0, ib = 0, it = 0;
+      uint32_t sa = 0, pha = 0, ib = 0, it = 0;
+      const uint32_t nsa = (uint32_t)p.nsa;
       int pn = 0;
       if (resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -524,8 +526,7 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
         for (int g = 0; g < ngroups; ++g) {
           const int tb = s_grp[g][0], te = s_grp[g][1];
           for (int c = 0; c < nkc; ++c) {
-            const uint32_t sa = ia & (kSA - 1);
-            mbar_wait(&fullA[sa], (ia / kSA) & 1u);
+            mbar_wait(&fullA[sa], pha);
             if (leader) probe_rec(p.probe, 1, 2, pn);
             tc_fence_after();
             const uint64_t ad_s = adesc0 + sa * a_slot16;
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
             }
             if (leader) probe_rec(p.probe, 1, 3, pn);
             if (leader) umma_commit(&emptyA[sa]);
-            ++ia;
+            if (++sa == nsa) { sa = 0; pha ^= 1u; }
           }
         }
         if (leader) umma_commit(&tfull[acc]);
@@ -761,8 +762,9 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   // keep every weight tile in shared memory for the CTA's lifetime whenever they fit next to the two A slots
   // (even at one CTA per SM: streaming them costs an mbarrier wait + a commit per tap, more than the tap's MMAs)
   p.b_resident = ((size_t)ntaps * p.nkc * b_slot + (size_t)kSA * a_slot + 1024 <= 200 * 1024) ? 1 : 0;
-  const size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
+  size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
+  p.nsa = kSA;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -781,6 +783,9 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   if (per_sm > per_sm_tmem) per_sm = per_sm_tmem;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
+  // deepen the A ring while the same number of CTAs still fits (two slots leave the producer one box ahead
+  // at most: the MMA warp waited 400-900 cycles per box for TMA latency)
+  while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= 200 * 1024) { smem += a_slot; ++p.nsa; }
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
   const dim3 grid(gx, N / p.N);
