@@ -243,6 +243,12 @@ int livae_unpool_bf16(const void* g_pooled, const uint8_t* idx, int B, int H, in
 int livae_upsample_pad_fwd_bf16(const void* x, int B, int H, int W, int C, void* out, livae_stream_t stream);
 int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
                                 livae_stream_t stream);
+/* the same + gb[C] (fp32, written) = sum of gx over (b,i,j): the bias gradient of the convolution whose
+   pre-activation gradient gx is (autograd of Conv2d bias, model.py:359-367); needs C/8 a power of two, W*C/8 <= 256 */
+int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
+                                     float* gb, livae_stream_t stream);
+/* gb[C] (fp32, written) = column sums of the bf16 matrix g[R,C] (bias gradient from a pre-activation gradient) */
+int livae_colsum_bf16(const void* g, int64_t R, int C, float* gb, livae_stream_t stream);
 int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,
                          void* out, livae_stream_t stream);
 int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, int L, int C, int HW,

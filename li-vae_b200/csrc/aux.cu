@@ -340,9 +340,12 @@ __device__ __forceinline__ void up_adj_hrow(const uint4* __restrict__ grow, cons
       for (int e = 0; e < 4; ++e) h.v[e] = __ffma2_rn(w, v.v[e], h.v[e]);
     }
 }
+// gb (optional, fp32 [C], zeroed by the caller): column sums of the values written to gx, i.e. the bias gradient
+// of the convolution whose pre-activation gradient gx is -- fused here because a separate pass re-read gx.
 __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uint4* __restrict__ g, int H, int W, int logc8,
                                                                     int rows_per_cta, const uint4* __restrict__ mask_y,
-                                                                    uint4* __restrict__ gx) {
+                                                                    uint4* __restrict__ gx, float* __restrict__ gb) {
+  __shared__ float s_colsum[256 * 8];
   const int Ho = 2 * H + 2, Wo = 2 * W + 2, C8 = 1 << logc8;
   const int b = blockIdx.y;
   const int i_begin = (int)blockIdx.x * rows_per_cta, i_end = min(H, i_begin + rows_per_cta);
@@ -353,9 +356,9 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
     const uint4* gcol = g + (int64_t)b * Ho * Wo * C8 + c;    // (row Y, column X) at gcol[(Y*Wo + X)*C8]
     // walk the upsampled rows u that touch source rows [i_begin, i_end): row u adds (1-f) E[u] to source row
     // i0(u) and f E[u] to i1(u); acc0 / acc1 are the running sums of source rows a and a+1
-    F8 acc0, acc1;
+    F8 acc0, acc1, csum;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { acc0.v[e] = make_float2(0.f, 0.f); acc1.v[e] = make_float2(0.f, 0.f); }
+    for (int e = 0; e < 4; ++e) { acc0.v[e] = make_float2(0.f, 0.f); acc1.v[e] = make_float2(0.f, 0.f); csum.v[e] = make_float2(0.f, 0.f); }
     int a = i_begin - 1;
     auto emit = [&]() {
       if (a < i_begin || a >= i_end) return;
@@ -369,6 +372,8 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
         }
       }
       gx[o] = f2_to_bf8(acc0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) csum.v[e] = __fadd2_rn(csum.v[e], acc0.v[e]);
     };
     const int u_lo = max(0, 2 * i_begin - 1), u_hi = min(2 * H - 1, 2 * i_end);
 #pragma unroll 1
@@ -398,6 +403,21 @@ __global__ void __launch_bounds__(256, 3) upsample_pad_bwd_walk_kernel(const uin
       for (int e = 0; e < 4; ++e) { acc0.v[e] = __ffma2_rn(w02, E.v[e], acc0.v[e]); acc1.v[e] = __ffma2_rn(w12, E.v[e], acc1.v[e]); }
     }
     emit();
+    if (gb) {      // host guarantees one pass of the t loop (W * C8 <= blockDim.x) when gb is given
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s_colsum[t * 8 + 2 * e] = csum.v[e].x; s_colsum[t * 8 + 2 * e + 1] = csum.v[e].y; }
+    }
+  }
+  if (gb) {
+    __syncthreads();
+    // threads t, t + C8, t + 2*C8, ... own the same 8 channels: one thread per channel sums them
+    const int C = C8 * 8, nt = W * C8;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      const int c = ch >> 3, e = ch & 7;
+      float sum = 0.f;
+      for (int t = c; t < nt; t += C8) sum += s_colsum[t * 8 + e];
+      atomicAdd(gb + ch, sum);
+    }
   }
 }
 
@@ -683,20 +703,40 @@ extern "C" int livae_upsample_pad_fwd_bf16(const void* x, int B, int H, int W, i
   return 0;
 }
 
+static int upsample_pad_bwd_bf16_impl(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
+                                      float* gb, livae_stream_t stream);
 extern "C" int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y,
                                            void* gx, livae_stream_t stream) {
+  return upsample_pad_bwd_bf16_impl(g, B, H, W, C, relu_mask_y, gx, nullptr, stream);
+}
+// the same, plus gb[C] (fp32, written) = sum over (b, i, j) of the gx values: the bias gradient of the
+// convolution that produced the up-sampled tensor's source (reference: autograd of model.py:359-367)
+extern "C" int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y,
+                                                void* gx, float* gb, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(gb, "upsample_pad_bwd_bias_bf16: null gb");
+  if (B == 0) return 0;
+  if (int e = require_sm100()) return e;
+  cudaError_t ce = cudaMemsetAsync(gb, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+  if (ce != cudaSuccess) { set_error("upsample_pad_bwd_bias_bf16 memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+  return upsample_pad_bwd_bf16_impl(g, B, H, W, C, relu_mask_y, gx, gb, stream);
+}
+static int upsample_pad_bwd_bf16_impl(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
+                                      float* gb, livae_stream_t stream) {
   LIVAE_CHECK_ARG(B >= 0 && H > 1 && W > 1 && C > 0, "upsample_pad_bwd_bf16: bad args");
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(g && gx, "upsample_pad_bwd_bf16: null pointer");
   if (int e = require_sm100()) return e;
   int64_t n = (int64_t)B * H * W * C;
   const int logc8 = (C & 7) == 0 ? log2_exact(C / 8) : -1;
-  if (logc8 >= 0 && B <= 65535 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0) {
+  const bool walk_ok = logc8 >= 0 && B <= 65535 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0;
+  LIVAE_CHECK_ARG(!gb || (walk_ok && (W << logc8) <= 256),
+                  "upsample_pad_bwd_bias_bf16: needs C/8 a power of two, W*C/8 <= 256 and 16-byte aligned pointers");
+  if (walk_ok) {
     const int nchunk = (H + kUpChunk - 1) / kUpChunk, rows = (H + nchunk - 1) / nchunk;
     int threads = ((W << logc8) + 31) & ~31;
     if (threads > 256) threads = 256;
     upsample_pad_bwd_walk_kernel<<<dim3(nchunk, B), threads, 0, (cudaStream_t)stream>>>((const uint4*)g, H, W, logc8, rows,
-                                                                                       (const uint4*)relu_mask_y, (uint4*)gx);
+                                                                                       (const uint4*)relu_mask_y, (uint4*)gx, gb);
   }
   else if ((C & 7) == 0 && (((uintptr_t)g | (uintptr_t)gx | (uintptr_t)relu_mask_y) & 15) == 0)
     upsample_pad_bwd_bf16v_kernel<<<sgrid(n / 8, 1), 256, 0, (cudaStream_t)stream>>>(

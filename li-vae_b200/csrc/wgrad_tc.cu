@@ -629,6 +629,19 @@ void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st) {
 }
 }}  // namespace livae::tc
 
+// gb[C] (fp32, written) = column sums of the bf16 matrix g[R, C]: a bias gradient from a pre-activation gradient
+extern "C" int livae_colsum_bf16(const void* g, int64_t R, int C, float* gb, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(R >= 0 && C > 0, "colsum_bf16: bad sizes");
+  LIVAE_CHECK_ARG(gb && (g || R == 0), "colsum_bf16: null pointer");
+  if (int e = require_sm100()) return e;
+  cudaError_t ce = cudaMemsetAsync(gb, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+  if (ce != cudaSuccess) { set_error("colsum_bf16 memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+  if (R == 0) return 0;
+  livae::tc::colsum_bf16(g, R, C, gb, (cudaStream_t)stream);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int64_t livae_tc_wgrad_ws_bytes(const livae_tc_conv_desc* d) {
   if (!d) return 0;
   return (int64_t)d->kh * d->kw * d->Cin * d->Cout * 4;

@@ -66,6 +66,8 @@ _SIGS = {
     "livae_unpool_bf16": "ppiiiips",
     "livae_upsample_pad_fwd_bf16": "piiiips",
     "livae_upsample_pad_bwd_bf16": "piiiipps",
+    "livae_upsample_pad_bwd_bias_bf16": "piiiippps",
+    "livae_colsum_bf16": "plips",
     "livae_decfc_fwd_bf16": "pppiiiips",
     "livae_decfc_bwd_bf16": "pppiiiippps",
     "livae_tc_conv": "t" + "p" * 5 + "s",

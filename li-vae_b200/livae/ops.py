@@ -495,7 +495,9 @@ def conv5pool_bwd(x, w, g_pooled, idx, want_dgrad=True):
     gw = torch.empty_like(w)
     gb = torch.empty(Co, dtype=torch.float32, device=x.device)
     ws = torch.empty(L.lib().livae_tc_conv5pool_wgrad_ws_bytes(Ci, Co) // 4, dtype=torch.float32, device=x.device)
-    call("livae_tc_conv5pool_wgrad", x, g4, B, H, W, Ci, Co, gw, gb, ws)
+    # bias gradient from the POOLED gradient (a quarter of the elements of its routed 4-phase form)
+    call("livae_colsum_bf16", g_pooled, B * (H // 2) * (W // 2), Co, gb)
+    call("livae_tc_conv5pool_wgrad", x, g4, B, H, W, Ci, Co, gw, None, ws)
     gx = None
     if want_dgrad:
         gx = torch.empty_like(x)

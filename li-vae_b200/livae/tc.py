@@ -233,8 +233,9 @@ class DecoderTc(Function):
         for i, (w, cin, cout) in zip((3, 2, 1), ((d3w, 64, 32), (d2w, 128, 64), (d1w, 256, 128))):
             y, u = ys[i], us[i - 1]
             gy = torch.empty_like(y)                              # pre-activation gradient of conv i
-            call("livae_upsample_pad_bwd_bf16", gu, B, hw, hw, cout, y, gy)
-            gw, gb = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0)
+            gb = _empty((cout,), torch.float32, dev)           # bias gradient fused into the adjoint kernel
+            call("livae_upsample_pad_bwd_bias_bf16", gu, B, hw, hw, cout, y, gy, gb)
+            gw, _ = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0, want_bias=False)
             gu = ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, cout, cin, 3, 3, 2), None, hw + 2, hw + 2, 3, 3, 1, 0)
             grads.append((gw, gb))
             hw //= 2

@@ -163,6 +163,16 @@ def test_upsample_pad_bf16_shapes(B, Cc, H, W):
         _call("livae_upsample_pad_bwd_bf16", _nhwc(gy).cuda().to(BF), B, H, W, Cc, mask, gx)
         want = _nhwc(x.grad) if mask is None else _nhwc(x.grad) * (mask.float().cpu() > 0)
         assert rel_l2(gx.float().cpu(), want) < 5e-3
+        if Cc % 8 == 0 and (Cc // 8) & (Cc // 8 - 1) == 0 and W * Cc // 8 <= 256:
+            # fused bias gradient: column sums of the same values (fp32, before the bf16 rounding of gx)
+            gx2 = torch.empty_like(gx); gb = torch.full((Cc,), float("nan"), device="cuda")
+            _call("livae_upsample_pad_bwd_bias_bf16", _nhwc(gy).cuda().to(BF), B, H, W, Cc, mask, gx2, gb)
+            assert torch.equal(gx2, gx)
+            assert rel_l2(gb.cpu(), want.sum((0, 1, 2))) < 1e-4
+    g2 = torch.tensor(rng.standard_normal((B * H * W, Cc)).astype(np.float32)).cuda().to(BF)
+    gb = torch.full((Cc,), float("nan"), device="cuda")
+    _call("livae_colsum_bf16", g2, B * H * W, Cc, gb)
+    assert rel_l2(gb.cpu(), g2.float().cpu().sum(0)) < 1e-5
 
 
 @pytest.mark.parametrize("B,Cc,hw,N", [(5, 32, 8, 32), (130, 256, 2, 4), (64, 32, 32, 32)])
