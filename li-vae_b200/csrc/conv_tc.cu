@@ -120,6 +120,7 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int nbase, int N, 
 }
 
 static constexpr int kThreads = 192;
+static constexpr int kThreadsEpi2 = 320;   // un-blocking epilogue (EPI = 2): 8 epilogue warps, two per TMEM lane quarter
 
 template <int STAGES>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -354,9 +355,12 @@ __device__ __forceinline__ void epilogue_pool4(uint32_t taddr, int N, bool valid
 // [B, 2*Hq, 2*Wq, Ci] (bf16), each masked by relu_mask (same layout) > 0.  The mask vectors of phase p+1 are
 // requested before phase p is processed (a global-load latency per 16 columns made this epilogue slower than
 // the tile's MMAs).  CI16 = Ci / 16 (1, 2 or 4).
+// The four phases are split between TWO warps per TMEM lane quarter (ph0 = 0 or 2): with one warp per quarter
+// this epilogue took 4600-5200 cycles per tile against 2350 for the tile's MMAs (probe), i.e. the un-blocking
+// data-gradient kernels were epilogue-bound.
 template <int CI16>
 __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int b, int qy, int qx, int Hq, int Wq,
-                                                 void* out, const __nv_bfloat16* __restrict__ relu_mask) {
+                                                 void* out, const __nv_bfloat16* __restrict__ relu_mask, int ph0) {
   constexpr int Ci = CI16 * 16;
   const bool use_mask = relu_mask != nullptr && valid;
   uint4 mnext[2 * CI16];
@@ -366,16 +370,17 @@ __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int
 #pragma unroll
     for (int i = 0; i < 2 * CI16; ++i) mnext[i] = __ldg(mp + i);
   };
-  if (use_mask) load_mask(0);
+  if (use_mask) load_mask(ph0);
 #pragma unroll
-  for (int ph = 0; ph < 4; ++ph) {
+  for (int pi = 0; pi < 2; ++pi) {
+    const int ph = ph0 + pi;
     uint32_t v[CI16][16];
 #pragma unroll
     for (int c = 0; c < CI16; ++c) tmem_ld16(taddr + (uint32_t)(ph * Ci + c * 16), v[c]);
     uint4 m[2 * CI16];
 #pragma unroll
     for (int i = 0; i < 2 * CI16; ++i) m[i] = mnext[i];
-    if (use_mask && ph < 3) load_mask(ph + 1);
+    if (use_mask && pi < 1) load_mask(ph + 1);
     tmem_ld_wait();
     if (!valid) continue;
     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix_of(ph) * Ci);
@@ -410,7 +415,7 @@ __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int
 // EPI = epilogue mode (HaloOpts): a template parameter so that the register-hungry pooled / un-blocking
 // epilogues do not cost the plain convolutions their occupancy.
 template <int KSTEPS, int EPI>
-__global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -437,19 +442,19 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSAmax; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI == 2 ? 8 : 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, ncols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.ntaps; i += kThreads) s_tapoff[i] = ((uint32_t)p.tap_shift[i] * row_bytes) >> 4;
-  for (int i = threadIdx.x; i < p.ngroups; i += kThreads) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
+  for (int i = threadIdx.x; i < p.ntaps; i += blockDim.x) s_tapoff[i] = ((uint32_t)p.tap_shift[i] * row_bytes) >> 4;
+  for (int i = threadIdx.x; i < p.ngroups; i += blockDim.x) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
   if (EPI == 1) {
-    for (int i = threadIdx.x; i < (p.N >> 2); i += kThreads) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < (p.N >> 2); i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   } else {
-    for (int i = threadIdx.x; i < p.N; i += kThreads) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -585,11 +590,11 @@ __global__ void __launch_bounds__(kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kerne
       else if (EPI == 1)
         epilogue_pool4(taddr, p.N, valid, ((int64_t)b * p.Hq + qy) * p.Wq + qx, p.out, p.pool_idx, s_bias);
       else if (p.N == 64)
-        epilogue_unblock<1>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
+        epilogue_unblock<1>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask, warp >= 6 ? 2 : 0);
       else if (p.N == 128)
-        epilogue_unblock<2>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
+        epilogue_unblock<2>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask, warp >= 6 ? 2 : 0);
       else
-        epilogue_unblock<4>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask);
+        epilogue_unblock<4>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask, warp >= 6 ? 2 : 0);
       probe_rec(pb, 2, 2, pn);
       tc_fence_before();
       __syncwarp();
@@ -794,7 +799,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     conv_tc_halo_kernel<2, 1><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   } else if (opts.epi_mode == 2) {
     if (p.kc != 64) return 1;
-    conv_tc_halo_kernel<4, 2><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    conv_tc_halo_kernel<4, 2><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
   } else if (p.kc == 64) conv_tc_halo_kernel<4, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv_tc_halo_kernel<2, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else conv_tc_halo_kernel<1, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
