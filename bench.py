@@ -312,7 +312,8 @@ def main():
         if read_loss:
             # e2e: host batches through the trainer's own prefetcher (livae.train.DevicePrefetcher, the loop
             # train_rvae_one_epoch runs): batch i+1 is copied from pinned memory while step i computes
-            feed = DevicePrefetcher(feed, device)
+            prefetch.loader = feed
+            feed = prefetch
         for batch in feed:
             out = step(batch)
             if read_loss:
@@ -329,6 +330,11 @@ def main():
     for i in range(args.warmup):
         out = step(batches[i % len(batches)])
     loss0 = out[1].item()
+    # warm-up of the e2e path too: the prefetcher's two staging slots (2 x 268 MB) are allocated on first use, and
+    # that first cudaMalloc cost 10-110 ms inside a 6-step timed region
+    prefetch = DevicePrefetcher((host[i % len(host)] for i in range(2)), device)
+    for b in prefetch:
+        step(b)[1].item()
     if not np.isfinite(loss0):
         raise SystemExit(f"non-finite loss {loss0}")
 
