@@ -49,6 +49,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 }
 
 static constexpr int kMaxTaps = 32;
+static constexpr int kActSplitK = 99;     // internal epilogue mode of conv_tc_kernel (never part of the ABI)
 struct ConvTcParams {
   int tiles_x, tiles_y;   // tiles per image in x / y (ragged last tiles are predicated)
   int tw, th, nb;         // tile = nb images x th rows x tw cols <= 128 pixels
@@ -68,6 +69,7 @@ struct ConvTcParams {
   const float* bias;      // may be null
   int act;
   const __nv_bfloat16* relu_mask;  // may be null: out *= (relu_mask > 0), same shape as out
+  int ksplit;             // > 1: blockIdx.z owns a slice of the K blocks and adds its raw partial sums to the (zeroed) fp32 out
 };
 
 // Epilogue of one accumulator row per thread: TMEM -> registers -> bias / activation / ReLU mask of the
@@ -81,6 +83,12 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int nbase, int N, 
       tmem_ld_wait();
       if (!valid) continue;
       const int c0 = nbase + cc;
+      if (act == kActSplitK) {     // split-K partial: raw sums, bias / activation applied by the finishing kernel
+        float* o = reinterpret_cast<float*>(out) + pix * Ntot + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + i), "f"(__uint_as_float(v[i])) : "memory");
+        continue;
+      }
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -163,14 +171,19 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   const int tx = tile % p.tiles_x; tile /= p.tiles_x;
   const int ty = tile % p.tiles_y; tile /= p.tiles_y;
   const int b0 = tile * p.nb;
-  const int nk = p.ntaps * p.nkc;
+  const int nk_all = p.ntaps * p.nkc;
+  // split-K (Linear layers: 16 pixel tiles but 256-512 K blocks): blockIdx.z owns K blocks [kb0, kb0 + nk)
+  const int kper = (nk_all + p.ksplit - 1) / p.ksplit;
+  const int kb0 = (int)blockIdx.z * kper;
+  const int nk = min(kper, nk_all - kb0);
 
   if (warp == 0) {
     if (lane == 0) {
       const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      for (int ki = 0; ki < nk; ++ki) {
+        const int kb = kb0 + ki;
+        const int s = ki % STAGES;
+        const uint32_t ph = (uint32_t)(ki / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
         const int tap = kb / p.nkc, c = kb - tap * p.nkc;
@@ -180,12 +193,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();      // whole-warp loop, one lane issues (tc_common.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
       const uint32_t lt = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
       const uint32_t sbo = 8u * row_bytes;
       const int ksteps = p.kc / 16;
-      for (int kb = 0; kb < nk; ++kb) {
+      for (int kb = 0; kb < nk; ++kb) {          // kb: index inside this CTA's K slice
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
@@ -195,11 +209,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
           const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (leader) umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+        if (leader) umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
       }
-      umma_commit(&accum_bar);        // accumulator complete
+      if (leader) umma_commit(&accum_bar);        // accumulator complete
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
@@ -214,8 +228,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32,
-                  p.bias, p.act, p.relu_mask);
+    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid && nk > 0, pix, p.out,
+                  p.out_f32, p.bias, p.ksplit > 1 ? kActSplitK : p.act, p.relu_mask);
     tc_fence_before();
   }
   __syncthreads();
@@ -629,6 +643,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb,
   }
 }
 
+// out[r][c] = act(out[r][c] + bias[c]) in place: finishes a split-K accumulation
+__global__ void bias_act_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t n, int C, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = out[i] + (bias ? __ldg(bias + (int)(i % C)) : 0.f);
+    if (act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
+    else if (act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
+    out[i] = a;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
@@ -860,6 +884,28 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
     attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * ((B + p.nb - 1) / p.nb);
+  // split-K when the output grid cannot fill the chip but K is long (nn.Linear over a flattened map: 16 tiles,
+  // 256-512 K blocks -- 16 CTAs streamed the 134 MB operand at 0.7 TB/s)
+  p.ksplit = 1;
+  const int nk = ntaps * p.nkc, ctas = tiles * (N / p.N);
+  if (out_f32 && !relu_mask && ctas * 4 <= kNumSMs && nk >= 32) {
+    int ks = (2 * kNumSMs + ctas - 1) / ctas;
+    if (ks > nk / 8) ks = nk / 8;
+    const int kper = (nk + ks - 1) / ks;
+    p.ksplit = (nk + kper - 1) / kper;
+  }
+  if (p.ksplit > 1) {
+    const int64_t n = (int64_t)B * Ho * Wo * N;
+    cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st);
+    if (ce != cudaSuccess) { set_error("tc_conv split-K memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+    conv_tc_kernel<STAGES><<<dim3(tiles, N / p.N, p.ksplit), kThreads, smem, st>>>(tmA, tmB, p);
+    LIVAE_CUDA_LAUNCH_CHECK();
+    if (bias || act != LIVAE_ACT_NONE) {
+      bias_act_rows_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>((float*)out, bias, n, N, act);
+      LIVAE_CUDA_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   conv_tc_kernel<STAGES><<<dim3(tiles, N / p.N), kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;

@@ -43,3 +43,14 @@ for name, feed, read in (("device batches, no read-back", lambda: (dbat[i % 3] f
             out[1].item()
     e1.record(); torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1) / N:.2f} ms/step (wall {1e3 * (time.perf_counter() - t0) / N:.2f})")
+
+# host-side issue time per iteration of the prefetched loop without read-back (is the host ever blocked?)
+torch.cuda.synchronize()
+ts = []
+t0 = time.perf_counter()
+for b in DevicePrefetcher((hbat[i % 3] for i in range(12)), dev):
+    step(b)
+    ts.append(time.perf_counter() - t0)
+torch.cuda.synchronize()
+tend = time.perf_counter() - t0
+print("host issue times (ms):", " ".join(f"{1e3 * (b - a):.1f}" for a, b in zip([0.0] + ts[:-1], ts)), f"| drained at {1e3 * tend:.1f} ms")
