@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
   const int ntiles = (npx + 127) >> 7;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = Cfg::F16 ? make_idesc_f16(128, C, 0, 0) : make_idesc_bf16(128, C, 0, 0);
       const uint32_t lt = RB == 64 ? 4u : 6u;
       const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 8u * RB, lt);
@@ -157,10 +158,9 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
             for (int hl = 0; hl < 2; ++hl)                 // D = A * Whi^T + A * Wlo^T: weights exact to ~2^-17
 #pragma unroll
               for (int ks = 0; ks < KPAD / 16; ++ks)
-                umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
-                         bd0 + ((hl * 2048u + ks * 32u) >> 4), idesc, (ks | hl) > 0 ? 1u : 0u);
-          umma_commit(&a_empty[s]);
-          umma_commit(&t_full[s]);
+                if (leader) umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
+                                     bd0 + ((hl * 2048u + ks * 32u) >> 4), idesc, (ks | hl) > 0 ? 1u : 0u);
+          if (leader) { umma_commit(&a_empty[s]); umma_commit(&t_full[s]); }
         }
     }
   } else if (warp <= 4) {
@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(192) col2im_tc_kernel(const __grid_constant__ 
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();      // whole-warp loop, elected lane issues
       const uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
       const uint32_t w_addr = smem_u32(sW);
       uint32_t it = 0;
@@ -444,10 +445,9 @@ __global__ void __launch_bounds__(192) col2im_tc_kernel(const __grid_constant__ 
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t ad = make_smem_desc(a_addr + ks * 32u, 16u, 512u, 4u);
             const uint64_t bd = make_smem_desc(w_addr + ks * 32u, 16u, 512u, 4u);
-            umma_f16(tmem_base + acc * 32u, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            if (leader) umma_f16(tmem_base + acc * 32u, ad, bd, idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&emptyA[s]);
-          umma_commit(&tfull[acc]);
+          if (leader) { umma_commit(&emptyA[s]); umma_commit(&tfull[acc]); }
         }
     }
   } else {
@@ -683,8 +683,9 @@ __global__ void __launch_bounds__(WgLayout<KIND>::THREADS, 1) tap_wgrad_tc_kerne
       }
     }
   } else if (warp < FIRSTB) {
-    // ------------------------------------------------------------------ MMA issuers
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuers (whole warps, elected lanes issue)
+    {
+      const bool leader = elect_one();
       const uint32_t wi = (uint32_t)(warp - 1);
       const uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A K-major, B MN-major
       const uint32_t ltb = RBB == 64 ? 4u : 6u;
@@ -700,14 +701,14 @@ __global__ void __launch_bounds__(WgLayout<KIND>::THREADS, 1) tap_wgrad_tc_kerne
         const uint64_t bd = bd0 + ((BTMA ? b * R_SLOT : a * U_SLOT) >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_f16(d_addr, ad + ((ks * 32u) >> 4), bd + ((ks * 16u * RBB) >> 4), idesc, (ks > 0 || !first) ? 1u : 0u);
+          if (leader) umma_f16(d_addr, ad + ((ks * 32u) >> 4), bd + ((ks * 16u * RBB) >> 4), idesc, (ks > 0 || !first) ? 1u : 0u);
         first = 0u;
-        umma_commit(&a_empty[a]);
-        if (BTMA) umma_commit(&b_empty[b]);
+        if (leader) umma_commit(&a_empty[a]);
+        if (BTMA && leader) umma_commit(&b_empty[b]);
         a += kWgIssuers; if (a >= kWgA) { a -= kWgA; pa ^= 1u; }
         b += kWgIssuers; if (b >= kWgB) { b -= kWgB; pb ^= 1u; }
       }
-      umma_commit(&accum_bar);
+      if (leader) umma_commit(&accum_bar);
     }
   } else {
     // ------------------------------------------------------------------ builders
@@ -970,8 +971,9 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
         }
     }
   } else if (warp < kFoldFirstB) {
-    // ------------------------------------------------------------------ MMA issuers (row g -> issuer g % 3)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuers (row g -> issuer g % 3; whole warps)
+    {
+      const bool leader = elect_one();
       const uint32_t wi = (uint32_t)(warp - 1);
       const uint32_t idesc = make_idesc_bf16(128, 64, 1, 0);    // A MN-major, B K-major
       // A: two M atoms of 64 (LBO = 2048 B), K atoms of 8 rows 1024 B apart; B: 32-byte rows, 8-row groups 256 B apart
@@ -987,15 +989,14 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
         tc_fence_after();
         const uint64_t ad = ad0 + ((a * A_BYTES) >> 4);
         const uint32_t boff = (y * 12u * 32u) >> 4;
-        umma_f16(d_addr, ad, bh0 + boff, idesc, first ? 0u : 1u);
-        umma_f16(d_addr, ad, bl0 + boff, idesc, 1u);
+        if (leader) { umma_f16(d_addr, ad, bh0 + boff, idesc, first ? 0u : 1u); umma_f16(d_addr, ad, bl0 + boff, idesc, 1u); }
         first = 0u;
-        umma_commit(&a_empty[a]);
+        if (leader) umma_commit(&a_empty[a]);
         // last row of an image handled by this issuer: the B arrays may be rebuilt once these MMAs are done
-        if (y + kFoldIssuers >= (uint32_t)H) umma_commit(&b_free);
+        if (y + kFoldIssuers >= (uint32_t)H && leader) umma_commit(&b_free);
         a += kFoldIssuers; if (a >= kFoldA) { a -= kFoldA; pa ^= 1u; }
       }
-      umma_commit(&accum_bar);
+      if (leader) umma_commit(&accum_bar);
     }
   } else {
     // ------------------------------------------------------------------ builders
