@@ -247,6 +247,15 @@ int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const
    pre-activation gradient gx is (autograd of Conv2d bias, model.py:359-367); needs C/8 a power of two, W*C/8 <= 256 */
 int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
                                      float* gb, livae_stream_t stream);
+/* Last layer of the plain VAE decoder on the tensor-core path: ConvTranspose2d(C -> 1, k4, s2, p1) + activation
+   (model.py:95-96, 111-113) and its backward.  x: bf16 [B,H,W,C] (C = 32); w: fp32 [C,1,4,4]; out / g: fp32 [B,2H,2W]
+   (g = PRE-activation gradient); gx: bf16 [B,H,W,C] times (relu_mask > 0); gw [C,1,4,4], gb [1] written. */
+int livae_thin_convt_c1_fwd(const void* x, const float* w, const float* bias, int B, int H, int W, int C, int act,
+                            float* out, livae_stream_t stream);
+int livae_thin_convt_c1_dgrad(const float* g, const float* w, const void* relu_mask, int B, int H, int W, int C,
+                              void* gx, livae_stream_t stream);
+int livae_thin_convt_c1_wgrad(const void* x, const float* g, int B, int H, int W, int C, float* gw, float* gb,
+                              livae_stream_t stream);
 /* gb[C] (fp32, written) = column sums of the bf16 matrix g[R,C] (bias gradient from a pre-activation gradient) */
 int livae_colsum_bf16(const void* g, int64_t R, int C, float* gb, livae_stream_t stream);
 int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,

@@ -68,6 +68,9 @@ _SIGS = {
     "livae_upsample_pad_bwd_bf16": "piiiipps",
     "livae_upsample_pad_bwd_bias_bf16": "piiiippps",
     "livae_colsum_bf16": "plips",
+    "livae_thin_convt_c1_fwd": "pppiiiiips",
+    "livae_thin_convt_c1_dgrad": "pppiiiips",
+    "livae_thin_convt_c1_wgrad": "ppiiiipps",
     "livae_decfc_fwd_bf16": "pppiiiips",
     "livae_decfc_bwd_bf16": "pppiiiippps",
     "livae_tc_conv": "t" + "p" * 5 + "s",

@@ -81,6 +81,11 @@ class VAEEncoder(nn.Module):
         self.fc_logvar = nn.Linear(flat_size, latent_dim)
 
     def forward(self, x):
+        if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, x.shape[1]):
+            cl = self.conv_layers
+            return tc.VAEEncoderTc.apply(x, cl[0].weight, cl[0].bias, cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias,
+                                         cl[6].weight, cl[6].bias, self.fc_mu.weight, self.fc_mu.bias,
+                                         self.fc_logvar.weight, self.fc_logvar.bias)
         h = _run_encoder_convs(self.conv_layers, x)
         mu = ops.linear_nhwc(h, self.fc_mu.weight, self.fc_mu.bias)
         logvar = ops.linear_nhwc(h, self.fc_logvar.weight, self.fc_logvar.bias)
@@ -106,6 +111,10 @@ class VAEDecoder(nn.Module):
 
     def forward(self, z):
         q = self.patch_size // 16
+        if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, self.out_channels):
+            dl = self.deconv_layers
+            return tc.VAEDecoderTc.apply(z, self.fc.weight, self.fc.bias, dl[0].weight, dl[0].bias, dl[2].weight,
+                                         dl[2].bias, dl[4].weight, dl[4].bias, dl[6].weight, dl[6].bias)
         h = ops.decoder_fc(z, self.fc.weight, self.fc.bias, 256, q)
         for n, i in enumerate((0, 2, 4, 6)):
             m = self.deconv_layers[i]

@@ -246,3 +246,122 @@ class DecoderTc(Function):
         call("livae_decfc_bwd_bf16", z, fcw, gy0, B, Ld, 256, q * q, gfcw, gfcb, gz)
         (g3w, g3b), (g2w, g2b), (g1w, g1b) = grads
         return gz, gfcw, gfcb, g1w, g1b, g2w, g2b, g3w, g3b, gd4w, gd4b
+
+
+# ------------------------------------------------------------------------------------------------
+# plain VAE (reference model.py:9-182; scripts/train_vae.py): the same conv stack without the STN, and a
+# ConvTranspose2d decoder.  ConvTranspose2d(k4,s2,p1) forward IS the stride-2 data-gradient kernel (its weight
+# [Cin,Cout,kh,kw] is the weight [Cout',Cin',kh,kw] of the convolution it is the adjoint of); its data gradient is
+# that convolution's forward and its weight gradient that convolution's weight gradient with input and output
+# gradient swapped.  The 32 -> 1 layer (N = 1) runs on the fp32 engine.
+# ------------------------------------------------------------------------------------------------
+class VAEEncoderTc(Function):
+    """(x, 12 parameters) -> (mu, logvar); reference VAEEncoder.forward, model.py:45-61"""
+
+    @staticmethod
+    def forward(ctx, x, c0w, c0b, c2w, c2b, c4w, c4b, c6w, c6b, muw, mub, lvw, lvb):
+        ops.require_cuda(x)
+        x = x.contiguous()
+        B, _, P, _ = x.shape
+        dev = x.device
+        Ld = muw.shape[0]
+        h, q16 = P // 2, P // 16
+        h1 = _empty((B, h, h, 32), BF, dev)
+        call("livae_thin_conv1c_fwd", 1, x, c0w, c0b, B, P, P, h1, None)
+        h2 = ops.tc_conv(h1, ops.tc_pack_weights(c2w, 64, 32, 4, 4, 0), c2b, 4, 4, 2, 1, ACT_RELU)
+        h3 = ops.tc_conv(h2, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 0), c4b, 4, 4, 2, 1, ACT_RELU)
+        h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
+        Npad = _pad16(2 * Ld)
+        wcat = torch.cat([muw, lvw], 0)
+        bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
+        bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb
+        mulv = _linear_fwd(h4.view(B, -1), wcat, 256, q16, q16, bcat, Npad, ACT_NONE)
+        ctx.save_for_backward(x, c2w, c4w, c6w, wcat, h1, h2, h3, h4)
+        ctx.dims = (B, P, Ld, Npad)
+        ctx.set_materialize_grads(False)
+        return mulv[:, :Ld].contiguous(), mulv[:, Ld:2 * Ld].contiguous()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mu, g_lv):
+        x, c2w, c4w, c6w, wcat, h1, h2, h3, h4 = ctx.saved_tensors
+        B, P, Ld, Npad = ctx.dims
+        dev = x.device
+        h, q4, q16 = P // 2, P // 4, P // 16
+        if g_mu is None and g_lv is None:
+            return (None,) * 13
+        g16 = torch.zeros((B, Npad), dtype=torch.float32, device=dev)
+        if g_mu is not None:
+            g16[:, :Ld] = g_mu
+        if g_lv is not None:
+            g16[:, Ld:2 * Ld] = g_lv
+        gwcat, gbcat, gh4 = _linear_bwd(h4.view(B, -1), wcat, 256, q16, q16, ops.cast(g16, BF), Npad, h4.view(B, -1))
+        gh4 = gh4.view(B, q16, q16, 256)
+        gw6, gb6 = ops.tc_conv_wgrad(h3, gh4, 4, 4, 2, 1)
+        gh3 = _dgrad_s2(gh4, c6w, 256, 128, P // 8, h3)
+        gw4, gb4 = ops.tc_conv_wgrad(h2, gh3, 4, 4, 2, 1)
+        gh2 = _dgrad_s2(gh3, c4w, 128, 64, q4, h2)
+        gw2, gb2 = ops.tc_conv_wgrad(h1, gh2, 4, 4, 2, 1)
+        gh1 = _dgrad_s2(gh2, c2w, 64, 32, h, h1)
+        gc0w = _empty((32, 1, 4, 4), torch.float32, dev); gc0b = _empty((32,), torch.float32, dev)
+        call("livae_thin_conv1c_wgrad", 1, x, gh1, None, B, P, P, gc0w, gc0b)
+        gmuw, glvw = gwcat[:Ld].contiguous(), gwcat[Ld:2 * Ld].contiguous()
+        gmub, glvb = gbcat[:Ld].contiguous(), gbcat[Ld:2 * Ld].contiguous()
+        return (None, gc0w, gc0b, gw2, gb2, gw4, gb4, gw6, gb6, gmuw.view(Ld, -1), gmub, glvw.view(Ld, -1), glvb)
+
+
+class VAEDecoderTc(Function):
+    """(z, 10 parameters) -> recon [B,1,P,P]; reference VAEDecoder.forward, model.py:100-113"""
+
+    @staticmethod
+    def forward(ctx, z, fcw, fcb, t1w, t1b, t2w, t2b, t3w, t3b, t4w, t4b):
+        ops.require_cuda(z)
+        z = z.contiguous()
+        B, Ld = z.shape
+        dev = z.device
+        q = int(round((fcw.shape[0] // 256) ** 0.5))
+        y0 = _empty((B, q, q, 256), BF, dev)
+        call("livae_decfc_fwd_bf16", z, fcw, fcb, B, Ld, 256, q * q, y0)
+        ys = [y0]
+        cur, hw = y0, q
+        for w, b, cin, cout in ((t1w, t1b, 256, 128), (t2w, t2b, 128, 64), (t3w, t3b, 64, 32)):
+            # ConvTranspose2d weight [cin, cout, 4, 4] == weight of the adjoint convolution cout -> cin
+            cur = ops.tc_conv_dgrad(cur, ops.tc_pack_weights(w, cin, cout, 4, 4, 2), b, 2 * hw, 2 * hw, 4, 4, 2, 1, ACT_RELU)
+            ys.append(cur)
+            hw *= 2
+        P = 2 * hw
+        recon = _empty((B, 1, P, P), torch.float32, dev)
+        call("livae_thin_convt_c1_fwd", cur, t4w, t4b, B, hw, hw, 32, ACT_SIGMOID, recon)     # N = 1: thin kernel
+        ctx.save_for_backward(z, fcw, t1w, t2w, t3w, t4w, recon, *ys)
+        ctx.dims = (B, Ld, q, P)
+        return recon
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_recon):
+        saved = ctx.saved_tensors
+        z, fcw, t1w, t2w, t3w, t4w, recon = saved[:7]
+        ys = saved[7:11]
+        B, Ld, q, P = ctx.dims
+        dev = z.device
+        hw = P // 2
+        gpre4 = torch.empty_like(recon)
+        call("livae_sigmoid_bwd", recon, g_recon.contiguous(), None, recon.numel(), gpre4)
+        gt4w = torch.empty_like(t4w); gt4b = _empty((1,), torch.float32, dev)
+        call("livae_thin_convt_c1_wgrad", ys[3], gpre4, B, hw, hw, 32, gt4w, gt4b)
+        g = _empty((B, hw, hw, 32), BF, dev)                     # pre-activation gradient of t3's output
+        call("livae_thin_convt_c1_dgrad", gpre4, t4w, ys[3], B, hw, hw, 32, g)
+        grads = []
+        for i, (w, cin, cout) in zip((3, 2, 1), ((t3w, 64, 32), (t2w, 128, 64), (t1w, 256, 128))):
+            y_in = ys[i - 1]                                      # [B, hw/2, hw/2, cin], post-ReLU input of layer i
+            gb = _empty((cout,), torch.float32, dev)
+            call("livae_colsum_bf16", g, B * hw * hw, cout, gb)
+            gw, _ = ops.tc_conv_wgrad(g, y_in, 4, 4, 2, 1, want_bias=False)          # [cin, cout, 4, 4]
+            g = ops.tc_conv(g, ops.tc_pack_weights(w, cin, cout, 4, 4, 0), None, 4, 4, 2, 1, ACT_NONE, relu_mask=y_in)
+            grads.append((gw, gb))
+            hw //= 2
+        gfcw = torch.empty_like(fcw); gfcb = _empty((fcw.shape[0],), torch.float32, dev)
+        gz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        call("livae_decfc_bwd_bf16", z, fcw, g, B, Ld, 256, q * q, gfcw, gfcb, gz)
+        (g3w, g3b), (g2w, g2b), (g1w, g1b) = grads
+        return gz, gfcw, gfcb, g1w, g1b, g2w, g2b, g3w, g3b, gt4w, gt4b

@@ -324,3 +324,38 @@ def test_device_prefetcher_order_and_values():
         seen += 1
     assert seen == 7 and len(DevicePrefetcher(host, dev)) == 7
     assert list(DevicePrefetcher([], dev)) == []
+
+
+@pytest.mark.tc_engine
+@pytest.mark.parametrize("case", [(64, 16, 16, 2024), (32, 4, 8, 5), (128, 2, 4, 9)])
+def test_vae_step_tensor_core_engine(case):
+    """plain VAE (model.py:9-182, train.py:67-147) on the tensor-core engine: ConvTranspose2d layers as the
+    stride-2 data-gradient kernel, against the oracle's fp32 step (1e-3 ELBO, 1e-2 reconstruction; decoder
+    gradients 1e-1 relative L2 -- the deepest one, decoder.fc, has passed through 4 bf16 layers forward and 4
+    backward and measures 7e-2 at B = 16; encoder gradients by direction and norm, as for the rVAE)."""
+    import livae
+    P, L, B, seed = case
+    params = O.make_params(O.vae_param_shapes(P, L), seed=seed)
+    x, _, _ = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    want, wgrads = O.vae_full_step(params, x, eps, beta=1.0)
+    m = livae.VAE(latent_dim=L, in_channels=1, patch_size=P)
+    m.load_state_dict(params, strict=True)
+    m.cuda()
+    with FixedEps(eps):
+        recon, mu, logvar = m(x.cuda())
+    loss, rl, kl = livae.VAELoss(beta=1.0)(recon, x.cuda(), mu, logvar)
+    loss.backward()
+    assert recon.shape == (B, 1, P, P)
+    assert abs(loss.item() - float(want["loss"])) <= 1e-3 * abs(float(want["loss"]))
+    assert rel_l2(recon.detach().cpu(), want["recon"]) < 1e-2
+    assert float((mu.detach().cpu() - want["mu"]).abs().max()) < 1.5e-2
+    for k, p in m.named_parameters():
+        w = wgrads[k]
+        if float(w.norm()) < 1e-7:
+            continue
+        g = p.grad.detach().cpu()
+        if k.startswith("decoder."):
+            assert rel_l2(g, w) < 1e-1, (k, rel_l2(g, w))
+        else:
+            assert _cos(g, w) > 0.9 and abs(float(g.norm()) / float(w.norm()) - 1.0) < 0.3, (k, _cos(g, w))

@@ -175,6 +175,33 @@ def test_upsample_pad_bf16_shapes(B, Cc, H, W):
     assert rel_l2(gb.cpu(), g2.float().cpu().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 8, 8), (2, 32, 32), (1, 5, 9)])
+def test_vae_last_deconv_thin_kernels(B, H, W):
+    """ConvTranspose2d(32 -> 1, k4, s2, p1) + Sigmoid (model.py:95-96) and its backward against torch-CPU fp32 on the
+    same bf16-rounded input: fp32 outputs 1e-4, the bf16 data gradient 5e-3."""
+    rng = np.random.default_rng(B * H + W)
+    x = _bf(torch.tensor(rng.standard_normal((B, 32, H, W)).astype(np.float32))).requires_grad_(True)
+    w = torch.tensor((rng.standard_normal((32, 1, 4, 4)) * 0.2).astype(np.float32), requires_grad=True)
+    b = torch.tensor(rng.standard_normal(1).astype(np.float32), requires_grad=True)
+    pre = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    y = torch.sigmoid(pre)
+    xd = _nhwc(x.detach()).cuda().to(BF)
+    out = torch.full((B, 1, 2 * H, 2 * W), float("nan"), device="cuda")
+    _call("livae_thin_convt_c1_fwd", xd, w.detach().cuda(), b.detach().cuda(), B, H, W, 32, 2, out)
+    assert rel_l2(out.cpu(), y.detach()) < 1e-4
+    gpre = torch.tensor(rng.standard_normal(tuple(pre.shape)).astype(np.float32))
+    (pre * gpre).sum().backward()
+    gw = torch.full((32, 1, 4, 4), float("nan"), device="cuda"); gb = torch.full((1,), float("nan"), device="cuda")
+    _call("livae_thin_convt_c1_wgrad", xd, gpre.cuda(), B, H, W, 32, gw, gb)
+    assert rel_l2(gw.cpu(), w.grad) < 1e-4 and rel_l2(gb.cpu(), b.grad) < 1e-4
+    mask = torch.tensor(rng.standard_normal((B, H, W, 32)).astype(np.float32)).cuda().to(BF)
+    for mk in (None, mask):
+        gx = torch.full((B, H, W, 32), float("nan"), dtype=BF, device="cuda")
+        _call("livae_thin_convt_c1_dgrad", gpre.cuda(), w.detach().cuda(), mk, B, H, W, 32, gx)
+        want = _nhwc(x.grad) if mk is None else _nhwc(x.grad) * (mk.float().cpu() > 0)
+        assert rel_l2(gx.float().cpu(), want) < 5e-3
+
+
 @pytest.mark.parametrize("B,Cc,hw,N", [(5, 32, 8, 32), (130, 256, 2, 4), (64, 32, 32, 32)])
 def test_linear_as_tensor_core_gemm(B, Cc, hw, N):
     """nn.Linear over an NHWC-flattened map (model.py:210-213, 321-324) via livae.tc._linear_fwd/_linear_bwd"""
