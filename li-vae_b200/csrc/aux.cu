@@ -447,6 +447,44 @@ __global__ void __launch_bounds__(256) decfc_fwd_kernel(const float* __restrict_
 // Weight-stationary bf16 variant: a thread owns 8 consecutive channels of one pixel (its 8 x L weights and
 // biases live in registers), walks a slice of the batch and writes one 16-byte vector per sample --
 // coalesced stores, no per-element index arithmetic, weights read once.  L <= 8.
+// the same with 4 channels (one 8-byte vector) per thread so that 16 latent columns of weights fit in registers
+__global__ void __launch_bounds__(256) decfc_fwd_ws4_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int B, int L, int C4, int HW,
+                                                            uint2* __restrict__ out) {
+  constexpr int LMAX = 16;
+  const int v = blockIdx.x * 256 + threadIdx.x;         // vector index inside one sample: p * C4 + c4
+  const int nv = HW * C4;
+  if (v >= nv) return;
+  const int p = v / C4, c0 = (v - p * C4) * 4;
+  float wr[4][LMAX], br[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = (c0 + j) * HW + p;
+    br[j] = bias[row];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) wr[j][l] = l < L ? w[(int64_t)row * L + l] : 0.f;
+  }
+  const int bchunk = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  for (int b = b0; b < b1; ++b) {
+    float zl[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) zl[l] = l < L ? __ldg(z + b * L + l) : 0.f;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = br[j];
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) a = fmaf(zl[l], wr[j][l], a);
+      o[j] = fmaxf(a, 0.f);
+    }
+    uint2 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+    h[0] = __floats2bfloat162_rn(o[0], o[1]); h[1] = __floats2bfloat162_rn(o[2], o[3]);
+    out[(int64_t)b * nv + v] = q;
+  }
+}
+
 template <int LMAX>
 __global__ void __launch_bounds__(256) decfc_fwd_ws_kernel(const float* __restrict__ z, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int B, int L, int C8, int HW,
@@ -483,7 +521,7 @@ __global__ void __launch_bounds__(256) decfc_fwd_ws_kernel(const float* __restri
 
 // gz[b,l] = sum_n gpre[b,n] w[n,l]; one CTA per sample
 // y == nullptr: gy is already the pre-activation gradient (tensor-core path convention)
-template <typename T>
+template <typename T, int LT = 4>
 __global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const T* __restrict__ gy, const T* __restrict__ y,
                                                           const float* __restrict__ w, int L, int C, int HW,
                                                           float* __restrict__ gz) {
@@ -492,18 +530,21 @@ __global__ void __launch_bounds__(256) decfc_bwd_z_kernel(const T* __restrict__ 
   int N = C * HW;
   const T* gyb = gy + (int64_t)b * N;
   const T* yb = y ? y + (int64_t)b * N : nullptr;
-  for (int l0 = 0; l0 < L; l0 += 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l0 = 0; l0 < L; l0 += LT) {          // LT latent columns per pass over gy (one pass when L <= LT)
+    float a[LT];
+#pragma unroll
+    for (int t = 0; t < LT; ++t) a[t] = 0.f;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       float g = Cvt<T>::ld(gyb, i);
       if (yb && !(Cvt<T>::ld(yb, i) > 0.f)) g = 0.f;
       int c = i % C, p = i / C;
       const float* wr = w + (int64_t)(c * HW + p) * L;
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < LT; ++t)
         if (l0 + t < L) a[t] = fmaf(g, wr[l0 + t], a[t]);
     }
-    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int t = 0; t < LT; ++t) {
       float s = block_sum(a[t], red);
       if (threadIdx.x == 0 && l0 + t < L) gz[b * L + l0 + t] = s;
       __syncthreads();
@@ -760,6 +801,12 @@ extern "C" int livae_decfc_fwd_bf16(const float* z, const float* w, const float*
     int gy = (kNumSMs * 8 + gx - 1) / gx;
     if (gy > B) gy = B;
     decfc_fwd_ws_kernel<4><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C / 8, HW, (uint4*)out);
+  } else if (L <= 16 && (C & 3) == 0 && ((uintptr_t)out & 7) == 0) {
+    const int nv = HW * (C / 4);
+    const int gx = (nv + 255) / 256;
+    int gy = (kNumSMs * 8 + gx - 1) / gx;
+    if (gy > B) gy = B;
+    decfc_fwd_ws4_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(z, w, bias, B, L, C / 4, HW, (uint2*)out);
   } else {
     decfc_fwd_kernel<__nv_bfloat16><<<sgrid((int64_t)B * C * HW, 2), 256, 0, (cudaStream_t)stream>>>(
         z, w, bias, B, L, C, HW, (__nv_bfloat16*)out);
@@ -779,7 +826,8 @@ extern "C" int livae_decfc_bwd_bf16(const float* z, const float* w, const void* 
   const __nv_bfloat16* g = (const __nv_bfloat16*)gy;
   int N = C * HW;
   if (gz) {
-    decfc_bwd_z_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);
+    if (L <= 4) decfc_bwd_z_kernel<__nv_bfloat16, 4><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);
+    else decfc_bwd_z_kernel<__nv_bfloat16, 16><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);
     LIVAE_CUDA_LAUNCH_CHECK();
   }
   if (gw) {
@@ -790,8 +838,10 @@ extern "C" int livae_decfc_bwd_bf16(const float* z, const float* w, const void* 
     int ysplit = (kNumSMs * 8 + nb - 1) / nb;
     if (ysplit > (B + 15) / 16) ysplit = (B + 15) / 16;
     if (ysplit < 1) ysplit = 1;
-    decfc_bwd_w_kernel<4, __nv_bfloat16><<<dim3(nb, ysplit), 128, 0, st>>>(g, (const __nv_bfloat16*)nullptr, z, B, L, C, HW,
-                                                                            gw, gb);
+    if (L <= 4)
+      decfc_bwd_w_kernel<4, __nv_bfloat16><<<dim3(nb, ysplit), 128, 0, st>>>(g, (const __nv_bfloat16*)nullptr, z, B, L, C, HW, gw, gb);
+    else      // 16 latent columns per pass over gy
+      decfc_bwd_w_kernel<16, __nv_bfloat16><<<dim3(nb, ysplit), 128, 0, st>>>(g, (const __nv_bfloat16*)nullptr, z, B, L, C, HW, gw, gb);
     LIVAE_CUDA_LAUNCH_CHECK();
   }
   return 0;

@@ -115,36 +115,51 @@ __global__ void __launch_bounds__(256) convt_c1_dgrad_kernel(const float* __rest
 
 // ---- weight + bias gradient ----------------------------------------------------------------------------
 //   gw[ci, ky, kx] = sum_{b, iy, ix} x[b, iy, ix, ci] * g[b, 2*iy - 1 + ky, 2*ix - 1 + kx];  gb = sum g
-// Thread (ci, tap pair) keeps two accumulators over the CTA's strip of input pixels: per pixel a warp reads the
-// pixel's C channels as one coalesced line and two gradient values as broadcasts.  CTA = C * 8 threads.
+// Thread (ci, ky) keeps the four kx accumulators over the CTA's strip of input ROWS: per pixel a warp reads the
+// pixel's C channels as one coalesced line and four gradient values as broadcasts; the row loop has no index
+// arithmetic, so the compiler keeps several pixels' loads in flight.  CTA = C * 4 threads.
 template <int C>
-__global__ void __launch_bounds__(C * 8) convt_c1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g,
-                                                               int B, int H, int W, int64_t px_per_cta,
+__global__ void __launch_bounds__(C * 4) convt_c1_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g,
+                                                               int B, int H, int W, int rows_per_cta,
                                                                float* __restrict__ gw, float* __restrict__ gb) {
-  const int ci = threadIdx.x % C, tp = threadIdx.x / C;      // tap pair tp: taps 2*tp, 2*tp + 1 (same ky)
-  const int ky = tp >> 1, kx0 = (tp & 1) * 2;
+  const int ci = threadIdx.x % C, ky = threadIdx.x / C;
   const int Ho = 2 * H, Wo = 2 * W;
-  const int64_t npx = (int64_t)B * H * W;
-  const int64_t p0 = (int64_t)blockIdx.x * px_per_cta, p1 = p0 + px_per_cta < npx ? p0 + px_per_cta : npx;
-  float a0 = 0.f, a1 = 0.f, sb = 0.f;
-  int ix = (int)(p0 % W), iy = (int)((p0 / W) % H);
-  int64_t b = p0 / ((int64_t)W * H);
-  for (int64_t p = p0; p < p1; ++p, ++ix) {
-    if (ix == W) { ix = 0; if (++iy == H) { iy = 0; ++b; } }
-    const float xv = __bfloat162float(x[p * C + ci]);
-    const int oy = 2 * iy - 1 + ky, ox = 2 * ix - 1 + kx0;
-    const bool oky = oy >= 0 && oy < Ho;
-    const float* gr = g + (b * Ho + oy) * Wo;
-    const float g0 = (oky && ox >= 0) ? __ldg(gr + ox) : 0.f;            // ox is 2*ix - 1 or 2*ix + 1: < Wo always
-    const float g1 = (oky && ox + 1 < Wo) ? __ldg(gr + ox + 1) : 0.f;    // ox + 1 is 2*ix or 2*ix + 2: >= 0 always
-    a0 = fmaf(xv, g0, a0);
-    a1 = fmaf(xv, g1, a1);
-    // bias gradient: the 2x2 output block of this input pixel, one element per thread ci = 0..3 of tap pair 0
-    if (gb && tp == 0 && ci < 4) sb += __ldg(g + (b * Ho + 2 * iy + (ci >> 1)) * Wo + 2 * ix + (ci & 1));
+  const int64_t nrows = (int64_t)B * H;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < nrows ? r0 + rows_per_cta : nrows;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t b = r / H; const int iy = (int)(r - b * H);
+    const int oy = 2 * iy - 1 + ky;
+    const __nv_bfloat16* xr = x + r * W * C + ci;
+    if (oy >= 0 && oy < Ho) {
+      const float* gr = g + (b * Ho + oy) * Wo;
+      {   // ix = 0: output column -1 does not exist
+        const float xv = __bfloat162float(xr[0]);
+        a[1] = fmaf(xv, __ldg(gr), a[1]); a[2] = fmaf(xv, __ldg(gr + 1), a[2]); a[3] = fmaf(xv, __ldg(gr + 2), a[3]);
+      }
+#pragma unroll 4
+      for (int ix = 1; ix < W - 1; ++ix) {
+        const float xv = __bfloat162float(xr[ix * C]);
+        const float* gp = gr + 2 * ix - 1;
+        a[0] = fmaf(xv, __ldg(gp), a[0]); a[1] = fmaf(xv, __ldg(gp + 1), a[1]);
+        a[2] = fmaf(xv, __ldg(gp + 2), a[2]); a[3] = fmaf(xv, __ldg(gp + 3), a[3]);
+      }
+      if (W > 1) {   // ix = W-1: output column 2W does not exist
+        const float xv = __bfloat162float(xr[(W - 1) * C]);
+        const float* gp = gr + 2 * W - 3;
+        a[0] = fmaf(xv, __ldg(gp), a[0]); a[1] = fmaf(xv, __ldg(gp + 1), a[1]); a[2] = fmaf(xv, __ldg(gp + 2), a[2]);
+      }
+    }
+    // bias gradient: the two output rows of this input row, summed by the threads of ky = 0 (C lanes stride the row)
+    if (gb && ky == 0)
+      for (int k = ci; k < 2 * Wo; k += C) sb += __ldg(g + (b * Ho + 2 * iy) * Wo + k);
   }
-  atomicAdd(gw + ci * 16 + ky * 4 + kx0, a0);
-  atomicAdd(gw + ci * 16 + ky * 4 + kx0 + 1, a1);
-  if (gb && tp == 0 && ci < 4) atomicAdd(gb, sb);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(gw + ci * 16 + ky * 4 + k, a[k]);
+  if (gb && ky == 0) {
+    sb = warp_sum(sb);
+    if ((threadIdx.x & 31) == 0) atomicAdd(gb, sb);
+  }
 }
 
 }  // namespace livae
@@ -186,7 +201,7 @@ extern "C" int livae_thin_convt_c1_dgrad(const float* g, const float* w, const v
 // gw: fp32 [C,1,4,4], gb: fp32 [1] (optional); both written
 extern "C" int livae_thin_convt_c1_wgrad(const void* x, const float* g, int B, int H, int W, int C, float* gw, float* gb,
                                          livae_stream_t stream) {
-  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0, "thin_convt_c1_wgrad: bad sizes");
+  LIVAE_CHECK_ARG(B >= 0 && H > 0 && W > 1, "thin_convt_c1_wgrad: bad sizes (W >= 2)");
   LIVAE_CHECK_ARG(C == 32, "thin_convt_c1_wgrad: C must be 32 (got %d)", C);
   LIVAE_CHECK_ARG(gw, "thin_convt_c1_wgrad: null gw");
   if (int e = require_sm100()) return e;
@@ -196,12 +211,12 @@ extern "C" int livae_thin_convt_c1_wgrad(const void* x, const float* g, int B, i
   if (ce != cudaSuccess) { set_error("thin_convt_c1_wgrad memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   if (B == 0) return 0;
   LIVAE_CHECK_ARG(x && g, "thin_convt_c1_wgrad: null pointer");
-  const int64_t npx = (int64_t)B * H * W;
-  int64_t ctas = kNumSMs * 8;
-  if (ctas > npx) ctas = npx;
-  const int64_t per = (npx + ctas - 1) / ctas;
-  ctas = (npx + per - 1) / per;
-  convt_c1_wgrad_kernel<32><<<(int)ctas, 256, 0, st>>>((const __nv_bfloat16*)x, g, B, H, W, per, gw, gb);
+  const int64_t nrows = (int64_t)B * H;
+  int64_t ctas = kNumSMs * 16;
+  if (ctas > nrows) ctas = nrows;
+  const int64_t per = (nrows + ctas - 1) / ctas;
+  ctas = (nrows + per - 1) / per;
+  convt_c1_wgrad_kernel<32><<<(int)ctas, 128, 0, st>>>((const __nv_bfloat16*)x, g, B, H, W, (int)per, gw, gb);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

@@ -128,21 +128,21 @@ def test_pool_unpool_upsample_decfc_bf16():
     gx = torch.empty(B, 6, 6, Cc, dtype=BF, device="cuda")
     _call("livae_upsample_pad_bwd_bf16", _nhwc(gy).cuda().to(BF), B, 6, 6, Cc, mask, gx)
     assert rel_l2(gx.float().cpu(), _nhwc(x.grad) * (mask.float().cpu() > 0)) < 5e-3
-    # decoder fc, bf16 out / pre-activation bf16 gradient in
-    Ld, q = 3, 2
-    z = torch.tensor(rng.standard_normal((B, Ld)).astype(np.float32), requires_grad=True)
-    w = torch.tensor(rng.standard_normal((256 * q * q, Ld)).astype(np.float32), requires_grad=True)
-    b = torch.tensor(rng.standard_normal(256 * q * q).astype(np.float32), requires_grad=True)
-    pre = F.linear(z, w, b).view(B, 256, q, q)
-    y0 = torch.empty(B, q, q, 256, dtype=BF, device="cuda")
-    _call("livae_decfc_fwd_bf16", z.detach().cuda(), w.detach().cuda(), b.detach().cuda(), B, Ld, 256, q * q, y0)
-    assert rel_l2(y0.float().cpu(), _nhwc(torch.relu(pre).detach())) < 5e-3
-    gp = _bf(torch.tensor(rng.standard_normal((B, 256, q, q)).astype(np.float32)))
-    (pre * gp).sum().backward()
-    gw = torch.empty_like(w).cuda(); gb = torch.empty(256 * q * q, device="cuda"); gz = torch.empty(B, Ld, device="cuda")
-    _call("livae_decfc_bwd_bf16", z.detach().cuda(), w.detach().cuda(), _nhwc(gp).cuda().to(BF), B, Ld, 256, q * q,
-          gw, gb, gz)
-    assert rel_l2(gw.cpu(), w.grad) < 1e-5 and rel_l2(gb.cpu(), b.grad) < 1e-5 and rel_l2(gz.cpu(), z.grad) < 1e-5
+    # decoder fc, bf16 out / pre-activation bf16 gradient in; latent sizes on each of the three kernel variants
+    for Ld, q in ((3, 2), (16, 2), (20, 1)):
+        z = torch.tensor(rng.standard_normal((B, Ld)).astype(np.float32), requires_grad=True)
+        w = torch.tensor(rng.standard_normal((256 * q * q, Ld)).astype(np.float32), requires_grad=True)
+        b = torch.tensor(rng.standard_normal(256 * q * q).astype(np.float32), requires_grad=True)
+        pre = F.linear(z, w, b).view(B, 256, q, q)
+        y0 = torch.empty(B, q, q, 256, dtype=BF, device="cuda")
+        _call("livae_decfc_fwd_bf16", z.detach().cuda(), w.detach().cuda(), b.detach().cuda(), B, Ld, 256, q * q, y0)
+        assert rel_l2(y0.float().cpu(), _nhwc(torch.relu(pre).detach())) < 5e-3
+        gp = _bf(torch.tensor(rng.standard_normal((B, 256, q, q)).astype(np.float32)))
+        (pre * gp).sum().backward()
+        gw = torch.empty_like(w).cuda(); gb = torch.empty(256 * q * q, device="cuda"); gz = torch.empty(B, Ld, device="cuda")
+        _call("livae_decfc_bwd_bf16", z.detach().cuda(), w.detach().cuda(), _nhwc(gp).cuda().to(BF), B, Ld, 256, q * q,
+              gw, gb, gz)
+        assert rel_l2(gw.cpu(), w.grad) < 1e-5 and rel_l2(gb.cpu(), b.grad) < 1e-5 and rel_l2(gz.cpu(), z.grad) < 1e-5
 
 
 @pytest.mark.parametrize("B,Cc,H,W", [(2, 256, 8, 8), (2, 32, 64, 64), (1, 64, 37, 21), (3, 8, 2, 2), (1, 24, 5, 7)])
