@@ -256,6 +256,12 @@ int livae_thin_convt_c1_dgrad(const float* g, const float* w, const void* relu_m
                               void* gx, livae_stream_t stream);
 int livae_thin_convt_c1_wgrad(const void* x, const float* g, int B, int H, int W, int C, float* gw, float* gb,
                               livae_stream_t stream);
+/* Per-step metric block (train.py:606-667, compute_ssim): mean of the box-filter SSIM map of two fp32 image batches
+   [planes = B*C, H, W] -- the five avg_pool2d(win, stride 1, pad win/2, zero padding counted) passes, the map and its
+   mean in one pass over the two images.  ws: livae_ssim_box_ws_floats(planes, H) floats; out: 1 float. */
+int64_t livae_ssim_box_ws_floats(int64_t planes, int H);
+int livae_ssim_box(const float* a, const float* b, int64_t planes, int H, int W, int win, float c1, float c2,
+                   float* ws, float* out, livae_stream_t stream);
 /* gb[C] (fp32, written) = column sums of the bf16 matrix g[R,C] (bias gradient from a pre-activation gradient) */
 int livae_colsum_bf16(const void* g, int64_t R, int C, float* gb, livae_stream_t stream);
 int livae_decfc_fwd_bf16(const float* z, const float* w, const float* bias, int B, int L, int C, int HW,

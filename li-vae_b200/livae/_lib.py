@@ -68,6 +68,7 @@ _SIGS = {
     "livae_upsample_pad_bwd_bf16": "piiiipps",
     "livae_upsample_pad_bwd_bias_bf16": "piiiippps",
     "livae_colsum_bf16": "plips",
+    "livae_ssim_box": "ppliiiffpps",
     "livae_thin_convt_c1_fwd": "pppiiiiips",
     "livae_thin_convt_c1_dgrad": "pppiiiips",
     "livae_thin_convt_c1_wgrad": "ppiiiipps",
@@ -131,6 +132,8 @@ def lib():
     L.livae_tc_conv5pool_wgrad_ws_bytes.argtypes = [C.c_int, C.c_int]
     L.livae_tc_conv_supported.restype = C.c_int
     L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
+    L.livae_ssim_box_ws_floats.restype = C.c_int64
+    L.livae_ssim_box_ws_floats.argtypes = [C.c_int64, C.c_int]
     L.livae_conv_out_shape.restype = None
     L.livae_conv_out_shape.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for name, sig in _SIGS.items():
@@ -145,7 +148,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
 
 
 def ptr(t):

@@ -69,16 +69,17 @@ def compute_psnr(img1: torch.Tensor, img2: torch.Tensor, max_val: float = 1.0) -
 
 
 def _ssim_dev(img1, img2, window_size: int = 11, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2):
-    # Observability metric (SURVEY.md section 8f "next #1"), not part of the five hot-path stages:
-    # kept on the 11x11 box filter of the reference (train.py:606-667).
-    ap = lambda t: torch.nn.functional.avg_pool2d(t, window_size, stride=1, padding=window_size // 2)
-    mu1, mu2 = ap(img1), ap(img2)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq = ap(img1 * img1) - mu1_sq
-    sigma2_sq = ap(img2 * img2) - mu2_sq
-    sigma12 = ap(img1 * img2) - mu1_mu2
-    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
-    return ssim_map.mean()
+    """mean box-filter SSIM map (reference train.py:606-667) as one fused pass over the two batches
+    (csrc/ssim.cu) instead of five avg_pool2d passes and a dozen elementwise kernels; device scalar."""
+    from ._lib import call, lib
+    a = img1.detach().contiguous().float(); b = img2.detach().contiguous().float()
+    ops.require_cuda(a, b)
+    assert a.shape == b.shape and a.dim() == 4
+    planes, H, W = a.shape[0] * a.shape[1], a.shape[2], a.shape[3]
+    ws = torch.empty(max(1, lib().livae_ssim_box_ws_floats(planes, H)), dtype=torch.float32, device=a.device)
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    call("livae_ssim_box", a, b, planes, H, W, window_size, float(C1), float(C2), ws, out)
+    return out[0]
 
 
 def compute_ssim(img1, img2, window_size: int = 11, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2) -> float:

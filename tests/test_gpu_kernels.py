@@ -364,3 +364,21 @@ def test_l2norm_clip_and_adamw(ops):
 def test_cpu_tensors_fail_loudly(ops):
     with pytest.raises(RuntimeError):
         ops.rot_sample(torch.zeros(1, 1, 8, 8), torch.zeros(1, 2), 1.0)
+
+
+@pytest.mark.parametrize("shape,win", [((3, 1, 128, 128), 11), ((2, 2, 37, 50), 11), ((1, 1, 16, 16), 5), ((4, 1, 64, 64), 11)])
+def test_ssim_box_matches_reference_formula(shape, win):
+    """fused box-filter SSIM (csrc/ssim.cu) against the reference's avg_pool2d formulation (train.py:606-667)"""
+    import torch.nn.functional as F
+    from livae.train import _ssim_dev
+    rng = np.random.default_rng(shape[2] + win)
+    a = torch.tensor(rng.random(shape).astype(np.float32))
+    b = (a + 0.1 * torch.tensor(rng.standard_normal(shape).astype(np.float32))).clamp(0, 1)
+    ap = lambda t: F.avg_pool2d(t, win, stride=1, padding=win // 2)
+    mu1, mu2 = ap(a.double()), ap(b.double())
+    s1, s2, s12 = ap(a.double() ** 2) - mu1 ** 2, ap(b.double() ** 2) - mu2 ** 2, ap(a.double() * b.double()) - mu1 * mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    want = (((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 ** 2 + mu2 ** 2 + c1) * (s1 + s2 + c2))).mean().item()
+    got = _ssim_dev(a.cuda(), b.cuda(), win).item()
+    assert abs(got - want) < 2e-5, (got, want)
+    assert abs(_ssim_dev(a.cuda(), a.cuda(), win).item() - 1.0) < 1e-5
