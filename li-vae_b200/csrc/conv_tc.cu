@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int total_tiles = p.tiles_x * p.tiles_y * p.B;
+  const long long cta_t0 = p.probe ? clock64() : 0ll;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -616,6 +617,8 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
     }
   }
   __syncthreads();
+  if (p.probe && threadIdx.x == 0 && blockIdx.x < 1024 && blockIdx.y == 0)     // role 3: whole-CTA span of every CTA
+    p.probe[3 * 1024 + blockIdx.x] = clock64() - cta_t0;
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ncols);

@@ -60,7 +60,9 @@ def _linear_bwd(x2d, w, Cb, kh, kw, g_bf, Npad, relu_mask):
 
 def _dgrad_s2(gy, w, Cout, Cin, hin, mask):
     """data gradient of an encoder 4x4 stride-2 convolution, masked by the ReLU of the layer below"""
-    if ops.dgrad_s2blk_supported(hin, hin, Cin, Cout):
+    # block form (one launch, N = 4*Cin, 4 of 9 taps per phase non-zero) wins while N <= 128; at Cin = 64 the four
+    # per-phase launches (N = 64, no zero taps) are 1.3x faster (tools/micro.py s2blk_64_128_32)
+    if Cin <= 32 and ops.dgrad_s2blk_supported(hin, hin, Cin, Cout):
         return ops.dgrad_s2blk(gy, w, hin, hin, relu_mask=mask)
     return ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, Cout, Cin, 4, 4, 2), None, hin, hin, 4, 4, 2, 1, relu_mask=mask)
 

@@ -47,6 +47,14 @@ for w in which:
             wp = ops.tc_pack_weights(wt, co, ci, k, k, 2)
             t = timeit(lambda: ops.tc_conv_dgrad(g, wp, None, hin, hin, k, k, st, pd))
         print(f"{w}: {t:.3f} ms  {fl / t / 1e9:.0f} TF/s")
+    elif w.startswith("s2blk_"):
+        _, ci, co, hin = w.split("_"); ci, co, hin = int(ci), int(co), int(hin)
+        g = torch.randn(B, hin // 2, hin // 2, co, device=dev).to(bf); wt = torch.randn(co, ci, 4, 4, device=dev)
+        mask = torch.randn(B, hin, hin, ci, device=dev).to(bf)
+        fl = 2.0 * B * (hin // 2) ** 2 * ci * co * 16
+        t = timeit(lambda: ops.dgrad_s2blk(g, wt, hin, hin, relu_mask=mask))
+        t2 = timeit(lambda: ops.tc_conv_dgrad(g, ops.tc_pack_weights(wt, co, ci, 4, 4, 2), None, hin, hin, 4, 4, 2, 1, relu_mask=mask))
+        print(f"{w}: block form {t:.3f} ms ({fl / t / 1e9:.0f} TF/s useful)   four phases {t2:.3f} ms ({fl / t2 / 1e9:.0f} TF/s)")
     elif w == "fwd_d3":
         x = torch.randn(B, 66, 66, 64, device=dev).to(bf); wt = torch.randn(32, 64, 3, 3, device=dev)
         wp = ops.tc_pack_weights(wt, 32, 64, 3, 3, 0)

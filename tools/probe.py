@@ -45,12 +45,16 @@ L.livae_set_probe(buf.data_ptr())
 run(); torch.cuda.synchronize()
 L.livae_set_probe(None)
 r = buf.cpu().tolist()
-for role, name in enumerate(("producer", "mma", "epilogue", "other")):
+spans = sorted(v for v in r[3 * 1024:4 * 1024] if v != 0)
+if spans:
+    print(f"--- {case} per-CTA spans ({len(spans)} CTAs): min {spans[0]}  median {spans[len(spans) // 2]}  max {spans[-1]} cycles")
+for role, name in enumerate(("producer", "mma", "epilogue")):
     recs = [(v >> 56, v & ((1 << 56) - 1)) for v in r[role * 1024:(role + 1) * 1024] if v != 0]
     if not recs:
         continue
     print(f"--- {case} {name}: {len(recs)} records; showing from #{first}")
     prev = recs[first - 1][1] if first > 0 and len(recs) > first else recs[0][1]
+    print(f"  total span {recs[-1][1] - recs[0][1]} cycles over {len(recs)} records")
     for i, (s, t) in enumerate(recs[first:first + 24]):
         print(f"  slot {s}  dt={t - prev:6d}")
         prev = t
