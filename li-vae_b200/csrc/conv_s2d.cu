@@ -206,7 +206,7 @@ extern "C" int livae_tc_conv5pool_wgrad(const void* x, const void* g_s2d, int B,
 
 // ---- 4x4 stride-2 pad-1 data gradient in block form (see pack_s2blk_kernel) ----
 extern "C" int livae_tc_dgrad_s2blk_supported(int Hin, int Win, int Cin, int Cout) {
-  return ((Hin | Win) & 1) == 0 && Hin >= 16 && Win >= 16 && (Cin == 16 || Cin == 32 || Cin == 64) &&
+  return ((Hin | Win) & 1) == 0 && Hin >= 16 && Win >= 16 && (Cin == 16 || Cin == 32) &&     // N = 4*Cin <= 128
          (Cout == 32 || (Cout % 64) == 0) ? 1 : 0;
 }
 // w fp32 [Cout][Cin][4][4] -> bf16 [9][4*Cin][Cout]
