@@ -59,6 +59,14 @@ int livae_patch_gather_f32(const float* images, int n_img, int H, int W,
 int livae_patch_gather_f64(const double* images, int n_img, int H, int W,
                            const int32_t* sites, int N, int P, float* out, livae_stream_t stream);
 /* a2 tail: per-patch min-max normalisation to [0,1] (data.py:553-558), in place */
+/* a2: sub-pixel patch gather == AdaptiveLatticeDataset.__getitem__ with transform=None before its min-max
+   (data.py:478-551): bilinear resampling of float32(img), zero outside the image, centred on the float site.
+   img_idx: int32 [N]; yx: float64 [N,2] (cy, cx); P even; out: fp32 [N,1,P,P].  Follow with livae_patch_minmax
+   (data.py:553-558).  Within 2e-5 of the reference (whose torchvision affine grid is fp32). */
+int livae_patch_gather_subpixel_f32(const float* images, int n_img, int H, int W, const int32_t* img_idx,
+                                    const double* yx, int N, int P, float* out, livae_stream_t stream);
+int livae_patch_gather_subpixel_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
+                                    const double* yx, int N, int P, float* out, livae_stream_t stream);
 int livae_patch_minmax(float* patches, int N, int P, livae_stream_t stream);
 
 /* ---- a6: fused rotate + bilinear sample (affine_grid + grid_sample) ------------------

@@ -58,6 +58,55 @@ __global__ void __launch_bounds__(256) patch_minmax_kernel(float* __restrict__ p
   }
 }
 
+// a2: sub-pixel gather (AdaptiveLatticeDataset.__getitem__ with transform=None, reference data.py:478-551):
+// the patch centred on the FLOAT site (cy, cx) is the bilinear resampling of float32(img), zero outside the image,
+// at (cy - P/2 + r, cx - P/2 + c) -- what the reference's integer ROI + sub-pixel TF.affine translate + centre
+// crops compute (for even P; its fp32 affine grid differs from this exact form by <= 2e-5).  Coordinates and
+// weights in double (a site near 4096 has an fp32 ulp of 5e-4 pixels), one rounding to float at the end.
+template <typename S>
+__global__ void __launch_bounds__(256) patch_gather_subpixel_kernel(
+    const S* __restrict__ images, int n_img, int H, int W, const int32_t* __restrict__ img_idx,
+    const double* __restrict__ yx, int N, int P, float* __restrict__ out) {
+  const int n = blockIdx.x;
+  const int img = img_idx[n];
+  const double cy = yx[2 * n], cx = yx[2 * n + 1];
+  const S* src = images + (int64_t)img * H * W;
+  float* dst = out + (int64_t)n * P * P;
+  const bool img_ok = img >= 0 && img < n_img;
+  const int rows_per_blk = (P + gridDim.y - 1) / gridDim.y;
+  const int r_beg = blockIdx.y * rows_per_blk, r_end = min(P, r_beg + rows_per_blk);
+  for (int i = r_beg * P + threadIdx.x; i < r_end * P; i += blockDim.x) {
+    const int r = i / P, c = i - r * P;
+    const double ys = cy - (double)(P / 2) + r, xs = cx - (double)(P / 2) + c;
+    const double fy0 = floor(ys), fx0 = floor(xs);
+    const int y0 = (int)fy0, x0 = (int)fx0;
+    const double fy = ys - fy0, fx = xs - fx0;
+    double acc = 0.0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        if (img_ok && yy >= 0 && yy < H && xx >= 0 && xx < W)
+          acc += (dy ? fy : 1.0 - fy) * (dx ? fx : 1.0 - fx) * (double)(float)src[(int64_t)yy * W + xx];
+      }
+    dst[i] = (float)acc;
+  }
+}
+
+template <typename S>
+int patch_gather_subpixel(const S* images, int n_img, int H, int W, const int32_t* img_idx, const double* yx, int N,
+                          int P, float* out, cudaStream_t st) {
+  LIVAE_CHECK_ARG(N >= 0 && P > 0 && (P & 1) == 0 && H > 0 && W > 0 && n_img > 0, "patch_gather_subpixel: bad sizes (P even)");
+  if (N == 0) return 0;
+  LIVAE_CHECK_ARG(images && img_idx && yx && out, "patch_gather_subpixel: null pointer");
+  if (int e = require_sm100()) return e;
+  const int bands = N >= 148 * 8 ? 1 : (P >= 64 ? 4 : 1);
+  patch_gather_subpixel_kernel<S><<<dim3(N, bands), 256, 0, st>>>(images, n_img, H, W, img_idx, yx, N, P, out);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename S>
 int patch_gather(const S* images, int n_img, int H, int W, const int32_t* sites, int N, int P,
                  float* out, cudaStream_t st) {
@@ -81,6 +130,14 @@ extern "C" int livae_patch_gather_f32(const float* images, int n_img, int H, int
 extern "C" int livae_patch_gather_f64(const double* images, int n_img, int H, int W, const int32_t* sites,
                                       int N, int P, float* out, livae_stream_t stream) {
   return livae::patch_gather<double>(images, n_img, H, W, sites, N, P, out, (cudaStream_t)stream);
+}
+extern "C" int livae_patch_gather_subpixel_f32(const float* images, int n_img, int H, int W, const int32_t* img_idx,
+                                               const double* yx, int N, int P, float* out, livae_stream_t stream) {
+  return livae::patch_gather_subpixel<float>(images, n_img, H, W, img_idx, yx, N, P, out, (cudaStream_t)stream);
+}
+extern "C" int livae_patch_gather_subpixel_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
+                                               const double* yx, int N, int P, float* out, livae_stream_t stream) {
+  return livae::patch_gather_subpixel<double>(images, n_img, H, W, img_idx, yx, N, P, out, (cudaStream_t)stream);
 }
 extern "C" int livae_patch_minmax(float* patches, int N, int P, livae_stream_t stream) {
   LIVAE_CHECK_ARG(N >= 0 && P > 0, "patch_minmax: bad args");

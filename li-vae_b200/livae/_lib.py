@@ -38,6 +38,8 @@ _SIGS = {
     "livae_patch_gather_f32": "piiipiips",
     "livae_patch_gather_f64": "piiipiips",
     "livae_patch_minmax": "piis",
+    "livae_patch_gather_subpixel_f32": "piiippiips",
+    "livae_patch_gather_subpixel_f64": "piiippiips",
     "livae_rot_sample_fwd": "ppfiiiips",
     "livae_rot_sample_bwd": "ppfpiiiipps",
     "livae_stn_head_fwd": "pipps",

@@ -355,6 +355,29 @@ def patch_gather(images, sites, P, out=None):
     return out
 
 
+def patch_gather_subpixel(images, img_idx, yx, P, out=None):
+    """images [n_img,H,W] float32/float64 (device), img_idx int32 [N], yx float64 [N,2] float sites (cy, cx) ->
+    float32 [N,1,P,P]: the sub-pixel crop of AdaptiveLatticeDataset.__getitem__ (data.py:478-551, transform=None)
+    before its min-max (apply patch_minmax_ for data.py:553-558)"""
+    if not images.is_cuda or not yx.is_cuda or not img_idx.is_cuda:
+        raise RuntimeError("livae.patch_gather_subpixel: device tensors required; there is no CPU path")
+    assert images.dim() == 3 and images.is_contiguous()
+    assert img_idx.dtype == torch.int32 and img_idx.is_contiguous()
+    assert yx.dtype == torch.float64 and yx.dim() == 2 and yx.shape[1] == 2 and yx.is_contiguous()
+    n_img, H, W = images.shape
+    N = yx.shape[0]
+    assert img_idx.numel() == N
+    if out is None:
+        out = torch.empty((N, 1, P, P), dtype=torch.float32, device=images.device)
+    if images.dtype == torch.float32:
+        call("livae_patch_gather_subpixel_f32", images, n_img, H, W, img_idx, yx, N, P, out)
+    elif images.dtype == torch.float64:
+        call("livae_patch_gather_subpixel_f64", images, n_img, H, W, img_idx, yx, N, P, out)
+    else:
+        raise RuntimeError(f"patch_gather_subpixel: unsupported image dtype {images.dtype}")
+    return out
+
+
 def patch_minmax_(patches):
     """in-place per-patch min-max normalisation to [0,1] (data.py:553-558)"""
     require_cuda(patches)

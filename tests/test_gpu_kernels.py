@@ -58,6 +58,35 @@ def test_patch_gather_multi_image_borders_empty(ops):
     assert empty.shape == (0, 1, P, P)
 
 
+def test_patch_gather_subpixel_golden_and_oracle(ops):
+    """a2: AdaptiveLatticeDataset.__getitem__ (data.py:478-560, transform=None): float sites, zero padding at the
+    image border, per-patch min-max.  Against the reference's own output (golden, 5e-5: its affine grid is fp32)
+    and against the float64 oracle (1e-6 before the min-max)."""
+    g = load_golden("patch_gather.npz")
+    img = synth_image(512, 300)
+    sites = g["sub_sites"]
+    n = len(sites)
+    idx = torch.zeros(n, dtype=torch.int32).cuda()
+    yx = torch.from_numpy(np.ascontiguousarray(sites, dtype=np.float64)).cuda()
+    for dt in (torch.float64, torch.float32):
+        imgs = torch.from_numpy(img).to(dt).cuda()[None].contiguous()
+        raw = ops.patch_gather_subpixel(imgs, idx, yx, 64)
+        want_raw = np.stack([OP.gather_subpixel(img, cy, cx, 64, 8, normalise=False) for cy, cx in sites])
+        assert np.abs(raw.cpu().numpy() - want_raw).max() < 1e-6
+        got = ops.patch_minmax_(raw).cpu().numpy()
+        assert np.abs(got - g["sub_out"]).max() < 5e-5
+    # large coordinates (fp32 ulp of 4096 is 5e-4 pixels: sites are float64) and a second image
+    rng = np.random.default_rng(9)
+    big = rng.random((2, 300, 4200))
+    s2 = np.array([[150.37, 4100.61], [149.5, 4150.25], [0.2, 0.7]])
+    i2 = np.array([1, 0, 1], dtype=np.int32)
+    raw = ops.patch_gather_subpixel(torch.from_numpy(big).cuda(), torch.from_numpy(i2).cuda(), torch.from_numpy(s2).cuda(), 32)
+    want = np.stack([OP.gather_subpixel(big[i], cy, cx, 32, 8, normalise=False) for i, (cy, cx) in zip(i2, s2)])
+    assert np.abs(raw.cpu().numpy() - want).max() < 1e-6
+    assert ops.patch_gather_subpixel(torch.from_numpy(big).cuda(), torch.zeros(0, dtype=torch.int32).cuda(),
+                                     torch.zeros((0, 2), dtype=torch.float64).cuda(), 32).shape == (0, 1, 32, 32)
+
+
 def test_patch_minmax(ops):
     rng = np.random.default_rng(6)
     p = rng.random((5, 1, 64, 64)).astype(np.float32) * 7 - 3
