@@ -200,6 +200,50 @@ def golden_patch_gather(livae):
     np.savez_compressed(os.path.join(OUT, "patch_gather.npz"), torch_version=torch.__version__, **res)
 
 
+def golden_augment(livae):
+    """a3 + the paired rotation: the reference's default_transform and Paired/AdaptiveLatticeDataset items
+    with Python `random` seeded; only the seeds, sites and OUTPUTS are stored (oracle/augment.draw_params
+    replays the draws)."""
+    import random
+    from livae.data import AdaptiveLatticeDataset, PairedAdaptiveLatticeDataset, default_transform
+    res = {}
+    # default_transform on a bare patch, with and without rotation
+    patch = torch.from_numpy(synth_image(48, 400).astype(np.float32))[None]
+    for k, rot in enumerate((False, True, False, True)):
+        random.seed(900 + k)
+        res[f"dt{k}"] = default_transform(patch, rotation=rot).numpy()
+    # dataset items: (P, pad) = (64, 8) reaches the ROI border under rotation, (32, 16) does not
+    for tag, P, pad, n in (("a", 64, 8, 5), ("b", 32, 16, 5)):
+        HW = 256
+        img = synth_image(HW, 410 + P)
+        rng = np.random.default_rng(420 + P)
+        sites = rng.uniform(P, HW - P, size=(n, 2))
+        sites[0] = (14.5, 17.5)                       # image border + round-half-even sites
+        sites[1] = (HW - 9.25, HW - 30.5)
+        res[f"sites_{tag}"] = sites
+        ds = PairedAdaptiveLatticeDataset.__new__(PairedAdaptiveLatticeDataset)
+        ds.patch_size = P; ds.padding = pad; ds.transform = default_transform
+        ds.images = [img]; ds.sample_coords = [sites]; ds.labels = [np.ones(n)]
+        random.seed(1000 + P)
+        items = [ds[i] for i in range(n)]
+        res[f"pair_{tag}_x"] = np.stack([it[0].numpy() for it in items])
+        res[f"pair_{tag}_r"] = np.stack([it[1].numpy() for it in items])
+        res[f"pair_{tag}_angle"] = np.array([it[2] for it in items])
+        ds.transform = None
+        random.seed(2000 + P)
+        items = [ds[i] for i in range(n)]
+        res[f"pairnt_{tag}_x"] = np.stack([it[0].numpy() for it in items])
+        res[f"pairnt_{tag}_r"] = np.stack([it[1].numpy() for it in items])
+        res[f"pairnt_{tag}_angle"] = np.array([it[2] for it in items])
+        ad = AdaptiveLatticeDataset.__new__(AdaptiveLatticeDataset)
+        ad.patch_size = P; ad.padding = pad; ad.transform = default_transform
+        ad.images = [img]; ad.sample_coords = [sites]; ad.labels = [np.ones(n)]
+        random.seed(3000 + P)
+        res[f"adapt_{tag}"] = np.stack([ad[i].numpy() for i in range(n)])
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), torch_version=torch.__version__,
+                        torchvision_version=__import__("torchvision").__version__, **res)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -210,6 +254,7 @@ def main():
     golden_vae_step(livae, P=64, L=16, B=4, seed=2468)
     golden_stn_pretrain(livae, P=32, B=4, seed=1357)
     golden_patch_gather(livae)
+    golden_augment(livae)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

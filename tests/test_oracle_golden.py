@@ -138,3 +138,50 @@ def test_global_index_walk():
     import pytest
     with pytest.raises(IndexError):
         OP.global_index_to_site([3, 0, 2], 5)
+
+
+def replay_augment_cases():
+    """(name, oracle output, golden output) for every case of tests/golden/augment.npz; the random draws
+    are replayed from the recorded seeds in the reference's draw order."""
+    import random
+
+    from oracle import augment as OA
+    g = load_golden("augment.npz")
+    patch = synth_image(48, 400).astype(np.float32)
+    for k, rot in enumerate((False, True, False, True)):
+        random.seed(900 + k)
+        p = OA.draw_params(rotation=rot)
+        yield f"dt{k}", OA.default_transform(patch, p)[None], g[f"dt{k}"]
+    for tag, P, pad in (("a", 64, 8), ("b", 32, 16)):
+        img = synth_image(256, 410 + P)
+        sites = g[f"sites_{tag}"]
+        random.seed(1000 + P)
+        for i, (cy, cx) in enumerate(sites):
+            p = OA.draw_params(rotation=False)
+            ang = random.uniform(0, 360)
+            x, r, a = OA.paired_item(img, cy, cx, P, pad, p, ang)
+            assert abs(a - g[f"pair_{tag}_angle"][i]) < 1e-12
+            yield f"pair_{tag}_x{i}", x, g[f"pair_{tag}_x"][i]
+            yield f"pair_{tag}_r{i}", r, g[f"pair_{tag}_r"][i]
+        random.seed(2000 + P)
+        for i, (cy, cx) in enumerate(sites):
+            ang = random.uniform(0, 360)
+            x, r, a = OA.paired_item(img, cy, cx, P, pad, None, ang)
+            yield f"pairnt_{tag}_x{i}", x, g[f"pairnt_{tag}_x"][i]
+            yield f"pairnt_{tag}_r{i}", r, g[f"pairnt_{tag}_r"][i]
+        random.seed(3000 + P)
+        for i, (cy, cx) in enumerate(sites):
+            p = OA.draw_params(rotation=False)
+            yield f"adapt_{tag}{i}", OA.adaptive_item(img, cy, cx, P, pad, p), g[f"adapt_{tag}"][i]
+
+
+def test_augment_and_paired_rotation_match_reference():
+    """a3 / paired items: float64 restatement vs the reference's torchvision fp32 grid maths.  Tolerance
+    1e-4 abs on [0,1] data: two chained bilinear resamplings of white-noise images (gradient ~1/px) with
+    fp32 grid rounding ~1e-5 px, amplified by the per-patch min-max."""
+    n = 0
+    for name, got, want in replay_augment_cases():
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() < 1e-4, (name, np.abs(got - want).max())
+        n += 1
+    assert n == 4 + 2 * (10 + 10 + 5)
