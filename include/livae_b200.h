@@ -68,6 +68,24 @@ int livae_patch_gather_subpixel_f32(const float* images, int n_img, int H, int W
 int livae_patch_gather_subpixel_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
                                     const double* yx, int N, int P, float* out, livae_stream_t stream);
 int livae_patch_minmax(float* patches, int N, int P, livae_stream_t stream);
+/* a2 with the ROI window: the [S,S] `patch_big` (S = P + 2*padding) of Adaptive/PairedAdaptiveLatticeDataset
+   .__getitem__ (data.py:496-546, 640-691).  As livae_patch_gather_subpixel, but only pixels inside the reference's
+   integer window of `roi` = P + max(16, 2*padding) pixels around round-half-even(site) are read (zero beyond
+   it, as after TF.pad + TF.affine(fill=None)).  roi even, >= S. */
+int livae_patch_gather_roi_f32(const float* images, int n_img, int H, int W, const int32_t* img_idx,
+                               const double* yx, int N, int S, int roi, float* out, livae_stream_t stream);
+int livae_patch_gather_roi_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
+                               const double* yx, int N, int S, int roi, float* out, livae_stream_t stream);
+/* a3: default_transform(rotation=False) on [N,S,S] patches (data.py:78-116): scale by scale[n] about the centre
+   (TF.affine, bilinear, zeros outside; skipped when flags[n] bit2 is set), flags[n] bit0 = hflip, bit1 = vflip, then torch.roll by
+   shift[n] = (shift_y, shift_x).  The draws are the caller's (Python `random` in the reference). out != in. */
+int livae_augment(const float* in, int N, int S, const float* scale, const int32_t* flags, const int32_t* shift,
+                  float* out, livae_stream_t stream);
+/* TF.rotate(angle_deg[n], bilinear, expand=False, fill=0) (mode 1; data.py:97-103, 698-704) or identity
+   (mode 0, angle_deg may be NULL) of [N,S,S] patches, TF.center_crop to [N,P,P] (data.py:710-713) and, if
+   normalise, the per-patch min-max of data.py:716-730 (constant patch -> zeros).  S - P even. out != in. */
+int livae_rotate_crop(const float* in, int N, int S, int P, const double* angle_deg, int mode, int normalise,
+                      float* out, livae_stream_t stream);
 
 /* ---- a6: fused rotate + bilinear sample (affine_grid + grid_sample) ------------------
  * replaces F.affine_grid + F.grid_sample(bilinear, reflection, align_corners=False) at

@@ -66,13 +66,21 @@ __global__ void __launch_bounds__(256) patch_minmax_kernel(float* __restrict__ p
 template <typename S>
 __global__ void __launch_bounds__(256) patch_gather_subpixel_kernel(
     const S* __restrict__ images, int n_img, int H, int W, const int32_t* __restrict__ img_idx,
-    const double* __restrict__ yx, int N, int P, float* __restrict__ out) {
+    const double* __restrict__ yx, int N, int P, int roi, float* __restrict__ out) {
   const int n = blockIdx.x;
   const int img = img_idx[n];
   const double cy = yx[2 * n], cx = yx[2 * n + 1];
   const S* src = images + (int64_t)img * H * W;
   float* dst = out + (int64_t)n * P * P;
   const bool img_ok = img >= 0 && img < n_img;
+  // roi > 0: the reference's integer ROI window of `roi` pixels around round-half-even(c) (data.py:496-511):
+  // nothing outside it is read, which matters when the crop is as large as the window (P + 2*padding)
+  int wy0 = 0, wy1 = H, wx0 = 0, wx1 = W;
+  if (roi > 0) {
+    const int yi = (int)rint(cy), xi = (int)rint(cx);
+    wy0 = max(0, yi - roi / 2); wy1 = min(H, yi - roi / 2 + roi);
+    wx0 = max(0, xi - roi / 2); wx1 = min(W, xi - roi / 2 + roi);
+  }
   const int rows_per_blk = (P + gridDim.y - 1) / gridDim.y;
   const int r_beg = blockIdx.y * rows_per_blk, r_end = min(P, r_beg + rows_per_blk);
   for (int i = r_beg * P + threadIdx.x; i < r_end * P; i += blockDim.x) {
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(256) patch_gather_subpixel_kernel(
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const int yy = y0 + dy, xx = x0 + dx;
-        if (img_ok && yy >= 0 && yy < H && xx >= 0 && xx < W)
+        if (img_ok && yy >= wy0 && yy < wy1 && xx >= wx0 && xx < wx1)
           acc += (dy ? fy : 1.0 - fy) * (dx ? fx : 1.0 - fx) * (double)(float)src[(int64_t)yy * W + xx];
       }
     dst[i] = (float)acc;
@@ -96,13 +104,14 @@ __global__ void __launch_bounds__(256) patch_gather_subpixel_kernel(
 
 template <typename S>
 int patch_gather_subpixel(const S* images, int n_img, int H, int W, const int32_t* img_idx, const double* yx, int N,
-                          int P, float* out, cudaStream_t st) {
+                          int P, int roi, float* out, cudaStream_t st) {
   LIVAE_CHECK_ARG(N >= 0 && P > 0 && (P & 1) == 0 && H > 0 && W > 0 && n_img > 0, "patch_gather_subpixel: bad sizes (P even)");
+  LIVAE_CHECK_ARG(roi == 0 || (roi >= P && (roi & 1) == 0), "patch_gather_subpixel: roi must be 0 or even and >= P");
   if (N == 0) return 0;
   LIVAE_CHECK_ARG(images && img_idx && yx && out, "patch_gather_subpixel: null pointer");
   if (int e = require_sm100()) return e;
   const int bands = N >= 148 * 8 ? 1 : (P >= 64 ? 4 : 1);
-  patch_gather_subpixel_kernel<S><<<dim3(N, bands), 256, 0, st>>>(images, n_img, H, W, img_idx, yx, N, P, out);
+  patch_gather_subpixel_kernel<S><<<dim3(N, bands), 256, 0, st>>>(images, n_img, H, W, img_idx, yx, N, P, roi, out);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }
@@ -133,11 +142,19 @@ extern "C" int livae_patch_gather_f64(const double* images, int n_img, int H, in
 }
 extern "C" int livae_patch_gather_subpixel_f32(const float* images, int n_img, int H, int W, const int32_t* img_idx,
                                                const double* yx, int N, int P, float* out, livae_stream_t stream) {
-  return livae::patch_gather_subpixel<float>(images, n_img, H, W, img_idx, yx, N, P, out, (cudaStream_t)stream);
+  return livae::patch_gather_subpixel<float>(images, n_img, H, W, img_idx, yx, N, P, 0, out, (cudaStream_t)stream);
 }
 extern "C" int livae_patch_gather_subpixel_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
                                                const double* yx, int N, int P, float* out, livae_stream_t stream) {
-  return livae::patch_gather_subpixel<double>(images, n_img, H, W, img_idx, yx, N, P, out, (cudaStream_t)stream);
+  return livae::patch_gather_subpixel<double>(images, n_img, H, W, img_idx, yx, N, P, 0, out, (cudaStream_t)stream);
+}
+extern "C" int livae_patch_gather_roi_f32(const float* images, int n_img, int H, int W, const int32_t* img_idx,
+                                          const double* yx, int N, int S, int roi, float* out, livae_stream_t stream) {
+  return livae::patch_gather_subpixel<float>(images, n_img, H, W, img_idx, yx, N, S, roi, out, (cudaStream_t)stream);
+}
+extern "C" int livae_patch_gather_roi_f64(const double* images, int n_img, int H, int W, const int32_t* img_idx,
+                                          const double* yx, int N, int S, int roi, float* out, livae_stream_t stream) {
+  return livae::patch_gather_subpixel<double>(images, n_img, H, W, img_idx, yx, N, S, roi, out, (cudaStream_t)stream);
 }
 extern "C" int livae_patch_minmax(float* patches, int N, int P, livae_stream_t stream) {
   LIVAE_CHECK_ARG(N >= 0 && P > 0, "patch_minmax: bad args");

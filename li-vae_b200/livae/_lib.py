@@ -40,6 +40,10 @@ _SIGS = {
     "livae_patch_minmax": "piis",
     "livae_patch_gather_subpixel_f32": "piiippiips",
     "livae_patch_gather_subpixel_f64": "piiippiips",
+    "livae_patch_gather_roi_f32": "piiippiiips",
+    "livae_patch_gather_roi_f64": "piiippiiips",
+    "livae_augment": "piipppps",
+    "livae_rotate_crop": "piiipiips",
     "livae_rot_sample_fwd": "ppfiiiips",
     "livae_rot_sample_bwd": "ppfpiiiipps",
     "livae_stn_head_fwd": "pipps",

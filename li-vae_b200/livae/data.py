@@ -1,0 +1,201 @@
+"""Device-side patch pipeline: the per-item work of the reference's datasets (`PatchDataset`,
+`AdaptiveLatticeDataset`, `PairedAdaptiveLatticeDataset` `__getitem__`, reference data.py:211-250, 478-560,
+617-735) and `default_transform` (data.py:78-116), done for a whole batch by CUDA kernels on images resident
+in HBM instead of by DataLoader worker processes.
+
+What stays with the reference (out of scope): finding the sites (`__init__`: band-pass,
+lattice constant, skimage peaks, KD-tree).  `DevicePatchSource.from_dataset` takes a dataset object the reference
+built (its `.images`, `.sample_coords` / `.atom_coords`, `.patch_size`, `.padding`, `.transform`).
+
+Random numbers: the reference draws from Python's global `random` per item (scale, [angle], hflip, vflip,
+shift_x, shift_y, then the pair angle).  The draws here are made on the host IN THE SAME ORDER from the same
+global `random`, so `random.seed(s)` followed by items i0, i1, ... yields the reference's patches (to the fp32
+tolerance of the bilinear resampling); only the pixel work moves to the device.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from livae import ops
+
+__all__ = ["default_transform", "draw_transform_params", "DevicePatchSource", "DevicePatchLoader"]
+
+
+def draw_transform_params(n: int, flip_prob: float = 0.5, jitter_amount: int = 4, rotation: bool = False):
+    """n consecutive default_transform draws from Python's `random`, in the reference's order (data.py:85-114).
+    -> dict of host numpy arrays: scale f32 [n], angle f64 [n] (nan if not rotation), flags i32 [n], shift i32 [n,2]"""
+    scale = np.empty(n, np.float32)
+    angle = np.full(n, np.nan, np.float64)
+    flags = np.zeros(n, np.int32)
+    shift = np.zeros((n, 2), np.int32)
+    for i in range(n):
+        scale[i] = random.uniform(0.9, 1.1)
+        if rotation:
+            angle[i] = random.uniform(0, 360)
+        if random.random() < flip_prob:
+            flags[i] |= 1
+        if random.random() < flip_prob:
+            flags[i] |= 2
+        if jitter_amount > 0:
+            sx = random.randint(-jitter_amount, jitter_amount)
+            sy = random.randint(-jitter_amount, jitter_amount)
+            shift[i] = (sy, sx)
+    return {"scale": scale, "angle": angle, "flags": flags, "shift": shift}
+
+
+def _apply_transform(big: torch.Tensor, p: dict, rotation: bool) -> torch.Tensor:
+    dev = big.device
+    scale = torch.from_numpy(p["scale"]).to(dev)
+    flags = torch.from_numpy(p["flags"]).to(dev)
+    shift = torch.from_numpy(p["shift"]).to(dev)
+    if not rotation:
+        return ops.augment(big, scale, flags, shift)
+    # scale -> rotate -> flips + roll (data.py:85-114): the rotation sits between the two halves of the fused kernel
+    zeros_i = torch.zeros_like(flags)
+    t = ops.augment(big, scale, zeros_i, torch.zeros_like(shift))
+    t = ops.rotate_crop(t, big.shape[-1], torch.from_numpy(p["angle"]).to(dev))
+    return ops.augment(t, scale, flags | 4, shift)
+
+
+def default_transform(patch: torch.Tensor, flip_prob: float = 0.5, jitter_amount: int = 4,
+                      rotation: bool = False) -> torch.Tensor:
+    """Reference signature (data.py:78-83).  `patch`: CUDA float32 [C,S,S] (one item, C == 1) or [N,1,S,S]
+    (a batch: one set of draws per patch, item order)."""
+    if not patch.is_cuda:
+        raise RuntimeError("livae.data.default_transform: CUDA tensor required; there is no CPU path")
+    single = patch.dim() == 3
+    x = patch.unsqueeze(0) if single else patch
+    if x.dim() != 4 or x.shape[1] != 1 or x.shape[-1] != x.shape[-2]:
+        raise ValueError("default_transform: expected [1,S,S] or [N,1,S,S]")
+    x = x.contiguous().float()
+    out = _apply_transform(x, draw_transform_params(x.shape[0], flip_prob, jitter_amount, rotation), rotation)
+    return out[0] if single else out
+
+
+class DevicePatchSource:
+    """Images + site lists resident on one GPU; batches of dataset items by index.
+
+    images: sequence of equally sized 2-D arrays (float64 like the reference caches them, or float32) or a
+    [n_img,H,W] tensor.  coords: per-image [n_i,2] arrays of (cy, cx) -- float sites (`sample_coords`) or integer
+    peaks (`atom_coords`).  transform: None or `default_transform` (anything else is refused: the device
+    kernels implement exactly that function)."""
+
+    def __init__(self, images, coords: Sequence, patch_size: int = 128, padding: int = 32,
+                 transform=None, device="cuda"):
+        if transform not in (None, default_transform) and getattr(transform, "__name__", "") != "default_transform":
+            raise ValueError("DevicePatchSource: transform must be None or default_transform")
+        self.transform = transform
+        self.patch_size, self.padding = int(patch_size), int(padding)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("DevicePatchSource: a CUDA device is required; there is no CPU path")
+        if isinstance(images, torch.Tensor):
+            imgs = images
+        else:
+            imgs = torch.from_numpy(np.stack([np.asarray(i) for i in images]))
+        if imgs.dim() != 3 or imgs.dtype not in (torch.float32, torch.float64):
+            raise ValueError("DevicePatchSource: images must be [n_img,H,W] float32/float64")
+        self.images = imgs.to(dev).contiguous()
+        self.counts = [len(c) for c in coords]
+        self._offsets = np.concatenate([[0], np.cumsum(self.counts)])
+        flat = [np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in coords]
+        self._yx = np.concatenate(flat) if flat else np.zeros((0, 2))
+        self._img = np.repeat(np.arange(len(coords), dtype=np.int32), self.counts)
+        self.device = dev
+
+    @classmethod
+    def from_dataset(cls, ds, device="cuda"):
+        """from a reference dataset object (PatchDataset: .atom_coords; Adaptive*: .sample_coords)"""
+        coords = getattr(ds, "sample_coords", None)
+        if coords is None:
+            coords = ds.atom_coords
+        return cls(ds.images, coords, ds.patch_size, ds.padding, getattr(ds, "transform", None), device)
+
+    def __len__(self):
+        return int(self._offsets[-1])
+
+    def _lookup(self, indices):
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        if idx.size and (idx.min() < 0 or idx.max() >= len(self)):
+            raise IndexError(f"Index out of range for dataset of size {len(self)}")      # data.py:217-220
+        return (torch.from_numpy(self._img[idx]).to(self.device),
+                torch.from_numpy(self._yx[idx]).to(self.device))
+
+    # --- PatchDataset.__getitem__, transform=None (data.py:211-250) -------------------------------------
+    def patch_batch(self, indices) -> torch.Tensor:
+        img, yx = self._lookup(indices)
+        sites = torch.cat([img.view(-1, 1), yx.round().to(torch.int32)], 1).contiguous()
+        return ops.patch_gather(self.images, sites, self.patch_size)
+
+    def _big(self, indices):
+        img, yx = self._lookup(indices)
+        S = self.patch_size + 2 * self.padding
+        roi = self.patch_size + max(16, 2 * self.padding)
+        return ops.patch_gather_roi(self.images, img, yx, S, roi)
+
+    # --- AdaptiveLatticeDataset.__getitem__ (data.py:478-560) -------------------------------------------
+    def adaptive_batch(self, indices) -> torch.Tensor:
+        big = self._big(indices)
+        if self.transform is not None:
+            big = _apply_transform(big, draw_transform_params(big.shape[0]), rotation=False)
+        return ops.rotate_crop(big, self.patch_size, None, normalise=True)
+
+    # --- PairedAdaptiveLatticeDataset.__getitem__ (data.py:617-735) -------------------------------------
+    def paired_batch(self, indices, angles_deg: Optional[Iterable[float]] = None):
+        """-> (patch [N,1,P,P], rotated [N,1,P,P], angle_rad float32 [N]) as the default collate of the
+        reference's items gives them.  Draw order per item: transform draws, then the pair angle."""
+        big = self._big(indices)
+        n = big.shape[0]
+        if self.transform is not None or angles_deg is None:
+            ang = np.empty(n, np.float64)
+            ps = []
+            for i in range(n):                       # per item: transform(rotation=False) draws, then the angle
+                if self.transform is not None:
+                    ps.append(draw_transform_params(1))
+                ang[i] = random.uniform(0, 360)
+            if angles_deg is not None:
+                ang = np.asarray(list(angles_deg), dtype=np.float64)
+            if ps:
+                p = {k: np.concatenate([q[k] for q in ps]) for k in ps[0]}
+                big = _apply_transform(big, p, rotation=False)
+        else:
+            ang = np.asarray(list(angles_deg), dtype=np.float64)
+        ang_dev = torch.from_numpy(ang).to(self.device)
+        patch = ops.rotate_crop(big, self.patch_size, None, normalise=True)
+        rotated = ops.rotate_crop(big, self.patch_size, ang_dev, normalise=True)
+        return patch, rotated, torch.deg2rad(ang_dev).float()
+
+
+class DevicePatchLoader:
+    """Minimal DataLoader stand-in over a DevicePatchSource: yields device batches in the shapes
+    `train_rvae_one_epoch` / `train_one_epoch` unpack (train.py:315-324, 67-75).  Shuffling uses a numpy
+    Generator (documented deviation: torch's DataLoader shuffles with the torch generator)."""
+
+    def __init__(self, source: DevicePatchSource, batch_size: int, mode: str = "paired", shuffle: bool = True,
+                 drop_last: bool = True, seed: int = 0, indices: Optional[Sequence[int]] = None):
+        if mode not in ("paired", "adaptive", "patch"):
+            raise ValueError("mode must be paired, adaptive or patch")
+        self.source, self.batch_size, self.mode = source, int(batch_size), mode
+        self.shuffle, self.drop_last = shuffle, drop_last
+        self._rng = np.random.default_rng(seed)
+        self._indices = np.arange(len(source)) if indices is None else np.asarray(indices, dtype=np.int64)
+
+    def __len__(self):
+        n = len(self._indices)
+        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def __iter__(self):
+        order = self._rng.permutation(self._indices) if self.shuffle else self._indices
+        for b in range(len(self)):
+            idx = order[b * self.batch_size:(b + 1) * self.batch_size]
+            if self.mode == "paired":
+                yield self.source.paired_batch(idx)
+            elif self.mode == "adaptive":
+                yield self.source.adaptive_batch(idx)
+            else:
+                yield self.source.patch_batch(idx)

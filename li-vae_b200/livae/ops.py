@@ -378,6 +378,56 @@ def patch_gather_subpixel(images, img_idx, yx, P, out=None):
     return out
 
 
+def patch_gather_roi(images, img_idx, yx, S, roi, out=None):
+    """the [N,1,S,S] `patch_big` of Adaptive/PairedAdaptiveLatticeDataset.__getitem__ (data.py:496-546): as
+    patch_gather_subpixel but reading only the reference's integer ROI window of `roi` pixels around round(site)"""
+    if not images.is_cuda or not yx.is_cuda or not img_idx.is_cuda:
+        raise RuntimeError("livae.patch_gather_roi: device tensors required; there is no CPU path")
+    assert images.dim() == 3 and images.is_contiguous()
+    assert img_idx.dtype == torch.int32 and img_idx.is_contiguous()
+    assert yx.dtype == torch.float64 and yx.dim() == 2 and yx.shape[1] == 2 and yx.is_contiguous()
+    n_img, H, W = images.shape
+    N = yx.shape[0]
+    assert img_idx.numel() == N
+    if out is None:
+        out = torch.empty((N, 1, S, S), dtype=torch.float32, device=images.device)
+    if images.dtype == torch.float32:
+        call("livae_patch_gather_roi_f32", images, n_img, H, W, img_idx, yx, N, S, roi, out)
+    elif images.dtype == torch.float64:
+        call("livae_patch_gather_roi_f64", images, n_img, H, W, img_idx, yx, N, S, roi, out)
+    else:
+        raise RuntimeError(f"patch_gather_roi: unsupported image dtype {images.dtype}")
+    return out
+
+
+def augment(patches, scale, flags, shift, out=None):
+    """default_transform(rotation=False) with given draws (data.py:78-116): patches [N,1,S,S] fp32, scale fp32 [N],
+    flags int32 [N] (bit0 hflip, bit1 vflip), shift int32 [N,2] (shift_y, shift_x) -> [N,1,S,S]"""
+    require_cuda(patches, scale)
+    N, S = patches.shape[0], patches.shape[-1]
+    assert patches.numel() == N * S * S and scale.numel() == N
+    assert flags.dtype == torch.int32 and flags.numel() == N and flags.is_cuda and flags.is_contiguous()
+    assert shift.dtype == torch.int32 and shift.numel() == 2 * N and shift.is_cuda and shift.is_contiguous()
+    if out is None:
+        out = torch.empty_like(patches)
+    call("livae_augment", patches, N, S, scale, flags, shift, out)
+    return out
+
+
+def rotate_crop(patches, P, angle_deg=None, normalise=False, out=None):
+    """TF.rotate(angle_deg, bilinear, fill=0) (or no rotation when angle_deg is None) -> TF.center_crop(P) ->
+    optional per-patch min-max (data.py:698-730).  patches [N,1,S,S] fp32, angle_deg float64 [N] -> [N,1,P,P]"""
+    require_cuda(patches)
+    N, S = patches.shape[0], patches.shape[-1]
+    assert patches.numel() == N * S * S
+    if angle_deg is not None:
+        assert angle_deg.dtype == torch.float64 and angle_deg.numel() == N and angle_deg.is_cuda
+    if out is None:
+        out = torch.empty((N, 1, P, P), dtype=torch.float32, device=patches.device)
+    call("livae_rotate_crop", patches, N, S, P, angle_deg, 0 if angle_deg is None else 1, int(normalise), out)
+    return out
+
+
 def patch_minmax_(patches):
     """in-place per-patch min-max normalisation to [0,1] (data.py:553-558)"""
     require_cuda(patches)

@@ -41,6 +41,35 @@ def test_binding_table_matches_header(libpath):
     _lib.lib()   # argtypes resolve for every entry
 
 
+def test_binding_arity_matches_header(libpath):
+    """every ctypes signature in livae/_lib.py has as many arguments, of the same pointer / scalar kind, as the
+    prototype in include/livae_b200.h (a wrong table is a host-side crash, not an error code)"""
+    from livae import _lib
+    src = open(os.path.join(ROOT, "include", "livae_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(livae_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    bad = []
+    for name, sig in _lib._SIGS.items():
+        assert name in protos, name
+        args = [a.strip() for a in protos[name].split(",") if a.strip()]
+        kinds = ""
+        for a in args:
+            if "livae_stream_t" in a:
+                kinds += "s"
+            elif "*" in a:
+                kinds += "p"
+            elif re.match(r"(const\s+)?(int64_t|long long)\b", a):
+                kinds += "l"
+            elif re.match(r"(const\s+)?(float|double)\b", a):
+                kinds += "f"
+            else:
+                kinds += "i"
+        want = sig.replace("d", "p").replace("t", "p")
+        if kinds != want:
+            bad.append((name, sig, kinds))
+    assert not bad, bad
+
+
 def test_no_cpu_fallback(libpath):
     import livae
     from livae import ops
