@@ -105,6 +105,13 @@ int livae_stn_head_fwd(const float* vec, int B, float* cs, float* theta, livae_s
 /* gvec = J^T (gcs + gtheta * (-s, c));  gcs / gtheta may be NULL */
 int livae_stn_head_bwd(const float* vec, const float* gcs, const float* gtheta, int B,
                        float* gvec, livae_stream_t stream);
+/* STN tail fused: Linear(32 -> 2) (model.py:213) + livae_stn_head_{fwd,bwd}.  f1: fp32 [B,K] post-ReLU fc1 output,
+   w9 [2,K], b9 [2], K == 32.  fwd writes vec [B,2], cs [B,2], theta [B] (may be NULL).  bwd: gcs / gtheta may be
+   NULL; writes gw9 [2,K], gb9 [2] and gf1 = (gvec w9) * (f1 > 0) as bf16 [B,K]. */
+int livae_stn_tail_fwd(const float* f1, const float* w9, const float* b9, int B, int K, float* vec, float* cs,
+                       float* theta, livae_stream_t stream);
+int livae_stn_tail_bwd(const float* f1, const float* w9, const float* vec, const float* gcs, const float* gtheta,
+                       int B, int K, float* gw9, float* gb9, void* gf1_bf16, livae_stream_t stream);
 /* (cos, sin) of an angle tensor, for get_rotation_matrix(theta) (model.py:220-235) */
 int livae_angle_to_cs(const float* theta, int B, float* cs, livae_stream_t stream);
 /* gtheta = -sin*gc + cos*gs */

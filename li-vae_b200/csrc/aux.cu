@@ -586,6 +586,83 @@ __global__ void __launch_bounds__(128) decfc_bwd_w_kernel(const T* __restrict__ 
   }
 }
 
+// Decoder.fc backward for small latent sizes in ONE pass over gy (bf16 [B, HW, C], already the pre-activation
+// gradient): gw[n,l] = sum_b g[b,n] z[b,l], gb[n] = sum_b g[b,n], gz[b,l] = sum_n g[b,n] w[n,l].  Thread = 8
+// consecutive channels of one pixel (one 16-byte load per batch row), CTA = 2048 features x a slice of the batch;
+// its weight rows live in registers.  gz partials: warp shuffle -> shared atomics -> one global atomic per
+// (row, l, CTA).  All three outputs are zeroed by the caller.  The two-kernel form above read gy twice with
+// scalar loads (0.33 ms at B = 2048, N = 16384 against 67 MB of traffic).
+template <int LT>
+__global__ void __launch_bounds__(256) decfc_bwd_fused_bf16_kernel(const uint4* __restrict__ gy,
+                                                                   const float* __restrict__ z,
+                                                                   const float* __restrict__ w, int B, int L, int C,
+                                                                   int HW, int rows_per_cta, float* __restrict__ gw,
+                                                                   float* __restrict__ gb, float* __restrict__ gz) {
+  extern __shared__ float sgz[];                       // [rows_per_cta][LT]
+  const int nvec = C * HW / 8;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = v < nvec;
+  const int b0 = blockIdx.y * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
+  for (int i = threadIdx.x; i < rows_per_cta * LT; i += blockDim.x) sgz[i] = 0.f;
+  __syncthreads();
+  const int c0 = ok ? (v * 8) % C : 0, p = ok ? (v * 8) / C : 0;
+  float wr[8][LT], aw[8][LT], ab[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    ab[e] = 0.f;
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+      aw[e][l] = 0.f;
+      wr[e][l] = (ok && l < L) ? w[(int64_t)((c0 + e) * HW + p) * L + l] : 0.f;
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  for (int b = b0; b < b1; ++b) {
+    float g[8];
+    if (ok) bf8_to_f(__ldg(gy + (int64_t)b * nvec + v), g);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    }
+    float zl[LT], pz[LT];
+#pragma unroll
+    for (int l = 0; l < LT; ++l) { zl[l] = l < L ? __ldg(z + b * L + l) : 0.f; pz[l] = 0.f; }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ab[e] += g[e];
+#pragma unroll
+      for (int l = 0; l < LT; ++l) {
+        aw[e][l] = fmaf(g[e], zl[l], aw[e][l]);
+        pz[l] = fmaf(g[e], wr[e][l], pz[l]);
+      }
+    }
+    if (gz) {
+#pragma unroll
+      for (int l = 0; l < LT; ++l) {
+        const float t = warp_sum(pz[l]);
+        if (lane == 0 && l < L) atomicAdd(&sgz[(b - b0) * LT + l], t);
+      }
+    }
+  }
+  if (ok) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t row = (int64_t)(c0 + e) * HW + p;
+      if (gb) atomicAdd(gb + row, ab[e]);
+#pragma unroll
+      for (int l = 0; l < LT; ++l)
+        if (l < L) atomicAdd(gw + row * L + l, aw[e][l]);
+    }
+  }
+  if (gz) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (b1 - b0) * LT; i += blockDim.x) {
+      const int l = i % LT;
+      if (l < L) atomicAdd(gz + (int64_t)(b0 + i / LT) * L + l, sgz[i]);
+    }
+  }
+}
+
 // ---- optimiser side ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n,
                                                     float* __restrict__ partial) {
@@ -825,6 +902,23 @@ extern "C" int livae_decfc_bwd_bf16(const float* z, const float* w, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* g = (const __nv_bfloat16*)gy;
   int N = C * HW;
+  if (L <= 4 && gw && C % 8 == 0 && (((uintptr_t)gy) & 15) == 0) {
+    cudaError_t ce;
+    if ((ce = cudaMemsetAsync(gw, 0, (size_t)N * L * sizeof(float), st)) != cudaSuccess ||
+        (gb && (ce = cudaMemsetAsync(gb, 0, (size_t)N * sizeof(float), st)) != cudaSuccess) ||
+        (gz && (ce = cudaMemsetAsync(gz, 0, (size_t)B * L * sizeof(float), st)) != cudaSuccess)) {
+      set_error("decfc_bwd_bf16: memset failed");
+      return (int)ce;
+    }
+    const int nb = (N / 8 + 255) / 256;
+    int rows = (B + 31) / 32;                     // ~32 batch slices: 8 x 32 CTAs at N = 16384
+    if (rows < 16) rows = 16;
+    if (rows > 256) rows = 256;
+    decfc_bwd_fused_bf16_kernel<4><<<dim3(nb, (B + rows - 1) / rows), 256, rows * 4 * sizeof(float), st>>>(
+        (const uint4*)gy, z, w, B, L, C, HW, rows, gw, gb, gz);
+    LIVAE_CUDA_LAUNCH_CHECK();
+    return 0;
+  }
   if (gz) {
     if (L <= 4) decfc_bwd_z_kernel<__nv_bfloat16, 4><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);
     else decfc_bwd_z_kernel<__nv_bfloat16, 16><<<B, 256, 0, st>>>(g, (const __nv_bfloat16*)nullptr, w, L, C, HW, gz);

@@ -49,6 +49,76 @@ __global__ void stn_head_bwd_kernel(const float* __restrict__ vec, const float* 
   }
 }
 
+// STN tail in one launch each way: Linear(32 -> 2) (model.py:213) + F.normalize + atan2 (model.py:245-261).
+// One warp per sample, lane = input feature.  Replaces a GEMM launch on a [B,32]x[32,2] problem plus the head.
+__global__ void __launch_bounds__(256) stn_tail_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ w9,
+                                                           const float* __restrict__ b9, int B,
+                                                           float* __restrict__ vec, float* __restrict__ cs,
+                                                           float* __restrict__ theta) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const float w0 = w9[lane], w1 = w9[32 + lane];
+  for (int b = warp; b < B; b += nwarp) {
+    const float f = f1[b * 32 + lane];
+    const float a = warp_sum(f * w0) + b9[0], d = warp_sum(f * w1) + b9[1];
+    if (lane == 0) {
+      vec[2 * b] = a; vec[2 * b + 1] = d;
+      const float n = fmaxf(sqrtf(a * a + d * d), 1e-6f);
+      const float c = a / n, s = d / n;
+      cs[2 * b] = c; cs[2 * b + 1] = s;
+      if (theta) theta[b] = atan2f(s, c);
+    }
+  }
+}
+
+// backward of the above: gvec from (gcs, gtheta) as stn_head_bwd_kernel, then gw9 = gvec^T f1, gb9 = sum gvec
+// (atomics on zeroed outputs, one per CTA and element) and gf1 = (gvec w9) * (f1 > 0) written as bf16 for the
+// tensor-core fc1 backward.
+__global__ void __launch_bounds__(256) stn_tail_bwd_kernel(const float* __restrict__ f1, const float* __restrict__ w9,
+                                                           const float* __restrict__ vec,
+                                                           const float* __restrict__ gcs,
+                                                           const float* __restrict__ gtheta, int B,
+                                                           float* __restrict__ gw9, float* __restrict__ gb9,
+                                                           __nv_bfloat16* __restrict__ gf1b) {
+  __shared__ float sw[8][66];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const float w0 = w9[lane], w1 = w9[32 + lane];
+  float aw0 = 0.f, aw1 = 0.f, ab0 = 0.f, ab1 = 0.f;
+  for (int b = warp; b < B; b += nwarp) {
+    const float a = vec[2 * b], d = vec[2 * b + 1];
+    const float nr = sqrtf(a * a + d * d);
+    const float n = fmaxf(nr, 1e-6f);
+    const float c = a / n, s = d / n;
+    float gc = gcs ? gcs[2 * b] : 0.f, gs = gcs ? gcs[2 * b + 1] : 0.f;
+    if (gtheta) {
+      const float r2 = c * c + s * s, gt = gtheta[b];
+      gc += -s / r2 * gt;
+      gs += c / r2 * gt;
+    }
+    float g0, g1;
+    if (nr > 1e-6f) {
+      const float dot = c * gc + s * gs;
+      g0 = (gc - c * dot) / n; g1 = (gs - s * dot) / n;
+    } else {
+      g0 = gc / n; g1 = gs / n;
+    }
+    const float f = f1[b * 32 + lane];
+    aw0 = fmaf(g0, f, aw0); aw1 = fmaf(g1, f, aw1);
+    ab0 += g0; ab1 += g1;
+    gf1b[b * 32 + lane] = __float2bfloat16_rn(f > 0.f ? fmaf(g0, w0, g1 * w1) : 0.f);
+  }
+  sw[wid][lane] = aw0; sw[wid][32 + lane] = aw1;
+  if (lane == 0) { sw[wid][64] = ab0; sw[wid][65] = ab1; }
+  __syncthreads();
+  if (threadIdx.x < 66) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sw[w][threadIdx.x];
+    atomicAdd(threadIdx.x < 64 ? gw9 + threadIdx.x : gb9 + (threadIdx.x - 64), t);
+  }
+}
+
 __global__ void angle_to_cs_kernel(const float* __restrict__ theta, int B, float* __restrict__ cs) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -217,6 +287,39 @@ extern "C" int livae_stn_head_fwd(const float* vec, int B, float* cs, float* the
   if (int e = require_sm100()) return e;
   if (B == 0) return 0;
   stn_head_fwd_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(vec, B, cs, theta);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_stn_tail_fwd(const float* f1, const float* w9, const float* b9, int B, int K, float* vec,
+                                  float* cs, float* theta, livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && K == 32, "stn_tail_fwd: the localisation head is Linear(32 -> 2) (model.py:213)");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(f1 && w9 && b9 && vec && cs, "stn_tail_fwd: null pointer");
+  if (int e = livae::require_sm100()) return e;
+  const int grid = B >= 8 * 296 ? 296 : (B + 7) / 8;
+  livae::stn_tail_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(f1, w9, b9, B, vec, cs, theta);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_stn_tail_bwd(const float* f1, const float* w9, const float* vec, const float* gcs,
+                                  const float* gtheta, int B, int K, float* gw9, float* gb9, void* gf1_bf16,
+                                  livae_stream_t stream) {
+  LIVAE_CHECK_ARG(B >= 0 && K == 32, "stn_tail_bwd: the localisation head is Linear(32 -> 2) (model.py:213)");
+  LIVAE_CHECK_ARG(gw9 && gb9, "stn_tail_bwd: null pointer");
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(gw9, 0, 64 * sizeof(float), (cudaStream_t)stream)) != cudaSuccess ||
+      (ce = cudaMemsetAsync(gb9, 0, 2 * sizeof(float), (cudaStream_t)stream)) != cudaSuccess) {
+    livae::set_error("stn_tail_bwd: memset failed");
+    return (int)ce;
+  }
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(f1 && w9 && vec && gf1_bf16, "stn_tail_bwd: null pointer");
+  if (int e = livae::require_sm100()) return e;
+  const int grid = B >= 8 * 64 ? 64 : (B + 7) / 8;
+  livae::stn_tail_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(f1, w9, vec, gcs, gtheta, B, gw9, gb9,
+                                                                     (__nv_bfloat16*)gf1_bf16);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

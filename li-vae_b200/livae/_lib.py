@@ -48,6 +48,8 @@ _SIGS = {
     "livae_rot_sample_bwd": "ppfpiiiipps",
     "livae_stn_head_fwd": "pipps",
     "livae_stn_head_bwd": "pppips",
+    "livae_stn_tail_fwd": "pppiippps",
+    "livae_stn_tail_bwd": "pppppiippps",
     "livae_angle_to_cs": "pips",
     "livae_angle_to_cs_bwd": "ppips",
     "livae_reparam_fwd": "pppips",

@@ -89,11 +89,9 @@ class EncoderTc(Function):
             call("livae_maxpool_bf16", a2f, B, h, h, 32, a2, idx2)
             del a2f
         f1 = _linear_fwd(a2.view(B, -1), w7, 32, q4, q4, b7, 32, ACT_RELU)           # fp32 [B,32]
-        d9 = L.ConvDesc(L.CONV, B, 1, 1, 32, 2, 1, 1, 1, 0, ACT_NONE, 0)
         vec = _empty((B, 2), torch.float32, dev)
-        call("livae_conv_fwd", C.byref(d9), f1, w9, b9, vec, None, None)
         cs = _empty((B, 2), torch.float32, dev); theta = _empty((B, 1), torch.float32, dev)
-        call("livae_stn_head_fwd", vec, B, cs, theta)
+        call("livae_stn_tail_fwd", f1, w9, b9, B, 32, vec, cs, theta)         # fc2 + normalize + atan2
         x_rot = torch.empty_like(x)
         call("livae_rot_sample_fwd", x, cs, 1.0, B, 1, P, P, x_rot)
         # --- encoder conv stack (model.py:289-298)
@@ -165,14 +163,11 @@ class EncoderTc(Function):
         B, P, Ld, Npad = ctx.dims
         dev = x.device
         h, q4 = P // 2, P // 4
-        gvec = _empty((B, 2), torch.float32, dev)
-        call("livae_stn_head_bwd", vec, gcs, g_theta.contiguous() if g_theta is not None else None, B, gvec)
-        # --- STN fc2 (fp32 engine), fc1, conv2 (tensor cores), conv1 (thin)
-        d9 = L.ConvDesc(L.CONV, B, 1, 1, 32, 2, 1, 1, 1, 0, ACT_NONE, 0)
-        gw9 = torch.empty_like(w9); gb9 = _empty((2,), torch.float32, dev); gf1 = torch.empty_like(f1)
-        call("livae_conv_bwd", C.byref(d9), f1, w9, vec, gvec, None, gw9, gb9, gf1)
+        # --- STN head + fc2 (one fused kernel), fc1, conv2 (tensor cores), conv1 (thin)
+        gw9 = torch.empty_like(w9); gb9 = _empty((2,), torch.float32, dev)
         gf1b = _empty((B, 32), BF, dev)
-        call("livae_relu_mask_cast_bf16", gf1, f1, gf1.numel(), gf1b)
+        call("livae_stn_tail_bwd", f1, w9, vec, gcs, g_theta.contiguous() if g_theta is not None else None, B, 32,
+             gw9, gb9, gf1b)
         gw7, gb7, ga2 = _linear_bwd(a2.view(B, -1), w7, 32, q4, q4, gf1b, 32, a2.view(B, -1))
         if ops.conv5pool_supported(B, h, h, 16, 32):
             gw3, gb3, ga1 = ops.conv5pool_bwd(a1, w3, ga2.contiguous(), idx2)

@@ -1,10 +1,17 @@
-import json, sys
-d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("value", round(d["value"]), "ms/step", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]), "launches", d.get("gpu_launches"))
-print("roofline", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in d["roofline"].items()})
-tot = 0
-for k in d["kernels"]:
-    tot += k["ms_per_step"]
-    tf = "-" if k["tflops"] is None else f"{k['tflops']:.1f}"
-    print(f"{k['ms_per_step']:8.3f} ms {k['calls_per_step']:4.0f}x {tf:>7} TF {k['gbs']:7.0f} GB/s  {k['kernel']}")
-print("sum", round(tot, 2))
+"""print the headline and the per-kernel-family table of a bench.py log"""
+import json
+import sys
+
+for path in sys.argv[1:]:
+    for l in open(path):
+        l = l.strip()
+        if not l.startswith("{"):
+            continue
+        d = json.loads(l)
+        k = d.pop("kernels", None)
+        print(path, "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]),
+              "launches", d.get("gpu_launches"), "roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3),
+              "step_frac", round(d["step_roofline"]["frac"], 3))
+        if k and "-k" in sys.argv[0:1] + sys.argv:
+            for e in k:
+                print(f"  {e['kernel']:45s} {e['ms_per_step']:.3f} x{e['calls_per_step']:.0f}")
