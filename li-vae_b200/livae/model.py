@@ -205,15 +205,32 @@ class Encoder(nn.Module):
     def forward(self, x):
         if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, x.shape[1]):
             loc, cl = self.rotation_stn.localization, self.conv_layers
-            return tc.EncoderTc.apply(x, loc[0].weight, loc[0].bias, loc[3].weight, loc[3].bias, loc[7].weight,
-                                      loc[7].bias, loc[9].weight, loc[9].bias, cl[0].weight, cl[0].bias,
-                                      cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight, cl[6].bias,
-                                      self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias)
+            mu, logvar, theta, x_rot = tc.EncoderTc.apply(
+                x, loc[0].weight, loc[0].bias, loc[3].weight, loc[3].bias, loc[7].weight,
+                loc[7].bias, loc[9].weight, loc[9].bias, cl[0].weight, cl[0].bias,
+                cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight, cl[6].bias,
+                self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias)
+            self._canonical = (x, theta, x_rot)
+            return mu, logvar, theta
         x_rotated, theta = self.rotation_stn(x)
         h = _run_encoder_convs(self.conv_layers, x_rotated)
         mu = ops.linear_nhwc(h, self.fc_mu.weight, self.fc_mu.bias)
         logvar = ops.linear_nhwc(h, self.fc_logvar.weight, self.fc_logvar.bias)
         return mu, logvar, theta
+
+
+def _take_canonical(self, x, theta):
+    """The STN's own rotated input, if the last forward of this encoder was for exactly (x, theta): it equals
+    rotate_to_canonical(x, theta) (reference train.py:670-677) in value and, through autograd, in gradient (the
+    normalise backward projects onto the tangent of the unit circle exactly as atan2 -> cos/sin does).  One-shot:
+    the cache is dropped so no batch is kept alive.  None when unavailable (fp32 engine, different tensors)."""
+    c, self._canonical = getattr(self, "_canonical", None), None
+    if c is not None and c[0] is x and c[1] is theta:
+        return c[2]
+    return None
+
+
+Encoder.take_canonical = _take_canonical
 
 
 class Decoder(nn.Module):

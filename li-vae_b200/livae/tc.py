@@ -111,11 +111,14 @@ class EncoderTc(Function):
                               h1, h2, h3, h4)
         ctx.dims = (B, P, Ld, Npad)
         ctx.set_materialize_grads(False)
-        return mu, logvar, theta
+        # x_rot is returned as a fourth, differentiable output: it IS rotate_to_canonical(x, theta)
+        # (train.py:675-677 resamples the same x with the same rotation), so the trainer can take it from
+        # Encoder.take_canonical instead of launching a second rot_sample forward + backward
+        return mu, logvar, theta, x_rot
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_mu, g_lv, g_theta):
+    def backward(ctx, g_mu, g_lv, g_theta, g_xrot_out=None):
         (x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, wcat, a1, idx1, a2, idx2, f1, vec, cs, x_rot,
          h1, h2, h3, h4) = ctx.saved_tensors
         B, P, Ld, Npad = ctx.dims
@@ -124,9 +127,13 @@ class EncoderTc(Function):
         if g_mu is None and g_lv is None:
             # only theta is consumed downstream (train.py:376-377, pretrain_stn.py:106-107): the
             # gradient reaches the STN localisation only
-            if g_theta is None:
+            gcs = None
+            if g_xrot_out is not None:
+                gcs = _empty((B, 2), torch.float32, dev)
+                call("livae_rot_sample_bwd", x, cs, 1.0, g_xrot_out.contiguous(), B, 1, P, P, None, gcs)
+            if g_theta is None and gcs is None:
                 return (None,) * 21
-            return EncoderTc._backward_stn(ctx, None, g_theta)
+            return EncoderTc._backward_stn(ctx, gcs, g_theta)
         # --- heads
         g16 = torch.zeros((B, Npad), dtype=torch.float32, device=dev)
         if g_mu is not None:
@@ -148,6 +155,8 @@ class EncoderTc(Function):
         call("livae_thin_conv1c_wgrad", 1, x_rot, gh1, None, B, P, P, gc0w, gc0b)
         g_xrot = torch.empty_like(x)
         call("livae_thin_conv1c_dgrad", gh1, c0w, B, P, P, g_xrot)
+        if g_xrot_out is not None:      # the canonical-MSE gradient arrives on the same tensor (linear in g)
+            call("livae_axpby_dev", g_xrot, None, g_xrot_out.contiguous(), None, g_xrot.numel(), g_xrot)
         gcs = _empty((B, 2), torch.float32, dev)
         call("livae_rot_sample_bwd", x, cs, 1.0, g_xrot, B, 1, P, P, None, gcs)
         stn = EncoderTc._backward_stn(ctx, gcs, g_theta)

@@ -103,6 +103,8 @@ def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_we
     reproduced by default.  elide_dead_encoder=True evaluates only the STN localisation (same
     results, the conv stack's mu/logvar are discarded at the call site)."""
     rotated_recon, canonical_recon, theta, mu, logvar = model(x)
+    take = getattr(getattr(model, "encoder", None), "take_canonical", None)
+    canonical_input = take(x, theta) if (take is not None and canonical_weight > 0) else None
     theta_rotated = None
     if x_rotated is not None:
         if elide_dead_encoder:
@@ -112,7 +114,8 @@ def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_we
     loss, recon_loss, kld_loss, cycle_loss = criterion(rotated_recon, x, mu, logvar, theta, theta_rotated, angle)
     canonical_loss = torch.zeros((), device=loss.device)
     if canonical_weight > 0 and canonical_recon is not None:
-        canonical_input = rotate_to_canonical(x, theta, model.encoder.rotation_stn)
+        if canonical_input is None:
+            canonical_input = rotate_to_canonical(x, theta, model.encoder.rotation_stn)
         canonical_loss = ops.elbo_sums(canonical_recon, canonical_input)[0] / canonical_recon.numel()
         loss = loss + canonical_weight * canonical_loss
     return loss, recon_loss, kld_loss, cycle_loss, canonical_loss, (rotated_recon, canonical_recon, theta, mu, logvar)
