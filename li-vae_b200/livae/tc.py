@@ -232,15 +232,19 @@ class DecoderTc(Function):
         call("livae_sigmoid_bwd", recon, g_recon.contiguous(), None, recon.numel(), gpre4)
         gd4w = torch.empty_like(d4w); gd4b = _empty((1,), torch.float32, dev)
         call("livae_thin_convc1_wgrad", u4, gpre4, B, P + 2, P + 2, gd4w, gd4b)
-        gu = _empty((B, P + 2, P + 2, 32), BF, dev)
-        call("livae_thin_conv1c_fwd", 2, gpre4, d4w, None, B, P, P, gu, None)
         grads = []
         hw = P // 2
+        gu = None
         for i, (w, cin, cout) in zip((3, 2, 1), ((d3w, 64, 32), (d2w, 128, 64), (d1w, 256, 128))):
             y, u = ys[i], us[i - 1]
             gy = torch.empty_like(y)                              # pre-activation gradient of conv i
             gb = _empty((cout,), torch.float32, dev)           # bias gradient fused into the adjoint kernel
-            call("livae_upsample_pad_bwd_bias_bf16", gu, B, hw, hw, cout, y, gy, gb)
+            if i == 3:
+                # d4's data gradient and the upsample/pad adjoint in one kernel: the [B,P+2,P+2,32] gradient of the
+                # up-sampled tensor is never written
+                call("livae_upconv_c1_bwd_data", gpre4, d4w, y, B, hw, hw, gy, gb)
+            else:
+                call("livae_upsample_pad_bwd_bias_bf16", gu, B, hw, hw, cout, y, gy, gb)
             gw, _ = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0, want_bias=False)
             gu = ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, cout, cin, 3, 3, 2), None, hw + 2, hw + 2, 3, 3, 1, 0)
             grads.append((gw, gb))
