@@ -287,6 +287,14 @@ int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, 
    gb: fp32 [32] (written, may be NULL) = sum of gy over (b,i,j).  H, W >= 4, H % 4 != 1, W % 16 != 1. */
 int livae_upconv_c1_bwd_data(const float* gpre, const float* w, const void* y_bf16, int B, int H, int W,
                              void* gy_bf16, float* gb, livae_stream_t stream);
+/* The whole backward of decoder d4 (Upsample x2 -> ReflectionPad2d(1) -> Conv3x3(32 -> 1), model.py:369-372) in one
+   kernel, replacing livae_thin_convc1_wgrad + livae_thin_conv1c_fwd(kind 2) + livae_upsample_pad_bwd_bias_bf16 and
+   both up-sampled [B,2H+2,2W+2,32] tensors.  gpre: fp32 [B,2H,2W] pre-activation gradient of the conv output;
+   w: fp32 [1,32,3,3]; x: bf16 [B,H,W,32] post-ReLU LOW-resolution input of the layer.  Written: gx bf16 [B,H,W,32]
+   = d/dx times (x > 0); gb_low fp32 [32] (may be NULL) = sum of gx over (b,i,j) (bias gradient of the layer
+   below); gw fp32 [1,32,3,3]; gb fp32 [1] (may be NULL) = sum of gpre.  H, W >= 4. */
+int livae_upconv_c1_bwd(const float* gpre, const float* w, const void* x_bf16, int B, int H, int W, void* gx_bf16,
+                        float* gb_low, float* gw, float* gb, livae_stream_t stream);
 /* Last layer of the plain VAE decoder on the tensor-core path: ConvTranspose2d(C -> 1, k4, s2, p1) + activation
    (model.py:95-96, 111-113) and its backward.  x: bf16 [B,H,W,C] (C = 32); w: fp32 [C,1,4,4]; out / g: fp32 [B,2H,2W]
    (g = PRE-activation gradient); gx: bf16 [B,H,W,C] times (relu_mask > 0); gw [C,1,4,4], gb [1] written. */

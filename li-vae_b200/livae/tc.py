@@ -231,7 +231,6 @@ class DecoderTc(Function):
         gpre4 = torch.empty_like(recon)
         call("livae_sigmoid_bwd", recon, g_recon.contiguous(), None, recon.numel(), gpre4)
         gd4w = torch.empty_like(d4w); gd4b = _empty((1,), torch.float32, dev)
-        call("livae_thin_convc1_wgrad", u4, gpre4, B, P + 2, P + 2, gd4w, gd4b)
         grads = []
         hw = P // 2
         gu = None
@@ -240,9 +239,9 @@ class DecoderTc(Function):
             gy = torch.empty_like(y)                              # pre-activation gradient of conv i
             gb = _empty((cout,), torch.float32, dev)           # bias gradient fused into the adjoint kernel
             if i == 3:
-                # d4's data gradient and the upsample/pad adjoint in one kernel: the [B,P+2,P+2,32] gradient of the
-                # up-sampled tensor is never written
-                call("livae_upconv_c1_bwd_data", gpre4, d4w, y, B, hw, hw, gy, gb)
+                # the whole backward of d4 (weight, bias, data gradient + upsample/pad adjoint + this layer's bias
+                # gradient) in one kernel over the LOW-resolution tensors (csrc/upconv_c1.cu)
+                call("livae_upconv_c1_bwd", gpre4, d4w, y, B, hw, hw, gy, gb, gd4w, gd4b)
             else:
                 call("livae_upsample_pad_bwd_bias_bf16", gu, B, hw, hw, cout, y, gy, gb)
             gw, _ = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0, want_bias=False)

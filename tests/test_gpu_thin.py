@@ -255,3 +255,33 @@ def test_decoder_d4_fused_data_gradient(B, H, W):
     gx = torch.empty(B, H, W, 32, dtype=BF, device="cuda")
     _call("livae_upsample_pad_bwd_bf16", gu, B, H, W, 32, ylow.cuda().to(BF), gx)
     assert rel_l2(gy.float().cpu(), gx.float().cpu()) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 64, 64), (3, 24, 40), (2, 8, 8), (2, 20, 36), (300, 16, 16)])
+def test_decoder_d4_fused_backward(B, H, W):
+    """livae_upconv_c1_bwd == autograd of Upsample(x2, bilinear) -> ReflectionPad2d(1) -> Conv3x3(32 -> 1)
+    (model.py:369-372): data gradient w.r.t. the low-resolution input (times its ReLU mask, bf16: 5e-3), the column
+    sums of that (bias gradient of the layer below), weight and bias gradient (fp32 accumulation of tf32 products:
+    1e-3).  B = 300 exercises the persistent loop (more tiles than CTAs)."""
+    rng = np.random.default_rng(B * 1000 + H + W)
+    x = _bf(torch.tensor(rng.standard_normal((B, 32, H, W)).astype(np.float32))).clamp_min(0).requires_grad_(True)
+    w = torch.tensor((rng.standard_normal((1, 32, 3, 3)) * 0.1).astype(np.float32), requires_grad=True)
+    bias = torch.zeros(1, requires_grad=True)
+    up = F.pad(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
+    y = F.conv2d(up, w, bias)
+    g = torch.tensor(rng.standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * g).sum().backward()
+    xl = _nhwc(x.detach())
+    want = _nhwc(x.grad) * (xl > 0)
+    gx = torch.empty(B, H, W, 32, dtype=BF, device="cuda")
+    gbl = torch.full((32,), 7.0, device="cuda")
+    gw = torch.full((1, 32, 3, 3), 7.0, device="cuda"); gb = torch.full((1,), 7.0, device="cuda")
+    _call("livae_upconv_c1_bwd", g.cuda().contiguous(), w.detach().cuda(), xl.cuda().to(BF), B, H, W, gx, gbl, gw, gb)
+    assert rel_l2(gx.float().cpu(), want) < 5e-3
+    assert rel_l2(gbl.cpu(), gx.float().cpu().sum((0, 1, 2))) < 1e-4
+    assert rel_l2(gw.cpu(), w.grad) < 1e-3
+    assert rel_l2(gb.cpu(), bias.grad) < 1e-4
+    # borders are where the closed-form weights differ: check the outer two rings separately
+    ring = torch.zeros(H, W, dtype=torch.bool)
+    ring[:2] = ring[-2:] = True; ring[:, :2] = True; ring[:, -2:] = True
+    assert rel_l2(gx.float().cpu()[:, ring], want[:, ring]) < 5e-3
