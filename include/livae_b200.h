@@ -287,6 +287,11 @@ int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, 
    gb: fp32 [32] (written, may be NULL) = sum of gy over (b,i,j).  H, W >= 4, H % 4 != 1, W % 16 != 1. */
 int livae_upconv_c1_bwd_data(const float* gpre, const float* w, const void* y_bf16, int B, int H, int W,
                              void* gy_bf16, float* gb, livae_stream_t stream);
+/* Decoder d4 forward (Upsample x2 bilinear -> ReflectionPad2d(1) -> Conv3x3(32 -> 1) + activation, model.py:369-372)
+   from the LOW-resolution input, == livae_upsample_pad_fwd_bf16 + livae_thin_convc1_fwd without the up-sampled
+   tensor (and without its bf16 rounding).  x: bf16 [B,H,W,32]; w: fp32 [1,32,3,3]; bias fp32 [1]; out fp32 [B,2H,2W]. */
+int livae_upconv_c1_fwd(const void* x_bf16, const float* w, const float* bias, int B, int H, int W, int act,
+                        float* out, livae_stream_t stream);
 /* The whole backward of decoder d4 (Upsample x2 -> ReflectionPad2d(1) -> Conv3x3(32 -> 1), model.py:369-372) in one
    kernel, replacing livae_thin_convc1_wgrad + livae_thin_conv1c_fwd(kind 2) + livae_upsample_pad_bwd_bias_bf16 and
    both up-sampled [B,2H+2,2W+2,32] tensors.  gpre: fp32 [B,2H,2W] pre-activation gradient of the conv output;

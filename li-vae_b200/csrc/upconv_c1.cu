@@ -446,6 +446,143 @@ __global__ void __launch_bounds__(256, 3) upconv_c1_bwd_kernel(const float* __re
   }
 }
 
+
+// =====================================================================================================================
+// Forward of the layer without the up-sampled tensor: V[i,j,tap] = sum_ci x[i,j,ci] w[ci,tap] (a 1x1 convolution to 9
+// channels at LOW resolution, bf16 mma.sync with hi/lo-split weights, fp32 accumulate), then
+// y[Y,X] = act(bias + sum_tap upP(V[.,.,tap])[Y+ky, X+kx]) with the same up_src / reflect index maps as the
+// materialising kernels (aux.cu), in fp32.  Algorithmic bytes per patch: x 64 HW + y 4 (2H)(2W).
+// =====================================================================================================================
+namespace {
+constexpr int kXT = kT + 2;            // 18: low-res rows / cols a 16x16 tile of outputs (x2) depends on
+constexpr int kXP = kXT * kXT;         // 324 positions
+constexpr int kVP = 9;                 // words per position in the V tile (odd: conflict-free gathers)
+
+struct Lerp { int a, b; float f; };
+// padded index p of the [2n+2] up-sampled + reflect-padded axis -> source taps, local to a tile whose first
+// source index is org; same numbers as up_src(unpad(p)) in aux.cu
+__device__ __forceinline__ Lerp pad_src(int p, int n, int org) {
+  int u = p - 1;
+  if (u < 0) u = -u;
+  if (u >= 2 * n) u = 4 * n - 2 - u;
+  Lerp r;
+  const int a = u > 0 ? (u - 1) >> 1 : 0;
+  r.f = u == 0 ? 0.f : ((u & 1) ? 0.25f : 0.75f);
+  r.a = a - org;
+  r.b = (a < n - 1 ? a + 1 : a) - org;
+  return r;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256, 3) upconv_c1_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ w,
+                                                               const float* __restrict__ bias, int H, int W, int act,
+                                                               float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* xs = smem;                                                // [kXP][kPitch] bf16, clamped x tile
+  float* Vs = reinterpret_cast<float*>(smem + kXP * kPitch);               // [kXP][kVP]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int b = blockIdx.z, i0 = blockIdx.y * kT, j0 = blockIdx.x * kT;
+  // ---- 1. x tile, source rows i0-1 .. i0+16 clamped to the image (the clamp IS the up-sampling's edge rule)
+  for (int e = tid; e < kXP * 4; e += 256) {
+    const int p = e >> 2, oc = e & 3;
+    const int i = min(max(i0 - 1 + p / kXT, 0), H - 1), j = min(max(j0 - 1 + p % kXT, 0), W - 1);
+    *reinterpret_cast<uint4*>(xs + p * kPitch + oc * 16) =
+        __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)b * H + i) * W + j) * kC) + oc);
+  }
+  // ---- B fragments (K = ci, N = tap): b0 = (k = 2t, 2t+1; n = g), b1 = (k = 2t+8, 2t+9; n = g); hi + lo halves
+  uint32_t bh[2][2][2], bl[2][2][2];                    // [k-step][n-tile][b0/b1]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ci = ks * 16 + 2 * tq + 8 * h, tap = nt * 8 + gq;
+        const float w0 = tap < 9 ? __ldg(w + ci * 9 + tap) : 0.f, w1 = tap < 9 ? __ldg(w + (ci + 1) * 9 + tap) : 0.f;
+        const float w0h = __bfloat162float(__float2bfloat16_rn(w0)), w1h = __bfloat162float(__float2bfloat16_rn(w1));
+        bh[ks][nt][h] = pack_bf16(w0h, w1h);
+        bl[ks][nt][h] = pack_bf16(w0 - w0h, w1 - w1h);
+      }
+  __syncthreads();
+  // ---- 2. V = x w  ([324 x 32] x [32 x 9]) by warp-level MMA
+  for (int mt = wid; mt * 16 < kXP; mt += 8) {
+    const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int pr = min(mt * 16 + row, kXP - 1);
+    float d[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(a, xs + pr * kPitch + ks * 32 + (lane >> 4) * 16);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        mma_bf16_16816(d[nt], a, bl[ks][nt][0], bl[ks][nt][1]);
+        mma_bf16_16816(d[nt], a, bh[ks][nt][0], bh[ks][nt][1]);
+      }
+    }
+    const int m0 = mt * 16 + gq, m1 = m0 + 8;
+    if (m0 < kXP) {
+      Vs[m0 * kVP + 2 * tq] = d[0][0]; Vs[m0 * kVP + 2 * tq + 1] = d[0][1];
+      if (tq == 0) Vs[m0 * kVP + 8] = d[1][0];
+    }
+    if (m1 < kXP) {
+      Vs[m1 * kVP + 2 * tq] = d[0][2]; Vs[m1 * kVP + 2 * tq + 1] = d[0][3];
+      if (tq == 0) Vs[m1 * kVP + 8] = d[1][2];
+    }
+  }
+  __syncthreads();
+  // ---- 3. y = act(bias + sum_tap upP(V[tap])[Y + ky, X + kx]); thread = one column X, four rows
+  const int X = tid & 31, Yq = (tid >> 5) * 4;
+  const int Xg = 2 * j0 + X;
+  if (Xg >= 2 * W) return;
+  Lerp cx[3];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx) cx[kx] = pad_src(Xg + kx, W, j0 - 1);
+  Lerp ry[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) ry[r] = pad_src(2 * i0 + Yq + r, H, i0 - 1);
+  const float bv = __ldg(bias);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int Yg = 2 * i0 + Yq + k;
+    if (Yg >= 2 * H) break;
+    float acc = bv;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const Lerp r = ry[k + ky];
+      const float* v0 = Vs + (r.a * kXT) * kVP + ky * 3;
+      const float* v1 = Vs + (r.b * kXT) * kVP + ky * 3;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const Lerp c = cx[kx];
+        // ATen's association: h0 * (w0 v00 + w1 v01) + h1 * (w0 v10 + w1 v11)
+        const float top = (1.f - c.f) * v0[c.a * kVP + kx] + c.f * v0[c.b * kVP + kx];
+        const float bot = (1.f - c.f) * v1[c.a * kVP + kx] + c.f * v1[c.b * kVP + kx];
+        acc += (1.f - r.f) * top + r.f * bot;
+      }
+    }
+    if (act == LIVAE_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+    else if (act == LIVAE_ACT_RELU) acc = fmaxf(acc, 0.f);
+    out[((int64_t)b * 2 * H + Yg) * (2 * W) + Xg] = acc;
+  }
+}
+
 }  // namespace livae
 
 extern "C" int livae_upconv_c1_bwd_data(const float* gpre, const float* w, const void* y_bf16, int B, int H, int W,
@@ -505,6 +642,27 @@ extern "C" int livae_upconv_c1_bwd(const float* gpre, const float* w, const void
   const int grid = (int)(n_tiles < 3 * kNumSMs ? n_tiles : 3 * kNumSMs);
   upconv_c1_bwd_kernel<<<grid, 256, smem, st>>>(gpre, w, (const __nv_bfloat16*)x_bf16, B, H, W,
                                                 (__nv_bfloat16*)gx_bf16, gb_low, gw, gb);
+  LIVAE_CUDA_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int livae_upconv_c1_fwd(const void* x_bf16, const float* w, const float* bias, int B, int H, int W, int act,
+                                   float* out, livae_stream_t stream) {
+  using namespace livae;
+  LIVAE_CHECK_ARG(B >= 0 && H >= 2 && W >= 2, "upconv_c1_fwd: bad sizes");
+  if (B == 0) return 0;
+  LIVAE_CHECK_ARG(x_bf16 && w && bias && out, "upconv_c1_fwd: null pointer");
+  LIVAE_CHECK_ARG((((uintptr_t)x_bf16) & 15) == 0 && B <= 65535, "upconv_c1_fwd: 16-byte alignment, B <= 65535");
+  if (int e = require_sm100()) return e;
+  const size_t smem = (size_t)kXP * kPitch + (size_t)kXP * kVP * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t ce = cudaFuncSetAttribute(upconv_c1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) { set_error("upconv_c1_fwd: cannot set %zu B of shared memory", smem); return (int)ce; }
+    attr_done = true;
+  }
+  dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, B);
+  upconv_c1_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, w, bias, H, W, act, out);
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
 }

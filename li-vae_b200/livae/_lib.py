@@ -70,6 +70,7 @@ _SIGS = {
     "livae_thin_convc1_wgrad": "ppiiipps",
     "livae_upconv_c1_bwd_data": "pppiiipps",
     "livae_upconv_c1_bwd": "pppiiipppps",
+    "livae_upconv_c1_fwd": "pppiiiips",
     "livae_sigmoid_bwd": "ppplps",
     "livae_relu_mask_cast_bf16": "pplps",
     "livae_maxpool_bf16": "piiiipps",

@@ -211,12 +211,11 @@ class DecoderTc(Function):
             cur = ops.tc_conv(u, ops.tc_pack_weights(w, cout, cin, 3, 3, 0), b, 3, 3, 1, 0, ACT_RELU)
             us.append(u); ys.append(cur)
             hw *= 2
-        u4 = _empty((B, 2 * hw + 2, 2 * hw + 2, 32), BF, dev)
-        call("livae_upsample_pad_fwd_bf16", cur, B, hw, hw, 32, u4)
         P = 2 * hw
         recon = _empty((B, 1, P, P), torch.float32, dev)
-        call("livae_thin_convc1_fwd", u4, d4w, d4b, B, P + 2, P + 2, ACT_SIGMOID, recon)
-        ctx.save_for_backward(z, fcw, d1w, d2w, d3w, d4w, recon, u4, *ys, *us)
+        # d4 (upsample -> pad -> 32->1 conv -> sigmoid) straight from the low-resolution map (csrc/upconv_c1.cu)
+        call("livae_upconv_c1_fwd", cur, d4w, d4b, B, hw, hw, ACT_SIGMOID, recon)
+        ctx.save_for_backward(z, fcw, d1w, d2w, d3w, d4w, recon, *ys, *us)
         ctx.dims = (B, Ld, q, P)
         return recon
 
@@ -224,8 +223,8 @@ class DecoderTc(Function):
     @once_differentiable
     def backward(ctx, g_recon):
         saved = ctx.saved_tensors
-        z, fcw, d1w, d2w, d3w, d4w, recon, u4 = saved[:8]
-        ys, us = saved[8:12], saved[12:15]
+        z, fcw, d1w, d2w, d3w, d4w, recon = saved[:7]
+        ys, us = saved[7:11], saved[11:14]
         B, Ld, q, P = ctx.dims
         dev = z.device
         gpre4 = torch.empty_like(recon)

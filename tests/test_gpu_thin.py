@@ -285,3 +285,20 @@ def test_decoder_d4_fused_backward(B, H, W):
     ring = torch.zeros(H, W, dtype=torch.bool)
     ring[:2] = ring[-2:] = True; ring[:, :2] = True; ring[:, -2:] = True
     assert rel_l2(gx.float().cpu()[:, ring], want[:, ring]) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 64, 64), (3, 24, 40), (2, 8, 8), (2, 20, 36), (1, 2, 2)])
+def test_decoder_d4_fused_forward(B, H, W):
+    """livae_upconv_c1_fwd == sigmoid(Conv3x3(ReflectionPad2d(1)(Upsample(x2, bilinear)(x)))) (model.py:369-372) in
+    fp32 from the bf16 low-resolution map: 2e-5 on the output."""
+    rng = np.random.default_rng(B * 1000 + H + W)
+    x = _bf(torch.tensor(rng.standard_normal((B, 32, H, W)).astype(np.float32))).clamp_min(0)
+    w = torch.tensor((rng.standard_normal((1, 32, 3, 3)) * 0.1).astype(np.float32))
+    bias = torch.tensor([0.05])
+    up = F.pad(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
+    pre = F.conv2d(up.double(), w.double(), bias.double()).float()
+    for act, want in ((2, torch.sigmoid(pre)), (0, pre)):
+        out = torch.empty(B, 1, 2 * H, 2 * W, device="cuda")
+        _call("livae_upconv_c1_fwd", _nhwc(x).cuda().to(BF), w.cuda(), bias.cuda(), B, H, W, act, out)
+        assert rel_l2(out.cpu(), want) < 2e-5, (act, rel_l2(out.cpu(), want))
+        assert (out.cpu() - want).abs().max() < 1e-4 * max(1.0, float(want.abs().max()))
