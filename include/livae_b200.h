@@ -280,13 +280,6 @@ int livae_upsample_pad_bwd_bf16(const void* g, int B, int H, int W, int C, const
    pre-activation gradient gx is (autograd of Conv2d bias, model.py:359-367); needs C/8 a power of two, W*C/8 <= 256 */
 int livae_upsample_pad_bwd_bias_bf16(const void* g, int B, int H, int W, int C, const void* relu_mask_y, void* gx,
                                      float* gb, livae_stream_t stream);
-/* Decoder d4 (Upsample x2 -> ReflectionPad2d(1) -> Conv3x3(32 -> 1), model.py:369-372) backward w.r.t. its
-   low-resolution input in one kernel: == livae_thin_conv1c_fwd(kind 2) followed by livae_upsample_pad_bwd_bias_bf16,
-   without the [B,2H+2,2W+2,32] intermediate.  gpre: fp32 [B,2H,2W] pre-activation gradient of the conv output;
-   w: fp32 [1,32,3,3]; y: bf16 [B,H,W,32] post-ReLU input of the layer (mask y > 0); gy: bf16 [B,H,W,32];
-   gb: fp32 [32] (written, may be NULL) = sum of gy over (b,i,j).  H, W >= 4, H % 4 != 1, W % 16 != 1. */
-int livae_upconv_c1_bwd_data(const float* gpre, const float* w, const void* y_bf16, int B, int H, int W,
-                             void* gy_bf16, float* gb, livae_stream_t stream);
 /* Decoder d4 forward (Upsample x2 bilinear -> ReflectionPad2d(1) -> Conv3x3(32 -> 1) + activation, model.py:369-372)
    from the LOW-resolution input, == livae_upsample_pad_fwd_bf16 + livae_thin_convc1_fwd without the up-sampled
    tensor (and without its bf16 rounding).  x: bf16 [B,H,W,32]; w: fp32 [1,32,3,3]; bias fp32 [1]; out fp32 [B,2H,2W]. */

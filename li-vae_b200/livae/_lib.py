@@ -68,7 +68,6 @@ _SIGS = {
     "livae_thin_conv1c_dgrad": "ppiiips",
     "livae_thin_convc1_fwd": "pppiiiips",
     "livae_thin_convc1_wgrad": "ppiiipps",
-    "livae_upconv_c1_bwd_data": "pppiiipps",
     "livae_upconv_c1_bwd": "pppiiipppps",
     "livae_upconv_c1_fwd": "pppiiiips",
     "livae_sigmoid_bwd": "ppplps",
