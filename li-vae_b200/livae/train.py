@@ -208,6 +208,7 @@ def _clip_and_norm(model, optimizer, max_norm):
     """-> device scalar: pre-clip global gradient norm (what clip_grad_norm_ returns)"""
     flat = getattr(optimizer, "flat_grad", None)
     if flat is not None:
+        optimizer.sync_grads()
         return ops.l2norm_clip_(flat, max_norm, apply=True)[0]
     return torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)
 
@@ -249,6 +250,8 @@ def train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight
                                                               canonical_weight)
     loss.backward()
     if reduce_grads is not None:
+        if hasattr(optimizer, "sync_grads"):
+            optimizer.sync_grads()            # the all-reduce reads the flat gradient buffer
         reduce_grads()
     pre = _clip_and_norm(model, optimizer, max_norm)
     optimizer.step()

@@ -359,3 +359,45 @@ def test_vae_step_tensor_core_engine(case):
             assert rel_l2(g, w) < 1e-1, (k, rel_l2(g, w))
         else:
             assert _cos(g, w) > 0.9 and abs(float(g.norm()) / float(w.norm()) - 1.0) < 0.3, (k, _cos(g, w))
+
+
+def test_flat_adamw_matches_torch_adamw_with_lazy_gradient_packing():
+    """livae.optim.FlatAdamW == torch.optim.AdamW (scripts/train_rvae.py:157-159) over several steps, through every
+    gradient hand-over mode: dropped gradients packed by sync_grads, two
+    backward passes accumulating, and no zero_grad at all (in-place accumulation into the flat views)."""
+    from livae.optim import FlatAdamW
+    torch.manual_seed(3)
+    shapes = [(7, 5), (13,), (3, 2, 3, 3), (1,)]
+    ref = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-2, weight_decay=1e-2)
+    o_mine = FlatAdamW(mine, lr=1e-2, weight_decay=1e-2)
+
+    def loss_of(ps, k, skip_last):
+        t = sum(((p * (i + 1 + k)) ** 2).sum() for i, p in enumerate(ps[:-1]))
+        return t if skip_last else t + (ps[-1] * 3.0).sum()
+
+    for k in range(6):
+        skip_last = False
+        for ps, o in ((ref, o_ref), (mine, o_mine)):
+            if k != 4:                                   # step 4: no zero_grad -> gradients accumulate on step 3's
+                o.zero_grad(set_to_none=True)
+            loss_of(ps, k, skip_last).backward()
+            if k == 1:
+                loss_of(ps, k + 10, False).backward()    # second backward accumulates
+        o_mine.sync_grads()
+        for a, b in zip(ref, mine):
+            if a.grad is None:
+                assert float(b.grad.abs().max()) == 0.0
+            else:
+                assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-4)   # parameters agree to 2e-5 after k steps
+            assert b.grad.data_ptr() >= o_mine.flat_grad.data_ptr()
+        o_ref.step(); o_mine.step()
+        for a, b in zip(ref, mine):
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), k
+    # a parameter that received no gradient: its slice of the flat buffer is zero (documented deviation: the flat
+    # update then treats it as a zero gradient, torch.optim would skip the tensor)
+    o_mine.zero_grad()
+    loss_of(mine, 0, True).backward()
+    o_mine.sync_grads()
+    assert float(mine[-1].grad.abs().max()) == 0.0 and float(mine[0].grad.abs().max()) > 0.0

@@ -28,6 +28,7 @@ def step(x):
     recon, mu, logvar = m(x)
     loss, _, _ = crit(recon, x, mu, logvar)
     loss.backward()
+    opt.sync_grads()
     ops.l2norm_clip_(opt.flat_grad, 5.0, apply=True)
     opt.step()
     return loss
