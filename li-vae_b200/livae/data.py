@@ -26,26 +26,41 @@ from livae import ops
 __all__ = ["default_transform", "draw_transform_params", "DevicePatchSource", "DevicePatchLoader"]
 
 
+def _draw(n: int, flip_prob: float, jitter_amount: int, rotation: bool, transform: bool, pair_angle: bool):
+    """n consecutive items' draws from Python's `random` in the reference's order: per item the default_transform
+    draws (scale, [angle], hflip, vflip, shift_x, shift_y; data.py:85-114) if `transform`, then the pair angle
+    (data.py:695) if `pair_angle`.  Plain lists in a tight loop: this runs on the host once per batch."""
+    u, r, ri = random.uniform, random.random, random.randint
+    scale, angle, flags, shift, pair = [], [], [], [], []
+    for _ in range(n):
+        if transform:
+            scale.append(u(0.9, 1.1))
+            if rotation:
+                angle.append(u(0, 360))
+            f = 1 if r() < flip_prob else 0
+            if r() < flip_prob:
+                f |= 2
+            flags.append(f)
+            if jitter_amount > 0:
+                sx = ri(-jitter_amount, jitter_amount)
+                sy = ri(-jitter_amount, jitter_amount)
+                shift.append((sy, sx))
+            else:
+                shift.append((0, 0))
+        if pair_angle:
+            pair.append(u(0, 360))
+    p = None
+    if transform:
+        p = {"scale": np.asarray(scale, np.float32),
+             "angle": np.asarray(angle, np.float64) if rotation else np.full(n, np.nan),
+             "flags": np.asarray(flags, np.int32).reshape(n), "shift": np.asarray(shift, np.int32).reshape(n, 2)}
+    return p, (np.asarray(pair, np.float64) if pair_angle else None)
+
+
 def draw_transform_params(n: int, flip_prob: float = 0.5, jitter_amount: int = 4, rotation: bool = False):
     """n consecutive default_transform draws from Python's `random`, in the reference's order (data.py:85-114).
     -> dict of host numpy arrays: scale f32 [n], angle f64 [n] (nan if not rotation), flags i32 [n], shift i32 [n,2]"""
-    scale = np.empty(n, np.float32)
-    angle = np.full(n, np.nan, np.float64)
-    flags = np.zeros(n, np.int32)
-    shift = np.zeros((n, 2), np.int32)
-    for i in range(n):
-        scale[i] = random.uniform(0.9, 1.1)
-        if rotation:
-            angle[i] = random.uniform(0, 360)
-        if random.random() < flip_prob:
-            flags[i] |= 1
-        if random.random() < flip_prob:
-            flags[i] |= 2
-        if jitter_amount > 0:
-            sx = random.randint(-jitter_amount, jitter_amount)
-            sy = random.randint(-jitter_amount, jitter_amount)
-            shift[i] = (sy, sx)
-    return {"scale": scale, "angle": angle, "flags": flags, "shift": shift}
+    return _draw(n, flip_prob, jitter_amount, rotation, True, False)[0]
 
 
 def _apply_transform(big: torch.Tensor, p: dict, rotation: bool) -> torch.Tensor:
@@ -107,6 +122,8 @@ class DevicePatchSource:
         self._yx = np.concatenate(flat) if flat else np.zeros((0, 2))
         self._img = np.repeat(np.arange(len(coords), dtype=np.int32), self.counts)
         self.device = dev
+        self._slots = [(None, None)] * 3          # pinned staging slots (buffer, event of the copy that used it)
+        self._slot_i = 0
 
     @classmethod
     def from_dataset(cls, ds, device="cuda"):
@@ -123,49 +140,79 @@ class DevicePatchSource:
         idx = np.asarray(indices, dtype=np.int64).reshape(-1)
         if idx.size and (idx.min() < 0 or idx.max() >= len(self)):
             raise IndexError(f"Index out of range for dataset of size {len(self)}")      # data.py:217-220
-        return (torch.from_numpy(self._img[idx]).to(self.device),
-                torch.from_numpy(self._yx[idx]).to(self.device))
+        return self._img[idx], self._yx[idx]
+
+    def _upload(self, cols):
+        """All per-item numbers of a batch (site, draws) as ONE float64 [n,k] array through a pinned staging slot
+        and one asynchronous copy: a pageable .to(device) per array would synchronise the host with the compute
+        stream six times per batch and stop the CPU from running ahead of the training step."""
+        n = cols[0].shape[0]
+        host = np.concatenate([np.asarray(c, dtype=np.float64).reshape(n, -1) for c in cols], axis=1)
+        k = host.shape[1]
+        slot = self._slot_i % len(self._slots)
+        self._slot_i += 1
+        buf, ev = self._slots[slot]
+        if buf is None or buf.shape[0] < n or buf.shape[1] != k:
+            buf = torch.empty((max(n, 1), k), dtype=torch.float64, pin_memory=True)
+        elif ev is not None:
+            ev.synchronize()                     # the copy that last used this slot has finished
+        buf.numpy()[:n] = host
+        dev = buf[:n].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._slots[slot] = (buf, ev)
+        return dev
 
     # --- PatchDataset.__getitem__, transform=None (data.py:211-250) -------------------------------------
     def patch_batch(self, indices) -> torch.Tensor:
         img, yx = self._lookup(indices)
-        sites = torch.cat([img.view(-1, 1), yx.round().to(torch.int32)], 1).contiguous()
-        return ops.patch_gather(self.images, sites, self.patch_size)
+        d = self._upload([img, np.round(yx)])
+        return ops.patch_gather(self.images, d.to(torch.int32).contiguous(), self.patch_size)
 
-    def _big(self, indices):
-        img, yx = self._lookup(indices)
+    def _big(self, d):
         S = self.patch_size + 2 * self.padding
         roi = self.patch_size + max(16, 2 * self.padding)
-        return ops.patch_gather_roi(self.images, img, yx, S, roi)
+        return ops.patch_gather_roi(self.images, d[:, 0].to(torch.int32).contiguous(), d[:, 1:3].contiguous(), S, roi)
+
+    @staticmethod
+    def _params_on_device(d, c0):
+        """columns c0.. of the uploaded array: scale, flags, shift_y, shift_x"""
+        return {"scale": d[:, c0].float().contiguous(), "flags": d[:, c0 + 1].to(torch.int32).contiguous(),
+                "shift": d[:, c0 + 2:c0 + 4].to(torch.int32).contiguous()}
 
     # --- AdaptiveLatticeDataset.__getitem__ (data.py:478-560) -------------------------------------------
     def adaptive_batch(self, indices) -> torch.Tensor:
-        big = self._big(indices)
+        img, yx = self._lookup(indices)
+        cols = [img, yx]
         if self.transform is not None:
-            big = _apply_transform(big, draw_transform_params(big.shape[0]), rotation=False)
+            p = draw_transform_params(len(img))
+            cols += [p["scale"], p["flags"], p["shift"]]
+        d = self._upload(cols)
+        big = self._big(d)
+        if self.transform is not None:
+            q = self._params_on_device(d, 3)
+            big = ops.augment(big, q["scale"], q["flags"], q["shift"])
         return ops.rotate_crop(big, self.patch_size, None, normalise=True)
 
     # --- PairedAdaptiveLatticeDataset.__getitem__ (data.py:617-735) -------------------------------------
     def paired_batch(self, indices, angles_deg: Optional[Iterable[float]] = None):
         """-> (patch [N,1,P,P], rotated [N,1,P,P], angle_rad float32 [N]) as the default collate of the
-        reference's items gives them.  Draw order per item: transform draws, then the pair angle."""
-        big = self._big(indices)
-        n = big.shape[0]
-        if self.transform is not None or angles_deg is None:
-            ang = np.empty(n, np.float64)
-            ps = []
-            for i in range(n):                       # per item: transform(rotation=False) draws, then the angle
-                if self.transform is not None:
-                    ps.append(draw_transform_params(1))
-                ang[i] = random.uniform(0, 360)
-            if angles_deg is not None:
-                ang = np.asarray(list(angles_deg), dtype=np.float64)
-            if ps:
-                p = {k: np.concatenate([q[k] for q in ps]) for k in ps[0]}
-                big = _apply_transform(big, p, rotation=False)
-        else:
+        reference's items gives them.  Draw order per item: transform draws, then the pair angle (drawn even when
+        angles_deg overrides it, so the random stream advances as in the reference)."""
+        img, yx = self._lookup(indices)
+        n = len(img)
+        p, ang = _draw(n, 0.5, 4, False, self.transform is not None, True)
+        if angles_deg is not None:
             ang = np.asarray(list(angles_deg), dtype=np.float64)
-        ang_dev = torch.from_numpy(ang).to(self.device)
+        cols = [img, yx, ang]
+        if p is not None:
+            cols += [p["scale"], p["flags"], p["shift"]]
+        d = self._upload(cols)
+        big = self._big(d)
+        if p is not None:
+            q = self._params_on_device(d, 4)
+            big = ops.augment(big, q["scale"], q["flags"], q["shift"])
+        ang_dev = d[:, 3].contiguous()
         patch = ops.rotate_crop(big, self.patch_size, None, normalise=True)
         rotated = ops.rotate_crop(big, self.patch_size, ang_dev, normalise=True)
         return patch, rotated, torch.deg2rad(ang_dev).float()
