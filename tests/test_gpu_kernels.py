@@ -395,7 +395,8 @@ def test_cpu_tensors_fail_loudly(ops):
         ops.rot_sample(torch.zeros(1, 1, 8, 8), torch.zeros(1, 2), 1.0)
 
 
-@pytest.mark.parametrize("shape,win", [((3, 1, 128, 128), 11), ((2, 2, 37, 50), 11), ((1, 1, 16, 16), 5), ((4, 1, 64, 64), 11)])
+@pytest.mark.parametrize("shape,win", [((3, 1, 128, 128), 11), ((2, 2, 37, 50), 11), ((1, 1, 16, 16), 5), ((4, 1, 64, 64), 11),
+                                       ((2, 1, 41, 36), 11), ((1, 2, 12, 8), 11)])
 def test_ssim_box_matches_reference_formula(shape, win):
     """fused box-filter SSIM (csrc/ssim.cu) against the reference's avg_pool2d formulation (train.py:606-667)"""
     import torch.nn.functional as F
