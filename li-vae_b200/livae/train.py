@@ -118,7 +118,15 @@ def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_we
             canonical_input = rotate_to_canonical(x, theta, model.encoder.rotation_stn)
         canonical_loss = ops.elbo_sums(canonical_recon, canonical_input)[0] / canonical_recon.numel()
         loss = loss + canonical_weight * canonical_loss
-    return loss, recon_loss, kld_loss, cycle_loss, canonical_loss, (rotated_recon, canonical_recon, theta, mu, logvar)
+    outs = _RvaeOutputs((rotated_recon, canonical_recon, theta, mu, logvar))
+    outs.canonical_input = canonical_input if (canonical_weight > 0 and canonical_recon is not None) else None
+    return loss, recon_loss, kld_loss, cycle_loss, canonical_loss, outs
+
+
+class _RvaeOutputs(tuple):
+    """the model's 5 outputs; `.canonical_input` additionally carries rotate_to_canonical(x, theta) when the step
+    computed it, so the metric block (train.py:419-427) does not resample the batch a second time"""
+    canonical_input = None
 
 
 class DevicePrefetcher:
@@ -277,8 +285,12 @@ def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger
             if theta is not None:
                 m["train_rotation_std"] = torch.std(theta)
             if canonical_recon is not None:
-                canonical_input = rotate_to_canonical(x, theta)
-                m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
+                canonical_input = getattr(outs, "canonical_input", None)
+                if canonical_input is not None:      # the step already formed it and its MSE (train.py:389-393)
+                    m["train_canonical_psnr"] = 20.0 * torch.log10(1.0 / torch.sqrt(_can_l))
+                else:
+                    canonical_input = rotate_to_canonical(x, theta)
+                    m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
                 m["train_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
             acc.add(**m)
         n_batches += 1

@@ -1,0 +1,181 @@
+"""GPU: the hot path at BASELINE.json's FULL sizes (C3: rVAE P=128, B=2048; C5-sized images), where the oracle is too
+slow to run, checked through size-independent properties: adjoint (dot-product) identities between forward and
+backward kernels, exact inverses of the index permutations, linearity of the batch-mean step in the batch (the
+data-parallel contract of SURVEY 8e: B samples on one rank == the mean of two ranks with B/2 each), and plain
+re-statements with ATen index arithmetic on the device as the checker.  Everything goes through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rvae as O
+from tests.test_gpu_step import FixedEps
+
+pytestmark = pytest.mark.gpu
+B, P = 2048, 128
+BF = torch.bfloat16
+
+
+def _call(*a):
+    from livae._lib import call
+    call(*a)
+
+
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+def test_rot_sample_adjoint_and_exact_angles_full_size():
+    """<R x, g> == <x, R^T g> with R^T from rot_sample_bwd's grad_input (both are our kernels; 1e-5), identity at
+    theta = 0 and a pure index permutation at theta = pi/2 (bit-exact against torch.rot90)."""
+    from livae import ops
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(B, 1, P, P, device="cuda", generator=g0)
+    g = torch.randn(B, 1, P, P, device="cuda", generator=g0)
+    th = torch.rand(B, device="cuda", generator=g0) * 6.2831853
+    cs = torch.stack([torch.cos(th), torch.sin(th)], 1).contiguous()
+    y = ops.rot_sample(x, cs, 1.0)
+    gx = torch.empty_like(x); gcs = torch.empty(B, 2, device="cuda")
+    _call("livae_rot_sample_bwd", x, cs, 1.0, g, B, 1, P, P, gx, gcs)
+    lhs, rhs = _dot(y, g), _dot(x, gx)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    ident = torch.tensor([[1.0, 0.0]], device="cuda").repeat(B, 1)
+    assert torch.equal(ops.rot_sample(x, ident, 1.0), x)
+    quarter = torch.tensor([[0.0, 1.0]], device="cuda").repeat(B, 1)
+    r90 = ops.rot_sample(x, quarter, 1.0)
+    # grid = R(theta) applied to the OUTPUT coordinate: (gx, gy) = (-ys, xs), i.e. out[i, j] = x[j, W-1-i]
+    assert torch.equal(r90, x.transpose(2, 3).flip(2))
+
+
+def test_decoder_d4_triple_identity_full_size():
+    """d4 is linear before the sigmoid: with y = J(w) x,  <y, g> == <x, J^T g> == <w, dL/dw>; forward from
+    livae_upconv_c1_fwd (act none, bias 0), both gradients from livae_upconv_c1_bwd, at B=2048, H=W=64.  x > 0 so
+    the ReLU mask is all ones."""
+    H = P // 2
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.rand(B, H, H, 32, device="cuda", generator=gen) + 0.05).to(BF)
+    w = torch.randn(1, 32, 3, 3, device="cuda", generator=gen) * 0.1
+    g = torch.randn(B, 1, P, P, device="cuda", generator=gen)
+    zero = torch.zeros(1, device="cuda")
+    y = torch.empty(B, 1, P, P, device="cuda")
+    _call("livae_upconv_c1_fwd", x, w, zero, B, H, H, 0, y)
+    gx = torch.empty_like(x)
+    gbl, gw, gb = torch.empty(32, device="cuda"), torch.empty_like(w), torch.empty(1, device="cuda")
+    _call("livae_upconv_c1_bwd", g.contiguous(), w, x, B, H, H, gx, gbl, gw, gb)
+    a, b_, c = _dot(y, g), _dot(x.float(), gx.float()), _dot(w, gw)
+    scale = max(abs(a), 1.0)
+    assert abs(a - c) <= 2e-4 * scale, (a, c)
+    # gx is stored in bf16: each of the 2.7e8 products x_i gx_i carries an independent relative rounding error of
+    # std 2^-9 / sqrt(3); the dot product (a sum with random signs, |a| << sum |x_i gx_i|) is compared at 6 sigma
+    noise = (2.0 ** -9 / 3 ** 0.5) * float(((x.double() * gx.double()) ** 2).sum()) ** 0.5
+    assert abs(a - b_) <= 6 * noise + 1e-4 * scale, (a, b_, noise)
+    assert abs(float(gb) - float(g.double().sum())) <= 1e-3 * g.numel() ** 0.5
+    assert torch.allclose(gbl, gx.float().sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+
+
+def test_elbo_sums_full_size_against_double():
+    from livae import ops
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    r = torch.rand(B, 1, P, P, device="cuda", generator=gen)
+    x = torch.rand(B, 1, P, P, device="cuda", generator=gen)
+    mu = torch.randn(B, 2, device="cuda", generator=gen)
+    lv = torch.randn(B, 2, device="cuda", generator=gen) * 0.3
+    s = ops.elbo_sums(r, x, mu, lv)
+    want0 = float(((r.double() - x.double()) ** 2).sum())
+    want1 = float((-0.5 * (1 + lv.double() - mu.double() ** 2 - lv.double().exp())).sum())
+    assert abs(float(s[0]) - want0) <= 1e-6 * want0 and abs(float(s[1]) - want1) <= 1e-5 * abs(want1)
+    perm = torch.randperm(B, device="cuda")
+    s2 = ops.elbo_sums(r[perm].contiguous(), x[perm].contiguous(), mu[perm].contiguous(), lv[perm].contiguous())
+    assert abs(float(s2[0]) - float(s[0])) <= 1e-6 * want0     # a checksum of checksums: order-independent
+
+
+def test_patch_gather_c5_sized_image_bit_exact():
+    """8192 peak-centred 128x128 crops from 4096x4096 images (C5's image size) == plain index arithmetic"""
+    from livae import ops
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    imgs = torch.rand(2, 4096, 4096, device="cuda", generator=gen)
+    n = 8192
+    sites = torch.stack([torch.randint(0, 2, (n,), device="cuda", generator=gen),
+                         torch.randint(0, 4096, (n,), device="cuda", generator=gen),
+                         torch.randint(0, 4096, (n,), device="cuda", generator=gen)], 1).to(torch.int32).contiguous()
+    got = ops.patch_gather(imgs, sites, P)
+    pad = torch.zeros(2, 4096 + 2 * P, 4096 + 2 * P, device="cuda")
+    pad[:, P:-P, P:-P] = imgs
+    ar = torch.arange(P, device="cuda")
+    yy = (sites[:, 1].long() + P - P // 2)[:, None, None] + ar[None, :, None]
+    xx = (sites[:, 2].long() + P - P // 2)[:, None, None] + ar[None, None, :]
+    want = pad[sites[:, 0].long()[:, None, None], yy, xx]
+    assert torch.equal(got[:, 0], want)
+
+
+def test_augment_permutations_invert_exactly_full_size():
+    """flips and rolls are index permutations: applying them twice / with the opposite shift restores the batch bit
+    for bit (B=2048, S=192 = P + 2*padding); rotate by 0 degrees is the identity to the fp32 grid rounding."""
+    from livae import ops
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    S = P + 64
+    big = torch.rand(B, 1, S, S, device="cuda", generator=gen)
+    flags = torch.randint(0, 4, (B,), device="cuda", generator=gen).to(torch.int32) | 4
+    shift = torch.randint(-4, 5, (B, 2), device="cuda", generator=gen).to(torch.int32)
+    one = torch.ones(B, device="cuda")
+    zero_shift = torch.zeros_like(shift)
+    fwd = ops.augment(big, one, flags, zero_shift)                       # flips only
+    assert torch.equal(ops.augment(fwd, one, flags, zero_shift), big)
+    only4 = torch.full_like(flags, 4)
+    rolled = ops.augment(big, one, only4, shift)
+    assert torch.equal(ops.augment(rolled, one, only4, (-shift).contiguous()), big)
+    rot0 = ops.rotate_crop(big, P, torch.zeros(B, dtype=torch.float64, device="cuda"))
+    assert float((rot0 - ops.rotate_crop(big, P)).abs().max()) < 5e-5      # fp32 grid of torchvision, white noise
+
+
+def test_full_batch_step_equals_mean_of_half_batches():
+    """SURVEY 8e parity contract at the benchmark size: the gradient of ONE FULL step (model(x) + encoder(x_rot) +
+    RVAELoss(beta=10, gamma=10, cycle) + 0.2 canonical) on B=2048 equals the mean of the gradients of its two
+    halves (what two data-parallel ranks would all-reduce), and the losses average likewise (1e-5).
+    Gradients are compared against the RUN-TO-RUN noise of the full batch itself: the split-K Linear layers add
+    their partial sums with fp32 atomics, the resulting 1e-7 jitter in the STN's fc1 moves theta by ~4e-6 rad and
+    the encoder's input by ~2e-5, which flips a few near-zero ReLU / max-pool decisions; two
+    identical runs therefore differ by up to a few 1e-3 in the deepest (STN) gradients and by < 1e-5 in the last
+    decoder layer (the floor is measured and reported).  Bounds: 2e-2 (STN, encoder, decoder.fc), 2e-3 (d1-d3), 1e-4 (d4)."""
+    import livae
+    from livae.train import rvae_step_loss
+    livae.set_engine("tc")
+    L = 2
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=11, stn_head_std=0.5)
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    from livae import ops
+    x = torch.rand(B, 1, P, P, device="cuda", generator=gen)
+    ang = torch.rand(B, device="cuda", generator=gen) * 6.2831853
+    xr = ops.rot_sample(x, ops.angle_to_cs(ang), 1.0)
+    eps = torch.randn(B, L, device="cuda", generator=gen)
+    m = livae.RVAE(latent_dim=L, in_channels=1, patch_size=P)
+    m.load_state_dict(params, strict=True)
+    m.cuda()
+    crit = livae.RVAELoss(beta=10.0, gamma=10.0)
+
+    def run(sl):
+        m.zero_grad(set_to_none=True)
+        with FixedEps(eps[sl].cpu()):
+            out = rvae_step_loss(m, crit, x[sl].contiguous(), xr[sl].contiguous(), ang[sl].contiguous(), 0.2)
+        out[0].backward()
+        return [float(v.detach()) for v in out[:5]], {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+    full_l, full_g = run(slice(0, B))
+    again_l, again_g = run(slice(0, B))                 # run-to-run noise floor (see the docstring)
+    a_l, a_g = run(slice(0, B // 2))
+    b_l, b_g = run(slice(B // 2, B))
+    for f, u, v in zip(full_l, a_l, b_l):
+        assert abs(f - 0.5 * (u + v)) <= 1e-5 * max(abs(f), 1e-3), (full_l, a_l, b_l)
+    report = []
+    for k in full_g:
+        mean = 0.5 * (a_g[k] + b_g[k])
+        den = float(full_g[k].norm())
+        if den < 1e-10:
+            continue
+        rel = float((full_g[k] - mean).norm()) / den
+        floor = float((full_g[k] - again_g[k]).norm()) / den
+        report.append((k, rel, floor))
+    for k, rel, floor in report:
+        # measured: floor and rel both 2e-3 .. 5e-3 for the STN, 2e-3 for the encoder, <= 1.5e-3 for decoder.fc,
+        # ~1e-4 for d1-d3, 1e-5 for d4.  A tiling or indexing error shows up as O(1).
+        bound = 1e-4 if k.startswith("decoder.deconv_layers.14") else (2e-3 if k.startswith("decoder.deconv") else 2e-2)
+        assert rel <= bound, (k, rel, floor, report)
