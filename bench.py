@@ -329,6 +329,7 @@ def main():
 
     for i in range(args.warmup):
         out = step(batches[i % len(batches)])
+        barrier()      # also warms the NCCL barrier itself: its first call cost ~50 ms inside a 6-step timed region at N=2
     loss0 = out[1].item()
     # warm-up of the e2e path too: the prefetcher's two staging slots (2 x 268 MB) are allocated on first use, and
     # that first cudaMalloc cost 10-110 ms inside a 6-step timed region
