@@ -247,7 +247,11 @@ int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float*
  * kind 0: STN conv1 1->16 5x5 p2 +ReLU +MaxPool (model.py:204-206): out bf16 [B,H/2,W/2,16] + pool_idx
  * kind 1: encoder c1 1->32 4x4 s2 p1 +ReLU (model.py:290):          out bf16 [B,H/2,W/2,32]
  * kind 2: data gradient of decoder d4 (32->1 3x3 p0, model.py:371): img = fp32 pre-activation
- *         gradient [B,H,W], out bf16 [B,H+2,W+2,32] */
+ *         gradient [B,H,W], out bf16 [B,H+2,W+2,32]
+ * Kind 2 and the two livae_thin_convc1_* entry points below are the MATERIALISING form of decoder d4 (they take /
+ * produce the up-sampled, reflect-padded tensor).  livae's model path uses livae_upconv_c1_fwd / _bwd instead (no
+ * up-sampled tensor); these stay exported for callers that already hold such a tensor and as the cross-check in
+ * tests/test_gpu_thin.py. */
 int livae_thin_conv1c_fwd(int kind, const float* img, const float* w, const float* bias, int B, int H,
                           int W, void* out_bf16, uint8_t* pool_idx, livae_stream_t stream);
 /* weight/bias gradients of kinds 0, 1; g: bf16 PRE-activation gradient (kind 0: pooled, routed by pool_idx) */
