@@ -1,0 +1,37 @@
+"""CPU: the phase-folded form of the decoder blocks (oracle/folded_upconv.py, the design of DESIGN.md section 7 item 1)
+equals Upsample -> ReflectionPad2d -> Conv2d (reference model.py:357-368) exactly -- values, data gradient and
+weight gradient -- including the border rows / columns where the reflected pad differs from the replicate formula."""
+import pytest
+import torch
+
+from oracle import folded_upconv as FU
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 3, 4, 4), (1, 8, 4, 16, 16), (2, 3, 2, 7, 5), (1, 4, 1, 2, 9)])
+def test_folded_block_is_exact(shape):
+    B, Ci, Co, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, Ci, H, W, dtype=torch.float64, generator=g, requires_grad=True)
+    w = torch.randn(Co, Ci, 3, 3, dtype=torch.float64, generator=g, requires_grad=True)
+    b = torch.randn(Co, dtype=torch.float64, generator=g)
+    gy = torch.randn(B, Co, 2 * H, 2 * W, dtype=torch.float64, generator=g)
+    ref = FU.reference_block(x, w, b)
+    gx_ref, gw_ref = torch.autograd.grad((ref * gy).sum(), (x, w))
+    got = FU.folded_block(x, w, b)
+    gx, gw = torch.autograd.grad((got * gy).sum(), (x, w))
+    assert (got - ref).abs().max() < 1e-12
+    assert (gx - gx_ref).abs().max() < 1e-12 and (gw - gw_ref).abs().max() < 1e-11
+    # without the corrections only the outermost output ring differs
+    t = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode="replicate"), FU.fold_weights(w))
+    y0 = t.reshape(B, 2, 2, Co, H, W).permute(0, 3, 4, 1, 5, 2).reshape(B, Co, 2 * H, 2 * W) + b.view(1, -1, 1, 1)
+    diff = (y0 - ref).abs()
+    assert diff[:, :, 1:-1, 1:-1].max() < 1e-12 and diff.max() > 1e-6
+
+
+def test_fold_unfold_are_adjoint():
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(3, 5, 3, 3, dtype=torch.float64, generator=g)
+    gwf = torch.randn(12, 5, 3, 3, dtype=torch.float64, generator=g)
+    lhs = (FU.fold_weights(w) * gwf).sum()
+    rhs = (w * FU.unfold_weight_grad(gwf, 3)).sum()
+    assert abs(float(lhs - rhs)) < 1e-10
