@@ -35,3 +35,26 @@ def test_fold_unfold_are_adjoint():
     lhs = (FU.fold_weights(w) * gwf).sum()
     rhs = (w * FU.unfold_weight_grad(gwf, 3)).sum()
     assert abs(float(lhs - rhs)) < 1e-10
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 4), (2, 6, 9), (4, 5, 4), (1, 8, 8)])
+def test_upconv_c1_algebra_matches_autograd(shape):
+    """oracle/upconv_c1.py (the V / S formulation and closed-form border weights of csrc/upconv_c1.cu) against torch
+    autograd of Upsample -> ReflectionPad2d -> Conv2d(C -> 1): forward, data, weight and bias gradient."""
+    import numpy as np
+
+    from oracle import upconv_c1 as U
+    C, H, W = shape
+    g0 = torch.Generator().manual_seed(7 * C + H + W)
+    x = torch.randn(1, C, H, W, dtype=torch.float64, generator=g0, requires_grad=True)
+    w = torch.randn(1, C, 3, 3, dtype=torch.float64, generator=g0, requires_grad=True)
+    b = torch.tensor([0.3], dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(1, 1, 2 * H, 2 * W, dtype=torch.float64, generator=g0)
+    ref = FU.reference_block(x, w, b)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad((ref * gy).sum(), (x, w, b))
+    y = U.forward(x[0].detach().numpy(), w[0].detach().numpy(), 0.3)
+    assert np.abs(y - ref[0, 0].detach().numpy()).max() < 1e-12
+    gx, gw, gb = U.backward(x[0].detach().numpy(), w[0].detach().numpy(), gy[0, 0].numpy())
+    assert np.abs(gx - gx_ref[0].numpy()).max() < 1e-12
+    assert np.abs(gw - gw_ref[0].numpy()).max() < 1e-12
+    assert abs(gb - float(gb_ref)) < 1e-12
