@@ -210,7 +210,9 @@ class Encoder(nn.Module):
                 loc[7].bias, loc[9].weight, loc[9].bias, cl[0].weight, cl[0].bias,
                 cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight, cl[6].bias,
                 self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias)
-            self._canonical = (x, theta, x_rot)
+            # one-shot cache for the trainer (see _take_canonical); training forwards only, so that an idle or
+            # evaluating model holds no batch and no autograd graph (deepcopy / pickling of the module stay possible)
+            self._canonical = (x, theta, x_rot) if torch.is_grad_enabled() else None
             return mu, logvar, theta
         x_rotated, theta = self.rotation_stn(x)
         h = _run_encoder_convs(self.conv_layers, x_rotated)

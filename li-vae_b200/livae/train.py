@@ -104,13 +104,17 @@ def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_we
     results, the conv stack's mu/logvar are discarded at the call site)."""
     rotated_recon, canonical_recon, theta, mu, logvar = model(x)
     take = getattr(getattr(model, "encoder", None), "take_canonical", None)
-    canonical_input = take(x, theta) if (take is not None and canonical_weight > 0) else None
+    canonical_input = take(x, theta) if take is not None else None      # always popped: no batch left on the module
+    if canonical_weight <= 0:
+        canonical_input = None
     theta_rotated = None
     if x_rotated is not None:
         if elide_dead_encoder:
             _, theta_rotated = model.encoder.rotation_stn.localize(x_rotated)
         else:
             _, _, theta_rotated = model.encoder(x_rotated)
+        if take is not None:
+            model.encoder._canonical = None      # drop the rotated pass's stash: nothing will ask for it
     loss, recon_loss, kld_loss, cycle_loss = criterion(rotated_recon, x, mu, logvar, theta, theta_rotated, angle)
     canonical_loss = torch.zeros((), device=loss.device)
     if canonical_weight > 0 and canonical_recon is not None:

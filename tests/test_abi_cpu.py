@@ -90,3 +90,20 @@ def test_state_dict_keys_match_reference_layout():
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == O.rvae_param_shapes(128, 2)
     v = livae.VAE(16, 1, 64)
     assert {k: tuple(t.shape) for k, t in v.state_dict().items()} == O.vae_param_shapes(64, 16)
+
+
+def test_canonical_cache_is_one_shot_and_identity_keyed():
+    """Encoder.take_canonical (the STN's rotated batch reused as rotate_to_canonical(x, theta), train.py:389): only
+    for exactly the tensors of the last forward, handed out once, and never left on the module afterwards."""
+    import copy
+
+    import livae
+    enc = livae.Encoder(1, 2, 32)
+    x, th, xr = torch.zeros(2, 1, 32, 32), torch.zeros(2, 1), torch.ones(2, 1, 32, 32)
+    assert enc.take_canonical(x, th) is None                      # nothing cached yet
+    enc._canonical = (x, th, xr)
+    assert enc.take_canonical(x.clone(), th) is None              # a different tensor object: refused, cache dropped
+    assert enc._canonical is None
+    enc._canonical = (x, th, xr)
+    assert enc.take_canonical(x, th) is xr and enc.take_canonical(x, th) is None
+    copy.deepcopy(enc)                                            # an idle module carries no batch / graph
