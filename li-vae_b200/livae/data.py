@@ -3,9 +3,19 @@
 617-735) and `default_transform` (data.py:78-116), done for a whole batch by CUDA kernels on images resident
 in HBM instead of by DataLoader worker processes.
 
-What stays with the reference (out of scope): finding the sites (`__init__`: band-pass,
-lattice constant, skimage peaks, KD-tree).  `DevicePatchSource.from_dataset` takes a dataset object the reference
-built (its `.images`, `.sample_coords` / `.atom_coords`, `.patch_size`, `.padding`, `.transform`).
+The dataset classes of the reference (`PatchDataset`, `AdaptiveLatticeDataset`, `PairedAdaptiveLatticeDataset`)
+are here with their constructor signatures, so scripts/train_rvae.py, train_vae.py and pretrain_stn.py build their
+DataLoaders unchanged.  Construction (band-pass, lattice constant, peaks, lattice-site extrapolation: one-shot host
+work, data.py:176-202, 299-473) runs on the host in vectorised numpy/scipy; `__getitem__` is the device path:
+  * in the main process an item is produced by the CUDA kernels and handed back as CPU tensors like the
+    reference's (`ds[i]`, DataLoader(num_workers=0));
+  * in a DataLoader WORKER process (no CUDA after fork) an item is only its RECIPE -- flat index plus the draws the
+    reference would have made from Python's `random`, in its order -- which the default collate function (a handler
+    registered in torch's `default_collate_fn_map`) packs into a `RecipeBatch`; the loader's pin-memory step
+    (`pin_memory=True` in all three scripts) runs in the main process and calls `RecipeBatch.pin_memory()`, where
+    the whole batch is gathered / augmented / rotated / normalised on the GPU.  The script receives the usual
+    `(patch, rotated, angle)` batch, already resident on the device.  Worker processes never touch the library.
+`DevicePatchSource.from_dataset` also accepts a dataset object built by the reference itself.
 
 Random numbers: the reference draws from Python's global `random` per item (scale, [angle], hflip, vflip,
 shift_x, shift_y, then the pair angle).  The draws here are made on the host IN THE SAME ORDER from the same
@@ -20,10 +30,14 @@ from typing import Iterable, Optional, Sequence
 
 import numpy as np
 import torch
+from torch.utils.data import Dataset, get_worker_info
+from torch.utils.data._utils.collate import default_collate_fn_map
 
 from livae import ops
 
-__all__ = ["default_transform", "draw_transform_params", "DevicePatchSource", "DevicePatchLoader"]
+__all__ = ["PatchDataset", "AdaptiveLatticeDataset", "PairedAdaptiveLatticeDataset", "default_transform",
+           "generate_lattice_grid", "get_clean_peaks", "peak_local_max", "draw_transform_params",
+           "DevicePatchSource", "DevicePatchLoader", "PatchRecipe", "RecipeBatch"]
 
 
 def _draw(n: int, flip_prob: float, jitter_amount: int, rotation: bool, transform: bool, pair_angle: bool):
