@@ -18,10 +18,10 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int require_sm100() {
-  static int cached = -1;
-  if (cached == 1) return 0;
+  static bool ok[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && ok[dev & 63]) return 0;
   if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
   int major = 0;
   e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -30,7 +30,7 @@ int require_sm100() {
     set_error("liblivae_sm100 is built for sm_100a only; device has compute capability major %d", major);
     return -2;
   }
-  cached = 1;
+  ok[dev & 63] = true;
   return 0;
 }
 }  // namespace livae

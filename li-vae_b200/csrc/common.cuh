@@ -34,6 +34,21 @@ void count_launch(int n = 1);
 // refuse to run anywhere but sm_100 (no fallback paths)
 int require_sm100();
 
+// "do this once PER DEVICE": cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the compute-capability check are
+// per-device state, so a process driving several GPUs must repeat them on each (a process-wide flag left every
+// device but the first without the > 48 KB shared-memory opt-in).
+struct OncePerDevice {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 static constexpr int kNumSMs = 148;
 
 template <typename T> struct Cvt;

@@ -809,14 +809,13 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
   p.nsa = kSA;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_tc_halo_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_tc_halo_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_tc_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_tc_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * B;
   // persistent grid: as many CTAs per SM as shared memory and the 512 TMEM columns allow
@@ -893,10 +892,9 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
   const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
   constexpr int STAGES = 4;
   const size_t smem = (size_t)STAGES * (a_slot + b_slot) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(conv_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * ((B + p.nb - 1) / p.nb);
   // split-K when the output grid cannot fill the chip but K is long (nn.Linear over a flattened map: 16 tiles,

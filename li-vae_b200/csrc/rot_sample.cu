@@ -314,11 +314,10 @@ extern "C" int livae_rot_sample_fwd(const float* img, const float* cs, float sgn
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = tile_bytes(H, W);
   if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static OncePerDevice attr_done;
+    if (attr_done.first()) {
       cudaFuncSetAttribute(rot_sample_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kMaxSmemImage);
-      attr_done = true;
     }
     rot_sample_fwd_kernel<true><<<B * C, 256, bytes, st>>>(img, cs, sgn, C, H, W, out);
   } else {
@@ -339,10 +338,9 @@ extern "C" int livae_rot_sample_bwd(const float* img, const float* cs, float sgn
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = tile_bytes(H, W);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(rot_sample_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
-    attr_done = true;
   }
   if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
     rot_sample_bwd_kernel<true><<<B, 256, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);

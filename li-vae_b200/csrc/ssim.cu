@@ -207,17 +207,16 @@ extern "C" int livae_ssim_box(const float* a, const float* b, int64_t planes, in
   const int R = kSsimRows + 2 * (win / 2);
   const size_t smem = ((size_t)2 * R * (W + 2 * (win / 2)) + (size_t)5 * R * W) * sizeof(float);
   LIVAE_CHECK_ARG(smem <= 200 * 1024, "ssim_box: image too wide for the shared-memory strip (W = %d, window %d)", W, win);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(ssim_box_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(ssim_box_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const int strips = (H + kSsimRows - 1) / kSsimRows;
   const size_t smem_vec = ((size_t)2 * R * (W + 16) + (size_t)5 * R * W) * sizeof(float);
   if (win == 11 && (W & 3) == 0 && smem_vec <= 200 * 1024 && ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0) {
-    static bool vec_attr = false;
-    if (!vec_attr) { cudaFuncSetAttribute(ssim_box11_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); vec_attr = true; }
+    static OncePerDevice vec_attr;
+    if (vec_attr.first()) { cudaFuncSetAttribute(ssim_box11_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
     ssim_box11_vec_kernel<<<dim3(strips, (unsigned)planes), 256, smem_vec, st>>>(a, b, H, W, c1, c2, ws);
   } else if (win == 11) ssim_box_kernel<11><<<dim3(strips, (unsigned)planes), 256, smem, st>>>(a, b, H, W, win, c1, c2, ws);
   else ssim_box_kernel<0><<<dim3(strips, (unsigned)planes), 256, smem, st>>>(a, b, H, W, win, c1, c2, ws);

@@ -496,8 +496,8 @@ extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g
     const int IWp = (W - 1) + 5;
     const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * W * 16 * 2;
     LIVAE_CHECK_ARG(smem <= 200 * 1024, "thin_conv1c_wgrad: image too wide for the staged kernel");
-    static bool attr0 = false;
-    if (!attr0) { cudaFuncSetAttribute(conv1c_wgrad_kernel<16, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr0 = true; }
+    static OncePerDevice attr0;
+    if (attr0.first()) { cudaFuncSetAttribute(conv1c_wgrad_kernel<16, 5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
     int bands = (H + RB - 1) / RB;
     int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
     conv1c_wgrad_kernel<16, 5, 1, true><<<dim3(bands, by), 256, smem, st>>>(img, g, pool_idx, B, H, W, H, W, 2, gw, gb);
@@ -512,8 +512,8 @@ extern "C" int livae_thin_conv1c_wgrad(int kind, const float* img, const void* g
     const int IWp = (W / 2 - 1) * 2 + 4;
     const size_t smem = (size_t)((IR * IWp + 3) & ~3) * 4 + (size_t)RB * (W / 2) * 32 * 2;
     LIVAE_CHECK_ARG(smem <= 200 * 1024, "thin_conv1c_wgrad: image too wide for the staged kernel");
-    static bool attr1 = false;
-    if (!attr1) { cudaFuncSetAttribute(conv1c_wgrad_kernel<32, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
+    static OncePerDevice attr1;
+    if (attr1.first()) { cudaFuncSetAttribute(conv1c_wgrad_kernel<32, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
     int bands = (H / 2 + RB - 1) / RB;
     int by = (kNumSMs * 3 + bands - 1) / bands; if (by > B) by = B;
     conv1c_wgrad_kernel<32, 4, 2, false><<<dim3(bands, by), 256, smem, st>>>(img, g, nullptr, B, H, W, H / 2, W / 2, 1, gw, gb);
@@ -575,8 +575,8 @@ extern "C" int livae_thin_convc1_wgrad(const void* x_bf16, const float* g, int B
   constexpr int RWB = 4;
   const size_t smem = (size_t)(RWB + 2) * W * 32 * 2 + (size_t)RWB * Wo * 4;
   LIVAE_CHECK_ARG(smem <= 200 * 1024 && (W * 32) % 8 == 0, "thin_convc1_wgrad: map too wide for the staged kernel");
-  static bool attrd = false;
-  if (!attrd) { cudaFuncSetAttribute(convc1_wgrad_kernel<32, 3, RWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attrd = true; }
+  static OncePerDevice attrd;
+  if (attrd.first()) { cudaFuncSetAttribute(convc1_wgrad_kernel<32, 3, RWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
   int bands = (Ho + RWB - 1) / RWB;
   int by = (kNumSMs * 4 + bands - 1) / bands; if (by > B) by = B;
   convc1_wgrad_kernel<32, 3, RWB><<<dim3(bands, by), 9 * 16 * 2, smem, st>>>((const __nv_bfloat16*)x_bf16, g, B, H, W, Ho, Wo,

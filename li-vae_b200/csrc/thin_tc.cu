@@ -345,8 +345,8 @@ static int launch_fwd(const float* img, const float* w, const float* bias, int B
   const size_t a_buf = (size_t)(Cfg::POOL ? 4 : 1) * 128 * Cfg::KPAD * 2;
   const size_t smem = 1024 + ns * a_buf + 4096 + (size_t)p.Hs * p.pitch * 2;
   if (smem > 110 * 1024) return 1;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv1c_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); attr = true; }
+  static OncePerDevice attr;
+  if (attr.first()) { cudaFuncSetAttribute(conv1c_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);}
   int occ = (int)((227 * 1024) / (smem + 1024));
   const int occ_tmem = 512 / (ns * (Cfg::POOL ? 4 : 1) * Cfg::C);
   if (occ > occ_tmem) occ = occ_tmem;
@@ -546,11 +546,10 @@ int thin_tc_col2im(int kind, const void* x, const float* w, const float* bias, i
     uint32_t box[2] = {32, 128};
     if (int e = make_tmap_bf16(&tmX, x, 2, dims, str, box, nullptr, 64)) return e;
   }
-  static bool attr = false;
-  if (!attr) {
+  static OncePerDevice attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(col2im_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     cudaFuncSetAttribute(col2im_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    attr = true;
   }
   int occ = (int)((227 * 1024) / (smem + 1024));
   if (occ > 4) occ = 4;
@@ -890,8 +889,8 @@ static int launch_wg(const float* src, const void* big, const uint8_t* idx, int 
   } else {
     memset(&tmB, 0, sizeof(tmB));
   }
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tap_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  static OncePerDevice attr;
+  if (attr.first()) { cudaFuncSetAttribute(tap_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);}
   int grid = kNumSMs;
   if (grid > B) grid = B;
   tap_wgrad_tc_kernel<KIND><<<grid, WgLayout<KIND>::THREADS, smem, st>>>(tmB, p);
@@ -1119,8 +1118,8 @@ static int launch_conv1_wgrad_fold(const float* img, const void* gp, const uint8
   FoldParams p;
   p.img = img; p.gp = gp; p.idx = idx; p.B = B; p.gw = gw; p.gb = gb;
   const size_t smem = 1024 + 2 * (size_t)kFoldBRows * 32 + (size_t)kFoldA * 4096 + (size_t)kFoldP * 4096;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv1_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static OncePerDevice attr;
+  if (attr.first()) { cudaFuncSetAttribute(conv1_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
   int grid = kNumSMs;
   if (grid > B) grid = B;
   conv1_wgrad_fold_kernel<<<grid, kFoldThreads, smem, st>>>(p);

@@ -431,11 +431,10 @@ extern "C" int livae_upconv_c1_bwd(const float* gpre, const float* w, const void
   LIVAE_CHECK_ARG((((uintptr_t)x_bf16 | (uintptr_t)gx_bf16) & 15) == 0, "upconv_c1_bwd: 16-byte alignment");
   if (int e = require_sm100()) return e;
   const size_t smem = (size_t)kG * kG * 4 + 256 * kSP * 4 + 2 * 256 * kPitch + (8 * 32 + 8) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     ce = cudaFuncSetAttribute(upconv_c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) { set_error("upconv_c1_bwd: cannot set %zu B of shared memory", smem); return (int)ce; }
-    attr_done = true;
   }
   const int64_t n_tiles = (int64_t)B * ((W + kT - 1) / kT) * ((H + kT - 1) / kT);
   const int grid = (int)(n_tiles < 3 * kNumSMs ? n_tiles : 3 * kNumSMs);
@@ -454,11 +453,10 @@ extern "C" int livae_upconv_c1_fwd(const void* x_bf16, const float* w, const flo
   LIVAE_CHECK_ARG((((uintptr_t)x_bf16) & 15) == 0 && B <= 65535, "upconv_c1_fwd: 16-byte alignment, B <= 65535");
   if (int e = require_sm100()) return e;
   const size_t smem = (size_t)kXP * kPitch + (size_t)kXP * kVP * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaError_t ce = cudaFuncSetAttribute(upconv_c1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) { set_error("upconv_c1_fwd: cannot set %zu B of shared memory", smem); return (int)ce; }
-    attr_done = true;
   }
   dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, B);
   upconv_c1_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, w, bias, H, W, act, out);

@@ -606,11 +606,10 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
     uint32_t box[4] = {(uint32_t)p.kcs, (uint32_t)p.TW, (uint32_t)TH, 1u};
     if (int e = make_tmap_bf16(&tmG, gy, 4, dims, str, box, nullptr, p.kcs * 2)) return e;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(wgrad_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   dim3 grid(gsets, splits);
   if (4u * stage_bytes + 1024u <= 200u * 1024u)
@@ -718,11 +717,10 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   const uint32_t b_bytes = (uint32_t)kPK * p.Cs * 2u;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   dim3 grid(gsets, splits);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice attr_done;
+  if (attr_done.first()) {
     cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   if (3u * stage_bytes + 1024u <= 200u * 1024u)
     wgrad_tc_kernel<3><<<grid, kWgThreads, 3 * stage_bytes + 1024, st>>>(tmX, tmG, p);

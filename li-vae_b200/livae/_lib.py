@@ -167,8 +167,8 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 # When set to a list, every call is bracketed by CUDA events on the launching stream and
@@ -180,11 +180,18 @@ def call(name, *args):
     """invoke an int-returning entry point; tensors -> device pointers; raises on error"""
     L = lib()
     conv = []
+    dev = None
     for a in args:
         if isinstance(a, torch.Tensor):
             conv.append(a.data_ptr())
+            if dev is None:
+                dev = a.device
         else:
             conv.append(a)
+    if dev is not None and dev.index != torch.cuda.current_device():
+        # tensors on another GPU than the thread's current one: launch in THEIR context, on their stream
+        with torch.cuda.device(dev):
+            return call(name, *args)
     if PROFILE is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

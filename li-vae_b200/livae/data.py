@@ -34,6 +34,8 @@ from torch.utils.data import Dataset, get_worker_info
 from torch.utils.data._utils.collate import default_collate_fn_map
 
 from livae import ops
+from livae.sites import (adaptive_sites, generate_lattice_grid, get_clean_peaks, inside_margin as _inside,
+                         peak_local_max, preprocess_image as _preprocess)
 
 __all__ = ["PatchDataset", "AdaptiveLatticeDataset", "PairedAdaptiveLatticeDataset", "default_transform",
            "generate_lattice_grid", "get_clean_peaks", "peak_local_max", "draw_transform_params",
@@ -177,11 +179,25 @@ class DevicePatchSource:
         self._slots[slot] = (buf, ev)
         return dev
 
-    # --- PatchDataset.__getitem__, transform=None (data.py:211-250) -------------------------------------
-    def patch_batch(self, indices) -> torch.Tensor:
+    # --- PatchDataset.__getitem__ (data.py:211-250) -----------------------------------------------------
+    def patch_batch(self, indices, draws=None) -> torch.Tensor:
+        """transform=None: the bit-exact integer crop.  With default_transform the reference crops P + 2*padding,
+        applies transform(patch_big, rotation=True) and centre-crops to P (data.py:240-248); same here."""
         img, yx = self._lookup(indices)
-        d = self._upload([img, np.round(yx)])
-        return ops.patch_gather(self.images, d.to(torch.int32).contiguous(), self.patch_size)
+        if self.transform is None:
+            d = self._upload([img, np.round(yx)])
+            return ops.patch_gather(self.images, d.to(torch.int32).contiguous(), self.patch_size)
+        p = draws[0] if draws is not None else draw_transform_params(len(img), rotation=True)
+        d = self._upload([img, np.round(yx), p["scale"], p["flags"], p["shift"], p["angle"]])
+        S = self.patch_size + 2 * self.padding
+        big = ops.patch_gather(self.images, d[:, :3].to(torch.int32).contiguous(), S)
+        q = self._params_on_device(d, 3)
+        zeros_i = torch.zeros_like(q["flags"])
+        # scale -> rotate -> flips + roll (data.py:85-114): the rotation sits between the two halves of `augment`
+        t = ops.augment(big, q["scale"], zeros_i, torch.zeros_like(q["shift"]))
+        t = ops.rotate_crop(t, S, d[:, 7].contiguous())
+        t = ops.augment(t, q["scale"], q["flags"] | 4, q["shift"])
+        return ops.rotate_crop(t, self.patch_size, None, normalise=False)
 
     def _big(self, d):
         S = self.patch_size + 2 * self.padding
@@ -195,11 +211,11 @@ class DevicePatchSource:
                 "shift": d[:, c0 + 2:c0 + 4].to(torch.int32).contiguous()}
 
     # --- AdaptiveLatticeDataset.__getitem__ (data.py:478-560) -------------------------------------------
-    def adaptive_batch(self, indices) -> torch.Tensor:
+    def adaptive_batch(self, indices, draws=None) -> torch.Tensor:
         img, yx = self._lookup(indices)
         cols = [img, yx]
         if self.transform is not None:
-            p = draw_transform_params(len(img))
+            p = draws[0] if draws is not None else draw_transform_params(len(img))
             cols += [p["scale"], p["flags"], p["shift"]]
         d = self._upload(cols)
         big = self._big(d)
@@ -209,13 +225,14 @@ class DevicePatchSource:
         return ops.rotate_crop(big, self.patch_size, None, normalise=True)
 
     # --- PairedAdaptiveLatticeDataset.__getitem__ (data.py:617-735) -------------------------------------
-    def paired_batch(self, indices, angles_deg: Optional[Iterable[float]] = None):
+    def paired_batch(self, indices, angles_deg: Optional[Iterable[float]] = None, draws=None):
         """-> (patch [N,1,P,P], rotated [N,1,P,P], angle_rad float32 [N]) as the default collate of the
         reference's items gives them.  Draw order per item: transform draws, then the pair angle (drawn even when
-        angles_deg overrides it, so the random stream advances as in the reference)."""
+        angles_deg overrides it, so the random stream advances as in the reference).  `draws` = (transform draws,
+        pair angles) made elsewhere (a DataLoader worker's recipes)."""
         img, yx = self._lookup(indices)
         n = len(img)
-        p, ang = _draw(n, 0.5, 4, False, self.transform is not None, True)
+        p, ang = draws if draws is not None else _draw(n, 0.5, 4, False, self.transform is not None, True)
         if angles_deg is not None:
             ang = np.asarray(list(angles_deg), dtype=np.float64)
         cols = [img, yx, ang]
@@ -260,3 +277,185 @@ class DevicePatchLoader:
                 yield self.source.adaptive_batch(idx)
             else:
                 yield self.source.patch_batch(idx)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# DataLoader-worker recipes
+# ------------------------------------------------------------------------------------------------------------
+_REGISTRY: dict = {}          # dataset key -> dataset object (main process; workers inherit a copy they never use)
+_NEXT_KEY = [0]
+
+
+class PatchRecipe:
+    """What a DataLoader worker returns for one item instead of pixels: the flat index and the item's random draws
+    (made from the worker's own `random`, seeded by torch per worker exactly as for the reference's items)."""
+    __slots__ = ("key", "index", "t", "angle")
+
+    def __init__(self, key, index, t, angle):
+        self.key, self.index, self.t, self.angle = key, int(index), t, angle
+
+    def __reduce__(self):
+        return (PatchRecipe, (self.key, self.index, self.t, self.angle))
+
+
+class RecipeBatch:
+    """A collated batch of recipes.  `pin_memory()` -- called by the DataLoader's pin-memory thread in the MAIN
+    process -- materialises it on the GPU; so does `materialise()` for loops that got it unpinned."""
+
+    def __init__(self, key, indices, t, angles):
+        self.key, self.indices, self.t, self.angles = key, indices, t, angles
+
+    def __len__(self):
+        return len(self.indices)
+
+    def materialise(self):
+        ds = _REGISTRY.get(self.key)
+        if ds is None:
+            raise RuntimeError("livae.data: recipe batch for a dataset that does not live in this process")
+        return ds._batch(self.indices, (self.t, self.angles))
+
+    def pin_memory(self):
+        return self.materialise()
+
+
+def _collate_recipes(batch, *, collate_fn_map=None):
+    first = batch[0]
+    t = None
+    if first.t is not None:
+        t = {k: np.concatenate([r.t[k] for r in batch]) for k in first.t}
+    ang = None if first.angle is None else np.asarray([r.angle for r in batch], dtype=np.float64)
+    return RecipeBatch(first.key, np.asarray([r.index for r in batch], dtype=np.int64), t, ang)
+
+
+default_collate_fn_map[PatchRecipe] = _collate_recipes
+
+
+class _DeviceDataset(Dataset):
+    """shared item plumbing of the three datasets"""
+    _kind = "patch"
+
+    def _register(self):
+        self._key = _NEXT_KEY[0]
+        _NEXT_KEY[0] += 1
+        _REGISTRY[self._key] = self
+        self._src = None
+
+    def _coords(self):
+        return self.sample_coords if hasattr(self, "sample_coords") else self.atom_coords
+
+    def __len__(self) -> int:
+        return int(sum(len(c) for c in self._coords()))
+
+    def source(self, device=None) -> DevicePatchSource:
+        """the images + sites on the GPU (uploaded on first use)"""
+        if self._src is None:
+            if get_worker_info() is not None:
+                raise RuntimeError("livae.data: DataLoader workers must not touch the GPU")
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self._src = DevicePatchSource(self.images, self._coords(), self.patch_size, self.padding,
+                                          self.transform, dev)
+        return self._src
+
+    def _draws(self, n):
+        has_t = self.transform is not None
+        if self._kind == "patch":
+            return (draw_transform_params(n, rotation=True) if has_t else None), None
+        return _draw(n, 0.5, 4, False, has_t, self._kind == "paired")
+
+    def _batch(self, indices, draws=None):
+        src = self.source()
+        if draws is None:
+            draws = self._draws(len(indices))
+        if self._kind == "paired":
+            return list(src.paired_batch(indices, draws=draws))
+        if self._kind == "adaptive":
+            return src.adaptive_batch(indices, draws=draws)
+        return src.patch_batch(indices, draws=draws)
+
+    def _check(self, idx):
+        n = len(self)
+        if idx < 0:
+            idx += n                    # Python indexing convenience; the reference walks the lists forward only
+        if not 0 <= idx < n:
+            raise IndexError(f"Index {idx} out of range for dataset of size {n}")        # data.py:217-220
+        return idx
+
+    def __getitem__(self, idx):
+        idx = self._check(int(idx))
+        if get_worker_info() is not None:
+            t, ang = self._draws(1)
+            return PatchRecipe(self._key, idx, t, None if ang is None else float(ang[0]))
+        out = self._batch([idx])
+        if self._kind == "paired":
+            patch, rotated, ang = out
+            return patch[0].cpu(), rotated[0].cpu(), float(ang[0])
+        return out[0].cpu()
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_src"] = None               # device tensors stay in the process that owns the GPU
+        return st
+
+
+class PatchDataset(_DeviceDataset):
+    """Patches centred on detected atoms (reference data.py:151-250): same constructor, attributes
+    (`images`, `atom_coords`, `patch_size`, `padding`, `transform`) and item semantics."""
+    _kind = "patch"
+
+    def __init__(self, images, patch_size: int, padding: int = 4, transform=default_transform):
+        from .utils import estimate_lattice_constant
+        self.patch_size, self.padding, self.transform = patch_size, padding, transform
+        print("Preprocessing images (caching)...")
+        self.images = [_preprocess(im) for im in images]
+        self.atom_coords = []
+        margin = patch_size // 2 + padding
+        for img in self.images:
+            spacing = estimate_lattice_constant(img)
+            coords = get_clean_peaks(img, min_distance=int(spacing * 0.15)).reshape(-1, 2)
+            ok = _inside(coords, img.shape, margin)
+            print(f"Detected {len(coords)} atoms, {int(ok.sum())} after edge exclusion.")
+            self.atom_coords.append(coords[ok])
+        self._register()
+
+
+class AdaptiveLatticeDataset(_DeviceDataset):
+    """Patches on every lattice site extrapolated from the detected atoms (reference data.py:292-560)."""
+    _kind = "adaptive"
+
+    def __init__(self, images, patch_size: int, padding: int = 48, transform=default_transform,
+                 detection_threshold: float = 0.6):
+        from .utils import estimate_lattice_constant
+        self.patch_size, self.padding, self.transform = patch_size, padding, transform
+        self.detection_threshold = detection_threshold
+        self.images = [_preprocess(im) for im in images]
+        self.sample_coords, self.labels = [], []
+        half = patch_size // 2 + padding
+        for img in self.images:
+            spacing = estimate_lattice_constant(img)
+            atoms = get_clean_peaks(img, min_distance=int(spacing * 0.15)).reshape(-1, 2)
+            atoms = atoms[_inside(atoms, img.shape, half)]
+            sites, labels = adaptive_sites(img, atoms, spacing, half, detection_threshold)
+            print(f"Adaptive lattice: {len(sites)} unique sites - "
+                  f"{int((labels == 1).sum())} with atoms, {int((labels == 0).sum())} empty sites")
+            self.sample_coords.append(sites)
+            self.labels.append(labels)
+        self._register()
+
+    @classmethod
+    def from_sites(cls, images, sample_coords, patch_size: int, padding: int = 48, transform=default_transform,
+                   labels=None):
+        """a dataset over GIVEN images (already pre-processed, float32/64 [H,W]) and per-image float (y, x) sites:
+        skips the site finding (synthetic lattices with analytic sites)"""
+        self = cls.__new__(cls)
+        self.patch_size, self.padding, self.transform = patch_size, padding, transform
+        self.detection_threshold = 0.6
+        self.images = list(images)
+        self.sample_coords = [np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in sample_coords]
+        self.labels = labels if labels is not None else [np.ones(len(c), dtype=np.int64) for c in self.sample_coords]
+        self._register()
+        return self
+
+
+class PairedAdaptiveLatticeDataset(AdaptiveLatticeDataset):
+    """(patch, patch rotated by a random angle, angle in radians) per lattice site (reference data.py:617-735)"""
+    _kind = "paired"

@@ -29,8 +29,10 @@ def supported(patch_size: int, latent_dim: int, in_channels: int) -> bool:
     return in_channels == 1 and patch_size % 16 == 0 and patch_size >= 32 and 2 * latent_dim <= 256
 
 
-def _pad16(n):
-    return (n + 15) // 16 * 16
+def _pad_heads(n):
+    """column count of the [fc_mu; fc_logvar] GEMM: the tensor-core kernels take 16, 32 or a multiple of 64 channels
+    (conv_tc.cu channels_ok, wgrad_tc.cu) -- e.g. latent_dim 20 -> 40 columns -> 64"""
+    return 16 if n <= 16 else 32 if n <= 32 else (n + 63) // 64 * 64
 
 
 def _empty(shape, dtype, dev):
@@ -101,7 +103,7 @@ class EncoderTc(Function):
         h3 = ops.tc_conv(h2, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 0), c4b, 4, 4, 2, 1, ACT_RELU)
         h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
         # --- heads (model.py:302-303, 321-324): one GEMM for [fc_mu; fc_logvar]
-        Npad = _pad16(2 * Ld)
+        Npad = _pad_heads(2 * Ld)
         wcat = torch.cat([muw, lvw], 0)
         bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
         bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb
@@ -279,7 +281,7 @@ class VAEEncoderTc(Function):
         h2 = ops.tc_conv(h1, ops.tc_pack_weights(c2w, 64, 32, 4, 4, 0), c2b, 4, 4, 2, 1, ACT_RELU)
         h3 = ops.tc_conv(h2, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 0), c4b, 4, 4, 2, 1, ACT_RELU)
         h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
-        Npad = _pad16(2 * Ld)
+        Npad = _pad_heads(2 * Ld)
         wcat = torch.cat([muw, lvw], 0)
         bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
         bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb

@@ -27,7 +27,9 @@ from . import ops
 
 __all__ = [
     "train_one_epoch", "evaluate", "train_rvae_one_epoch", "evaluate_rvae", "rotate_to_canonical",
-    "rvae_step_loss", "train_rvae_step", "MetricLogger", "compute_psnr", "compute_ssim", "get_rotation_stats",
+    "evaluate_rotation_invariance", "log_reconstructions_tensorboard", "compute_atom_position_accuracy",
+    "log_scalar_metrics_tensorboard", "rvae_step_loss", "train_rvae_step", "MetricLogger", "compute_psnr",
+    "compute_ssim", "get_rotation_stats",
 ]
 
 
@@ -199,8 +201,14 @@ class DevicePrefetcher:
         return len(self.loader)
 
 
+def _materialise(batch):
+    """a livae.data.RecipeBatch that reached the loop un-pinned (DataLoader(pin_memory=False)) -> device tensors"""
+    return batch.materialise() if hasattr(batch, "materialise") else batch
+
+
 def _unpack_rvae_batch(batch, device):
     """reference train.py:316-339"""
+    batch = _materialise(batch)
     if isinstance(batch, (list, tuple)):
         if len(batch) == 3:
             x, x_rotated, angle = batch
@@ -313,12 +321,14 @@ def train_one_epoch(model, data_loader, optimizer, criterion, metric_logger, dev
     n_batches = 0
     canonical_batches = 0
     for x in DevicePrefetcher(data_loader, device):
+        x = _materialise(x)
         if isinstance(x, (list, tuple)):
             x = x[0]
         x = x.to(device, non_blocking=True)
         optimizer.zero_grad(set_to_none=getattr(optimizer, "flat_grad", None) is None)
         outputs = model(x)
         canonical_recon = None
+        canonical_input = None
         theta = None
         if len(outputs) == 3:
             recon, mu, logvar = outputs
@@ -326,6 +336,10 @@ def train_one_epoch(model, data_loader, optimizer, criterion, metric_logger, dev
             loss, recon_l, kld_l = criterion(recon, x, mu, logvar)
         elif len(outputs) == 5:
             rotated_recon, canonical_recon, theta, mu, logvar = outputs
+            # pop the encoder's one-shot stash of its rotated input (it IS rotate_to_canonical(x, theta), which the
+            # reference computes here and discards, train.py:85-91): nothing stays pinned on the module
+            take = getattr(getattr(model, "encoder", None), "take_canonical", None)
+            canonical_input = take(x, theta) if take is not None else None
             loss, recon_l, kld_l = criterion(rotated_recon, x, mu, logvar)
         else:
             raise ValueError(f"Unexpected model output length: {len(outputs)}")
@@ -339,9 +353,10 @@ def train_one_epoch(model, data_loader, optimizer, criterion, metric_logger, dev
                      train_grad_norm=_post_clip_norm(pre, 5.0))
             m["train_rotation_std"] = torch.std(theta) if theta is not None else torch.zeros((), device=device)
             if canonical_recon is not None and theta is not None:
-                canonical_input = rotate_to_canonical(x, theta)
-                m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input)
-                m["train_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
+                if canonical_input is None:
+                    canonical_input = rotate_to_canonical(x, theta)
+                m["train_canonical_psnr"] = _psnr_dev(canonical_recon, canonical_input.detach())
+                m["train_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input.detach())
                 canonical_batches += 1
             acc.add(**m)
         n_batches += 1
@@ -360,6 +375,7 @@ def evaluate(model, data_loader, criterion, metric_logger, device, canonical_wei
     canonical_batches = 0
     with torch.no_grad():
         for x in data_loader:
+            x = _materialise(x)
             if isinstance(x, (list, tuple)):
                 x = x[0]
             x = x.to(device)
@@ -421,3 +437,111 @@ def evaluate_rvae(model, data_loader, criterion, metric_logger, device, canonica
         m["val_canonical_ssim"] = _ssim_dev(canonical_recon, canonical_input)
         acc.add(**m)
     metric_logger.update(**acc.averages(1))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Logging / analysis helpers the reference's scripts import next to the training loops (train.py:680-936).
+# Off the hot path: they run a forward pass through the same kernels and hand CPU tensors to TensorBoard.
+# ------------------------------------------------------------------------------------------------------------
+def _split_outputs(outputs):
+    if len(outputs) == 3:
+        return outputs[0], None, None, outputs[1]
+    if len(outputs) == 5:
+        return outputs[0], outputs[1], outputs[2], outputs[3]
+    raise ValueError(f"Unexpected model output length: {len(outputs)}")
+
+
+def log_reconstructions_tensorboard(model, images, writer, global_step: int, device, tag: str = "recon",
+                                    normalize: bool = True, nrow: int | None = None) -> None:
+    """[original | reconstruction | abs diff] image grids, plus the canonical-frame triple for an rVAE
+    (reference train.py:791-853)"""
+    from torchvision.utils import make_grid
+    model.eval()
+    with torch.no_grad():
+        x = _materialise(images)
+        if isinstance(x, (list, tuple)):
+            x = x[0]
+        x_dev = x.to(device)
+        rotated_recon, canonical_recon, theta, _ = _split_outputs(model(x_dev))
+        x_cpu, r_cpu = x_dev.detach().cpu(), rotated_recon.detach().cpu()
+        n = nrow or x_cpu.size(0)
+        grid = make_grid(torch.cat([x_cpu, r_cpu, (x_cpu - r_cpu).abs()], dim=0), nrow=n, normalize=normalize)
+        writer.add_image(f"{tag}/original_recon_diff", grid, global_step)
+        stn = getattr(getattr(model, "encoder", None), "rotation_stn", None)
+        if canonical_recon is not None and theta is not None and stn is not None:
+            c_in = rotate_to_canonical(x_dev, theta, stn).detach().cpu()
+            c_rec = canonical_recon.detach().cpu()
+            grid = make_grid(torch.cat([c_in, c_rec, (c_in - c_rec).abs()], dim=0), nrow=n, normalize=normalize)
+            writer.add_image(f"{tag}/canonical_original_recon_diff", grid, global_step)
+
+
+def log_scalar_metrics_tensorboard(writer, metrics: dict, global_step: int, prefix: str = "") -> None:
+    """reference train.py:928-936"""
+    for name, value in metrics.items():
+        writer.add_scalar(f"{prefix}{name}", value, global_step)
+
+
+def evaluate_rotation_invariance(model, images: torch.Tensor, angles=(0, 45, 90, 135, 180, 225, 270, 315),
+                                 device=torch.device("cuda"), max_batches: int | None = None) -> dict:
+    """Latent variance / reconstruction error / angle error of the model over rotated copies of a few images
+    (reference train.py:680-788).  The rotations (TF.rotate, bilinear, fill 0) run in the `rotate_crop` kernel.
+    Deviation, on purpose: the reference reads the predicted angle as atan2(theta[0,1], theta[0,0]), which raises
+    IndexError for the real RVAE's theta [B,1]; a one-column theta is taken as the angle itself."""
+    model.eval()
+    angles = [float(a) for a in angles]
+    if images.dim() != 4:
+        raise ValueError("images must have shape [B, C, H, W]")
+    lat_var, rmse, psnr, ssim, ang_err = [], [], [], [], []
+    S = images.shape[-1]
+    with torch.no_grad():
+        for i, img in enumerate(images):
+            if max_batches is not None and i >= max_batches:
+                break
+            x = img.to(device).float().reshape(1, 1, S, S).expand(len(angles), 1, S, S).contiguous()
+            deg = torch.tensor(angles, dtype=torch.float64, device=x.device)
+            rotated = ops.rotate_crop(x, S, deg)
+            outs = model(rotated)
+            if len(outs) != 5:
+                raise ValueError(f"Unexpected model output length: {len(outs)}")
+            rotated_recon, _, theta, mu, _ = outs
+            back = ops.rotate_crop(rotated_recon.contiguous(), S, -deg)
+            lat_var.append(torch.var(mu, dim=0).mean().item())
+            for r in back:
+                r = r.unsqueeze(0)
+                rmse.append(torch.sqrt(torch.mean((r - x[:1]) ** 2)).item())
+                psnr.append(compute_psnr(r, x[:1]))
+                ssim.append(compute_ssim(r, x[:1]))
+            if theta is not None:
+                pred = (torch.atan2(theta[:, 1], theta[:, 0]) if theta.shape[1] >= 2 else theta[:, 0]) * (180.0 / np.pi)
+                d = (pred.cpu().double() - torch.tensor(angles, dtype=torch.float64)).abs()
+                ang_err.append(float(torch.minimum(d, 360 - d).mean()))
+    mean = lambda v: float(np.mean(v)) if v else 0.0
+    return {"rotation_latent_variance": mean(lat_var), "rotation_recon_rmse": mean(rmse),
+            "rotation_recon_psnr": mean(psnr), "rotation_recon_ssim": mean(ssim), "rotation_angle_error": mean(ang_err)}
+
+
+def compute_atom_position_accuracy(original: torch.Tensor, reconstruction: torch.Tensor, lattice_spacing: float,
+                                   threshold_ratio: float = 0.35) -> dict:
+    """peak positions of a patch vs those of its reconstruction (reference train.py:856-925); host-side analysis"""
+    from scipy.spatial.distance import cdist
+    from .data import peak_local_max
+
+    def plane(t):
+        if t.dim() == 3:
+            t = t[0] if t.size(0) == 1 else t.mean(dim=0)
+        return t.detach().cpu().numpy()
+
+    a, b = plane(original), plane(reconstruction)
+    if lattice_spacing <= 0:
+        raise ValueError("lattice_spacing must be positive")
+    dmin = max(int(lattice_spacing * threshold_ratio), 1)
+    pa, pb = peak_local_max(a, min_distance=dmin), peak_local_max(b, min_distance=dmin)
+    if pa.size == 0 or pb.size == 0:
+        return {"atom_detection_rate": 0.0, "atom_position_accuracy": 0.0, "atom_mean_position_error": float("inf"),
+                "n_original_atoms": int(pa.shape[0]) if pa.size else 0,
+                "n_reconstructed_atoms": int(pb.shape[0]) if pb.size else 0}
+    nearest = cdist(pa, pb).min(axis=1)
+    return {"atom_detection_rate": float(pb.shape[0] / pa.shape[0]),
+            "atom_position_accuracy": float((nearest < lattice_spacing * threshold_ratio).sum() / pa.shape[0]),
+            "atom_mean_position_error": float(nearest.mean()),
+            "n_original_atoms": int(pa.shape[0]), "n_reconstructed_atoms": int(pb.shape[0])}
