@@ -279,15 +279,17 @@ def train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight
 
 
 def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger, device,
-                         canonical_weight: float = 0.2, scaler=None, grad_max_norm: float | None = None) -> None:
-    """reference train.py:286-445"""
+                         canonical_weight: float = 0.2, scaler=None, grad_max_norm: float | None = None,
+                         reduce_grads=None) -> None:
+    """reference train.py:286-445.  `reduce_grads` (not in the reference, keyword only in practice): a callable run
+    between backward and clip -- livae.parallel.GradAverager under data parallelism."""
     model.train()
     acc = _DevAccum(device)
     n_batches = 0
     max_norm = grad_max_norm if grad_max_norm is not None else 20.0
     for batch in DevicePrefetcher(data_loader, device):
         x, loss, recon_l, kld_l, cycle_l, _can_l, outs, pre = train_rvae_step(
-            model, optimizer, criterion, batch, device, canonical_weight, max_norm)
+            model, optimizer, criterion, batch, device, canonical_weight, max_norm, reduce_grads)
         rotated_recon, canonical_recon, theta, mu, logvar = outs
         with torch.no_grad():
             m = dict(train_loss=loss, train_recon_loss=recon_l, train_kld_loss=kld_l, train_cycle_loss=cycle_l,

@@ -1,0 +1,27 @@
+"""Real-NCCL data-parallel parity: 2 ranks x B/2 with one all-reduce of the flat gradient buffer
+(livae.parallel.GradAverager) == 1 rank x B, on gradients after clipping and on parameters after one FlatAdamW step.
+Needs two GPUs on the box (`gpurun --gpus 2`); the CPU twin with gloo is tests/test_parallel_cpu.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_ranks_equal_one_rank_on_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--check-dp"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)["check_dp"]
+    assert res["ranks"] == 2
+    assert res["grad_rel_l2_after_clip"] < 5e-3, res
+    assert res["param_max_abs_diff_after_adamw"] < 2e-5, res
+    assert res["ok"]

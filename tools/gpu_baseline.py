@@ -37,3 +37,19 @@ for name, amp in (("fp32", None), ("amp_fp16", torch.float16), ("amp_bf16", torc
         torch.cuda.reset_peak_memory_stats()
         print(key, res[key], flush=True)
 print(json.dumps(res))
+
+# where the stock-ATen step spends its time: one profiled fp32 step and one autocast-fp16 step
+from torch.profiler import ProfilerActivity, profile
+for name, amp in (("fp32", None), ("amp_fp16", torch.float16)):
+    t = A.AtenTrainer(params, dev, amp=amp)
+    x, xr, ang = batches[0]
+    for _ in range(2):
+        t.step(x, xr, ang, eps[0])
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        t.step(x, xr, ang, eps[0])
+        torch.cuda.synchronize()
+    print(f"---- top CUDA kernels of one {name} ATen step (B={B})")
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
+    del t
+    torch.cuda.empty_cache()
