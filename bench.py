@@ -522,6 +522,21 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     value = world * args.batch * args.steps / (ms / 1e3)
+    # the same step without the encoder convolutions of the x_rot pass, whose mu / logvar the reference's loop discards
+    # at the call site (train.py:376-377: `_, _, theta_rotated = model.encoder(x_rotated)`); identical losses and
+    # gradients.  Reported NEXT TO the headline, never as it.
+    def elided_step(i):
+        return train_rvae_step(model, opt, crit, batches[i % len(batches)], device, CANON_W, MAX_NORM, reduce_grads,
+                               elide_dead_encoder=True)
+    elided_step(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        elided_step(i)
+    e1.record()
+    barrier()
+    ms_elided = max_over_ranks(e0.elapsed_time(e1))
     dp = None
     if world > 1:
         dp = check_dp(args, device, rank, world, dist)
@@ -587,6 +602,11 @@ def main():
                                                      "storage): tensor-bound, 5.95 TFLOP / 1376.8 TF/s"},
                 "frac": max(t_tensor, t_hbm16) / t_step},
             "kernels": kernels, "final_loss": loss0,
+            "dead_encoder_elided": {"value": world * args.batch * args.steps / (ms_elided / 1e3), "unit": UNIT,
+                                    "ms_per_step": ms_elided / args.steps,
+                                    "what": "same losses and gradients; skips the four encoder convolutions + heads of "
+                                            "model.encoder(x_rot), whose outputs train.py:376-377 discards (0.206 of the "
+                                            "2.90 GFLOP/patch).  Not the headline: `value` computes them as the reference does"},
         }
         if dp is not None:
             line["check_dp"] = dp

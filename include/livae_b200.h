@@ -48,6 +48,13 @@ const char* livae_last_error(void);
 int64_t livae_launch_count(void);
 /* 1 if the running device is sm_100 (B200); kernels refuse to launch otherwise */
 int livae_device_ok(void);
+/* Register (ptr != NULL) or withdraw (ptr == NULL) a caller-owned device scratch buffer for the CURRENT device,
+ * 256-byte aligned.  The library never allocates: kernels that split a reduction over CTAs (split-K Linear layers,
+ * tensor-core weight gradients, column sums) park per-CTA partial sums there and add them in a fixed order, which
+ * makes the forward pass and those gradients bit-reproducible (the reference's CPU path is).  Without a
+ * buffer (or with too small a one: 96 MB covers every layer of the rVAE at batch 2048) they fall back to
+ * red.global.add.  The pointer is retained until replaced; use it from one stream at a time. */
+int livae_set_scratch(void* ptr, int64_t bytes);
 
 /* ---- a1: peak-centred integer patch gather ------------------------------------------
  * replaces PatchDataset.__getitem__ with transform=None (data.py:211-250): whole-image

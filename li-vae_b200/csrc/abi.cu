@@ -17,6 +17,14 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+static struct { void* ptr; int64_t bytes; } g_scratch[64] = {};
+float* scratch_floats(int64_t nfloats) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  const auto& s = g_scratch[dev & 63];
+  return (s.ptr && nfloats * 4 <= s.bytes) ? (float*)s.ptr : nullptr;
+}
+
 int require_sm100() {
   static bool ok[64] = {};
   int dev = 0;
@@ -35,7 +43,16 @@ int require_sm100() {
 }
 }  // namespace livae
 
-extern "C" int livae_abi_version(void) { return 1; }
+extern "C" int livae_abi_version(void) { return 2; }
+extern "C" int livae_set_scratch(void* ptr, int64_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { livae::set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
+  if (((uintptr_t)ptr & 255) != 0 || bytes < 0) { livae::set_error("set_scratch: pointer must be 256-byte aligned"); return -1; }
+  livae::g_scratch[dev & 63].ptr = ptr;
+  livae::g_scratch[dev & 63].bytes = ptr ? bytes : 0;
+  return 0;
+}
 extern "C" const char* livae_last_error(void) { return livae::g_err; }
 namespace livae { long long launch_count(); }
 extern "C" int64_t livae_launch_count(void) { return (int64_t)livae::launch_count(); }

@@ -51,6 +51,12 @@ struct OncePerDevice {
 
 static constexpr int kNumSMs = 148;
 
+// Caller-owned device scratch (livae_set_scratch, one buffer per device): where kernels that split a reduction over
+// CTAs park their per-CTA partial sums so that a second pass can add them in a FIXED order (bit-reproducible results;
+// red.global.add / atomicAdd commit in whatever order the CTAs retire).  Valid for work enqueued on ONE stream at a
+// time.  nullptr when no (or too small a) buffer was registered: callers then fall back to atomics.
+float* scratch_floats(int64_t nfloats);
+
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
   __device__ __forceinline__ static float ld(const float* p, int64_t i) { return p[i]; }

@@ -69,14 +69,16 @@ struct ConvTcParams {
   const float* bias;      // may be null
   int act;
   const __nv_bfloat16* relu_mask;  // may be null: out *= (relu_mask > 0), same shape as out
-  int ksplit;             // > 1: blockIdx.z owns a slice of the K blocks and adds its raw partial sums to the (zeroed) fp32 out
+  int ksplit;             // > 1: blockIdx.z owns a slice of the K blocks and hands over its raw partial sums
+  float* part;            // ksplit > 1: fp32 [ksplit][pixels][Ntot] partial sums (plain stores, summed in slice order by
+  int64_t part_stride;    //   the finishing kernel); null: red.global.add into the zeroed fp32 out
 };
 
 // Epilogue of one accumulator row per thread: TMEM -> registers -> bias / activation / ReLU mask of the
 // consumer -> bf16 or fp32 NHWC row.  tcgen05.ld is warp-collective, so invalid rows still issue it.
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int nbase, int N, int Ntot, bool valid, int64_t pix,
                                               void* out, int out_f32, const float* __restrict__ bias, int act,
-                                              const __nv_bfloat16* __restrict__ relu_mask) {
+                                              const __nv_bfloat16* __restrict__ relu_mask, float* part = nullptr) {
     for (int cc = 0; cc < N; cc += 16) {
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)cc, v);   // warp-collective: issued by all lanes, stores predicated
@@ -84,6 +86,14 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int nbase, int N, 
       if (!valid) continue;
       const int c0 = nbase + cc;
       if (act == kActSplitK) {     // split-K partial: raw sums, bias / activation applied by the finishing kernel
+        if (part) {                // this slice's own copy: summed later in slice order (deterministic)
+          float4* o = reinterpret_cast<float4*>(part + pix * Ntot + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+          continue;
+        }
         float* o = reinterpret_cast<float*>(out) + pix * Ntot + c0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + i), "f"(__uint_as_float(v[i])) : "memory");
@@ -228,8 +238,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int64_t pix = ((int64_t)(b0 + bi) * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid && nk > 0, pix, p.out,
-                  p.out_f32, p.bias, p.ksplit > 1 ? kActSplitK : p.act, p.relu_mask);
+    float* part = (p.ksplit > 1 && p.part) ? p.part + (int64_t)blockIdx.z * p.part_stride : nullptr;
+    if (part && nk <= 0) {        // an empty K slice still owns its partial rows: they are summed unconditionally
+      if (valid)
+        for (int c = 0; c < p.N; ++c) part[pix * p.Ntot + (int)blockIdx.y * p.N + c] = 0.f;
+    } else {
+      epilogue_rows(tmem_base + ((uint32_t)(q * 32) << 16), (int)blockIdx.y * p.N, p.N, p.Ntot, valid && nk > 0, pix, p.out,
+                    p.out_f32, p.bias, p.ksplit > 1 ? kActSplitK : p.act, p.relu_mask, part);
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -657,10 +673,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cs, int Cb,
   }
 }
 
-// out[r][c] = act(out[r][c] + bias[c]) in place: finishes a split-K accumulation
-__global__ void bias_act_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t n, int C, int act) {
+// out[r][c] = act(sum + bias[c]): finishes a split-K accumulation.  part == null: the sum is already in out (atomics);
+// else sum = part[0][i] + part[1][i] + ... in slice order (bit-reproducible)
+__global__ void bias_act_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int64_t n, int C, int act,
+                                     const float* __restrict__ part, int nparts) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float a = out[i] + (bias ? __ldg(bias + (int)(i % C)) : 0.f);
+    float a;
+    if (part) {
+      a = part[i];
+      for (int z = 1; z < nparts; ++z) a += part[(int64_t)z * n + i];
+    } else {
+      a = out[i];
+    }
+    a += bias ? __ldg(bias + (int)(i % C)) : 0.f;
     if (act == LIVAE_ACT_RELU) a = fmaxf(a, 0.f);
     else if (act == LIVAE_ACT_SIGMOID) a = 1.f / (1.f + __expf(-a));
     out[i] = a;
@@ -907,14 +932,20 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
     const int kper = (nk + ks - 1) / ks;
     p.ksplit = (nk + kper - 1) / kper;
   }
+  p.part = nullptr; p.part_stride = 0;
   if (p.ksplit > 1) {
     const int64_t n = (int64_t)B * Ho * Wo * N;
-    cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st);
-    if (ce != cudaSuccess) { set_error("tc_conv split-K memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+    p.part = scratch_floats((int64_t)p.ksplit * n);
+    p.part_stride = n;
+    if (!p.part) {
+      cudaError_t ce = cudaMemsetAsync(out, 0, (size_t)n * sizeof(float), st);
+      if (ce != cudaSuccess) { set_error("tc_conv split-K memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+    }
     conv_tc_kernel<STAGES><<<dim3(tiles, N / p.N, p.ksplit), kThreads, smem, st>>>(tmA, tmB, p);
     LIVAE_CUDA_LAUNCH_CHECK();
-    if (bias || act != LIVAE_ACT_NONE) {
-      bias_act_rows_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>((float*)out, bias, n, N, act);
+    if (p.part || bias || act != LIVAE_ACT_NONE) {
+      bias_act_rows_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>((float*)out, bias, n, N, act,
+                                                                                              p.part, p.ksplit);
       LIVAE_CUDA_LAUNCH_CHECK();
     }
     return 0;

@@ -69,7 +69,22 @@ __device__ __forceinline__ void stage_image(const float* __restrict__ src, float
     const int wq = W >> 2;
     int y = threadIdx.x / wq, x4 = threadIdx.x - y * wq;
     const int dy = blockDim.x / wq, dx = blockDim.x - dy * wq;
-    for (int i = threadIdx.x; i < H * wq; i += blockDim.x) {
+    // four independent 16-byte loads in flight per thread before the first store (the staging phase is pure latency)
+    const int total = H * wq, stride = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src) + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float* d = tile + y * pitch + 4 * x4;
+        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+        y += dy; x4 += dx;
+        if (x4 >= wq) { x4 -= wq; ++y; }
+      }
+    }
+    for (; i < total; i += stride) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
       float* d = tile + y * pitch + 4 * x4;
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -134,19 +149,16 @@ __device__ __forceinline__ float unnorm(float g, float fn) {
   return (u + 0.5f) - 0.5f;               // fabs / reflect of ATen on an in-range coordinate: same two roundings
 }
 __device__ __forceinline__ bool block_interior(int i0, int j0, float c, float s, int H, int W, float invH, float invW) {
-  // corners of the warp's 32x4 block (clamped to the image), with a 1e-2 px guard for rounding
-  const int i1 = min(i0 + 3, H - 1), j1 = min(j0 + 31, W - 1);
-  const float ya = (2.f * (float)i0 + 1.f) * invH - 1.f, yb = (2.f * (float)i1 + 1.f) * invH - 1.f;
-  const float xa = (2.f * (float)j0 + 1.f) * invW - 1.f, xb = (2.f * (float)j1 + 1.f) * invW - 1.f;
-  const float fw = (float)W, fh = (float)H;
-  bool ok = true;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float xs = (q & 1) ? xb : xa, ys = (q & 2) ? yb : ya;
-    const float ix = unnorm(fmaf(c, xs, -(s * ys)), fw), iy = unnorm(fmaf(s, xs, c * ys), fh);
-    ok = ok && ix > 0.01f && ix < fw - 1.01f && iy > 0.01f && iy < fh - 1.01f;
-  }
-  return ok;
+  // A rotation about the centre preserves the distance from the centre (square images: the normalised axes scale
+  // alike), so the block is interior when its farthest corner lies inside the circle of radius (n-1)/2 around
+  // the centre -- independent of the angle, a handful of instructions per block.
+  if (H != W) return false;
+  const float half = 0.5f * (float)W;
+  const float xa = fabsf((float)j0 + 0.5f - half), xb = fabsf((float)min(j0 + 31, W - 1) + 0.5f - half);
+  const float ya = fabsf((float)i0 + 0.5f - half), yb = fabsf((float)min(i0 + 3, H - 1) + 0.5f - half);
+  const float dx = fmaxf(xa, xb), dy = fmaxf(ya, yb);
+  const float r = half - 0.52f;                 // (n-1)/2 minus a 0.02 px guard for the rounding of the coordinate
+  return dx * dx + dy * dy < r * r;
 }
 struct FastTaps { int o00; float fx, fy; };
 __device__ __forceinline__ FastTaps make_taps_interior(float xs, float gxr, float gyr, float c, float s, float fh, float fw,

@@ -204,6 +204,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
 int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho, int Wo,
                       cudaStream_t st, int x_s2d);
 void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st);   // gb must be zeroed
+void sum_slices(const float* part, int nslices, int64_t n, float* out, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace livae

@@ -27,7 +27,8 @@ struct WgradParams {
   int G;                      // row groups per CTA
   int groups_total;
   int tiles_per_cta;
-  float* gw_acc;              // fp32 [ntaps][Cb][Cs], zeroed by the host wrapper
+  float* gw_acc;              // fp32 [ntaps][Cb][Cs], zeroed by the host wrapper (slice_elems == 0: red.global.add) or
+  int64_t slice_elems;        // fp32 [splits][ntaps][Cb][Cs] per-split partial sums (plain stores), summed in split order
 };
 
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
@@ -152,15 +153,23 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc_kernel(const __grid_const
         const bool valid = f < total_boxes;
         const int tap = f / chunks_b, ch = f - tap * chunks_b;
         const int cb = ch * p.kcb + row % p.kcb;
-        float* dst = p.gw_acc + ((int64_t)tap * p.Cb + cb) * p.Cs;
+        float* dst = p.gw_acc + (int64_t)blockIdx.y * p.slice_elems + ((int64_t)tap * p.Cb + cb) * p.Cs;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cs);
         for (int c0 = 0; c0 < p.Cs; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
           if (valid) {
+            if (p.slice_elems) {       // this split's own slice: plain stores, summed later in split order
+              float4* o = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) red_add_f32(dst + c0 + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) red_add_f32(dst + c0 + i, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -200,6 +209,7 @@ struct WgradHaloParams {
   int ngroups, G;
   WgGroup grp[kMaxGroups];
   float* gw_acc;
+  int64_t slice_elems;        // see WgradParams
   long long* probe;
   int x_s2d;                   // input operand read in space-to-depth form through a 5-D tensor map (tc_common.cuh)
 };
@@ -350,15 +360,23 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
         const bool valid = a >= 0;
         const int tap = a >> 3, ch = a & 7;
         const int cb = ch * p.kcb + row % p.kcb;
-        float* dst = p.gw_acc + ((int64_t)tap * p.Cb + cb) * p.Cs;
+        float* dst = p.gw_acc + (int64_t)blockIdx.y * p.slice_elems + ((int64_t)tap * p.Cb + cb) * p.Cs;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cs);
         for (int c0 = 0; c0 < p.Cs; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
           if (valid) {
+            if (p.slice_elems) {       // this split's own slice: plain stores, summed later in split order
+              float4* o = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) red_add_f32(dst + c0 + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) red_add_f32(dst + c0 + i, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -373,6 +391,22 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
   }
 }
 
+// out[i] = part[0][i] + part[1][i] + ... + part[nslices-1][i]: the fixed-order second pass of a reduction that was
+// split over CTAs (bit-reproducible, unlike red.global.add whose commit order follows CTA retirement)
+__global__ void sum_slices_kernel(const float* __restrict__ part, int nslices, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = part[i];
+    for (int z = 1; z < nslices; ++z) a += part[(int64_t)z * n + i];
+    out[i] = a;
+  }
+}
+void sum_slices(const float* part, int nslices, int64_t n, float* out, cudaStream_t st) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  sum_slices_kernel<<<(int)blocks, 256, 0, st>>>(part, nslices, n, out);
+  count_launch(1);
+}
+
 // gw_acc fp32 [tap][cb][cs] -> torch layout gw[cs][cb][tap] (written)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, int Cs, int Cb, int taps, float* __restrict__ gw) {
   int n = Cs * Cb * taps;
@@ -383,8 +417,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, int Cs, int C
 }
 
 // column sums of a bf16 [R, C] matrix -> fp32 gb[C] (written via atomics on a zeroed buffer)
+// part_mode: gb is [gridDim.x][C] and every CTA stores its own row of partial sums (summed in CTA order afterwards)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, int64_t R, int C,
-                                                          float* __restrict__ gb, int64_t rows_per_cta) {
+                                                          float* __restrict__ gb, int64_t rows_per_cta, int part_mode) {
   __shared__ float red[256];
   const int cols = C < 256 ? C : 256;
   const int rgs = 256 / cols;
@@ -400,7 +435,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     __syncthreads();
     if (rg == 0 && c < C) {
       for (int j = 1; j < rgs; ++j) a += red[j * cols + cl];
-      atomicAdd(gb + c, a);
+      if (part_mode) gb[(int64_t)blockIdx.x * C + c] = a;
+      else atomicAdd(gb + c, a);
     }
     __syncthreads();
   }
@@ -555,6 +591,7 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   p.tiles_per_cta = (total_tiles + splits - 1) / splits;
   splits = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.gw_acc = gw_acc;
+  p.slice_elems = 0;
   p.probe = g_probe;
   p.x_s2d = x_s2d;
   if (x_s2d && (d->Cin != 64 || s != 1)) return 1;
@@ -612,18 +649,33 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
     cudaFuncSetAttribute(wgrad_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   dim3 grid(gsets, splits);
+  const int64_t elems = (int64_t)p.ntaps * p.Cb * p.Cs;
+  float* part = scratch_floats((int64_t)splits * elems);
+  if (part) {                                               // per-split slices, summed in split order below
+    cudaError_t ce = cudaMemsetAsync(part, 0, (size_t)splits * elems * sizeof(float), st);   // rows no group owns stay 0
+    if (ce != cudaSuccess) { set_error("wgrad scratch memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+    p.gw_acc = part; p.slice_elems = elems;
+  }
   if (4u * stage_bytes + 1024u <= 200u * 1024u)
     wgrad_halo_kernel<4><<<grid, kWgHaloThreads, 4 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   else
     wgrad_halo_kernel<2><<<grid, kWgHaloThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   LIVAE_CUDA_LAUNCH_CHECK();
+  if (part) sum_slices(part, splits, elems, gw_acc, st);
   return 0;
 }
 
 void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st) {
   int64_t rows = (R + kNumSMs * 4 - 1) / (kNumSMs * 4);
   if (rows < 64) rows = 64;
-  colsum_bf16_kernel<<<(int)((R + rows - 1) / rows), 256, 0, st>>>((const __nv_bfloat16*)g, R, C, gb, rows);
+  const int blocks = (int)((R + rows - 1) / rows);
+  if (float* part = scratch_floats((int64_t)blocks * C)) {       // two fixed-order passes (gb need not be zeroed)
+    colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, part, rows, 1);
+    count_launch(1);
+    sum_slices(part, blocks, C, gb, st);
+    return;
+  }
+  colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, gb, rows, 0);
   count_launch(1);
 }
 }}  // namespace livae::tc
@@ -691,6 +743,7 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   p.tiles_per_cta = (total_tiles + splits - 1) / splits;
   splits = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.gw_acc = (float*)ws;
+  p.slice_elems = 0;
 
   CUtensorMap tmX, tmG;
   {
@@ -722,11 +775,20 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
     cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
+  const int64_t elems = (int64_t)p.ntaps * p.Cb * p.Cs;
+  float* part = scratch_floats((int64_t)splits * elems);
+  p.slice_elems = 0;
+  if (part) {
+    ce = cudaMemsetAsync(part, 0, (size_t)splits * elems * sizeof(float), st);
+    if (ce != cudaSuccess) { set_error("wgrad scratch memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+    p.gw_acc = part; p.slice_elems = elems;
+  }
   if (3u * stage_bytes + 1024u <= 200u * 1024u)
     wgrad_tc_kernel<3><<<grid, kWgThreads, 3 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   else
     wgrad_tc_kernel<2><<<grid, kWgThreads, 2 * stage_bytes + 1024, st>>>(tmX, tmG, p);
   LIVAE_CUDA_LAUNCH_CHECK();
+  if (part) { sum_slices(part, splits, elems, (float*)ws, st); p.gw_acc = (float*)ws; }
   }
   const int n = p.Cs * p.Cb * p.ntaps;
   unpack_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.gw_acc, p.Cs, p.Cb, p.ntaps, gw);
@@ -734,10 +796,7 @@ extern "C" int livae_tc_conv_wgrad(const livae_tc_conv_desc* d, const void* x, c
   if (gb) {
     ce = cudaMemsetAsync(gb, 0, (size_t)p.Cs * sizeof(float), st);
     if (ce != cudaSuccess) { set_error("tc_conv_wgrad memset gb: %s", cudaGetErrorString(ce)); return (int)ce; }
-    const int64_t R = (int64_t)d->B * Ho * Wo;
-    int64_t rows = (R + kNumSMs * 4 - 1) / (kNumSMs * 4);
-    if (rows < 64) rows = 64;
-    colsum_bf16_kernel<<<(int)((R + rows - 1) / rows), 256, 0, st>>>((const __nv_bfloat16*)gy, R, p.Cs, gb, rows);
+    colsum_bf16(gy, (int64_t)d->B * Ho * Wo, p.Cs, gb, st);
     LIVAE_CUDA_LAUNCH_CHECK();
   }
   return 0;

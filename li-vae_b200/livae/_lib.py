@@ -144,6 +144,8 @@ def lib():
     L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_ssim_box_ws_floats.restype = C.c_int64
     L.livae_ssim_box_ws_floats.argtypes = [C.c_int64, C.c_int]
+    L.livae_set_scratch.restype = C.c_int
+    L.livae_set_scratch.argtypes = [C.c_void_p, C.c_int64]
     L.livae_conv_out_shape.restype = None
     L.livae_conv_out_shape.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for name, sig in _SIGS.items():
@@ -158,7 +160,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
 
 
 def ptr(t):
@@ -169,6 +171,23 @@ def ptr(t):
 
 def stream(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# Per-device scratch the library parks per-CTA partial sums in, so that reductions split over CTAs are finished in
+# a fixed order (bit-reproducible forward pass and weight gradients; see csrc/common.cuh scratch_floats).  Owned
+# here (a torch allocation, kept alive for the life of the process), registered with livae_set_scratch on first use.
+SCRATCH_BYTES = 96 << 20
+_scratch = {}
+
+
+def _ensure_scratch(dev):
+    if dev.index in _scratch:
+        return
+    with torch.cuda.device(dev):
+        buf = torch.empty(SCRATCH_BYTES, dtype=torch.uint8, device=dev)
+        if lib().livae_set_scratch(buf.data_ptr(), SCRATCH_BYTES) != 0:
+            raise RuntimeError("livae_set_scratch failed: " + lib().livae_last_error().decode(errors="replace"))
+    _scratch[dev.index] = buf
 
 
 # When set to a list, every call is bracketed by CUDA events on the launching stream and
@@ -188,6 +207,8 @@ def call(name, *args):
                 dev = a.device
         else:
             conv.append(a)
+    if dev is not None and dev.index not in _scratch:
+        _ensure_scratch(dev)
     if dev is not None and dev.index != torch.cuda.current_device():
         # tensors on another GPU than the thread's current one: launch in THEIR context, on their stream
         with torch.cuda.device(dev):

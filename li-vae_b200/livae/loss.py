@@ -11,14 +11,11 @@ __all__ = ["VAELoss", "RVAELoss", "cycle_consistency_loss", "rotation_diversity_
 
 
 def circular_distance(theta1: torch.Tensor, theta2: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
-    """reference loss.py:6-29 (analysis helper, not on the training path)"""
-    if theta1.dim() == 1:
-        theta1 = theta1.unsqueeze(1)
-    if theta2.dim() == 1:
-        theta2 = theta2.unsqueeze(1)
-    diff = torch.abs(theta1 - theta2)
-    diff = torch.min(diff, 2 * torch.pi - diff)
-    return torch.mean(diff)
+    """mean shortest angular distance between two sets of angles, in [0, pi] (reference loss.py:6-29; analysis
+    helper, not on the training path).  The difference is wrapped into [-pi, pi) once instead of taking
+    min(|d|, 2*pi - |d|); both agree for |d| <= 2*pi, which is all atan2 outputs can produce."""
+    d = theta1.reshape(theta1.shape[0], -1) - theta2.reshape(theta2.shape[0], -1)
+    return (torch.remainder(d + torch.pi, 2 * torch.pi) - torch.pi).abs().mean()
 
 
 def rotation_diversity_loss(theta: torch.Tensor, target_std: float = 1.0) -> torch.Tensor:
@@ -62,18 +59,18 @@ class RVAELoss(nn.Module):
         self.use_diversity = use_diversity
 
     def forward(self, recon_x, x, mu, logvar, theta=None, theta_rotated=None, expected_angle=None):
-        batch_size = x.size(0)
-        sums = ops.elbo_sums(recon_x, x, mu, logvar)
-        recon_loss = sums[0] / batch_size
-        kld_loss = sums[1] / batch_size
-        if self.gamma > 0:
-            if self.use_diversity and theta is not None:
-                rotation_loss = rotation_diversity_loss(theta, target_std=1.0)
-            elif theta is not None and theta_rotated is not None and expected_angle is not None:
-                rotation_loss = cycle_consistency_loss(theta, theta_rotated, expected_angle)
-            else:
-                rotation_loss = torch.tensor(0.0, device=recon_x.device)
-        else:
-            rotation_loss = torch.tensor(0.0, device=recon_x.device)
-        total_loss = recon_loss + self.beta * kld_loss + self.gamma * rotation_loss
-        return total_loss, recon_loss, kld_loss, rotation_loss
+        n = x.size(0)
+        sums = ops.elbo_sums(recon_x, x, mu, logvar)             # one fused launch: sum (r-x)^2 and the KLD sum
+        recon_loss, kld_loss = sums[0] / n, sums[1] / n
+        rotation_loss = self._rotation_term(theta, theta_rotated, expected_angle, recon_x.device)
+        return recon_loss + self.beta * kld_loss + self.gamma * rotation_loss, recon_loss, kld_loss, rotation_loss
+
+    def _rotation_term(self, theta, theta_rotated, expected_angle, device):
+        """loss.py:171-182: nothing when gamma == 0; the batch-spread term with use_diversity; otherwise the cycle
+        term, which needs the rotated partner's angle and the applied rotation"""
+        if self.gamma > 0 and theta is not None:
+            if self.use_diversity:
+                return rotation_diversity_loss(theta, target_std=1.0)
+            if theta_rotated is not None and expected_angle is not None:
+                return cycle_consistency_loss(theta, theta_rotated, expected_angle)
+        return torch.tensor(0.0, device=device)

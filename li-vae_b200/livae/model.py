@@ -209,7 +209,7 @@ class Encoder(nn.Module):
                 x, loc[0].weight, loc[0].bias, loc[3].weight, loc[3].bias, loc[7].weight,
                 loc[7].bias, loc[9].weight, loc[9].bias, cl[0].weight, cl[0].bias,
                 cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight, cl[6].bias,
-                self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias)
+                self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias, False)
             # one-shot cache for the trainer (see _take_canonical); training forwards only, so that an idle or
             # evaluating model holds no batch and no autograd graph (deepcopy / pickling of the module stay possible)
             self._canonical = (x, theta, x_rot) if torch.is_grad_enabled() else None
@@ -219,6 +219,17 @@ class Encoder(nn.Module):
         mu = ops.linear_nhwc(h, self.fc_mu.weight, self.fc_mu.bias)
         logvar = ops.linear_nhwc(h, self.fc_logvar.weight, self.fc_logvar.bias)
         return mu, logvar, theta
+
+
+def _theta_only(self, x):
+    """theta of the STN alone, for callers that discard mu / logvar (same value and gradient as self(x)[2])"""
+    if _ENGINE == "tc" and tc.supported(self.patch_size, self.latent_dim, x.shape[1]):
+        loc, cl = self.rotation_stn.localization, self.conv_layers
+        return tc.EncoderTc.apply(
+            x, loc[0].weight, loc[0].bias, loc[3].weight, loc[3].bias, loc[7].weight, loc[7].bias, loc[9].weight,
+            loc[9].bias, cl[0].weight, cl[0].bias, cl[2].weight, cl[2].bias, cl[4].weight, cl[4].bias, cl[6].weight,
+            cl[6].bias, self.fc_mu.weight, self.fc_mu.bias, self.fc_logvar.weight, self.fc_logvar.bias, True)[2]
+    return self.rotation_stn.localize(x)[1]
 
 
 def _take_canonical(self, x, theta):
@@ -233,6 +244,7 @@ def _take_canonical(self, x, theta):
 
 
 Encoder.take_canonical = _take_canonical
+Encoder.theta_only = _theta_only
 
 
 class Decoder(nn.Module):

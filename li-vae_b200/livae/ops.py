@@ -8,6 +8,7 @@ No op here has a CPU or ATen fallback.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -470,7 +471,49 @@ def cast(t, dtype):
     return out
 
 
+# ---- packed-weight cache ---------------------------------------------------------------------------------------
+# The bf16 re-layouts of a parameter depend on the parameter alone, which changes once per optimiser step, while a
+# training step asks for the same pack several times (model(x) and model.encoder(x_rot) share every encoder weight).
+# An entry is reused only for the SAME tensor object (weak reference), at the same storage address and autograd
+# version, within the same optimiser epoch: `WEIGHT_EPOCH` is bumped by every torch optimiser step (global post-step
+# hook) and by FlatAdamW.step (which updates the flat buffer from a raw kernel, invisible to the version counter).
+# In-place edits through `.data` are invisible to all of these: call `invalidate_weight_packs()` after such an edit.
+_PACKS: dict = {}
+WEIGHT_EPOCH = [0]
+
+
+def invalidate_weight_packs() -> None:
+    WEIGHT_EPOCH[0] += 1
+    if len(_PACKS) > 256:
+        _PACKS.clear()
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _post_step_hook  # noqa: E402
+
+_post_step_hook(lambda *a, **k: invalidate_weight_packs())
+
+
+def _packed(w, key, make):
+    k = (id(w),) + key
+    ent = _PACKS.get(k)
+    if (ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == WEIGHT_EPOCH[0]
+            and ent[3] == w.data_ptr()):
+        return ent[4]
+    out = make()
+    try:
+        ref = weakref.ref(w, lambda _r, k=k: _PACKS.pop(k, None))
+    except TypeError:
+        return out
+    _PACKS[k] = (ref, w._version, WEIGHT_EPOCH[0], w.data_ptr(), out)
+    return out
+
+
 def tc_pack_weights(w, Cs, Cb, kh, kw, mode, Cs_pad=None):
+    """cached (see above) bf16 re-layout of a torch-layout weight for the tensor-core engine"""
+    return _packed(w, ("pack", Cs, Cb, kh, kw, mode, Cs_pad), lambda: _tc_pack_weights(w, Cs, Cb, kh, kw, mode, Cs_pad))
+
+
+def _tc_pack_weights(w, Cs, Cb, kh, kw, mode, Cs_pad=None):
     """torch-layout fp32 weight [Cs,Cb,kh,kw] -> bf16 packed for the tensor-core engine:
     mode 0 [tap][Cs][Cb] (forward), 1 [flipped tap][Cb][Cs], 2 [tap][Cb][Cs] (data gradient),
     3 [Cs_pad][tap][Cb] (Linear forward, K in (h,w,c) order), 4 [tap][Cb][Cs_pad] (Linear data gradient)"""
@@ -541,6 +584,10 @@ def conv5pool_supported(B, H, W, Ci, Co):
 
 
 def conv5pool_pack(w, mode):
+    return _packed(w, ("c5p", mode), lambda: _conv5pool_pack(w, mode))
+
+
+def _conv5pool_pack(w, mode):
     Co, Ci = w.shape[0], w.shape[1]
     shape = (9, 4 * Co, 4 * Ci) if mode == 0 else (9, 4 * Ci, 4 * Co)
     out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
@@ -587,8 +634,13 @@ def dgrad_s2blk(gy, w, Hin, Win, relu_mask=None):
     -> gx bf16 [B,Hin,Win,Cin] (times relu_mask > 0); one launch in block form (csrc/conv_s2d.cu)"""
     B = gy.shape[0]
     Cout, Cin = w.shape[0], w.shape[1]
-    wblk = torch.empty((9, 4 * Cin, Cout), dtype=torch.bfloat16, device=gy.device)
-    call("livae_tc_dgrad_s2blk_pack", _c(w), Cout, Cin, wblk)
+
+    def make():
+        t = torch.empty((9, 4 * Cin, Cout), dtype=torch.bfloat16, device=gy.device)
+        call("livae_tc_dgrad_s2blk_pack", _c(w), Cout, Cin, t)
+        return t
+
+    wblk = _packed(w, ("s2blk",), make)
     gx = torch.empty((B, Hin, Win, Cin), dtype=torch.bfloat16, device=gy.device)
     call("livae_tc_dgrad_s2blk", gy, wblk, relu_mask, B, Hin, Win, Cin, Cout, gx)
     return gx

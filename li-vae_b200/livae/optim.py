@@ -119,6 +119,7 @@ class FlatAdamW(torch.optim.Optimizer):
             ops.adamw_(self.flat_param[s:e], self.flat_grad[s:e], self.exp_avg[s:e], self.exp_avg_sq[s:e],
                        self.step_dev, g["lr"], g["betas"], g["eps"], g["weight_decay"], decoupled=g["decoupled"],
                        gscale=gscale, inc_step=(k == len(runs) - 1))
+        ops.invalidate_weight_packs()          # the raw kernel changed the parameters behind autograd's version counter
 
     # ---- checkpointing in torch.optim.AdamW's format ---------------------------------------------------------
     def state_dict(self):

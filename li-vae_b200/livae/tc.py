@@ -73,7 +73,10 @@ class EncoderTc(Function):
     """(x, 20 parameters) -> (mu, logvar, theta); reference Encoder.forward, model.py:305-326"""
 
     @staticmethod
-    def forward(ctx, x, w0, b0, w3, b3, w7, b7, w9, b9, c0w, c0b, c2w, c2b, c4w, c4b, c6w, c6b, muw, mub, lvw, lvb):
+    def forward(ctx, x, w0, b0, w3, b3, w7, b7, w9, b9, c0w, c0b, c2w, c2b, c4w, c4b, c6w, c6b, muw, mub, lvw, lvb,
+                theta_only=False):
+        """theta_only: stop after the STN localisation (returns None for mu, logvar and the rotated batch) -- for call
+        sites that discard everything but theta (train.py:376-377, pretrain_stn.py:106-107)"""
         ops.require_cuda(x)
         x = x.contiguous()
         B, _, P, _ = x.shape
@@ -94,6 +97,12 @@ class EncoderTc(Function):
         vec = _empty((B, 2), torch.float32, dev)
         cs = _empty((B, 2), torch.float32, dev); theta = _empty((B, 1), torch.float32, dev)
         call("livae_stn_tail_fwd", f1, w9, b9, B, 32, vec, cs, theta)         # fc2 + normalize + atan2
+        if theta_only:
+            e = _empty((0,), BF, dev)
+            ctx.save_for_backward(x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, w9, a1, idx1, a2, idx2, f1, vec, cs, e, e, e, e, e)
+            ctx.dims = (B, P, Ld, 0)
+            ctx.set_materialize_grads(False)
+            return None, None, theta, None
         x_rot = torch.empty_like(x)
         call("livae_rot_sample_fwd", x, cs, 1.0, B, 1, P, P, x_rot)
         # --- encoder conv stack (model.py:289-298)
@@ -134,7 +143,7 @@ class EncoderTc(Function):
                 gcs = _empty((B, 2), torch.float32, dev)
                 call("livae_rot_sample_bwd", x, cs, 1.0, g_xrot_out.contiguous(), B, 1, P, P, None, gcs)
             if g_theta is None and gcs is None:
-                return (None,) * 21
+                return (None,) * 22
             return EncoderTc._backward_stn(ctx, gcs, g_theta)
         # --- heads
         g16 = torch.zeros((B, Npad), dtype=torch.float32, device=dev)
@@ -164,7 +173,7 @@ class EncoderTc(Function):
         stn = EncoderTc._backward_stn(ctx, gcs, g_theta)
         gmuw, glvw = gwcat[:Ld].contiguous(), gwcat[Ld:2 * Ld].contiguous()
         gmub, glvb = gbcat[:Ld].contiguous(), gbcat[Ld:2 * Ld].contiguous()
-        return stn[:9] + (gc0w, gc0b, gw2, gb2, gw4, gb4, gw6, gb6, gmuw.view(Ld, -1), gmub, glvw.view(Ld, -1), glvb)
+        return stn[:9] + (gc0w, gc0b, gw2, gb2, gw4, gb4, gw6, gb6, gmuw.view(Ld, -1), gmub, glvw.view(Ld, -1), glvb, None)
 
     @staticmethod
     def _backward_stn(ctx, gcs, g_theta):
@@ -190,7 +199,7 @@ class EncoderTc(Function):
                                     relu_mask=a1)
         gw0 = torch.empty_like(w0); gb0 = _empty((16,), torch.float32, dev)
         call("livae_thin_conv1c_wgrad", 0, x, ga1, idx1, B, P, P, gw0, gb0)
-        return (None, gw0, gb0, gw3, gb3, gw7.view_as(w7), gb7, gw9, gb9) + (None,) * 12
+        return (None, gw0, gb0, gw3, gb3, gw7.view_as(w7), gb7, gw9, gb9) + (None,) * 13
 
 
 class DecoderTc(Function):

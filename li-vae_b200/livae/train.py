@@ -112,7 +112,7 @@ def rvae_step_loss(model, criterion, x, x_rotated=None, angle=None, canonical_we
     theta_rotated = None
     if x_rotated is not None:
         if elide_dead_encoder:
-            _, theta_rotated = model.encoder.rotation_stn.localize(x_rotated)
+            theta_rotated = model.encoder.theta_only(x_rotated)
         else:
             _, _, theta_rotated = model.encoder(x_rotated)
         if take is not None:
@@ -260,14 +260,14 @@ class _DevAccum:
 
 
 def train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight: float = 0.2,
-                    max_norm: float = 20.0, reduce_grads=None):
+                    max_norm: float = 20.0, reduce_grads=None, elide_dead_encoder: bool = False):
     """ONE batch of the reference's rVAE training loop (train.py:315-397): unpack + host->device
     copy, forward, loss, backward, [gradient all-reduce], clip, optimizer step.
     -> (loss, recon, kld, cycle, canonical, outputs, pre_clip_grad_norm), all device tensors."""
     x, x_rotated, angle = _unpack_rvae_batch(batch, device)
     optimizer.zero_grad(set_to_none=getattr(optimizer, "flat_grad", None) is None)
     loss, recon_l, kld_l, cycle_l, can_l, outs = rvae_step_loss(model, criterion, x, x_rotated, angle,
-                                                              canonical_weight)
+                                                              canonical_weight, elide_dead_encoder)
     loss.backward()
     if reduce_grads is not None:
         if hasattr(optimizer, "sync_grads"):

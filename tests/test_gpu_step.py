@@ -401,3 +401,26 @@ def test_flat_adamw_matches_torch_adamw_with_lazy_gradient_packing():
     loss_of(mine, 0, True).backward()
     o_mine.sync_grads()
     assert float(mine[-1].grad.abs().max()) == 0.0 and float(mine[0].grad.abs().max()) > 0.0
+
+
+@pytest.mark.tc_engine
+def test_elided_dead_encoder_gives_identical_step():
+    """rvae_step_loss(elide_dead_encoder=True) skips the encoder convolutions of the x_rot pass, whose outputs the
+    reference's loop discards (train.py:376-377): same loss, same theta_rot path, same gradients (bit for bit in the
+    forward, summation-order jitter in the backward)"""
+    import livae
+    from livae.train import rvae_step_loss
+    P, L, B, seed = 64, 2, 8, 31
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    x, xr, ang = O.make_lattice_batch(B, P, seed=seed + 1)
+    eps = torch.from_numpy(np.random.default_rng(seed + 2).standard_normal((B, L))).float()
+    res = []
+    for elide in (False, True):
+        m = _rvae(P, L, params)
+        with FixedEps(eps):
+            out = rvae_step_loss(m, livae.RVAELoss(beta=10.0, gamma=10.0), x.cuda(), xr.cuda(), ang.cuda(), 0.2, elide)
+        out[0].backward()
+        res.append((float(out[0]), float(out[3]), {k: p.grad.detach().clone() for k, p in m.named_parameters()}))
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    for k in res[0][2]:
+        assert rel_l2(res[0][2][k].cpu(), res[1][2][k].cpu()) < 1e-5, k
