@@ -249,6 +249,12 @@ int livae_tc_dgrad_s2blk(const void* gy, const void* wblk, const void* relu_mask
                          int Cout, void* gx, livae_stream_t stream);
 /* Linear weight gradient: tensor-core layout [N][(h,w,c)] -> torch [N][(c,h,w)] */
 int livae_permute_linear_grad(const float* src_hwc, int N, int C, int HW, float* dst_chw, livae_stream_t stream);
+/* Data gradient of a wide nn.Linear (STN fc1, model.py:211; latent heads, model.py:302-303) whose output is only J =
+ * 16 / 32 / 64 wide: gx bf16 [B][K] = (mask > 0) * (g bf16 [B][J] @ w^T), w = bf16 [K][J] (livae_tc_pack_weights mode
+ * 4), mask = the bf16 [B][K] activation whose ReLU is being differentiated (may be NULL).  HBM-bound: 128-byte row
+ * segments in and out (csrc/skinny.cu). */
+int livae_linear_dgrad(const void* g, const void* w_kj, const void* mask, int B, int K, int J, void* gx,
+                       livae_stream_t stream);
 
 /* ---- thin 1-channel layers around the tensor-core convolutions (SIMT, bf16 on the wide side) ----
  * kind 0: STN conv1 1->16 5x5 p2 +ReLU +MaxPool (model.py:204-206): out bf16 [B,H/2,W/2,16] + pool_idx

@@ -679,9 +679,15 @@ __global__ void bias_act_rows_kernel(float* __restrict__ out, const float* __res
                                      const float* __restrict__ part, int nparts) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float a;
-    if (part) {
-      a = part[i];
-      for (int z = 1; z < nparts; ++z) a += part[(int64_t)z * n + i];
+    if (part) {          // four independent chains (a serial chain waits one L2 round trip per slice), fixed association
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int z = 0;
+      for (; z + 3 < nparts; z += 4) {
+        a0 += part[(int64_t)z * n + i]; a1 += part[(int64_t)(z + 1) * n + i];
+        a2 += part[(int64_t)(z + 2) * n + i]; a3 += part[(int64_t)(z + 3) * n + i];
+      }
+      for (; z < nparts; ++z) a0 += part[(int64_t)z * n + i];
+      a = (a0 + a1) + (a2 + a3);
     } else {
       a = out[i];
     }

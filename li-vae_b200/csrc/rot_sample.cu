@@ -186,8 +186,10 @@ struct BlockWalk {
   }
 };
 
+// 512 threads x 3 CTAs per SM (32 registers, 66 KB of shared memory each): the gathers are dependent shared-memory
+// loads, and 8 warps per CTA left each scheduler with two warps in a CTA's compute phase
 template <bool kSmem>
-__global__ void __launch_bounds__(256) rot_sample_fwd_kernel(
+__global__ void __launch_bounds__(512, 3) rot_sample_fwd_kernel(
     const float* __restrict__ img, const float* __restrict__ cs, float sgn, int C, int H, int W,
     float* __restrict__ out) {
   extern __shared__ __align__(16) float s_img[];
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(256) rot_sample_fwd_kernel(
 // of the tile.  One 66 KB tile instead of image + accumulator side by side keeps 3 CTAs per SM resident.
 // kSmem = false (image larger than shared memory): taps from global memory, global atomics on a pre-zeroed gimg.
 template <bool kSmem>
-__global__ void __launch_bounds__(256) rot_sample_bwd_kernel(
+__global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
     const float* __restrict__ img, const float* __restrict__ cs, float sgn,
     const float* __restrict__ gout, int C, int H, int W, float* __restrict__ gimg,
     float* __restrict__ gcs) {
@@ -418,9 +420,9 @@ extern "C" int livae_rot_sample_fwd(const float* img, const float* cs, float sgn
       cudaFuncSetAttribute(rot_sample_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kMaxSmemImage);
     }
-    rot_sample_fwd_kernel<true><<<B * C, 256, bytes, st>>>(img, cs, sgn, C, H, W, out);
+    rot_sample_fwd_kernel<true><<<B * C, 512, bytes, st>>>(img, cs, sgn, C, H, W, out);
   } else {
-    rot_sample_fwd_kernel<false><<<B * C, 256, 0, st>>>(img, cs, sgn, C, H, W, out);
+    rot_sample_fwd_kernel<false><<<B * C, 512, 0, st>>>(img, cs, sgn, C, H, W, out);
   }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;
@@ -442,13 +444,13 @@ extern "C" int livae_rot_sample_bwd(const float* img, const float* cs, float sgn
     cudaFuncSetAttribute(rot_sample_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
   }
   if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
-    rot_sample_bwd_kernel<true><<<B, 256, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+    rot_sample_bwd_kernel<true><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   } else {
     if (gimg) {
       cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)B * C * H * W * sizeof(float), st);
       if (e != cudaSuccess) { set_error("rot_sample_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    rot_sample_bwd_kernel<false><<<B, 256, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
+    rot_sample_bwd_kernel<false><<<B, 512, 0, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   }
   LIVAE_CUDA_LAUNCH_CHECK();
   return 0;

@@ -391,19 +391,40 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
   }
 }
 
-// out[i] = part[0][i] + part[1][i] + ... + part[nslices-1][i]: the fixed-order second pass of a reduction that was
-// split over CTAs (bit-reproducible, unlike red.global.add whose commit order follows CTA retirement)
-__global__ void sum_slices_kernel(const float* __restrict__ part, int nslices, int64_t n, float* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float a = part[i];
-    for (int z = 1; z < nslices; ++z) a += part[(int64_t)z * n + i];
-    out[i] = a;
+// out[i] = sum over slices z of part[z][i]: the fixed-order second pass of a reduction that was split over CTAs
+// (bit-reproducible, unlike red.global.add whose commit order follows CTA retirement).  `lanes` (a power of two
+// <= 32) threads share one element: lane l adds slices l, l + lanes, ... with four independent accumulators (the
+// loads of a serial `a += part[z]` chain would each wait a full L2 round trip), then the lanes are combined by a
+// shuffle tree -- the association is a function of (nslices, lanes) only.
+__global__ void sum_slices_kernel(const float* __restrict__ part, int nslices, int64_t n, float* __restrict__ out, int lanes) {
+  const int64_t total = n * lanes;           // every thread of a block runs the same number of iterations (full-mask shuffles)
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gtid = base + threadIdx.x;
+    const int64_t i = gtid / lanes;
+    const int l = (int)(gtid - i * lanes);
+    const bool live = i < n;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (live) {
+      int z = l;
+      for (; z + 3 * lanes < nslices; z += 4 * lanes) {
+        a0 += part[(int64_t)z * n + i];
+        a1 += part[(int64_t)(z + lanes) * n + i];
+        a2 += part[(int64_t)(z + 2 * lanes) * n + i];
+        a3 += part[(int64_t)(z + 3 * lanes) * n + i];
+      }
+      for (; z < nslices; z += lanes) a0 += part[(int64_t)z * n + i];
+    }
+    float a = (a0 + a1) + (a2 + a3);
+    for (int o = lanes >> 1; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o, lanes);
+    if (live && l == 0) out[i] = a;
   }
 }
 void sum_slices(const float* part, int nslices, int64_t n, float* out, cudaStream_t st) {
-  int64_t blocks = (n + 255) / 256;
+  int lanes = 1;
+  while (lanes < 32 && n * lanes < 16384 && lanes * 8 <= nslices) lanes <<= 1;    // few elements, many slices: share them
+  int64_t blocks = (n * lanes + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  sum_slices_kernel<<<(int)blocks, 256, 0, st>>>(part, nslices, n, out);
+  sum_slices_kernel<<<(int)blocks, 256, 0, st>>>(part, nslices, n, out, lanes);
   count_launch(1);
 }
 

@@ -63,6 +63,7 @@ _SIGS = {
     "livae_conv_bwd": "d" + "p" * 8 + "s",
     "livae_tc_pack_weights": "piiiiiips",
     "livae_permute_linear_grad": "piiips",
+    "livae_linear_dgrad": "pppiiips",
     "livae_thin_conv1c_fwd": "ipppiiipps",
     "livae_thin_conv1c_wgrad": "ipppiiipps",
     "livae_thin_conv1c_dgrad": "ppiiips",

@@ -55,8 +55,13 @@ def _linear_bwd(x2d, w, Cb, kh, kw, g_bf, Npad, relu_mask):
     gw = _empty((N, K), torch.float32, w.device)
     call("livae_permute_linear_grad", gw_hwc, N, Cb, kh * kw, gw)
     wp = ops.tc_pack_weights(w, N, Cb, kh, kw, 4, Cs_pad=Npad).view(1, K, Npad)
-    gx = ops.tc_conv(g_bf.view(B, 1, 1, Npad), wp, None, 1, 1, 1, 0, ACT_NONE, out_f32=False,
-                     relu_mask=relu_mask.view(B, 1, 1, K) if relu_mask is not None else None).view(B, K)
+    if Npad <= 64 and K % 8 == 0:
+        # J = Npad <= 64: writing B x K and reading the mask is the whole cost -> coalesced skinny kernel (csrc/skinny.cu)
+        gx = _empty((B, K), BF, w.device)
+        call("livae_linear_dgrad", g_bf, wp, relu_mask, B, K, Npad, gx)
+    else:
+        gx = ops.tc_conv(g_bf.view(B, 1, 1, Npad), wp, None, 1, 1, 1, 0, ACT_NONE, out_f32=False,
+                         relu_mask=relu_mask.view(B, 1, 1, K) if relu_mask is not None else None).view(B, K)
     return gw, gb[:N].contiguous(), gx
 
 

@@ -58,7 +58,17 @@ def get_rotation_stats(rotations: torch.Tensor) -> tuple[float, float]:
     return torch.mean(angles).item(), torch.std(angles).item()
 
 
+def _on_device(*ts):
+    """metric helpers accept host tensors like the reference's (tests, notebooks): they are staged to the current CUDA
+    device -- the arithmetic still runs in the kernels, there is no CPU implementation"""
+    if all(t.is_cuda for t in ts):
+        return ts
+    dev = next((t.device for t in ts if t.is_cuda), None) or torch.device("cuda", torch.cuda.current_device())
+    return tuple(t.to(dev) for t in ts)
+
+
 def _psnr_dev(img1, img2, max_val: float = 1.0):
+    img1, img2 = _on_device(img1.detach().float().contiguous(), img2.detach().float().contiguous())
     mse = ops.elbo_sums(img1, img2)[0] / img1.numel()
     return 20.0 * torch.log10(max_val / torch.sqrt(mse))
 
@@ -74,7 +84,7 @@ def _ssim_dev(img1, img2, window_size: int = 11, C1: float = 0.01 ** 2, C2: floa
     """mean box-filter SSIM map (reference train.py:606-667) as one fused pass over the two batches
     (csrc/ssim.cu) instead of five avg_pool2d passes and a dozen elementwise kernels; device scalar."""
     from ._lib import call, lib
-    a = img1.detach().contiguous().float(); b = img2.detach().contiguous().float()
+    a, b = _on_device(img1.detach().contiguous().float(), img2.detach().contiguous().float())
     ops.require_cuda(a, b)
     assert a.shape == b.shape and a.dim() == 4
     planes, H, W = a.shape[0] * a.shape[1], a.shape[2], a.shape[3]

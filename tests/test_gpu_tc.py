@@ -201,3 +201,23 @@ def test_dgrad_stride2_block_form(B, H, Cin, Cout):
     gx = ops.dgrad_s2blk(nhwc(g).cuda().to(torch.bfloat16), w.cuda(), H, H, relu_mask=mask)
     want = nhwc(x.grad) * (mask.float().cpu() > 0)
     assert rel_l2(gx.float().cpu(), want) < 5e-3, rel_l2(gx.float().cpu(), want)
+
+
+@pytest.mark.parametrize("B,K,J", [(70, 1024, 32), (33, 520, 16), (256, 4096, 64), (5, 8, 16)])
+def test_linear_dgrad_skinny_kernel(B, K, J):
+    """csrc/skinny.cu: gx = (mask > 0) * (g @ w^T) for the wide Linear layers, against fp32 matmul of the same bf16
+    operands; ragged B / K (not multiples of the 32 x 512 block tile)"""
+    from livae._lib import call
+    g = torch.Generator(device="cuda").manual_seed(B + K + J)
+    gg = torch.randn(B, J, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(K, J, device="cuda", generator=g) / J ** 0.5).to(torch.bfloat16)
+    mask = torch.randn(B, K, device="cuda", generator=g).clamp_min(0).to(torch.bfloat16)
+    out = torch.full((B, K), 7.0, device="cuda", dtype=torch.bfloat16)
+    call("livae_linear_dgrad", gg, w, mask, B, K, J, out)
+    want = (gg.float() @ w.float().t()) * (mask.float() > 0)
+    assert float((out.float() - want).abs().max()) <= 1e-2 * float(want.abs().max())
+    assert bool(((out.float() == 0) | (mask.float() > 0)).all())
+    out2 = torch.empty_like(out)
+    call("livae_linear_dgrad", gg, w, None, B, K, J, out2)
+    want2 = gg.float() @ w.float().t()
+    assert float((out2.float() - want2).abs().max()) <= 1e-2 * float(want2.abs().max())
