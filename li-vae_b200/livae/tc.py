@@ -39,6 +39,22 @@ def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
+def _heads_cat(muw, mub, lvw, lvb, Npad):
+    """[fc_mu; fc_logvar] as ONE weight [2L, K] and one zero-padded bias [Npad], cached per optimiser epoch like the
+    packed weights (ops._packed): the concatenation, the bias fill and both bf16 packs of the result used to be redone
+    by every encoder pass (two per step)"""
+    Ld = muw.shape[0]
+
+    def make():
+        wcat = torch.cat([muw.detach(), lvw.detach()], 0)
+        bcat = torch.zeros(Npad, dtype=torch.float32, device=muw.device)
+        bcat[:Ld] = mub.detach(); bcat[Ld:2 * Ld] = lvb.detach()
+        return wcat, bcat
+
+    others = tuple(v for t in (lvw, mub, lvb) for v in (id(t), t._version, t.data_ptr()))
+    return ops._packed(muw, ("heads", Npad) + others, make)
+
+
 def _linear_fwd(x2d, w, Cb, kh, kw, bias_pad, Npad, act, out_f32=True):
     """nn.Linear over an NHWC-flattened map as a 1x1 tensor-core convolution; x2d bf16 [B, kh*kw*Cb]"""
     B, K = x2d.shape
@@ -118,9 +134,7 @@ class EncoderTc(Function):
         h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
         # --- heads (model.py:302-303, 321-324): one GEMM for [fc_mu; fc_logvar]
         Npad = _pad_heads(2 * Ld)
-        wcat = torch.cat([muw, lvw], 0)
-        bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
-        bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb
+        wcat, bcat = _heads_cat(muw, mub, lvw, lvb, Npad)
         mulv = _linear_fwd(h4.view(B, -1), wcat, 256, q16, q16, bcat, Npad, ACT_NONE)
         mu = mulv[:, :Ld].contiguous(); logvar = mulv[:, Ld:2 * Ld].contiguous()
         ctx.save_for_backward(x, w0, w3, w7, w9, c0w, c2w, c4w, c6w, wcat, a1, idx1, a2, idx2, f1, vec, cs, x_rot,
@@ -296,9 +310,7 @@ class VAEEncoderTc(Function):
         h3 = ops.tc_conv(h2, ops.tc_pack_weights(c4w, 128, 64, 4, 4, 0), c4b, 4, 4, 2, 1, ACT_RELU)
         h4 = ops.tc_conv(h3, ops.tc_pack_weights(c6w, 256, 128, 4, 4, 0), c6b, 4, 4, 2, 1, ACT_RELU)
         Npad = _pad_heads(2 * Ld)
-        wcat = torch.cat([muw, lvw], 0)
-        bcat = torch.zeros(Npad, dtype=torch.float32, device=dev)
-        bcat[:Ld] = mub; bcat[Ld:2 * Ld] = lvb
+        wcat, bcat = _heads_cat(muw, mub, lvw, lvb, Npad)
         mulv = _linear_fwd(h4.view(B, -1), wcat, 256, q16, q16, bcat, Npad, ACT_NONE)
         ctx.save_for_backward(x, c2w, c4w, c6w, wcat, h1, h2, h3, h4)
         ctx.dims = (B, P, Ld, Npad)
