@@ -272,12 +272,12 @@ class _ElboSumsFn(Function):
     @staticmethod
     def forward(ctx, recon, x, mu, logvar):
         recon = _c(recon); x = _c(x)
-        require_cuda(recon, x, mu, logvar)
-        assert recon.numel() == x.numel()
         n_lat = 0
         if mu is not None:
-            mu = _c(mu); logvar = _c(logvar)
+            mu = _c(mu); logvar = _c(logvar)        # heads of foreign models may be strided slices of one tensor
             n_lat = mu.numel()
+        require_cuda(recon, x, mu, logvar)
+        assert recon.numel() == x.numel()
         sums = torch.empty(2, dtype=torch.float32, device=x.device)
         scratch = _get_scratch(x.device, "elbo", L.lib().livae_elbo_scratch_floats())
         call("livae_elbo_fwd", recon, x, recon.numel(), mu, logvar, n_lat, sums, scratch)
@@ -501,7 +501,7 @@ def _packed(w, key, make):
         return ent[4]
     out = make()
     try:
-        ref = weakref.ref(w, lambda _r, k=k: _PACKS.pop(k, None))
+        ref = weakref.ref(w, lambda _r, k=k, d=_PACKS: d.pop(k, None))
     except TypeError:
         return out
     _PACKS[k] = (ref, w._version, WEIGHT_EPOCH[0], w.data_ptr(), out)

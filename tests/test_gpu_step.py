@@ -395,12 +395,17 @@ def test_flat_adamw_matches_torch_adamw_with_lazy_gradient_packing():
         o_ref.step(); o_mine.step()
         for a, b in zip(ref, mine):
             assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), k
-    # a parameter that received no gradient: its slice of the flat buffer is zero (documented deviation: the flat
-    # update then treats it as a zero gradient, torch.optim would skip the tensor)
+    # a parameter that received no gradient: like torch.optim it keeps grad None and is skipped by the update (no
+    # weight decay, no moment decay); its slice of the flat gradient buffer is zero so the global norm ignores it
     o_mine.zero_grad()
     loss_of(mine, 0, True).backward()
     o_mine.sync_grads()
-    assert float(mine[-1].grad.abs().max()) == 0.0 and float(mine[0].grad.abs().max()) > 0.0
+    assert mine[-1].grad is None and float(mine[0].grad.abs().max()) > 0.0
+    off = o_mine._offs[-1]
+    assert float(o_mine.flat_grad[off:off + mine[-1].numel()].abs().max()) == 0.0
+    before = mine[-1].detach().clone()
+    o_mine.step()
+    assert torch.equal(mine[-1], before)
 
 
 @pytest.mark.tc_engine

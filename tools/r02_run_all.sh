@@ -17,6 +17,14 @@ python tools/ncu_times.py $O/${T}_ncu_launches_bench_step.csv > $O/${T}_ncu_laun
 echo "== ncu full capture of the top families"
 timeout 1200 ncu --set full --clock-control none --import-source on \
   -k regex:'conv1_wgrad_fold|upconv_c1|rot_sample|upsample_pad_bwd|upsample_pad_fwd|conv_tc_halo|conv1c_tc|elbo' \
-  --launch-skip 150 -c 70 -o $O/${T}_top python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e > $O/${T}_ncu_full.log 2>&1
+  --launch-skip 150 -c 45 -o $O/${T}_top python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e > $O/${T}_ncu_full.log 2>&1
 ncu -i $O/${T}_top.ncu-rep --page raw --csv > $O/${T}_ncu_full_top.csv 2>/dev/null
-python tools/ncu_extract.py $O/${T}_ncu_full_top.csv > $O/${T}_ncu_full_top.txt 2>&1; head -40 $O/${T}_ncu_full_top.txt | cut -c1-220
+python tools/ncu_extract.py $O/${T}_ncu_full_top.csv > $O/${T}_ncu_full_top.txt 2>&1; head -50 $O/${T}_ncu_full_top.txt | cut -c1-220
+rm -f $O/${T}_top.ncu-rep        # tens of MB with --import-source; gpurun copies back at most 64 MiB
+python - <<PY
+import csv
+rows = list(csv.reader(open("$O/${T}_ncu_full_top.csv")))
+keep = [i for i, h in enumerate(rows[0]) if any(s in h for s in ("Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput", "sm__pipe_tensor", "sm__inst_issued", "sm__warps_active", "launch__registers", "lts__t_sector_hit_rate", "sm__throughput", "l1tex__data_bank_conflicts", "smsp__inst_executed.sum", "launch__occupancy"))]
+csv.writer(open("$O/${T}_ncu_full_top_selected.csv", "w")).writerows([[r[i] for i in keep] for r in rows if len(r) >= len(rows[0])])
+PY
+rm -f $O/${T}_ncu_full_top.csv
