@@ -148,17 +148,21 @@ __device__ __forceinline__ float unnorm(float g, float fn) {
   const float u = ((g + 1.f) * fn - 1.f) * 0.5f;
   return (u + 0.5f) - 0.5f;               // fabs / reflect of ATen on an in-range coordinate: same two roundings
 }
+// Warp-cooperative and exact: lanes 0..3 each map one corner of the warp's 32x4 block through the SAME coordinate
+// arithmetic as the pixels (an affine map sends the block onto a parallelogram: corners inside => everything inside),
+// one vote decides for the warp.  Must be called by all 32 lanes.  (A test on the distance from the centre is
+// cheaper still but can never pass for the two outer 32-pixel column blocks of a 128-wide image -- half the blocks.)
 __device__ __forceinline__ bool block_interior(int i0, int j0, float c, float s, int H, int W, float invH, float invW) {
-  // A rotation about the centre preserves the distance from the centre (square images: the normalised axes scale
-  // alike), so the block is interior when its farthest corner lies inside the circle of radius (n-1)/2 around
-  // the centre -- independent of the angle, a handful of instructions per block.
-  if (H != W) return false;
-  const float half = 0.5f * (float)W;
-  const float xa = fabsf((float)j0 + 0.5f - half), xb = fabsf((float)min(j0 + 31, W - 1) + 0.5f - half);
-  const float ya = fabsf((float)i0 + 0.5f - half), yb = fabsf((float)min(i0 + 3, H - 1) + 0.5f - half);
-  const float dx = fmaxf(xa, xb), dy = fmaxf(ya, yb);
-  const float r = half - 0.52f;                 // (n-1)/2 minus a 0.02 px guard for the rounding of the coordinate
-  return dx * dx + dy * dy < r * r;
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  if (lane < 4) {
+    const int i = (lane & 2) ? min(i0 + 3, H - 1) : i0, j = (lane & 1) ? min(j0 + 31, W - 1) : j0;
+    const float ys = (2.f * (float)i + 1.f) * invH - 1.f, xs = (2.f * (float)j + 1.f) * invW - 1.f;
+    const float fw = (float)W, fh = (float)H;
+    const float ix = unnorm(fmaf(c, xs, -(s * ys)), fw), iy = unnorm(fmaf(s, xs, c * ys), fh);
+    ok = ix > 0.01f && ix < fw - 1.01f && iy > 0.01f && iy < fh - 1.01f;      // 1e-2 px guard for rounding
+  }
+  return __all_sync(0xffffffffu, ok);
 }
 struct FastTaps { int o00; float fx, fy; };
 __device__ __forceinline__ FastTaps make_taps_interior(float xs, float gxr, float gyr, float c, float s, float fh, float fw,
@@ -211,11 +215,12 @@ __global__ void __launch_bounds__(512, 3) rot_sample_fwd_kernel(
   const bool vec_ok = (W & 3) == 0 && (((uintptr_t)dst) & 15) == 0;
   for (BlockWalk w(H, W); w.valid(); w.next()) {
     const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+    const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
     if (i >= H || j0 >= W) continue;
     const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
     const float gxr = -(s * ys), gyr = c * ys;
     float o[4];
-    if (block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW)) {        // warp-uniform
+    if (interior && j0 + 3 < W) {
       const float jf = small_int_to_float(j0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -281,13 +286,14 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
       const float* tap = kSmem ? s_tile : src;
       for (BlockWalk w(H, W); w.valid(); w.next()) {
         const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+        const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
         if (i >= H || j0 >= W) continue;
         const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
         const float gxr = -(s * ys), gyr = c * ys;
         float g4[4] = {0.f, 0.f, 0.f, 0.f};
         if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4*>(go + i * W + j0)); g4[0] = q.x; g4[1] = q.y; g4[2] = q.z; g4[3] = q.w; }
         else for (int k = 0; k < 4 && j0 + k < W; ++k) g4[k] = __ldg(go + i * W + j0 + k);
-        if (block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW) && j0 + 3 < W) {      // (first term warp-uniform)
+        if (interior && j0 + 3 < W) {
           const float jf = small_int_to_float(j0);
           float bc = 0.f, bs = 0.f;            // multx = W/2, multy = H/2 are applied once per block
 #pragma unroll
@@ -333,13 +339,14 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
       }
       for (BlockWalk w(H, W); w.valid(); w.next()) {
         const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
+        const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
         if (i >= H || j0 >= W) continue;
         const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
         const float gxr = -(s * ys), gyr = c * ys;
         float g4[4] = {0.f, 0.f, 0.f, 0.f};
         if (vec_ok) { const float4 q = __ldg(reinterpret_cast<const float4*>(go + i * W + j0)); g4[0] = q.x; g4[1] = q.y; g4[2] = q.z; g4[3] = q.w; }
         else for (int k = 0; k < 4 && j0 + k < W; ++k) g4[k] = __ldg(go + i * W + j0 + k);
-        if (block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW) && j0 + 3 < W) {
+        if (interior && j0 + 3 < W) {
           const float jf = small_int_to_float(j0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
