@@ -137,8 +137,13 @@ __device__ __forceinline__ void fetch_taps(const float* __restrict__ tap, const 
   }
 }
 
+// Warp block shape: kBW x kBH pixels, lane = 4 consecutive pixels of one row.  16 x 8 rather than 32 x 4: a block that
+// touches the image border is never interior (border pixels rotate outside), and with 32-pixel-wide blocks half the
+// blocks of a 128-wide image touch the left or right border; 16 x 8 leaves 2 of 8 column blocks and 2 of 16 row blocks.
+// A row segment of a warp's store is 64 bytes (two full 32-byte sectors).
+static constexpr int kBW = 16, kBH = 128 / kBW, kBLX = kBW / 4;
 // ---- interior fast path -------------------------------------------------------------------------------------------
-// A rotation about the patch centre maps a 32x4 block of output pixels onto a rotated rectangle; when its four
+// A rotation about the patch centre maps a warp's block of output pixels onto a rotated rectangle; when its four
 // corners land inside [0, n-1] so does every pixel of it (convexity), and then reflect + clip are the identity on
 // the coordinate (mult = +n/2) and all four taps are in range.  The per-pixel work shrinks from ~75 to ~40
 // instructions: the kernels are issue-bound, not HBM-bound, so this is what moves them towards the copy rate.  The
@@ -148,7 +153,7 @@ __device__ __forceinline__ float unnorm(float g, float fn) {
   const float u = ((g + 1.f) * fn - 1.f) * 0.5f;
   return (u + 0.5f) - 0.5f;               // fabs / reflect of ATen on an in-range coordinate: same two roundings
 }
-// Warp-cooperative and exact: lanes 0..3 each map one corner of the warp's 32x4 block through the SAME coordinate
+// Warp-cooperative and exact: lanes 0..3 each map one corner of the warp's block through the SAME coordinate
 // arithmetic as the pixels (an affine map sends the block onto a parallelogram: corners inside => everything inside),
 // one vote decides for the warp.  Must be called by all 32 lanes.  (A test on the distance from the centre is
 // cheaper still but can never pass for the two outer 32-pixel column blocks of a 128-wide image -- half the blocks.)
@@ -156,7 +161,7 @@ __device__ __forceinline__ bool block_interior(int i0, int j0, float c, float s,
   const int lane = threadIdx.x & 31;
   bool ok = true;
   if (lane < 4) {
-    const int i = (lane & 2) ? min(i0 + 3, H - 1) : i0, j = (lane & 1) ? min(j0 + 31, W - 1) : j0;
+    const int i = (lane & 2) ? min(i0 + kBH - 1, H - 1) : i0, j = (lane & 1) ? min(j0 + kBW - 1, W - 1) : j0;
     const float ys = (2.f * (float)i + 1.f) * invH - 1.f, xs = (2.f * (float)j + 1.f) * invW - 1.f;
     const float fw = (float)W, fh = (float)H;
     const float ix = unnorm(fmaf(c, xs, -(s * ys)), fw), iy = unnorm(fmaf(s, xs, c * ys), fh);
@@ -175,11 +180,11 @@ __device__ __forceinline__ FastTaps make_taps_interior(float xs, float gxr, floa
   return t;
 }
 
-// Walks the image in 32x4-pixel warp blocks (lane = 4 consecutive pixels of one row), warps round-robin.
+// Walks the image in kBW x kBH-pixel warp blocks, warps round-robin.
 struct BlockWalk {
   int bx, by, bw, bh, nwarps;
   __device__ __forceinline__ BlockWalk(int H, int W) {
-    bw = (W + 31) >> 5; bh = (H + 3) >> 2; nwarps = blockDim.x >> 5;
+    bw = (W + kBW - 1) / kBW; bh = (H + kBH - 1) / kBH; nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     by = warp / bw; bx = warp - by * bw;
   }
@@ -211,11 +216,11 @@ __global__ void __launch_bounds__(512, 3) rot_sample_fwd_kernel(
   const float invW = 1.f / (float)W, invH = 1.f / (float)H;
   const float fw = (float)W, fh = (float)H;
   const int lane = threadIdx.x & 31;
-  const int lx = lane & 7, ly = lane >> 3;
+  const int lx = lane % kBLX, ly = lane / kBLX;
   const bool vec_ok = (W & 3) == 0 && (((uintptr_t)dst) & 15) == 0;
   for (BlockWalk w(H, W); w.valid(); w.next()) {
-    const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
-    const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
+    const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
+    const bool interior = block_interior(w.by * kBH, w.bx * kBW, c, s, H, W, invH, invW);   // all lanes vote
     if (i >= H || j0 >= W) continue;
     const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
     const float gxr = -(s * ys), gyr = c * ys;
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
   const float invW = 1.f / (float)W, invH = 1.f / (float)H;
   const float fw = (float)W, fh = (float)H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int lx = lane & 7, ly = lane >> 3;
+  const int lx = lane % kBLX, ly = lane / kBLX;
   const int pitch = kSmem ? tile_pitch(W) : W;
   float acc_c = 0.f, acc_s = 0.f;
   for (int ch = 0; ch < C; ++ch) {
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
       }
       const float* tap = kSmem ? s_tile : src;
       for (BlockWalk w(H, W); w.valid(); w.next()) {
-        const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
-        const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
+        const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
+        const bool interior = block_interior(w.by * kBH, w.bx * kBW, c, s, H, W, invH, invW);   // all lanes vote
         if (i >= H || j0 >= W) continue;
         const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
         const float gxr = -(s * ys), gyr = c * ys;
@@ -338,8 +343,8 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
         __syncthreads();
       }
       for (BlockWalk w(H, W); w.valid(); w.next()) {
-        const int i = w.by * 4 + ly, j0 = w.bx * 32 + lx * 4;
-        const bool interior = block_interior(w.by * 4, w.bx * 32, c, s, H, W, invH, invW);   // all lanes vote
+        const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
+        const bool interior = block_interior(w.by * kBH, w.bx * kBW, c, s, H, W, invH, invW);   // all lanes vote
         if (i >= H || j0 >= W) continue;
         const float ys = (2.f * small_int_to_float(i) + 1.f) * invH - 1.f;
         const float gxr = -(s * ys), gyr = c * ys;

@@ -39,7 +39,21 @@ elif case == "wgrad_d3":
 elif case == "wgrad_d1":
     x = torch.randn(B, 18, 18, 256, device=dev).to(bf); g = torch.randn(B, 16, 16, 128, device=dev).to(bf)
     run = lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)
+if case.startswith("dg_") or case.startswith("fw_"):
+    # generic: dg_/fw_<Cin>_<Cout>_<k>_<stride>_<pad>_<Hin>
+    _, ci, co, k, st, pd, hin = case.split("_"); ci, co, k, st, pd, hin = map(int, (ci, co, k, st, pd, hin))
+    ho = (hin + 2 * pd - k) // st + 1
+    wt = torch.randn(co, ci, k, k, device=dev)
+    if case.startswith("dg_"):
+        g = torch.randn(B, ho, ho, co, device=dev).to(bf); wp = ops.tc_pack_weights(wt, co, ci, k, k, 2)
+        run = lambda: ops.tc_conv_dgrad(g, wp, None, hin, hin, k, k, st, pd)
+    else:
+        x = torch.randn(B, hin, hin, ci, device=dev).to(bf); wp = ops.tc_pack_weights(wt, co, ci, k, k, 0)
+        run = lambda: ops.tc_conv(x, wp, None, k, k, st, pd, 1)
 run(); torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+print(f"--- {case}: {e0.elapsed_time(e1):.3f} ms untraced")
 buf = torch.zeros(4096, dtype=torch.int64, device=dev)
 L.livae_set_probe(buf.data_ptr())
 run(); torch.cuda.synchronize()
