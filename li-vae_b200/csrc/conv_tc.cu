@@ -282,10 +282,8 @@ struct ConvTcHaloParams {
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
   long long* probe;
   int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
-  uint32_t stage_off;     // != 0: byte offset (from the aligned shared-memory base) of the 4 x 4 KB epilogue staging tiles
 };
 
-static int g_epi_staged = 1;   // livae_tc_set_halo_mode bit 1 clears it (A/B comparisons)
 static constexpr int kSA = 2, kSAmax = 4, kSB = 4;   // A ring: kSA..kSAmax slots (p.nsa), as many as fit without costing a resident CTA
 
 // Epilogue of one accumulator row per thread, 32 columns per pass: both tcgen05.ld and the ReLU-mask loads
@@ -344,66 +342,6 @@ __device__ __forceinline__ void epilogue_rows32(uint32_t taddr, int nbase, int N
         o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
-  }
-}
-
-// bf16 epilogue through shared memory.  With one accumulator row (= one output pixel) per thread, a warp's store
-// instruction touched 32 different 128-byte lines with 16 bytes each; the probe (tools/probe.py) showed the epilogue,
-// not the MMAs, setting the pace of the N <= 128 layers (4.5 k cycles per 128-pixel tile against 0.9-2 k of MMA
-// issue on the d3 data gradient: ~1 k scattered 16-byte stores per tile through the LSU).  Here every thread drops
-// its row (up to 64 channels = 128 bytes per pass) into a per-warp 4 KB tile, XOR-swizzled by row so that both the
-// row-wise writes and the transposed reads are conflict-free, and the warp then stores pixel rows as whole 128-byte
-// (64-channel passes) or 64-byte (32-channel pass) segments; the consumer's ReLU mask is read the same way.
-__device__ __forceinline__ void epilogue_rows_staged(uint32_t taddr, int nbase, int N, int Ntot, bool valid, int64_t pix,
-                                                     __nv_bfloat16* __restrict__ out, const float* __restrict__ sbias, int act,
-                                                     const __nv_bfloat16* __restrict__ relu_mask, uint8_t* __restrict__ stage,
-                                                     int lane) {
-  const uint32_t sw = (uint32_t)lane & 7u;
-  for (int cc = 0; cc < N; cc += 64) {
-    const int ncol = (N - cc) < 64 ? (N - cc) : 64;          // 64 or 32 (N is 32 or a multiple of 64)
-    for (int sub = 0; sub < ncol; sub += 32) {
-      uint32_t v[32];
-      tmem_ld16(taddr + (uint32_t)(cc + sub), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-      tmem_ld16(taddr + (uint32_t)(cc + sub) + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a0 = __uint_as_float(v[8 * j + 2 * i]) + sbias[cc + sub + 8 * j + 2 * i];
-          float a1 = __uint_as_float(v[8 * j + 2 * i + 1]) + sbias[cc + sub + 8 * j + 2 * i + 1];
-          if (act == LIVAE_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-          else if (act == LIVAE_ACT_SIGMOID) { a0 = 1.f / (1.f + __expf(-a0)); a1 = 1.f / (1.f + __expf(-a1)); }
-          __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
-          w[i] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        const uint32_t chunk = (uint32_t)((sub >> 3) + j);
-        *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-    __syncwarp();
-    const int lpr = ncol >> 3;                 // lanes per pixel row: 8 (128-byte segments) or 4 (64-byte segments)
-    const int rpi = 32 / lpr;                  // pixel rows per store instruction
-    const int c = lane % lpr, rsub = lane / lpr;
-    for (int k = 0; k < 32 / rpi; ++k) {
-      const int r = k * rpi + rsub;
-      uint4 w = *reinterpret_cast<const uint4*>(stage + r * 128 + ((((uint32_t)c) ^ ((uint32_t)r & 7u)) << 4));
-      const long long pr = __shfl_sync(0xffffffffu, (long long)pix, r);
-      const int vr = __shfl_sync(0xffffffffu, valid ? 1 : 0, r);
-      if (!vr) continue;
-      const int64_t off = pr * Ntot + nbase + cc + c * 8;
-      if (relu_mask) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(relu_mask + off));
-        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m);
-        __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(&w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (!(__bfloat162float(mb[i]) > 0.f)) wb[i] = __float2bfloat16_rn(0.f);
-      }
-      *reinterpret_cast<uint4*>(out + off) = w;
-    }
-    __syncwarp();
   }
 }
 
@@ -691,11 +629,7 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
       };
       if (EPI == 0) {
         wait_acc();
-        if (p.stage_off)
-          epilogue_rows_staged(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, reinterpret_cast<__nv_bfloat16*>(p.out),
-                               s_bias, p.act, p.relu_mask, smem + p.stage_off + (uint32_t)q * 4096u, lane);
-        else
-          epilogue_rows32(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
+        epilogue_rows32(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
       } else if (EPI == 1) {
         wait_acc();
         epilogue_pool4(taddr, p.N, valid, ((int64_t)b * p.Hq + qy) * p.Wq + qx, p.out, p.pool_idx, s_bias);
@@ -906,9 +840,6 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   size_t smem = (size_t)kSA * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot + 1024;
   if (smem > 200 * 1024) return 1;
   p.nsa = kSA;
-  // coalescing epilogue (bf16 NHWC store, plain mode): 4 warps x 4 KB of staging after the operand rings
-  const bool staged = g_epi_staged && opts.epi_mode == 0 && !out_f32 && (p.N == 32 || p.N % 64 == 0) && smem + 16 * 1024 <= 200 * 1024;
-  if (staged) smem += 16 * 1024;
   static OncePerDevice attr_done;
   if (attr_done.first()) {
     cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -929,7 +860,6 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   // deepen the A ring while the same number of CTAs still fits (two slots leave the producer one box ahead
   // at most: the MMA warp waited 400-900 cycles per box for TMA latency)
   while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= 200 * 1024) { smem += a_slot; ++p.nsa; }
-  p.stage_off = staged ? (uint32_t)((size_t)p.nsa * a_slot + (size_t)(p.b_resident ? ntaps * p.nkc : kSB) * b_slot) : 0u;
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
   const dim3 grid(gx, N / p.N);
@@ -1144,5 +1074,4 @@ extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, 
 extern "C" void livae_set_probe(void* dev_ptr) { g_probe = (long long*)dev_ptr; }
 
 // tuning / test hook: 0 = per-tap boxes only, 1 = halo kernel where eligible
-// bit 1 set (mode 3): halo kernel with the direct (un-staged) epilogue, for A/B comparisons of the coalescing epilogue
-extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = (mode & 1) ? 1 : 0; g_epi_staged = (mode & 2) ? 0 : 1; }
+extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; }
