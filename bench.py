@@ -343,11 +343,19 @@ def check_dp(args, device, rank, world, dist):
     if rank == 0:
         opt1 = run(solo, torch.arange(B, device=device), lambda o: None)
         gd = float((opt.flat_grad - opt1.flat_grad).norm() / opt1.flat_grad.norm())
-        pd = float((opt.flat_param - opt1.flat_param).abs().max())
+        dparam = (opt.flat_param - opt1.flat_param).abs()
+        # Adam's first update is lr * g / (|g| + eps): where |g| is within a few eps (1e-8) of zero -- dead units -- the
+        # update is decided by summation-order noise (2e-9 absolute here) on BOTH sides, so those elements are reported
+        # separately and the parameter comparison is made where the update is a function of the gradient
+        live = opt1.flat_grad.abs() > 1e-6
+        pd = float(dparam[live].max())
         res = {"ranks": world, "global_batch": B, "grad_rel_l2_after_clip": gd, "param_max_abs_diff_after_adamw": pd,
-               "ok": bool(gd < 5e-3 and pd < 2e-5),
+               "param_max_abs_diff_incl_adam_eps_regime": float(dparam.max()),
+               "adam_eps_regime_fraction": float(1.0 - live.float().mean()),
+               "ok": bool(gd < 1e-4 and pd < 1e-5),
                "note": "same kernels per sample; the difference is fp32 summation order of the weight-gradient partial "
-                       "sums (bf16 storage is per sample and identical on both sides)"}
+                       "sums (bf16 storage is per sample and identical on both sides).  Parameters are compared on the "
+                       "elements with |g| > 1e-6 after clipping; elsewhere lr*g/(|g|+1e-8) amplifies 1e-9 noise to O(lr)"}
     dist.barrier()
     return res
 
