@@ -105,9 +105,6 @@ int livae_rot_sample_fwd(const float* img, const float* cs, float sgn, int B, in
  * not accumulated; already multiplied by sgn for the sin component). */
 int livae_rot_sample_bwd(const float* img, const float* cs, float sgn, const float* gout,
                          int B, int C, int H, int W, float* gimg, float* gcs, livae_stream_t stream);
-/* test / tuning hook: 0 = general kernels only; 1 (default) = the reflect-padded-tile kernels for square
- * single-channel images (branch-free taps; csrc/rot_sample.cu) */
-void livae_rot_sample_set_mode(int mode);
 
 /* ---- a4 tail: rotation head ------------------------------------------------------------
  * F.normalize(vec, eps=1e-6) -> (cos, sin); theta = atan2(sin, cos)   (model.py:245-261) */

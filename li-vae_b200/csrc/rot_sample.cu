@@ -413,224 +413,7 @@ __global__ void __launch_bounds__(512, 2) rot_sample_bwd_kernel(
 
 static constexpr int kMaxSmemImage = 200 * 1024;  // bytes of one staged image / gradient tile
 
-// =====================================================================================================================
-// Reflect-padded tile variant (square single-channel images, the model's case).
-//
-// grid_sample's "reflection" padding followed by its clip to [0, n-1] is exactly bilinear sampling of the image
-// extended SYMMETRICALLY (index -k -> k-1, n-1+k -> n-k): a coordinate in (-0.5, 0) lands between tile pixels -1 and
-// 0, both copies of pixel 0 (the clipped value, zero coordinate gradient), a coordinate further out between the
-// mirrored pixels with the mirrored weights (the sign flip of the coordinate gradient comes out of the tap difference).
-// A rotation about the centre moves a pixel at most 0.2072 n beyond the border, so with a tile padded by
-// pad = 0.2072 n + 2 EVERY output pixel takes the branch-free path: unnormalise, floor, four unconditional taps --
-// ~40 instructions instead of ~100 for the reflect / clip / predicated-tap path, which the border blocks (half the
-// blocks of a 128-wide image) otherwise take.  The kernels were issue-bound at 81 % issue-slot utilisation (ncu), so
-// the instruction count is what sets their time.  One persistent CTA per SM (padded tile 136 KB + a 64 KB landing
-// buffer at n = 128): image i+1 arrives by cp.async while image i is being sampled.
-// The backward scatter accumulates into the padded tile too and folds the halo back (<= 2 x 2 tile positions per pixel)
-// when it writes grad_input: still no global atomics, one coalesced write.
-// =====================================================================================================================
-static constexpr int kPadThreads = 512;
-__host__ __device__ __forceinline__ int rs_pad(int n) { return (int)(0.2072f * (float)n) + 2; }
-__device__ __forceinline__ int mirror(int t, int n) { return t < 0 ? -t - 1 : (t >= n ? 2 * n - 1 - t : t); }
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ void land_image(float* __restrict__ S, const float* __restrict__ src, int n) {
-  for (int i = threadIdx.x; i < (n * n) >> 2; i += blockDim.x) cp_async16(S + 4 * i, src + 4 * i);
-  cp_async_commit();
-}
-// T[(n + 2 pad) x pitch] = symmetric extension of the n x n image in S
-__device__ __forceinline__ void build_padded(float* __restrict__ T, const float* __restrict__ S, int n, int pad, int pitch) {
-  const int np = n + 2 * pad, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int ty = warp; ty < np; ty += nw) {
-    const float* srow = S + mirror(ty - pad, n) * n;
-    float* trow = T + ty * pitch;
-    for (int tx = lane; tx < np; tx += 32) trow[tx] = srow[mirror(tx - pad, n)];
-  }
-}
-struct PadTaps { int o; float fx, fy; };
-// branch-free taps in the padded tile; fpad = (float)pad.  Same unnormalisation as ATen: ((g + 1) n - 1) / 2.
-__device__ __forceinline__ PadTaps pad_taps(float xs, float gxr, float gyr, float c, float s, float fn, int pad, int pitch) {
-  PadTaps t;
-  const float ux = ((fmaf(c, xs, gxr) + 1.f) * fn - 1.f) * 0.5f, uy = ((fmaf(s, xs, gyr) + 1.f) * fn - 1.f) * 0.5f;
-  const int x0 = __float2int_rd(ux), y0 = __float2int_rd(uy);
-  // (float)x0 without the conversion pipe: x0 + pad >= 0 is a small integer (see small_int_to_float)
-  const float fpad = small_int_to_float(pad);
-  t.fx = ux - (small_int_to_float(x0 + pad) - fpad); t.fy = uy - (small_int_to_float(y0 + pad) - fpad);
-  t.o = (y0 + pad) * pitch + (x0 + pad);
-  return t;
-}
-
-__global__ void __launch_bounds__(kPadThreads, 1) rot_sample_fwd_pad_kernel(const float* __restrict__ img, const float* __restrict__ cs,
-                                                                           float sgn, int nimg, int n, float* __restrict__ out) {
-  extern __shared__ __align__(16) float sm[];
-  const int pad = rs_pad(n), np = n + 2 * pad, pitch = np | 1;
-  float* S = sm;                       // landing buffer, 16-byte aligned
-  float* T = sm + n * n;
-  const float fn = (float)n, inv = 1.f / fn;
-  const int lane = threadIdx.x & 31;
-  const int lx = lane % kBLX, ly = lane / kBLX;
-  int im = blockIdx.x;
-  if (im >= nimg) return;
-  land_image(S, img + (int64_t)im * n * n, n);
-  for (; im < nimg; im += gridDim.x) {
-    cp_async_wait_all();
-    __syncthreads();                   // S complete; everybody is done with the previous image's T
-    build_padded(T, S, n, pad, pitch);
-    __syncthreads();
-    if (im + (int)gridDim.x < nimg) land_image(S, img + (int64_t)(im + gridDim.x) * n * n, n);
-    const float c = cs[2 * im], s = sgn * cs[2 * im + 1];
-    float* dst = out + (int64_t)im * n * n;
-    for (BlockWalk w(n, n); w.valid(); w.next()) {
-      const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
-      if (i >= n || j0 >= n) continue;
-      const float ys = (2.f * (float)i + 1.f) * inv - 1.f;
-      const float gxr = -(s * ys), gyr = c * ys;
-      const float jf = (float)j0;
-      float o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float xs = (2.f * (jf + (float)k) + 1.f) * inv - 1.f;
-        const PadTaps t = pad_taps(xs, gxr, gyr, c, s, fn, pad, pitch);
-        const float* q = T + t.o;
-        const float v00 = q[0], v01 = q[1], v10 = q[pitch], v11 = q[pitch + 1];
-        const float ax = 1.f - t.fx, ay = 1.f - t.fy;
-        o[k] = v00 * (ax * ay) + v01 * (t.fx * ay) + v10 * (ax * t.fy) + v11 * (t.fx * t.fy);
-      }
-      *reinterpret_cast<float4*>(dst + i * n + j0) = make_float4(o[0], o[1], o[2], o[3]);      // n % 4 == 0
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kPadThreads, 1) rot_sample_bwd_pad_kernel(const float* __restrict__ img, const float* __restrict__ cs,
-                                                                           float sgn, const float* __restrict__ gout, int nimg,
-                                                                           int n, float* __restrict__ gimg, float* __restrict__ gcs) {
-  extern __shared__ __align__(16) float sm[];
-  __shared__ float red[2][32];
-  const int pad = rs_pad(n), np = n + 2 * pad, pitch = np | 1;
-  float* S = sm;
-  float* T = sm + n * n;
-  const float fn = (float)n, inv = 1.f / fn, half = 0.5f * fn;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int lx = lane % kBLX, ly = lane / kBLX;
-  int im = blockIdx.x;
-  if (im >= nimg) return;
-  if (gcs) land_image(S, img + (int64_t)im * n * n, n);
-  for (; im < nimg; im += gridDim.x) {
-    const float c = cs[2 * im], s = sgn * cs[2 * im + 1];
-    const float* go = gout + (int64_t)im * n * n;
-    if (gcs) {
-      cp_async_wait_all();
-      __syncthreads();
-      build_padded(T, S, n, pad, pitch);
-      __syncthreads();
-      if (im + (int)gridDim.x < nimg) land_image(S, img + (int64_t)(im + gridDim.x) * n * n, n);
-      float acc_c = 0.f, acc_s = 0.f;
-      for (BlockWalk w(n, n); w.valid(); w.next()) {
-        const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
-        if (i >= n || j0 >= n) continue;
-        const float ys = (2.f * (float)i + 1.f) * inv - 1.f;
-        const float gxr = -(s * ys), gyr = c * ys;
-        const float jf = (float)j0;
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(go + i * n + j0));
-        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-        float bc = 0.f, bs = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float xs = (2.f * (jf + (float)k) + 1.f) * inv - 1.f;
-          const PadTaps t = pad_taps(xs, gxr, gyr, c, s, fn, pad, pitch);
-          const float* q = T + t.o;
-          const float v00 = q[0], v01 = q[1], v10 = q[pitch], v11 = q[pitch + 1];
-          const float gix = (-(1.f - t.fy) * v00 + (1.f - t.fy) * v01 - t.fy * v10 + t.fy * v11) * gg[k];
-          const float giy = (-(1.f - t.fx) * v00 - t.fx * v01 + (1.f - t.fx) * v10 + t.fx * v11) * gg[k];
-          bc += gix * xs + giy * ys;           // affine_grid backward: base_grid^T @ grad_grid for [[c,-s],[s,c]]
-          bs += -gix * ys + giy * xs;
-        }
-        acc_c += bc; acc_s += bs;
-      }
-      acc_c = warp_sum(acc_c) * half;          // d(ix)/d(gx) = n / 2 everywhere on the extended image
-      acc_s = warp_sum(acc_s) * half;
-      if (lane == 0) { red[0][warp] = acc_c; red[1][warp] = acc_s; }
-      __syncthreads();
-      if (warp == 0) {
-        float a = lane < nwarps ? red[0][lane] : 0.f, d = lane < nwarps ? red[1][lane] : 0.f;
-        a = warp_sum(a); d = warp_sum(d);
-        if (lane == 0) { gcs[2 * im] = a; gcs[2 * im + 1] = sgn * d; }
-      }
-    }
-    if (gimg) {
-      __syncthreads();                 // phase A (and its `red` exchange) is over: T becomes the accumulator
-      for (int k = threadIdx.x; k < np * pitch; k += blockDim.x) T[k] = 0.f;
-      __syncthreads();
-      for (BlockWalk w(n, n); w.valid(); w.next()) {
-        const int i = w.by * kBH + ly, j0 = w.bx * kBW + lx * 4;
-        if (i >= n || j0 >= n) continue;
-        const float ys = (2.f * (float)i + 1.f) * inv - 1.f;
-        const float gxr = -(s * ys), gyr = c * ys;
-        const float jf = (float)j0;
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(go + i * n + j0));
-        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float xs = (2.f * (jf + (float)k) + 1.f) * inv - 1.f;
-          const PadTaps t = pad_taps(xs, gxr, gyr, c, s, fn, pad, pitch);
-          float* q = T + t.o;
-          const float ax = 1.f - t.fx, ay = 1.f - t.fy, g = gg[k];
-          atomicAdd(q, ax * ay * g);
-          atomicAdd(q + 1, t.fx * ay * g);
-          atomicAdd(q + pitch, ax * t.fy * g);
-          atomicAdd(q + pitch + 1, t.fx * t.fy * g);
-        }
-      }
-      __syncthreads();
-      // fold the halo back: pixel (y, x) collects its own tile position and the mirrored ones
-      float* gi = gimg + (int64_t)im * n * n;
-      const int nq = n >> 2;
-      for (int k = threadIdx.x; k < n * nq; k += blockDim.x) {
-        const int y = k / nq, x0 = (k - y * nq) << 2;
-        int rows[2]; int nr = 1;
-        rows[0] = y + pad;
-        if (y < pad) rows[nr++] = pad - 1 - y;
-        else if (y >= n - pad) rows[nr++] = 2 * n - 1 - y + pad;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int x = x0 + e;
-          int cols[2]; int nc = 1;
-          cols[0] = x + pad;
-          if (x < pad) cols[nc++] = pad - 1 - x;
-          else if (x >= n - pad) cols[nc++] = 2 * n - 1 - x + pad;
-          float a = 0.f;
-          for (int r = 0; r < nr; ++r)
-            for (int q = 0; q < nc; ++q) a += T[rows[r] * pitch + cols[q]];
-          o[e] = a;
-        }
-        *reinterpret_cast<float4*>(gi + y * n + x0) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-      // (the next iteration's first __syncthreads orders these reads before T is rebuilt)
-      if (!gcs) __syncthreads();
-    }
-  }
-}
-
-static size_t pad_smem_bytes(int n) {
-  const int pad = rs_pad(n), np = n + 2 * pad, pitch = np | 1;
-  return ((size_t)n * n + (size_t)np * pitch) * sizeof(float);
-}
-static bool pad_path_ok(int C, int H, int W, const void* a, const void* b) {
-  return C == 1 && H == W && (W & 3) == 0 && W >= 8 && 2 * rs_pad(W) < W && pad_smem_bytes(W) <= 220 * 1024 &&
-         (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
-}
-static int g_rs_pad = 1;
-
 }  // namespace livae
-
-// test / tuning hook: 0 = general kernels only, 1 = reflect-padded tile kernels where eligible (default)
-extern "C" void livae_rot_sample_set_mode(int mode) { livae::g_rs_pad = mode ? 1 : 0; }
 
 static size_t tile_bytes(int H, int W) { return (size_t)(H + 1) * livae::tile_pitch(W) * sizeof(float); }
 
@@ -643,11 +426,7 @@ extern "C" int livae_rot_sample_fwd(const float* img, const float* cs, float sgn
   if (int e = require_sm100()) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = tile_bytes(H, W);
-  if (g_rs_pad && pad_path_ok(C, H, W, img, out)) {
-    static OncePerDevice pad_attr;
-    if (pad_attr.first()) cudaFuncSetAttribute(rot_sample_fwd_pad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    rot_sample_fwd_pad_kernel<<<B < kNumSMs ? B : kNumSMs, kPadThreads, pad_smem_bytes(W), st>>>(img, cs, sgn, B, W, out);
-  } else if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
+  if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
     static OncePerDevice attr_done;
     if (attr_done.first()) {
       cudaFuncSetAttribute(rot_sample_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -676,11 +455,7 @@ extern "C" int livae_rot_sample_bwd(const float* img, const float* cs, float sgn
   if (attr_done.first()) {
     cudaFuncSetAttribute(rot_sample_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemImage);
   }
-  if (g_rs_pad && pad_path_ok(C, H, W, img, gout) && (((uintptr_t)gimg) & 15) == 0) {
-    static OncePerDevice pad_attr;
-    if (pad_attr.first()) cudaFuncSetAttribute(rot_sample_bwd_pad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    rot_sample_bwd_pad_kernel<<<B < kNumSMs ? B : kNumSMs, kPadThreads, pad_smem_bytes(W), st>>>(img, cs, sgn, gout, B, W, gimg, gcs);
-  } else if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
+  if (bytes <= (size_t)kMaxSmemImage && ((uintptr_t)img & 15) == 0) {
     rot_sample_bwd_kernel<true><<<B, 512, bytes, st>>>(img, cs, sgn, gout, C, H, W, gimg, gcs);
   } else {
     if (gimg) {

@@ -145,8 +145,6 @@ def lib():
     L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_ssim_box_ws_floats.restype = C.c_int64
     L.livae_ssim_box_ws_floats.argtypes = [C.c_int64, C.c_int]
-    L.livae_rot_sample_set_mode.restype = None
-    L.livae_rot_sample_set_mode.argtypes = [C.c_int]
     L.livae_set_scratch.restype = C.c_int
     L.livae_set_scratch.argtypes = [C.c_void_p, C.c_int64]
     L.livae_conv_out_shape.restype = None
@@ -163,7 +161,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_rot_sample_set_mode", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
 
 
 def ptr(t):

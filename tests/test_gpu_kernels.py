@@ -412,36 +412,3 @@ def test_ssim_box_matches_reference_formula(shape, win):
     got = _ssim_dev(a.cuda(), b.cuda(), win).item()
     assert abs(got - want) < 2e-5, (got, want)
     assert abs(_ssim_dev(a.cuda(), a.cuda(), win).item() - 1.0) < 1e-5
-
-
-def test_rot_sample_padded_tile_kernels_match_general_kernels(ops):
-    """the reflect-padded-tile kernels (square single-channel images) against the general reflect / clip kernels on
-    the same inputs: forward, grad_input and the (cos, sin) gradients, incl. angles that push corners 26 px outside"""
-    from livae._lib import call, lib
-    L = lib()
-    for n, B in ((128, 9), (32, 5), (16, 4)):
-        g = torch.Generator(device="cuda").manual_seed(n)
-        x = torch.rand(B, 1, n, n, device="cuda", generator=g)
-        go = torch.randn(B, 1, n, n, device="cuda", generator=g)
-        th = torch.tensor([0.0, np.pi / 4, 0.3, -2.2, np.pi / 2, 3.0, -0.785, 1.0, 5.5])[:B].cuda()
-        cs = torch.stack([torch.cos(th), torch.sin(th)], 1).contiguous()
-        res = {}
-        for mode in (0, 1):
-            L.livae_rot_sample_set_mode(mode)
-            for sgn in (1.0, -1.0):
-                out = torch.empty_like(x); gx = torch.empty_like(x); gcs = torch.empty(B, 2, device="cuda")
-                gcs_only = torch.empty(B, 2, device="cuda"); gx_only = torch.empty_like(x)
-                call("livae_rot_sample_fwd", x, cs, sgn, B, 1, n, n, out)
-                call("livae_rot_sample_bwd", x, cs, sgn, go, B, 1, n, n, gx, gcs)
-                call("livae_rot_sample_bwd", x, cs, sgn, go, B, 1, n, n, None, gcs_only)
-                call("livae_rot_sample_bwd", x, cs, sgn, go, B, 1, n, n, gx_only, None)
-                res[(mode, sgn)] = (out, gx, gcs, gcs_only, gx_only)
-        L.livae_rot_sample_set_mode(1)
-        for sgn in (1.0, -1.0):
-            a, b = res[(0, sgn)], res[(1, sgn)]
-            assert float((a[0] - b[0]).abs().max()) < 2e-5
-            assert float((a[1] - b[1]).abs().max()) < 1e-4 * max(1.0, float(a[1].abs().max()))
-            gen = [i for i in range(B) if i not in (0, 4)]        # multiples of pi/2 sit on derivative discontinuities
-            assert rel_l2(b[2][gen].cpu(), a[2][gen].cpu()) < 1e-4
-            assert torch.equal(b[2], b[3]) or rel_l2(b[3].cpu(), b[2].cpu()) < 1e-6
-            assert float((b[4] - b[1]).abs().max()) < 1e-5 * max(1.0, float(b[1].abs().max()))
