@@ -28,7 +28,7 @@ from . import ops
 __all__ = [
     "train_one_epoch", "evaluate", "train_rvae_one_epoch", "evaluate_rvae", "rotate_to_canonical",
     "evaluate_rotation_invariance", "log_reconstructions_tensorboard", "compute_atom_position_accuracy",
-    "log_scalar_metrics_tensorboard", "rvae_step_loss", "train_rvae_step", "MetricLogger", "compute_psnr",
+    "log_scalar_metrics_tensorboard", "rvae_step_loss", "train_rvae_step", "GraphedRvaeStep", "MetricLogger", "compute_psnr",
     "compute_ssim", "get_rotation_stats",
 ]
 
@@ -286,6 +286,75 @@ def train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight
     pre = _clip_and_norm(model, optimizer, max_norm)
     optimizer.step()
     return x, loss, recon_l, kld_l, cycle_l, can_l, outs, pre
+
+
+class GraphedRvaeStep:
+    """`train_rvae_step` as two CUDA graphs (forward + loss + backward + gradient packing | clip + AdamW), replayed per
+    batch.  One training step is ~190 kernel launches issued from Python (4-5 ms of host time): irrelevant at 2048
+    patches per GPU (18 ms of GPU work) but the whole cost at 256 (2.5 ms of GPU work), the strong-scaling case of
+    SURVEY 8e.  The gradient all-reduce (`reduce_grads`) runs eagerly between the two graphs.  Needs
+    livae.optim.FlatAdamW (its flat buffers are the static memory the second graph works on) and batches of one fixed
+    shape; the first call captures (after two warm-up runs whose effect on parameters and optimiser state is undone).
+    Returns what train_rvae_step returns; the tensors are static graph memory, valid until the next call."""
+
+    def __init__(self, model, optimizer, criterion, device, canonical_weight: float = 0.2, max_norm: float = 20.0,
+                 reduce_grads=None, elide_dead_encoder: bool = False):
+        if getattr(optimizer, "flat_grad", None) is None:
+            raise ValueError("GraphedRvaeStep needs livae.optim.FlatAdamW")
+        self.model, self.opt, self.crit, self.device = model, optimizer, criterion, torch.device(device)
+        self.cw, self.max_norm, self.reduce, self.elide = canonical_weight, max_norm, reduce_grads, elide_dead_encoder
+        self.g_fwd = self.g_opt = None
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad()
+        out = rvae_step_loss(self.model, self.crit, self.sx, self.sxr, self.sang, self.cw, self.elide)
+        out[0].backward()
+        self.opt.sync_grads()
+        return out
+
+    def _update(self):
+        pre = _clip_and_norm(self.model, self.opt, self.max_norm)
+        self.opt.step()
+        return pre
+
+    def _capture(self, x, xr, ang):
+        o = self.opt
+        self.sx, self.sxr, self.sang = x.clone(), xr.clone(), ang.clone()
+        keep = [t.clone() for t in (o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_dev)]
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd()
+                if self.reduce is not None:
+                    self.reduce()
+                self._update()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.g_fwd, self.g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            self.outs = self._fwd_bwd()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
+            self.pre = self._update()
+        for dst, src in zip((o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_dev), keep):     # undo warm-up + capture
+            dst.copy_(src)
+        ops.invalidate_weight_packs()
+
+    def __call__(self, batch):
+        x, xr, ang = _unpack_rvae_batch(batch, self.device)
+        if xr is None or ang is None:
+            raise ValueError("GraphedRvaeStep: paired batches (x, x_rotated, angle) only")
+        if self.g_fwd is None:
+            self._capture(x, xr, ang)
+        elif x.shape != self.sx.shape:
+            raise ValueError("GraphedRvaeStep: batch shape changed (drop_last=True keeps it fixed)")
+        self.sx.copy_(x); self.sxr.copy_(xr); self.sang.copy_(ang)
+        self.g_fwd.replay()
+        if self.reduce is not None:
+            self.reduce()
+        self.g_opt.replay()
+        ops.invalidate_weight_packs()          # the replay changed the parameters; eager code must re-pack
+        loss, recon_l, kld_l, cycle_l, can_l, outs = self.outs
+        return self.sx, loss, recon_l, kld_l, cycle_l, can_l, outs, self.pre
 
 
 def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger, device,

@@ -429,3 +429,41 @@ def test_elided_dead_encoder_gives_identical_step():
     assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
     for k in res[0][2]:
         assert rel_l2(res[0][2][k].cpu(), res[1][2][k].cpu()) < 1e-5, k
+
+
+@pytest.mark.tc_engine
+def test_cuda_graph_step_equals_eager_step():
+    """livae.train.GraphedRvaeStep (two CUDA graphs replayed per batch) trains exactly like train_rvae_step: same
+    losses and, after three steps on three different batches, the same parameters; the warm-up runs of the capture
+    leave no trace in the parameters or the optimiser state"""
+    import copy
+    import livae
+    from livae.optim import FlatAdamW
+    from livae.train import GraphedRvaeStep, train_rvae_step
+    P, L, B, seed = 32, 2, 16, 77
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    batches = [tuple(t.cuda() for t in O.make_lattice_batch(B, P, seed=seed + 1 + k)) for k in range(3)]
+    eps = torch.from_numpy(np.random.default_rng(seed).standard_normal((B, L))).float().cuda()
+    dev = torch.device("cuda")
+    results = []
+    for graphed in (False, True):
+        m = _rvae(P, L, params)
+        opt = FlatAdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)
+        crit = livae.RVAELoss(beta=10.0, gamma=10.0)
+        step = GraphedRvaeStep(m, opt, crit, dev, 0.2, 20.0) if graphed else None
+        losses = []
+        orig = torch.randn_like
+        torch.randn_like = lambda t, **k: eps.reshape(t.shape)            # device-resident: nothing to copy under capture
+        try:
+            for b in batches:
+                out = step(b) if graphed else train_rvae_step(m, opt, crit, b, dev, 0.2, 20.0)
+                losses.append(float(out[1]))
+        finally:
+            torch.randn_like = orig
+        results.append((losses, copy.deepcopy({k: v.detach().cpu() for k, v in m.state_dict().items()}), float(opt.step_dev)))
+    (l0, p0, s0), (l1, p1, s1) = results
+    assert s0 == s1 == 3.0
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a), (l0, l1)
+    for k in p0:
+        assert float((p0[k] - p1[k]).abs().max()) <= 2e-5, k
