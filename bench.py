@@ -259,6 +259,15 @@ def describe_call(name, a):
         macs = d.B * ho * wo * d.Cout * d.kh * d.kw * d.Cin
         key = f"{name[6:]}[{d.Cin}->{d.Cout} k{d.kh} s{d.stride} {d.Hin}x{d.Win}]"
         return key, 2.0 * macs, by
+    if name.startswith("livae_tc_conv5pool_") and name[19:] in ("fwd", "dgrad", "wgrad"):
+        # STN conv2 in space-to-depth form (csrc/conv_s2d.cu): a tensor-core GEMM; 5x5x(Ci->Co) MACs per input pixel
+        ints = [v for v in a if isinstance(v, int)]
+        Bb, H, W, Ci, Co = ints[:5]
+        return name[6:], 2.0 * Bb * H * W * Ci * Co * 25, by
+    if name == "livae_tc_dgrad_s2blk":
+        ints = [v for v in a if isinstance(v, int)]
+        Bb, Hin, Win, Cin, Cout = ints[:5]
+        return name[6:], 2.0 * Bb * (Hin // 2) * (Win // 2) * Cin * Cout * 16, by
     if name.startswith("livae_thin_conv"):
         ints = [v for v in a if isinstance(v, int)]
         return f"{name[6:]}[{','.join(str(v) for v in ints[:4])}]", 0.0, by
