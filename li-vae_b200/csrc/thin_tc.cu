@@ -61,15 +61,21 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // A. 1 -> C forward
 // =============================================================================================
 template <int KIND> struct FwdCfg;
-// STN conv1: 5x5 p2, ReLU, 2x2 max-pool.  K order (ky, kx padded to 6): 30 -> 32
+// STN conv1: 5x5 p2, ReLU, 2x2 max-pool.  One A row per POOLED pixel = its 6x6 input window (K = 36 -> 48, three
+// K steps of a 128-byte row); the N = 64 columns are (pool position, channel) with the 5x5 filter placed at the
+// position's offset inside the window, so the A row is the window exactly as it lies in the staged image (18 words,
+// no shifts) and one tile is 6 MMAs instead of 16.
 // F16: operands in fp16 instead of bf16 -- the image is in [0, 1] (min-max normalised patches, data.py:553-558)
 // and the filter weights are O(1), so fp16's 11-bit mantissa costs nothing in range and rounds the image 8x finer.
-template <> struct FwdCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, KW2 = 6, KPAD = 32, POOL = 1, FLIP = 0, RELU = 1, F16 = 1 }; };
+// WLO: a second weight tile holding the rounding residual (w ~= hi + lo, exact to ~2^-17).  Off for the two layers
+// whose output is stored as bf16 (8-bit mantissa): fp16 weights (2^-11) sit below that rounding and below the fp16
+// image they multiply, and the residual tile doubled the MMA count and cost the fourth A slot its shared memory.
+template <> struct FwdCfg<0> { enum { C = 16, KS = 5, S = 1, PAD = 2, KW2 = 6, KPAD = 64, POOL = 1, FLIP = 0, RELU = 1, F16 = 1, WLO = 0 }; };
 // encoder c1: 4x4 s2 p1, ReLU.  K = 16
-template <> struct FwdCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 0, RELU = 1, F16 = 1 }; };
+template <> struct FwdCfg<1> { enum { C = 32, KS = 4, S = 2, PAD = 1, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 0, RELU = 1, F16 = 1, WLO = 0 }; };
 // data gradient of decoder d4 (3x3 p0): full correlation with the flipped filter, pad 2.  K (ky, kx padded to 4): 12 -> 16
 // (bf16: the image here is a gradient of arbitrary scale)
-template <> struct FwdCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 1, RELU = 0, F16 = 0 }; };
+template <> struct FwdCfg<2> { enum { C = 32, KS = 3, S = 1, PAD = 2, KW2 = 4, KPAD = 16, POOL = 0, FLIP = 1, RELU = 0, F16 = 0, WLO = 1 }; };
 
 struct FwdParams {
   const float* img; const float* w; const float* bias;
@@ -79,52 +85,71 @@ struct FwdParams {
   void* out; uint8_t* idx;
 };
 
-// Warp roles (288 threads): warp 0 = MMA issuer, warps 1-4 = builders (one A row per thread), warps 5-8 =
-// epilogue.  NS {A tile, TMEM accumulator} slots with full/empty mbarriers keep the three roles on
-// different tiles at once: a tile's latency chain (gather -> fence -> MMA -> tcgen05.ld -> stores) is
-// long compared with its work, so throughput comes from overlapping tiles, not from any single step.
-static constexpr int kFwdThreads = 288;
+// Warp roles (416 threads): warp 0 = MMA issuer, warps 1-8 = builders (one A row per thread) in two groups that take
+// alternate tiles, warps 9-12 = epilogue.  Cycle accounting of the round-2 kernel (one builder group): the issuer
+// waited for an A tile 53 % of the time and the epilogue for an accumulator 58 %; a builder's chain per tile (shared
+// loads -> wait -> swizzled stores -> proxy fence -> arrive) is ~1200 cycles of latency for ~100 instructions, and
+// staging the next image (scattered 4-byte loads with a division per word) took a third of the kernel.  Hence two
+// builder groups, and staging by all eight builder warps as coalesced row loads with 12 requests in flight per
+// thread from an image the issuer warp has already pulled into L2.
+static constexpr int kFwdThreads = 416;
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 
 template <int KIND>
-__global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1c_tc_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 2) conv1c_tc_kernel(const FwdParams p) {
   using Cfg = FwdCfg<KIND>;
   constexpr int C = Cfg::C, KS = Cfg::KS, PAD = Cfg::PAD, KW2 = Cfg::KW2, KPAD = Cfg::KPAD;
   constexpr bool POOL = Cfg::POOL != 0;
-  constexpr uint32_t RB = KPAD * 2;                 // bytes per A / W row (64 or 32)
-  constexpr int NSUB = POOL ? 4 : 1;
-  constexpr int NCOL = NSUB * C;                    // TMEM columns per accumulator
-  constexpr uint32_t A_SUB = 128u * RB;
-  constexpr uint32_t A_BUF = NSUB * A_SUB;
-  constexpr int NS = POOL ? 2 : 4;                  // pipeline slots
+  constexpr uint32_t RB = KPAD * 2;                 // bytes per A / W row (128, 64 or 32)
+  constexpr int NCOL = POOL ? 4 * C : C;            // TMEM columns per accumulator = UMMA N
+  constexpr int KSTEPS = POOL ? 3 : KPAD / 16;      // pooled layer: K = 36 of the 64-element row
+  constexpr uint32_t A_BUF = 128u * RB;
+  constexpr uint32_t W_HALF = (uint32_t)NCOL * RB;  // bytes of one weight tile (hi or lo part)
+  constexpr int NS = 4;                             // A-tile slots (builders -> MMA); even: a slot keeps its builder group
+  constexpr int NT = 4;                             // TMEM accumulators (MMA -> epilogue)
+  constexpr int NHL = Cfg::WLO ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = NT * NCOL;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], t_full[NS], t_empty[NS];
+  __shared__ __align__(8) uint64_t a_full[NS], a_empty[NS], t_full[NT], t_empty[NT];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[32];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + NS * A_BUF;                    // two weight tiles: bf16 hi part, bf16 lo part (w ~= hi + lo)
-  uint32_t* simg32 = reinterpret_cast<uint32_t*>(sW + 4096);
+  uint8_t* sW = smem + NS * A_BUF;                    // weight tile(s): rounded weights [, rounding residual]
+  uint32_t* simg32 = reinterpret_cast<uint32_t*>(sW + NHL * W_HALF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pitch2 = p.pitch >> 1;
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NT; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(&tmem_base_s, NS * NCOL); tmem_relinquish(); }
-  // weight tile W[c][k], k = ky * KW2 + kx, zero in the padding slots
-  for (int i = tid; i < C * KPAD; i += kFwdThreads) {
-    const int c = i / KPAD, k = i % KPAD;
-    const int ky = k / KW2, kx = k % KW2;
+  if (warp == 0) { tmem_alloc(&tmem_base_s, TMEM_COLS); tmem_relinquish(); }
+  // weight tile W[n][k], k = ky * KW2 + kx, zero in the padding slots; pooled layer: n = (pool position, c) and the
+  // filter sits at the position's offset (dy, dx) inside the 6x6 window
+  for (int i = tid; i < NCOL * KPAD; i += kFwdThreads) {
+    const int n = i / KPAD, k = i % KPAD;
+    const int c = POOL ? (n & (C - 1)) : n;
+    const int ky = k / KW2 - (POOL ? (n / C) >> 1 : 0), kx = k % KW2 - (POOL ? (n / C) & 1 : 0);
     float v = 0.f;
-    if (ky < KS && kx < KS) {
+    if (k < KW2 * KW2 && ky >= 0 && ky < KS && kx >= 0 && kx < KS) {
       const int t = ky * KS + kx;
       v = p.w[c * KS * KS + (Cfg::FLIP ? KS * KS - 1 - t : t)];
     }
     const uint32_t hl = Cfg::F16 ? split_hi_lo_f16(v) : split_hi_lo(v);
-    const uint32_t o = swz_off((uint32_t)c, (uint32_t)k >> 3, RB) + (k & 7) * 2;
+    const uint32_t o = swz_off((uint32_t)n, (uint32_t)k >> 3, RB) + (k & 7) * 2;
     *reinterpret_cast<uint16_t*>(sW + o) = (uint16_t)(hl & 0xffffu);
-    *reinterpret_cast<uint16_t*>(sW + 2048 + o) = (uint16_t)(hl >> 16);
+    if (Cfg::WLO) *reinterpret_cast<uint16_t*>(sW + W_HALF + o) = (uint16_t)(hl >> 16);
+  }
+  if (POOL && warp >= 1 && warp <= 4) {      // K elements 40..47 of every A row: read by the third K step, never rewritten
+    for (int s = 0; s < NS; ++s)
+      *reinterpret_cast<uint4*>(sA + s * A_BUF + swz_off((uint32_t)(tid - 32), 5u, RB)) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid < 32) sbias[tid] = (p.bias && tid < C) ? p.bias[tid] : 0.f;
   fence_proxy_async();
@@ -141,60 +166,79 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
     {
       const bool leader = elect_one();
-      const uint32_t idesc = Cfg::F16 ? make_idesc_f16(128, C, 0, 0) : make_idesc_bf16(128, C, 0, 0);
-      const uint32_t lt = RB == 64 ? 4u : 6u;
+      const uint32_t idesc = Cfg::F16 ? make_idesc_f16(128, NCOL, 0, 0) : make_idesc_bf16(128, NCOL, 0, 0);
+      const uint32_t lt = RB == 128 ? 2u : RB == 64 ? 4u : 6u;
       const uint64_t ad0 = make_smem_desc(smem_u32(sA), 16u, 8u * RB, lt);
       const uint64_t bd0 = make_smem_desc(smem_u32(sW), 16u, 8u * RB, lt);
       uint32_t it = 0;
-      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+        if (img + (int)gridDim.x < p.B) {      // the builders stage the next image from L2 instead of HBM
+          const char* nx = reinterpret_cast<const char*>(p.img + (int64_t)(img + (int)gridDim.x) * p.H * p.W);
+          for (int l = lane; l < p.H * p.W * 4 / 128; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + l * 128));
+        }
         for (int tile = 0; tile < ntiles; ++tile, ++it) {
-          const uint32_t s = it % NS, ph = (it / NS) & 1u;
-          mbar_wait(&t_empty[s], ph ^ 1u);
-          mbar_wait(&a_full[s], ph);
+          const uint32_t s = it % NS, st = it % NT;
+          mbar_wait(&t_empty[st], ((it / NT) & 1u) ^ 1u);
+          mbar_wait(&a_full[s], (it / NS) & 1u);
           tc_fence_after();
 #pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub)
+          for (int hl = 0; hl < NHL; ++hl)                 // WLO: D = A * Whi^T + A * Wlo^T
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl)                 // D = A * Whi^T + A * Wlo^T: weights exact to ~2^-17
-#pragma unroll
-              for (int ks = 0; ks < KPAD / 16; ++ks)
-                if (leader) umma_f16(tmem_base + s * NCOL + (uint32_t)(sub * C), ad0 + ((s * A_BUF + sub * A_SUB + ks * 32u) >> 4),
-                                     bd0 + ((hl * 2048u + ks * 32u) >> 4), idesc, (ks | hl) > 0 ? 1u : 0u);
-          if (leader) { umma_commit(&a_empty[s]); umma_commit(&t_full[s]); }
-        }
-    }
-  } else if (warp <= 4) {
-    // ------------------------------------------------------------------ builders
-    const int bt = tid - 32;
-    uint32_t it = 0;
-    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // every builder is done reading the previous image
-      const float* im = p.img + (int64_t)img * p.H * p.W;
-      {
-        // 4 words (8 pixels) per thread per batch: all loads are issued before the first use
-        const int nw = p.Hs * pitch2;
-        for (int i0 = bt; i0 < nw; i0 += 128 * 4) {
-          float v0[4], v1[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = min(i0 + u * 128, nw - 1);
-            const int r = i / pitch2, c = (i - r * pitch2) * 2;
-            const int iy = r - PAD, ix = c - PAD;
-            const int iyc = min(max(iy, 0), p.H - 1);
-            const float a = __ldg(im + iyc * p.W + min(max(ix, 0), p.W - 1));
-            const float b = __ldg(im + iyc * p.W + min(max(ix + 1, 0), p.W - 1));
-            const bool oky = iy >= 0 && iy < p.H;
-            v0[u] = (oky && ix >= 0 && ix < p.W) ? a : 0.f;
-            v1[u] = (oky && ix + 1 >= 0 && ix + 1 < p.W) ? b : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (i0 + u * 128 < nw) simg32[i0 + u * 128] = Cfg::F16 ? pack_f16x2(v0[u], v1[u]) : pack_bf16x2(v0[u], v1[u]);
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              if (leader) umma_f16(tmem_base + st * NCOL, ad0 + ((s * A_BUF + ks * 32u) >> 4),
+                                   bd0 + ((hl * W_HALF + ks * 32u) >> 4), idesc, (ks | hl) > 0 ? 1u : 0u);
+          if (leader) { umma_commit(&a_empty[s]); umma_commit(&t_full[st]); }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  } else if (warp <= 8) {
+    // ------------------------------------------------------------------ builders
+    const int bw = warp - 1;
+    const uint32_t grp = (uint32_t)bw >> 2;               // tiles with it % 2 == grp
+    const int bt = (bw & 3) * 32 + lane;                  // A row of this thread
+    uint32_t it = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // every builder is done reading the previous image
+      const float* im = p.img + (int64_t)img * p.H * p.W;
+      // stage the zero-padded image as fp16 / bf16 pairs: one warp per row, consecutive lanes = consecutive words, the
+      // loads of four rows (12 per thread) are issued before the first use
+      for (int r0 = bw; r0 < p.Hs; r0 += 8 * 4) {
+        float va[4][3], vb[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + 8 * u, iy = r - PAD;
+          const bool rowok = r < p.Hs && iy >= 0 && iy < p.H;
+          const float* rp = im + (rowok ? iy : 0) * p.W;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int c = lane + 32 * k, ix = 2 * c - PAD;
+            float a = 0.f, b = 0.f;
+            if (rowok && c < pitch2) {
+              if ((PAD & 1) == 0) {                       // even padding: the pair is one aligned 8-byte load, in or out as a whole
+                if (ix >= 0 && ix < p.W) { const float2 t = __ldg(reinterpret_cast<const float2*>(rp + ix)); a = t.x; b = t.y; }
+              } else {
+                if (ix >= 0 && ix < p.W) a = __ldg(rp + ix);
+                if (ix + 1 >= 0 && ix + 1 < p.W) b = __ldg(rp + ix + 1);
+              }
+            }
+            va[u][k] = a; vb[u][k] = b;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + 8 * u;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int c = lane + 32 * k;
+            if (r < p.Hs && c < pitch2)
+              simg32[r * pitch2 + c] = Cfg::F16 ? pack_f16x2(va[u][k], vb[u][k]) : pack_bf16x2(va[u][k], vb[u][k]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       int pp = bt;                                        // this thread's pixel of the current tile
       for (int tile = 0; tile < ntiles; ++tile, ++it, pp += 128) {
+        if ((it & 1u) != grp) continue;
         const uint32_t s = it % NS;
         uint8_t* a_buf = sA + s * A_BUF;
         const int pc = pp < npx ? pp : npx - 1;           // rows past the end: any finite data
@@ -207,22 +251,12 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
 #pragma unroll
             for (int j = 0; j < 3; ++j) wd[i][j] = base[i * pitch2 + j];
           mbar_wait(&a_empty[s], ((it / NS) & 1u) ^ 1u);
+          const uint32_t* k = &wd[0][0];                     // the window IS the A row: 18 words, K index u * 6 + v
 #pragma unroll
-          for (int sb = 0; sb < 4; ++sb) {
-            const int dy = sb >> 1, dx = sb & 1;
-            uint32_t k[16];
-#pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
-              const uint32_t r0 = wd[dy + ky][0], r1 = wd[dy + ky][1], r2 = wd[dy + ky][2];
-              if (dx == 0) { k[ky * 3] = r0; k[ky * 3 + 1] = r1; k[ky * 3 + 2] = r2; }
-              else { k[ky * 3] = __funnelshift_r(r0, r1, 16); k[ky * 3 + 1] = __funnelshift_r(r1, r2, 16); k[ky * 3 + 2] = r2 >> 16; }
-            }
-            k[15] = 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(a_buf + sb * A_SUB + swz_off((uint32_t)bt, (uint32_t)j, RB)) =
-                  make_uint4(k[4 * j], k[4 * j + 1], k[4 * j + 2], k[4 * j + 3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)bt, (uint32_t)j, RB)) =
+                make_uint4(k[4 * j], k[4 * j + 1], k[4 * j + 2], k[4 * j + 3]);
+          *reinterpret_cast<uint4*>(a_buf + swz_off((uint32_t)bt, 4u, RB)) = make_uint4(k[16], k[17], 0u, 0u);
         } else if (KIND == 1) {
           const uint32_t* base = simg32 + (2 * gy) * pitch2 + gx;
           uint32_t k[8];
@@ -259,44 +293,48 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;                               // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    float bias_r[16];                                     // pooled layer only (the others read sbias)
-#pragma unroll
-    for (int c = 0; c < 16; ++c) bias_r[c] = sbias[c];
     uint32_t it = 0;
     for (int img = blockIdx.x; img < p.B; img += gridDim.x)
       for (int tile = 0; tile < ntiles; ++tile, ++it) {
-        const uint32_t s = it % NS;
+        const uint32_t s = it % NT;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s * NCOL;
         const int pp = tile * 128 + row;
         const bool valid = pp < npx;
-        mbar_wait(&t_full[s], (it / NS) & 1u);
+        mbar_wait(&t_full[s], (it / NT) & 1u);
         tc_fence_after();
         if (POOL) {
-          uint32_t v[4][16];
+          // two passes of 8 channels (4 pool positions x 8 columns each): 32 live accumulator registers
+          uint32_t ow[8]; uint32_t iw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int sb = 0; sb < 4; ++sb) tmem_ld16(taddr + (uint32_t)(sb * 16), v[sb]);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[s]);
-          if (valid) {
-            uint32_t ow[8]; uint32_t iw[4] = {0u, 0u, 0u, 0u};
+          for (int c0 = 0; c0 < 16; c0 += 8) {
+            uint32_t v[4][8];
 #pragma unroll
-            for (int c = 0; c < 16; c += 2) {
+            for (int sb = 0; sb < 4; ++sb) tmem_ld8(taddr + (uint32_t)(sb * 16 + c0), v[sb]);
+            tmem_ld_wait();
+            if (c0 == 8) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&t_empty[s]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
               float best[2]; uint32_t bi[2];
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const float b = bias_r[c + j];
-                best[j] = fmaxf(__uint_as_float(v[0][c + j]) + b, 0.f); bi[j] = 0u;
-#pragma unroll
-                for (int sb = 1; sb < 4; ++sb) {
-                  const float a = fmaxf(__uint_as_float(v[sb][c + j]) + b, 0.f);
-                  if (a > best[j]) { best[j] = a; bi[j] = (uint32_t)sb; }
-                }
+                // max-pool commutes with the shared bias and the ReLU: pool the raw sums (first maximum in scan
+                // order), then bias + ReLU once.  Where all four ReLU outputs tie at zero the reference reports
+                // position 0; the gradient there is removed by the ReLU mask either way.
+                const float v0 = __uint_as_float(v[0][c + j]), v1 = __uint_as_float(v[1][c + j]);
+                const float v2 = __uint_as_float(v[2][c + j]), v3 = __uint_as_float(v[3][c + j]);
+                const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                bi[j] = v0 == m ? 0u : v1 == m ? 1u : v2 == m ? 2u : 3u;
+                best[j] = fmaxf(m + sbias[c0 + c + j], 0.f);
               }
-              ow[c >> 1] = pack_bf16x2(best[0], best[1]);
-              iw[c >> 2] |= (bi[0] << ((c & 3) * 8)) | (bi[1] << (((c & 3) + 1) * 8));
+              ow[(c0 + c) >> 1] = pack_bf16x2(best[0], best[1]);
+              iw[(c0 + c) >> 2] |= (bi[0] << ((c & 3) * 8)) | (bi[1] << (((c & 3) + 1) * 8));
             }
+          }
+          if (valid) {
             const int64_t o = (int64_t)img * npx + pp;
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o * 16);
             op[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
@@ -329,7 +367,7 @@ __global__ void __launch_bounds__(kFwdThreads, FwdCfg<KIND>::POOL ? 2 : 3) conv1
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, NS * NCOL); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 template <int KIND>
@@ -341,16 +379,17 @@ static int launch_fwd(const float* img, const float* w, const float* bias, int B
   p.Hs = (Ho - 1) * Cfg::S + Cfg::KS;
   p.pitch = ((Wo - 1) * Cfg::S + Cfg::KW2 + 2 + 1) & ~1;
   p.out = out; p.idx = idx;
-  const int ns = Cfg::POOL ? 2 : 4;
-  const size_t a_buf = (size_t)(Cfg::POOL ? 4 : 1) * 128 * Cfg::KPAD * 2;
-  const size_t smem = 1024 + ns * a_buf + 4096 + (size_t)p.Hs * p.pitch * 2;
+  const int ns = 4;
+  const size_t a_buf = (size_t)128 * Cfg::KPAD * 2;
+  const size_t wbytes = (Cfg::WLO ? 2 : 1) * (size_t)(Cfg::POOL ? 4 : 1) * Cfg::C * Cfg::KPAD * 2;
+  const size_t smem = 1024 + ns * a_buf + wbytes + (size_t)p.Hs * p.pitch * 2;
   if (smem > 110 * 1024) return 1;
   static OncePerDevice attr;
   if (attr.first()) { cudaFuncSetAttribute(conv1c_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);}
   int occ = (int)((227 * 1024) / (smem + 1024));
-  const int occ_tmem = 512 / (ns * (Cfg::POOL ? 4 : 1) * Cfg::C);
+  const int occ_tmem = 512 / (4 * (Cfg::POOL ? 4 : 1) * Cfg::C);
   if (occ > occ_tmem) occ = occ_tmem;
-  if (occ > (Cfg::POOL ? 2 : 3)) occ = Cfg::POOL ? 2 : 3;
+  if (occ > 2) occ = 2;
   if (occ < 1) occ = 1;
   int grid = kNumSMs * occ;
   if (grid > B) grid = B;
@@ -363,6 +402,7 @@ int thin_tc_conv1c_fwd(int kind, const float* img, const float* w, const float* 
                        void* out_bf16, uint8_t* pool_idx, cudaStream_t st) {
   if ((H & 1) || (W & 1) || H < 4 || W < 4) return 1;
   if ((((uintptr_t)out_bf16 | (uintptr_t)pool_idx) & 15) != 0) return 1;
+  if (((uintptr_t)img & 7) != 0) return 1;       // the image rows are staged with 8-byte loads
   if (kind == 0) return launch_fwd<0>(img, w, bias, B, H, W, H, W, out_bf16, pool_idx, st);
   if (kind == 1) return launch_fwd<1>(img, w, bias, B, H, W, H / 2, W / 2, out_bf16, nullptr, st);
   return launch_fwd<2>(img, w, nullptr, B, H, W, H + 2, W + 2, out_bf16, nullptr, st);
@@ -912,21 +952,29 @@ static int launch_wg(const float* src, const void* big, const uint8_t* idx, int 
 // 256 MMAs per image instead of 1024, every one with all 128 accumulator rows useful, and an eighth of the
 // thread-side operand assembly of the tap-row formulation above.  gw[c][ky][kx] = sum_ph D[(ph,c)][(ky, ph+kx)].
 static int g_fold = 1;
-static constexpr int kFoldA = 6, kFoldP = 8, kFoldIssuers = 3, kFoldTeams = 2, kFoldTeamW = 8;
+// Stage = kFoldRows image rows (two pooled rows): a builder team's latency chain per stage (mbarrier wait -> shared
+// loads -> selects -> swizzled stores -> fence.proxy.async -> arrive, ~1000 cycles) is independent of how much each
+// thread stores, so with one row per stage (round 1) the kernel ran at 5 % of its issue bound.
+static constexpr int kFoldRows = 4, kFoldA = 4, kFoldP = 10, kFoldIssuers = 2, kFoldTeams = 2, kFoldTeamW = 8;
 static constexpr int kFoldFirstB = 1 + kFoldIssuers;
 static constexpr int kFoldThreads = 32 * (kFoldFirstB + kFoldTeams * kFoldTeamW);
 static constexpr uint32_t kFoldBRows = 1600;          // 132 * 12 = 1584 rows + the tail the last window reads
+static constexpr uint32_t kFoldRowBytes = 4096, kFoldABytes = kFoldRows * kFoldRowBytes, kFoldPSlot = 6144;
 
 struct FoldParams {
   const float* img; const void* gp; const uint8_t* idx;
   int B;
   float* gw; float* gb;
+  float* part;          // [gridDim.x][400] weight partials then [gridDim.x][16] bias partials (summed in CTA order); null: atomics
 };
 
 __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const FoldParams p) {
   constexpr int H = 128, W = 128, Hp = 64, Wp = 64;
-  constexpr uint32_t A_BYTES = 4096, P_SLOT = 4096, B_ARR = kFoldBRows * 32u;
+  constexpr uint32_t A_BYTES = kFoldABytes, P_SLOT = kFoldPSlot, B_ARR = kFoldBRows * 32u;
   constexpr int NBUILD = 32 * kFoldTeams * kFoldTeamW;
+  constexpr uint32_t SPI = H / kFoldRows;               // stages per image
+  static_assert(kFoldA % kFoldIssuers == 0 && kFoldA % kFoldTeams == 0, "ring owners");
+  static_assert(kFoldP % kFoldTeams == 0 && kFoldRows == 4, "a stage is two pooled rows");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kFoldA], a_empty[kFoldA], p_full[kFoldP], p_empty[kFoldP], b_free, accum_bar;
   __shared__ uint32_t tmem_base_s;
@@ -936,18 +984,18 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
   uint8_t* sBlo = sBhi + B_ARR;
   uint8_t* sA = sBlo + B_ARR;
   uint8_t* sP = sA + kFoldA * A_BYTES;
-  float* sD = reinterpret_cast<float*>(sA);            // epilogue scratch [128][65], after the pipeline drained (33 KB: A + P rings)
+  float* sD = reinterpret_cast<float*>(sA);            // epilogue scratch [128][65], after the pipeline drained (33 KB of the A ring)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < kFoldA; ++s) { mbar_init(&a_full[s], kFoldTeamW); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < kFoldP; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], kFoldTeams * kFoldTeamW); }
+    for (int s = 0; s < kFoldP; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], kFoldTeamW); }
     mbar_init(&b_free, kFoldIssuers);
     mbar_init(&accum_bar, kFoldIssuers);
     fence_barrier_init();
   }
   if (tid < 16) s_gb[tid] = 0.f;
-  if (warp == 1) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -957,20 +1005,30 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: pooled gradient rows + argmax
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int img = blockIdx.x; img < p.B; img += gridDim.x)
-        for (int py = 0; py < Hp; ++py, ++g) {
+    uint32_t g = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      if (lane == 0) {
+        // one slot = one stage = two pooled rows (contiguous in both tensors): two bulk copies per 6 KB -- a copy
+        // per pooled row kept this single lane, which shares its scheduler with busy builder warps, behind the builders
+        const char* gsrc = reinterpret_cast<const char*>(p.gp) + (int64_t)img * Hp * Wp * 32;
+        const uint8_t* isrc = p.idx + (int64_t)img * Hp * Wp * 16;
+        for (uint32_t st = 0; st < SPI; ++st, ++g) {
           const uint32_t s = g % kFoldP;
           mbar_wait(&p_empty[s], ((g / kFoldP) & 1u) ^ 1u);
-          const int64_t ps = ((int64_t)img * Hp + py) * Wp;
-          mbar_arrive_expect_tx(&p_full[s], Wp * 48u);
-          bulk_load_1d(sP + s * P_SLOT, reinterpret_cast<const __nv_bfloat16*>(p.gp) + ps * 16, Wp * 32u, &p_full[s]);
-          bulk_load_1d(sP + s * P_SLOT + 2048, p.idx + ps * 16, Wp * 16u, &p_full[s]);
+          mbar_arrive_expect_tx(&p_full[s], 2u * Wp * 48u);
+          bulk_load_1d(sP + s * P_SLOT, gsrc + st * (2u * Wp * 32u), 2u * Wp * 32u, &p_full[s]);
+          bulk_load_1d(sP + s * P_SLOT + 4096, isrc + st * (2u * Wp * 16u), 2u * Wp * 16u, &p_full[s]);
         }
+      } else if (img + (int)gridDim.x < p.B) {
+        // the other lanes pull the NEXT image of this CTA into L2 while this one is processed: the B-array build is
+        // the one phase in which the MMA pipeline is empty, and its first-touch misses were most of its cost
+        const char* nx = reinterpret_cast<const char*>(p.img + (int64_t)(img + (int)gridDim.x) * H * W);
+        for (int l = lane - 1; l < H * W * 4 / 128; l += 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + l * 128));
+      }
+      __syncwarp();
     }
   } else if (warp < kFoldFirstB) {
-    // ------------------------------------------------------------------ MMA issuers (row g -> issuer g % 3; whole warps)
+    // ------------------------------------------------------------------ MMA issuers (stage sg -> issuer sg % 2; whole warps)
     {
       const bool leader = elect_one();
       const uint32_t wi = (uint32_t)(warp - 1);
@@ -980,19 +1038,22 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
       const uint64_t bh0 = make_smem_desc(smem_u32(sBhi), 16u, 256u, 6u);
       const uint64_t bl0 = make_smem_desc(smem_u32(sBlo), 16u, 256u, 6u);
       const uint32_t d_addr = tmem_base + wi * 64u;
-      const uint32_t total = (uint32_t)nimg * H;
+      const uint32_t total = (uint32_t)nimg * SPI;
       uint32_t a = wi % kFoldA, pa = 0u, first = 1u;
-      for (uint32_t g = wi; g < total; g += kFoldIssuers) {
-        const uint32_t y = g % H;
+      for (uint32_t sg = wi; sg < total; sg += kFoldIssuers) {
+        const uint32_t ys = sg % SPI;
         mbar_wait(&a_full[a], pa);
         tc_fence_after();
-        const uint64_t ad = ad0 + ((a * A_BYTES) >> 4);
-        const uint32_t boff = (y * 12u * 32u) >> 4;
-        if (leader) { umma_f16(d_addr, ad, bh0 + boff, idesc, first ? 0u : 1u); umma_f16(d_addr, ad, bl0 + boff, idesc, 1u); }
-        first = 0u;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)kFoldRows; ++r) {
+          const uint64_t ad = ad0 + ((a * A_BYTES + r * kFoldRowBytes) >> 4);
+          const uint32_t boff = ((ys * kFoldRows + r) * 12u * 32u) >> 4;
+          if (leader) { umma_f16(d_addr, ad, bh0 + boff, idesc, first ? 0u : 1u); umma_f16(d_addr, ad, bl0 + boff, idesc, 1u); }
+          first = 0u;
+        }
         if (leader) umma_commit(&a_empty[a]);
-        // last row of an image handled by this issuer: the B arrays may be rebuilt once these MMAs are done
-        if (y + kFoldIssuers >= (uint32_t)H && leader) umma_commit(&b_free);
+        // last stage of an image handled by this issuer: the B arrays may be rebuilt once these MMAs are done
+        if (ys + kFoldIssuers >= SPI && leader) umma_commit(&b_free);
         a += kFoldIssuers; if (a >= kFoldA) { a -= kFoldA; pa ^= 1u; }
       }
       if (leader) umma_commit(&accum_bar);
@@ -1007,61 +1068,88 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
     // MN-major, 128-byte swizzled: M atom (ph / 4) * 2048 + K atom (xg / 8) * 1024 + K row (xg % 8) * 128 + 16-byte chunk
     const uint32_t a_off = (uint32_t)(ph >> 2) * 2048u + (uint32_t)(xg >> 3) * 1024u + (uint32_t)(xg & 7) * 128u +
                            ((((uint32_t)(ph & 3) * 2u + (uint32_t)h) ^ (uint32_t)(xg & 7)) << 4);
-    float gsum[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
-    uint32_t gbase = 0, ii = 0;
-    for (int img = blockIdx.x; img < p.B; img += gridDim.x, gbase += H, ++ii) {
+    const uint32_t xbit = (uint32_t)(x & 1), xm = xbit * 0x01010101u;
+    float gsum[4] = {0.f, 0.f, 0.f, 0.f};                          // channels h * 8 + xbit * 4 + {0..3}
+    uint32_t ii = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++ii) {
       // ---- B arrays of this image: R[r*12 + j][xg] = imgpad[r][8*xg + j] (hi and lo)
       if (ii > 0) mbar_wait(&b_free, (ii - 1) & 1u);             // the previous image's MMAs are done reading them
       const float* im = p.img + (int64_t)img * H * W;
+#pragma unroll 2
       for (int c = bt; c < 132 * 12 * 2; c += NBUILD) {           // chunk = (row n, 8 consecutive xg)
         const int n = c >> 1, kh = c & 1;
         const int r = n / 12, j = n - r * 12;
         const int iy = r - 2;
+        const bool rowok = iy >= 0 && iy < H;
+        // elements ix = 64*kh + 8*e + j - 2: only the first of the left chunk and the last of the right one can
+        // fall outside the row
+        const float* rp = im + (rowok ? iy : 0) * W + 64 * kh + j - 2;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ix = 8 * (kh * 8 + e) + j - 2;
-          v[e] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(im + iy * W + ix) : 0.f;
-        }
-        uint32_t hl[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) hl[e] = split_hi_lo(v[e]);
+        for (int e = 1; e < 7; ++e) v[e] = __ldg(rp + 8 * e);
+        v[0] = (kh || j >= 2) ? __ldg(rp) : 0.f;
+        v[7] = (!kh || j < 10) ? __ldg(rp + 56) : 0.f;
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { hi[e] = __byte_perm(hl[2 * e], hl[2 * e + 1], 0x5410); lo[e] = __byte_perm(hl[2 * e], hl[2 * e + 1], 0x7632); }
+        for (int e = 0; e < 4; ++e) {                               // two elements per conversion instruction
+          const uint32_t h2 = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+          const float r0 = v[2 * e] - __uint_as_float(h2 << 16), r1 = v[2 * e + 1] - __uint_as_float(h2 & 0xffff0000u);
+          hi[e] = rowok ? h2 : 0u;
+          lo[e] = rowok ? pack_bf16x2(r0, r1) : 0u;
+        }
         const uint32_t o = swz_off((uint32_t)n, (uint32_t)kh, 32u);
         *reinterpret_cast<uint4*>(sBhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(sBlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");
-      // ---- one A tile per image row: un-pool the gradient row y
-      for (int y = team; y < H; y += kFoldTeams) {
-        const uint32_t g = gbase + (uint32_t)y;
-        const uint32_t a = g % kFoldA;
-        const uint32_t gp_ = (gbase >> 1) + (uint32_t)(y >> 1);   // global pooled-row counter
-        const uint32_t ps = gp_ % kFoldP;
-        mbar_wait(&p_full[ps], (gp_ / kFoldP) & 1u);
-        const int local = (x >> 1) * 2 + h;                       // 16-byte units of the pooled slot
-        const uint4 pg = *reinterpret_cast<const uint4*>(sP + ps * P_SLOT + local * 16);
-        const uint2 pi = *reinterpret_cast<const uint2*>(sP + ps * P_SLOT + 2048 + local * 8);
-        const uint32_t pos = (uint32_t)(((y & 1) << 1) | (x & 1));
-        const uint32_t gv[4] = {pg.x, pg.y, pg.z, pg.w};
-        uint32_t ov[4];
+      // ---- one A stage per two pooled rows: un-pool them into the four image rows they came from
+      for (uint32_t ys = (uint32_t)team; ys < SPI; ys += kFoldTeams) {
+        const uint32_t sg = ii * SPI + ys;                         // global stage counter
+        const uint32_t a = sg % kFoldA;
+        const int local = (x >> 1) * 2 + h;                        // 16-byte units of the pooled slot
+        uint4 pg[2]; uint2 pi[2];
+        const uint32_t ps = sg % kFoldP;
+        mbar_wait(&p_full[ps], (sg / kFoldP) & 1u);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t iw = e < 2 ? pi.x : pi.y;
-          const uint32_t i0 = (iw >> ((e & 1) * 16)) & 0xffu, i1 = (iw >> ((e & 1) * 16 + 8)) & 0xffu;
-          ov[e] = (i0 == pos ? (gv[e] & 0xffffu) : 0u) | (i1 == pos ? (gv[e] & 0xffff0000u) : 0u);
-          gsum[2 * e] += __uint_as_float(ov[e] << 16);
-          gsum[2 * e + 1] += __uint_as_float(ov[e] & 0xffff0000u);
+        for (int pr = 0; pr < 2; ++pr) {
+          pg[pr] = *reinterpret_cast<const uint4*>(sP + ps * P_SLOT + pr * 2048 + local * 16);
+          pi[pr] = *reinterpret_cast<const uint2*>(sP + ps * P_SLOT + 4096 + pr * 1024 + local * 8);
+        }
+        uint32_t ov[4][4];
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const uint32_t gv[4] = {pg[pr].x, pg[pr].y, pg[pr].z, pg[pr].w};
+          // argmax bytes (0..3) -> per-byte flags in bit 7: position (yy, x & 1) matches iff byte ^ xbit is 0 (yy = 0)
+          // or 2 (yy = 1); PRMT with sign replication then widens a flag byte to the 16-bit mask of its channel
+          uint32_t f[2][2];
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const uint32_t t = (w ? pi[pr].y : pi[pr].x) ^ xm;
+            const uint32_t a7 = t << 7, a6 = t << 6;
+            f[w][0] = ~(a7 | a6) & 0x80808080u;
+            f[w][1] = (a6 & ~a7) & 0x80808080u;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int yy = 0; yy < 2; ++yy) {
+              uint32_t m;
+              if (e & 1) asm("prmt.b32 %0, %1, %1, 0xbbaa;" : "=r"(m) : "r"(f[e >> 1][yy]));
+              else asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m) : "r"(f[e >> 1][yy]));
+              ov[pr * 2 + yy][e] = gv[e] & m;
+            }
+          // bias gradient = sum of the pooled gradient: the two threads of a pooled pixel take four channels each
+          const uint32_t wa = xbit ? gv[2] : gv[0], wb = xbit ? gv[3] : gv[1];
+          gsum[0] += __uint_as_float(wa << 16); gsum[1] += __uint_as_float(wa & 0xffff0000u);
+          gsum[2] += __uint_as_float(wb << 16); gsum[3] += __uint_as_float(wb & 0xffff0000u);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_empty[ps]);                // pooled slot consumed (it is in registers)
-        mbar_wait(&a_empty[a], ((g / kFoldA) & 1u) ^ 1u);
-        *reinterpret_cast<uint4*>(sA + a * A_BYTES + a_off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        if (lane == 0) mbar_arrive(&p_empty[ps]);                  // pooled slot consumed (it is in registers)
+        mbar_wait(&a_empty[a], ((sg / kFoldA) & 1u) ^ 1u);
+#pragma unroll
+        for (int r = 0; r < kFoldRows; ++r)
+          *reinterpret_cast<uint4*>(sA + a * A_BYTES + r * kFoldRowBytes + a_off) = make_uint4(ov[r][0], ov[r][1], ov[r][2], ov[r][3]);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[a]);
@@ -1069,12 +1157,12 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
     }
     // ---- bias gradient: channel (h*8 + e) summed over this thread's pixels, then over the CTA
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
       float v = gsum[e];
-      // lanes with equal h: xor-shuffle over the x bits of the lane index (bits 1..4)
+      // lanes with equal (h, x & 1) = lane bits 0, 1: xor-shuffle over the other bits
 #pragma unroll
-      for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((lane >> 1) == 0) atomicAdd(&s_gb[h * 8 + e], v);
+      for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < 4) atomicAdd(&s_gb[h * 8 + (int)xbit * 4 + e], v);
     }
     // ---- epilogue: D[(ph,c)][(ky,j)] summed over the issuers' accumulators -> gw[c][ky][kx] += D[..][(ky, ph+kx)]
     mbar_wait(&accum_bar, 0);
@@ -1086,7 +1174,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
       float acc[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-      for (uint32_t wi = 0; wi < (uint32_t)kFoldIssuers && wi < (uint32_t)nimg * H; ++wi) {
+      for (uint32_t wi = 0; wi < (uint32_t)kFoldIssuers; ++wi) {
 #pragma unroll
         for (int cc = 0; cc < 64; cc += 16) {
           uint32_t v[16];
@@ -1098,32 +1186,45 @@ __global__ void __launch_bounds__(kFoldThreads, 1) conv1_wgrad_fold_kernel(const
       }
 #pragma unroll
       for (int c = 0; c < 64; ++c) sD[m * 65 + c] = acc[c];
-      __syncwarp();
-      const int mph = m >> 4, mc = m & 15;
-      for (int t = 0; t < 25; ++t) {
-        const int ky = t / 5, kx = t - ky * 5;
-        atomicAdd(p.gw + mc * 25 + t, sD[m * 65 + ky * 12 + mph + kx]);
-      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NBUILD) : "memory");
-    if (p.gb && bt < 16) atomicAdd(p.gb + bt, s_gb[bt]);
+    // one value per weight and CTA (the eight pixel phases are summed here): round 2's 3200 atomics per CTA on 400
+    // addresses cost a third of the kernel
+    if (bt < 400) {
+      const int c = bt / 25, t = bt - c * 25;
+      const int ky = t / 5, kx = t - ky * 5;
+      float a = 0.f;
+#pragma unroll
+      for (int ph = 0; ph < 8; ++ph) a += sD[(ph * 16 + c) * 65 + ky * 12 + ph + kx];
+      if (p.part) p.part[(int64_t)blockIdx.x * 400 + bt] = a;
+      else atomicAdd(p.gw + bt, a);
+    } else if (bt < 416) {
+      const float a = s_gb[bt - 400];
+      if (p.part) p.part[(int64_t)gridDim.x * 400 + (int64_t)blockIdx.x * 16 + (bt - 400)] = a;
+      else if (p.gb) atomicAdd(p.gb + (bt - 400), a);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 static int launch_conv1_wgrad_fold(const float* img, const void* gp, const uint8_t* idx, int B, float* gw, float* gb,
                                    cudaStream_t st) {
   FoldParams p;
   p.img = img; p.gp = gp; p.idx = idx; p.B = B; p.gw = gw; p.gb = gb;
-  const size_t smem = 1024 + 2 * (size_t)kFoldBRows * 32 + (size_t)kFoldA * 4096 + (size_t)kFoldP * 4096;
+  const size_t smem = 1024 + 2 * (size_t)kFoldBRows * 32 + (size_t)kFoldA * kFoldABytes + (size_t)kFoldP * kFoldPSlot;
   static OncePerDevice attr;
-  if (attr.first()) { cudaFuncSetAttribute(conv1_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);}
+  if (attr.first()) { cudaFuncSetAttribute(conv1_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);}
   int grid = kNumSMs;
   if (grid > B) grid = B;
+  p.part = scratch_floats((int64_t)grid * 416);
   conv1_wgrad_fold_kernel<<<grid, kFoldThreads, smem, st>>>(p);
   LIVAE_CUDA_LAUNCH_CHECK();
+  if (p.part) {                      // fixed-order sums over the CTAs: bit-reproducible (gw / gb are written)
+    sum_slices(p.part, grid, 400, gw, st);
+    if (gb) sum_slices(p.part + (int64_t)grid * 400, grid, 16, gb, st);
+  }
   return 0;
 }
 

@@ -45,7 +45,10 @@ def test_stn_conv1_fwd_and_wgrad(B, P):
     # differ wherever bf16 rounding of image / weights ties the pool, which is not the wgrad's business
     iy, ix = ind // P, ind % P
     ref_idx = _nhwc(((iy % 2) * 2 + (ix % 2)).to(torch.uint8)).cuda()
-    agree = (ref_idx == idx).float().mean().item()
+    # compared where the pooled output is positive: elsewhere all four ReLU outputs tie at zero, the reference
+    # reports position 0, the kernel the position of the largest raw sum, and the ReLU mask removes the gradient
+    live = _nhwc(y.detach() > 0).cuda()
+    agree = (ref_idx == idx)[live].float().mean().item()
     assert agree > 0.97, agree
     _call("livae_thin_conv1c_wgrad", 0, x.cuda(), _nhwc(g).cuda().to(BF), ref_idx, B, P, P, gw, gb)
     assert rel_l2(gw.cpu(), w.grad) < 1e-4
