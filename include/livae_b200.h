@@ -241,6 +241,35 @@ int livae_tc_conv5pool_dgrad(const void* g_s2d, const void* wpacked1, const void
 int64_t livae_tc_conv5pool_wgrad_ws_bytes(int Ci, int Co);
 int livae_tc_conv5pool_wgrad(const void* x, const void* g_s2d, int B, int H, int W, int Ci, int Co, float* gw, float* gb,
                              void* ws, livae_stream_t stream);
+
+/* Decoder blocks d1-d3, Upsample(x2, bilinear) -> ReflectionPad2d(1) -> Conv2d(Cin->Cout, 3x3) -> ReLU (reference
+ * model.py:356-368), phase-folded onto the LOW-resolution input (csrc/upfold.cu): one convolution Cin -> 4*Cout over
+ * h x w pixels; the up-sampled tensor and its gradient are never formed.  x bf16 [B,h,w,Cin], y / gz bf16 [B,2h,2w,Cout].
+ *   pack    w fp32 [Cout][Cin][3][3] -> wf bf16 [9][4*Cout][Cin] (forward), wd bf16 [9][Cin][4*Cout] (data gradient)
+ *   strips  the border terms of the layer input: s_tb bf16 [2B,4,2w+2,Cin], s_lr bf16 [2B,4,2h+2,Cin] (transposed), two live
+ *           and two zero rows each, so that a whole batch is ONE tall image [1,8B,.,Cin] for livae_tc_conv; its pad-0
+ *           3x3 convolution with w (s_tb) / w transposed in (ky,kx) (s_lr) into fp32 is corr_tb [2B,4,2w,Cout] /
+ *           corr_lr [2B,4,2h,Cout] (rows 0,1 of every group of 4 are used)
+ *   fwd     y = ReLU(folded conv(x) + bias); the two outermost rows / columns are left as conv + bias
+ *   ring    those rows / columns: y = ReLU(y + corr)
+ *   gather  g_tb bf16 [2B,4,2w,Cout] / g_lr bf16 [2B,4,2h,Cout] = the two outermost rows / columns of gz + two zero rows
+ *   dgrad   gx bf16 [B,h,w,Cin] = (folded data gradient of gz) * (x_mask > 0), x_mask = x (the ReLU output below)
+ *   patch   gx += (x_mask > 0) * adjoint(strips)(gs_tb, gs_lr); gs_* fp32 = livae_tc_conv_dgrad of g_tb / g_lr
+ *   wgrad   gw fp32 [Cout][Cin][3][3] = unfolded folded weight gradient + gw_tb + transpose(gw_lr) (either may be NULL) */
+int livae_upfold_supported(int B, int h, int w, int Cin, int Cout);
+int livae_upfold_pack(const float* w, int Cout, int Cin, void* wf, void* wd, livae_stream_t stream);
+int livae_upfold_strips(const void* x, int B, int h, int w, int Cin, void* s_tb, void* s_lr, livae_stream_t stream);
+int livae_upfold_fwd(const void* x, const void* wf, const float* bias, int B, int h, int w, int Cin, int Cout, void* y,
+                     livae_stream_t stream);
+int livae_upfold_ring(const float* corr_tb, const float* corr_lr, int B, int h, int w, int Cout, void* y, livae_stream_t stream);
+int livae_upfold_gather(const void* gz, int B, int h, int w, int Cout, void* g_tb, void* g_lr, livae_stream_t stream);
+int livae_upfold_dgrad(const void* gz, const void* wd, const void* x_mask, int B, int h, int w, int Cin, int Cout, void* gx,
+                       livae_stream_t stream);
+int livae_upfold_patch(const float* gs_tb, const float* gs_lr, const void* x_mask, int B, int h, int w, int Cin, void* gx,
+                       livae_stream_t stream);
+int64_t livae_upfold_wgrad_ws_bytes(int Cin, int Cout);
+int livae_upfold_wgrad(const void* x, const void* gz, const float* gw_tb, const float* gw_lr, int B, int h, int w, int Cin,
+                       int Cout, float* gw, void* ws, livae_stream_t stream);
 /* data gradient of a 4x4 stride-2 pad-1 convolution as one 3x3 convolution over the gy grid that writes whole
  * 2x2 blocks of gx (csrc/conv_s2d.cu); wblk = livae_tc_dgrad_s2blk_pack(w fp32 [Cout][Cin][4][4]) bf16 [9][4*Cin][Cout] */
 int livae_tc_dgrad_s2blk_supported(int Hin, int Win, int Cin, int Cout);

@@ -138,7 +138,7 @@ extern "C" int livae_tc_conv5pool_fwd(const void* x, const void* wpacked0, const
   block_taps(tdy, tdx, tw);
   const int Hb = H / 2, Wb = W / 2;
   int rc = launch_conv_tc_halo(x, B, Hb, Wb, 4 * Ci, wpacked0, 9, 4 * Co, Hb, Wb, Hb, Wb, 1, 0, 0, 1, 9, tdy, tdx, tw, y, 0,
-                               bias, LIVAE_ACT_RELU, nullptr, (cudaStream_t)stream, HaloOpts{1, 1, idx});
+                               bias, LIVAE_ACT_RELU, nullptr, (cudaStream_t)stream, HaloOpts{1, 1, idx, 0});
   if (rc == 1) { set_error("tc_conv5pool_fwd: shape rejected by the halo kernel"); return -1; }
   return rc;
 }
@@ -171,7 +171,7 @@ extern "C" int livae_tc_conv5pool_dgrad(const void* g_s2d, const void* wpacked1,
   block_taps(tdy, tdx, tw);
   const int Hb = H / 2, Wb = W / 2;
   int rc = launch_conv_tc_halo(g_s2d, B, Hb, Wb, 4 * Co, wpacked1, 9, 4 * Ci, Hb, Wb, Hb, Wb, 1, 0, 0, 1, 9, tdy, tdx, tw, gx, 0,
-                               nullptr, LIVAE_ACT_NONE, relu_mask, (cudaStream_t)stream, HaloOpts{0, 2, nullptr});
+                               nullptr, LIVAE_ACT_NONE, relu_mask, (cudaStream_t)stream, HaloOpts{0, 2, nullptr, 0});
   if (rc == 1) { set_error("tc_conv5pool_dgrad: shape rejected by the halo kernel"); return -1; }
   return rc;
 }
@@ -230,7 +230,7 @@ extern "C" int livae_tc_dgrad_s2blk(const void* gy, const void* wblk, const void
   block_taps(tdy, tdx, tw);
   const int Ho = Hin / 2, Wo = Win / 2;
   int rc = launch_conv_tc_halo(gy, B, Ho, Wo, Cout, wblk, 9, 4 * Cin, Ho, Wo, Ho, Wo, 1, 0, 0, 1, 9, tdy, tdx, tw, gx, 0,
-                               nullptr, LIVAE_ACT_NONE, relu_mask, (cudaStream_t)stream, HaloOpts{0, 2, nullptr});
+                               nullptr, LIVAE_ACT_NONE, relu_mask, (cudaStream_t)stream, HaloOpts{0, 2, nullptr, 0});
   if (rc == 1) { set_error("tc_dgrad_s2blk: shape rejected by the halo kernel"); return -1; }
   return rc;
 }

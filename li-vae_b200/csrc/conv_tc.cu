@@ -282,8 +282,11 @@ struct ConvTcHaloParams {
   void* out; int out_f32; const float* bias; int act; const __nv_bfloat16* relu_mask;
   long long* probe;
   int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
+  int s2d_cpr;                                // a_s2d: K chunks per pixel row of the 2x2 block (2C / kc)
+  int up_cout;                                // epi_mode 3 (epilogue_upfold)
 };
 
+static constexpr int kHaloSmemMax = 225 * 1024;     // dynamic shared memory opt-in of the halo kernels (SM: 227 KB = 232448 B incl. ~1.3 KB static)
 static constexpr int kSA = 2, kSAmax = 4, kSB = 4;   // A ring: kSA..kSAmax slots (p.nsa), as many as fit without costing a resident CTA
 
 // Epilogue of one accumulator row per thread, 32 columns per pass: both tcgen05.ld and the ReLU-mask loads
@@ -341,6 +344,46 @@ __device__ __forceinline__ void epilogue_rows32(uint32_t taddr, int nbase, int N
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
         o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
+    }
+  }
+}
+
+// The same for a bf16 output whose ReLU-mask vectors (N <= 128 columns: 16 x 8 bf16) are already in registers
+__device__ __forceinline__ void epilogue_rows32_premask(uint32_t taddr, int nbase, int N, int Ntot, bool valid, int64_t pix,
+                                                        void* out, const float* __restrict__ sbias, int act,
+                                                        const uint4 (&m)[16]) {
+#pragma unroll
+  for (int p32 = 0; p32 < 4; ++p32) {
+    const int cc = p32 * 32;
+    if (cc >= N) break;
+    const bool two = cc + 16 < N;
+    uint32_t v[32];
+    tmem_ld16(taddr + (uint32_t)cc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    if (two) tmem_ld16(taddr + (uint32_t)cc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+    tmem_ld_wait();
+    if (!valid) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m[p32 * 4 + h * 2 + j]);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float a0 = __uint_as_float(v[h * 16 + j * 8 + i]) + sbias[cc + h * 16 + j * 8 + i];
+          float a1 = __uint_as_float(v[h * 16 + j * 8 + i + 1]) + sbias[cc + h * 16 + j * 8 + i + 1];
+          if (act == LIVAE_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+          else if (act == LIVAE_ACT_SIGMOID) { a0 = 1.f / (1.f + __expf(-a0)); a1 = 1.f / (1.f + __expf(-a1)); }
+          if (!(__bfloat162float(mb[i]) > 0.f)) a0 = 0.f;
+          if (!(__bfloat162float(mb[i + 1]) > 0.f)) a1 = 0.f;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+          w[j * 4 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      }
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + pix * Ntot + nbase + cc + h * 16);
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
 }
@@ -444,6 +487,39 @@ __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int
   }
 }
 
+// epi_mode 3 (phase-folded Upsample(x2) -> ReflectionPad(1) -> Conv3x3 -> ReLU, csrc/upfold.cu): the N = 4*Cout
+// accumulator columns of low-resolution pixel (qy,qx) are its four output pixels (2qy+py, 2qx+px), phase-major;
+// out = ReLU(acc + bias) goes to the plain NHWC tensor [B, 2Hq, 2Wq, Cout].  The two outermost output rows / columns
+// still lack their border correction: they are stored WITHOUT the ReLU and finished by upfold_ring_kernel (adding the
+// correction here cost a dependent global-load round trip per 32 columns: 7900 instead of 2900 cycles per tile).
+__device__ __forceinline__ void epilogue_upfold(uint32_t taddr, int nbase, int N, int Cout, bool valid, int b, int qy,
+                                                int qx, int Hq, int Wq, __nv_bfloat16* __restrict__ out,
+                                                const float* __restrict__ sbias) {
+  const int Ho = 2 * Hq, Wo = 2 * Wq;
+  for (int cc = 0; cc < N; cc += 32) {
+    uint32_t v[32];
+    tmem_ld16(taddr + (uint32_t)cc, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    tmem_ld16(taddr + (uint32_t)cc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+    const int n0 = nbase + cc;
+    const int ph = n0 / Cout, c0 = n0 - ph * Cout;       // Cout is a multiple of 32: the 32 columns share a phase
+    const int Y = 2 * qy + (ph >> 1), X = 2 * qx + (ph & 1);
+    const float lo = (Y < 2 || Y >= Ho - 2 || X < 2 || X >= Wo - 2) ? -3.0e38f : 0.f;
+    tmem_ld_wait();
+    if (!valid) continue;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a0 = fmaxf(__uint_as_float(v[2 * i]) + sbias[cc + 2 * i], lo);
+      const float a1 = fmaxf(__uint_as_float(v[2 * i + 1]) + sbias[cc + 2 * i + 1], lo);
+      __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+      w[i] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + Y) * Wo + X) * Cout + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+}
+
 // Persistent: grid.x CTAs walk the tile list round-robin.  The accumulator is double-buffered in
 // TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld, activation, global stores) overlaps the
 // TMA + MMA main loop of tile i+1, and barrier/TMEM/tensor-map setup is paid once per CTA.
@@ -454,11 +530,11 @@ __device__ __forceinline__ void epilogue_unblock(uint32_t taddr, bool valid, int
 // EPI = epilogue mode (HaloOpts): a template parameter so that the register-hungry pooled / un-blocking
 // epilogues do not cost the plain convolutions their occupancy.
 template <int KSTEPS, int EPI>
-__global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t fullA[kSAmax], emptyA[kSAmax], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
+  __shared__ __align__(8) uint64_t fullA[kSAmax], emptyA[kSAmax], fullB[kSB], emptyB[kSB], tfull[4], tempty[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_tapoff[kMaxTaps];        // row shift of each tap in descriptor address units (16 B)
   __shared__ int s_grp[4][2];                    // tap_begin, tap_end of each group
@@ -474,14 +550,18 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   uint8_t* smemB = smem + (uint32_t)p.nsa * a_slot;
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
-  const uint32_t ncols = 2u * acc_cols;
+  // TMEM accumulators: two (double buffer); EPI 3 / 4: as many as the 512 columns hold, up to four.  One accumulator's
+  // cycle is its tile's MMAs plus its epilogue, so with two the kernel ran at (MMA + epilogue) / 2 per tile whenever the
+  // epilogue was the longer half (folded decoder: 4000-4700 vs 2400-3800 cycles, mostly the scattered 16-byte stores).
+  const uint32_t nacc = (EPI == 3 || EPI == 4) ? (512u / acc_cols < 4u ? 512u / acc_cols : 4u) : 2u;
+  const uint32_t ncols = nacc * acc_cols;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSAmax; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI == 2 ? 8 : 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI == 2 ? 8 : 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -492,6 +572,8 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   for (int i = threadIdx.x; i < p.ngroups; i += blockDim.x) { s_grp[i][0] = p.grp[i].tap_begin; s_grp[i][1] = p.grp[i].tap_end; }
   if (EPI == 1) {
     for (int i = threadIdx.x; i < (p.N >> 2); i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  } else if (EPI == 3) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[((int)blockIdx.y * p.N + i) % p.up_cout] : 0.f;
   } else {
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[(int)blockIdx.y * p.N + i] : 0.f;
   }
@@ -526,7 +608,8 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
             mbar_wait(&emptyA[sa], pha ^ 1u);
             probe_rec(p.probe, 0, 1, pn);
             mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            if (p.a_s2d) tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], 0, x0 + G.dx, 2 * (y0 + G.dy) + c, b);
+            if (p.a_s2d) tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], (c % p.s2d_cpr) * p.kc, x0 + G.dx,
+                                     2 * (y0 + G.dy) + c / p.s2d_cpr, b);
             else tma_load_4d(smem + (uint32_t)sa * a_slot, &tmA, &fullA[sa], c * p.kc, x0 + G.dx, y0 + G.dy, b);
             if (++sa == p.nsa) { sa = 0; pha ^= 1u; }
             if (p.b_resident) continue;
@@ -561,9 +644,9 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
       int pn = 0;
       if (resident) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u;
+        const uint32_t acc = it % nacc;
         if (leader) probe_rec(p.probe, 1, 0, pn);
-        mbar_wait(&tempty[acc], ((it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+        mbar_wait(&tempty[acc], ((it / nacc) & 1u) ^ 1u);   // epilogue has drained this buffer
         if (leader) probe_rec(p.probe, 1, 1, pn);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + acc * acc_cols;
@@ -611,28 +694,51 @@ __global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
     const int px = row & 15, py = row >> 4;
     int it = 0, pn = 0;
     long long* pb = (warp == 2 && lane == 0) ? p.probe : nullptr;
+    // EPI 3 / 4: eight epilogue warps in two groups, group g owns accumulator g (alternate tiles): a warp's chain per tile
+    // (tcgen05.ld passes, mask / store latency: 4000-4700 cycles measured) may then take two tiles' worth of MMA time
+    const int egrp = (EPI == 3 || EPI == 4) ? (warp >= 6 ? 1 : 0) : -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (egrp >= 0 && (it & 1) != egrp) continue;
       int t3 = tile;
       const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
       const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
       const int b = t3;
-      const int acc = it & 1;
+      const int acc = (int)((uint32_t)it % nacc);
       const int qy = ty * 8 + py, qx = tx * p.tw + px;
       const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
       const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
       probe_rec(pb, 2, 0, pn);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
       auto wait_acc = [&]() {
-        mbar_wait(&tfull[acc], (uint32_t)(it >> 1) & 1u);
+        mbar_wait(&tfull[acc], ((uint32_t)it / nacc) & 1u);
         probe_rec(pb, 2, 1, pn);
         tc_fence_after();
       };
       if (EPI == 0) {
         wait_acc();
         epilogue_rows32(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, p.out_f32, s_bias, p.act, p.relu_mask);
+      } else if (EPI == 4) {
+        {   // EPI 4 = EPI 0 for a bf16 output with a ReLU mask and N <= 128 (its own instantiation: 64 more registers)
+          // all ReLU-mask vectors of the row are requested BEFORE waiting for the accumulator (as epilogue_unblock
+          // does): issued per 32-column pass after it, each pass exposed a global-load round trip (~2500 cycles per
+          // pass on the folded decoder's data gradients, more than the tile's MMAs)
+          uint4 m[16];
+          const int nv = p.N >> 3;
+          if (valid) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + pix * p.Ntot + (int)blockIdx.y * p.N);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i < nv) m[i] = __ldg(mp + i);
+          }
+          wait_acc();
+          epilogue_rows32_premask(taddr, (int)blockIdx.y * p.N, p.N, p.Ntot, valid, pix, p.out, s_bias, p.act, m);
+        }
       } else if (EPI == 1) {
         wait_acc();
         epilogue_pool4(taddr, p.N, valid, ((int64_t)b * p.Hq + qy) * p.Wq + qx, p.out, p.pool_idx, s_bias);
+      } else if (EPI == 3) {
+        wait_acc();
+        epilogue_upfold(taddr, (int)blockIdx.y * p.N, p.N, p.up_cout, valid, b, qy, qx, p.Hq, p.Wq,
+                        reinterpret_cast<__nv_bfloat16*>(p.out), s_bias);
       } else if (p.N == 64)
         epilogue_unblock<1>(taddr, valid, b, qy, qx, p.Hq, p.Wq, p.out, p.relu_mask, warp >= 6 ? 2 : 0, wait_acc);
       else      // N = 128 (the launcher admits 64 and 128 only: at N = 256 the mask registers spill)
@@ -756,9 +862,11 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
                         const float* bias, int act, const void* relu_mask, cudaStream_t st, HaloOpts opts) {
   ConvTcHaloParams p;
   p.a_s2d = opts.a_s2d; p.epi_mode = opts.epi_mode; p.pool_idx = opts.pool_idx;
-  if (opts.a_s2d && (Cin != 64 || in_stride != 1)) return 1;
-  if (opts.epi_mode != 0 && N != 64 && N != 128 && N != 256) return 1;
+  p.s2d_cpr = 1; p.up_cout = opts.up_cout;
+  if (opts.a_s2d && ((Cin != 64 && Cin % 128 != 0) || in_stride != 1)) return 1;
+  if ((opts.epi_mode == 1 || opts.epi_mode == 2) && N != 64 && N != 128 && N != 256) return 1;
   if (opts.epi_mode == 2 && N == 256) return 1;
+  if (opts.epi_mode == 3 && (opts.up_cout % 32 != 0 || N != 4 * opts.up_cout || Cin % 64 != 0 || out_f32)) return 1;
   const int s = in_stride;
   // group taps by the parity class of their input offset; inside a group taps are whole-row/col shifts
   int gkey[4][2]; int ng = 0;
@@ -798,7 +906,10 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + 7) / 8;
   p.Hq = Hq; p.Wq = Wq; p.Ho = Ho; p.Wo = Wo; p.os = os; p.oy0 = oy0; p.ox0 = ox0; p.in_stride = s;
   p.kc = Cin >= 64 ? 64 : Cin;
-  if (opts.a_s2d) p.kc = Cin / 2;          // one K chunk per pixel row of the 2x2 block (see the tensor map below)
+  if (opts.a_s2d) {                        // K chunks never straddle a pixel row of the 2x2 block (see the tensor map below)
+    p.kc = Cin / 2 < 64 ? Cin / 2 : 64;
+    p.s2d_cpr = (Cin / 2) / p.kc;
+  }
   p.nkc = Cin / p.kc;
   int nchunk = N;
   if (N > 256) { nchunk = 256; while (N % nchunk != 0) nchunk -= 16; }
@@ -816,7 +927,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     const uint64_t C = (uint64_t)Cin / 4, Wf = 2 * (uint64_t)Win, Hf = 2 * (uint64_t)Hin;
     uint64_t dims[4] = {2 * C, (uint64_t)Win, Hf, (uint64_t)B};
     uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
-    uint32_t box[4] = {(uint32_t)(2 * C), 16u, (uint32_t)(2 * p.box_rows), 1u};
+    uint32_t box[4] = {(uint32_t)p.kc, 16u, (uint32_t)(2 * p.box_rows), 1u};
     uint32_t es[4] = {1, 1, 2, 1};
     if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
   } else {
@@ -842,24 +953,31 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   p.nsa = kSA;
   static OncePerDevice attr_done;
   if (attr_done.first()) {
-    cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
+    cudaFuncSetAttribute(conv_tc_halo_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemMax);
   }
+  // plain epilogue with the ReLU-mask vectors prefetched (see EPI 4 in the kernel)
+  const bool premask = opts.epi_mode == 0 && relu_mask != nullptr && !out_f32 && p.N <= 128 && p.kc == 64 && opts.a_s2d;
   const int tiles = p.tiles_x * p.tiles_y * B;
   // persistent grid: as many CTAs per SM as shared memory and the 512 TMEM columns allow
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
   int per_sm = (int)(220 * 1024 / (smem + 1024));
   int per_sm_tmem = (int)(512 / (2 * acc_cols));
+  if (opts.epi_mode == 3 || premask) per_sm_tmem = 1;       // these take up to four accumulators (see the kernel)
   if (per_sm > per_sm_tmem) per_sm = per_sm_tmem;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   // deepen the A ring while the same number of CTAs still fits (two slots leave the producer one box ahead
   // at most: the MMA warp waited 400-900 cycles per box for TMA latency)
-  while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= 200 * 1024) { smem += a_slot; ++p.nsa; }
+  // (up to the whole 227 KB of the SM when the CTA is alone on it: with resident weights of 144 KB the folded decoder
+  // kernels had two slots, i.e. ONE box in flight, and ran at one TMA round trip -- 4000+ cycles -- per tile)
+  while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= (size_t)kHaloSmemMax) { smem += a_slot; ++p.nsa; }
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
   const dim3 grid(gx, N / p.N);
@@ -869,7 +987,11 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   } else if (opts.epi_mode == 2) {
     if (p.kc != 64) return 1;
     conv_tc_halo_kernel<4, 2><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
-  } else if (p.kc == 64) conv_tc_halo_kernel<4, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else if (opts.epi_mode == 3) {
+    if (p.kc != 64) return 1;
+    conv_tc_halo_kernel<4, 3><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
+  } else if (premask) conv_tc_halo_kernel<4, 4><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
+  else if (p.kc == 64) conv_tc_halo_kernel<4, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv_tc_halo_kernel<2, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else conv_tc_halo_kernel<1, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   LIVAE_CUDA_LAUNCH_CHECK();
@@ -884,7 +1006,7 @@ static int launch_conv_tc(const void* in, int B, int Hin, int Win, int Cin, cons
   LIVAE_CHECK_ARG(ntaps >= 1 && ntaps <= kMaxTaps, "tc_conv: too many taps (%d)", ntaps);
   if (g_halo_mode != 0 && ntaps > 1 && Wq >= 8 && Hq >= 4) {
     int rc = launch_conv_tc_halo(in, B, Hin, Win, Cin, wpacked, wtaps, N, Hq, Wq, Ho, Wo, os, oy0, ox0, in_stride,
-                                 ntaps, tdy, tdx, tw_idx, out, out_f32, bias, act, relu_mask, st, HaloOpts{0, 0, nullptr});
+                                 ntaps, tdy, tdx, tw_idx, out, out_f32, bias, act, relu_mask, st, HaloOpts{0, 0, nullptr, 0});
     if (rc != 1) return rc;   // 1 = shape not eligible, fall through to the per-tap kernel
   }
   ConvTcParams p;

@@ -195,14 +195,16 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 // epi_mode 0: plain NHWC store; 1: N = 4*Co columns are the four pixels of a 2x2 block -> bias + ReLU +
 //        max-pool over them, pooled bf16 [B,Hq,Wq,Co] + argmax (pool_idx); 2: N = 4*Ci columns are written
 //        back as the four pixels of the block of a plain NHWC tensor [B,2*Hq,2*Wq,Ci] (relu_mask in that layout)
-struct HaloOpts { int a_s2d; int epi_mode; uint8_t* pool_idx; };
+//        3: N = 4*up_cout columns = the four output pixels of the phase-folded up-sampling convolution: bias + ReLU
+//        (none on the two outermost rows / columns, finished by upfold.cu), written to [B,2*Hq,2*Wq,up_cout]
+struct HaloOpts { int a_s2d; int epi_mode; uint8_t* pool_idx; int up_cout; };
 int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
                         int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
                         const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
                         const float* bias, int act, const void* relu_mask, cudaStream_t st, HaloOpts opts);
 // returns 0 = launched, 1 = shape not eligible
 int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho, int Wo,
-                      cudaStream_t st, int x_s2d);
+                      cudaStream_t st, int x_s2d);   // x_s2d: bit 0 = x, bit 1 = gy read block-wise (2x2 blocks as channels)
 void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st);   // gb must be zeroed
 void sum_slices(const float* part, int nslices, int64_t n, float* out, cudaStream_t st);
 

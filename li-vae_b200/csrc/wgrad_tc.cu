@@ -211,7 +211,9 @@ struct WgradHaloParams {
   float* gw_acc;
   int64_t slice_elems;        // see WgradParams
   long long* probe;
-  int x_s2d;                   // input operand read in space-to-depth form through a 5-D tensor map (tc_common.cuh)
+  int x_s2d;                   // input operand read in space-to-depth form through a strided tensor map (tc_common.cuh)
+  int g_cpr;                   // > 0: gy is a plain NHWC tensor [B,2Ho,2Wo,Cs/4] read block-wise (channels = (ey,ex,c));
+                               //      g_cpr = channel chunks per pixel row of the 2x2 block
 };
 
 template <int STAGES>
@@ -279,8 +281,13 @@ __global__ void __launch_bounds__(kWgHaloThreads) wgrad_halo_kernel(const __grid
           probe_rec(p.probe, 0, 1, pn);
           mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           uint8_t* st = smem + (uint32_t)s * stage_bytes;
-          for (int c = 0; c < nboxg; ++c)
-            tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], c * p.kcs, tx * p.TW, ty * p.TH, b);
+          for (int c = 0; c < nboxg; ++c) {
+            if (p.g_cpr)
+              tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], (c % p.g_cpr) * p.kcs, tx * p.TW,
+                          2 * ty * p.TH + c / p.g_cpr, b);
+            else
+              tma_load_4d(st + a_region + (uint32_t)c * gbox_slot, &tmG, &full_bar[s], c * p.kcs, tx * p.TW, ty * p.TH, b);
+          }
           for (int i = 0; i < p.nbox; ++i) {
             if (!((need >> i) & 1u)) continue;
             if (p.x_s2d)   // chunk = pixel row inside the 2x2 block (HaloOpts in tc_common.cuh)
@@ -481,7 +488,8 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   WgradHaloParams p;
   p.Cb = d->Cin; p.Cs = d->Cout; p.ntaps = kh * kw; p.stride = s; p.B = d->B;
   p.kcb = p.Cb >= 64 ? 64 : p.Cb;
-  if (x_s2d) p.kcb = p.Cb / 2;
+  if (x_s2d & 1) p.kcb = p.Cb / 2;
+  const bool g_s2d = (x_s2d & 2) != 0;       // bit 1: gy read block-wise (WgradHaloParams::g_cpr)
   p.kcs = p.Cs >= 64 ? 64 : p.Cs;
   const int nchunk = p.Cb / p.kcb;
   if (nchunk > 8) return 1;
@@ -614,8 +622,13 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   p.gw_acc = gw_acc;
   p.slice_elems = 0;
   p.probe = g_probe;
-  p.x_s2d = x_s2d;
-  if (x_s2d && (d->Cin != 64 || s != 1)) return 1;
+  p.x_s2d = x_s2d & 1;
+  p.g_cpr = 0;
+  if (p.x_s2d && (d->Cin != 64 || s != 1)) return 1;
+  if (g_s2d) {
+    if (s != 1 || p.Cs % 128 != 0 || p.Cs > 256) return 1;      // run of a pixel row = Cs/2 >= 64 channels; UMMA N <= 256
+    p.g_cpr = (p.Cs / 2) / p.kcs;
+  }
   const int nboxg = p.Cs / p.kcs;
   const uint32_t gbox_slot = ((uint32_t)(TH * p.TW * p.kcs * 2) + 1023u) & ~1023u;
   // a CTA keeps only the boxes its row groups read (a contiguous range of box ids: groups are ordered
@@ -644,7 +657,7 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
   const int TH = p.TH, Hbox = TH + max_sy;
 
   CUtensorMap tmX, tmG;
-  if (x_s2d) {
+  if (p.x_s2d) {
     const uint64_t C = (uint64_t)d->Cin / 4, Wf = 2 * (uint64_t)d->Win, Hf = 2 * (uint64_t)d->Hin;
     uint64_t dims[4] = {2 * C, (uint64_t)d->Win, Hf, (uint64_t)d->B};
     uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
@@ -658,7 +671,14 @@ int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy
     uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
     if (int e = make_tmap_bf16(&tmX, x, 4, dims, str, box, es, p.kcb * 2)) return e;
   }
-  {
+  if (g_s2d) {       // see launch_conv_tc_halo: {(ex, c): 2C contiguous, X: stride 2C, pixel row 2*Y + ey (element stride 2), B}
+    const uint64_t C = (uint64_t)d->Cout / 4, Wf = 2 * (uint64_t)Wo, Hf = 2 * (uint64_t)Ho;
+    uint64_t dims[4] = {2 * C, (uint64_t)Wo, Hf, (uint64_t)d->B};
+    uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
+    uint32_t box[4] = {(uint32_t)p.kcs, (uint32_t)p.TW, (uint32_t)(2 * TH), 1u};
+    uint32_t es[4] = {1, 1, 2, 1};
+    if (int e = make_tmap_bf16(&tmG, gy, 4, dims, str, box, es, p.kcs * 2)) return e;
+  } else {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->B};
     uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)Wo * d->Cout * 2, (uint64_t)Ho * Wo * d->Cout * 2};
     uint32_t box[4] = {(uint32_t)p.kcs, (uint32_t)p.TW, (uint32_t)TH, 1u};

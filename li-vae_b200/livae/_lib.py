@@ -96,6 +96,14 @@ _SIGS = {
     "livae_unpool_s2d_bf16": "ppiiiips",
     "livae_tc_conv5pool_dgrad": "pppiiiiips",
     "livae_tc_conv5pool_wgrad": "ppiiiiippps",
+    "livae_upfold_pack": "piipps",
+    "livae_upfold_strips": "piiiipps",
+    "livae_upfold_fwd": "pppiiiiips",
+    "livae_upfold_ring": "ppiiiips",
+    "livae_upfold_gather": "piiiipps",
+    "livae_upfold_dgrad": "pppiiiiips",
+    "livae_upfold_patch": "pppiiiips",
+    "livae_upfold_wgrad": "ppppiiiiipps",
     "livae_upsample_pad_fwd": "piiiips",
     "livae_upsample_pad_bwd": "piiiipps",
     "livae_decfc_fwd": "pppiiiips",
@@ -141,6 +149,10 @@ def lib():
     L.livae_tc_conv5pool_supported.argtypes = [C.c_int] * 5
     L.livae_tc_conv5pool_wgrad_ws_bytes.restype = C.c_int64
     L.livae_tc_conv5pool_wgrad_ws_bytes.argtypes = [C.c_int, C.c_int]
+    L.livae_upfold_supported.restype = C.c_int
+    L.livae_upfold_supported.argtypes = [C.c_int] * 5
+    L.livae_upfold_wgrad_ws_bytes.restype = C.c_int64
+    L.livae_upfold_wgrad_ws_bytes.argtypes = [C.c_int, C.c_int]
     L.livae_tc_conv_supported.restype = C.c_int
     L.livae_tc_conv_supported.argtypes = [C.POINTER(TcConvDesc)]
     L.livae_ssim_box_ws_floats.restype = C.c_int64
@@ -161,7 +173,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_upfold_supported", "livae_upfold_wgrad_ws_bytes", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
 
 
 def ptr(t):

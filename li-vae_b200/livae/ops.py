@@ -644,3 +644,79 @@ def dgrad_s2blk(gy, w, Hin, Win, relu_mask=None):
     gx = torch.empty((B, Hin, Win, Cin), dtype=torch.bfloat16, device=gy.device)
     call("livae_tc_dgrad_s2blk", gy, wblk, relu_mask, B, Hin, Win, Cin, Cout, gx)
     return gx
+
+
+# ---- decoder blocks d1-d3 phase-folded onto the low-resolution input (csrc/upfold.cu; model.py:356-368)
+def upfold_supported(B, h, w, Cin, Cout):
+    return bool(L.lib().livae_upfold_supported(B, h, w, Cin, Cout))
+
+
+def _upfold_pack(w):
+    Cout, Cin = w.shape[0], w.shape[1]
+    wf = torch.empty((9, 4 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((9, Cin, 4 * Cout), dtype=torch.bfloat16, device=w.device)
+    call("livae_upfold_pack", _c(w), Cout, Cin, wf, wd)
+    return wf, wd
+
+
+def upfold_pack(w):
+    """(forward, data-gradient) folded weight packs of a [Cout,Cin,3,3] weight, cached per optimiser epoch"""
+    return _packed(w, ("upfold",), lambda: _upfold_pack(w))
+
+
+def _strip_packs(w, mode):
+    """mode-0 / mode-2 packs of the layer's own weight (top / bottom strips) and of its (ky,kx)-transpose (the left /
+    right strips are stored transposed)"""
+    Cout, Cin = w.shape[0], w.shape[1]
+    wt = _packed(w, ("upfold_wT",), lambda: w.detach().transpose(2, 3).contiguous())
+    return (tc_pack_weights(w, Cout, Cin, 3, 3, mode),
+            _packed(w, ("upfold_wT_pack", mode), lambda: _tc_pack_weights(wt, Cout, Cin, 3, 3, mode)))
+
+
+def upfold_fwd(x, w, bias):
+    """x bf16 [B,h,w,Cin] -> y bf16 [B,2h,2w,Cout] = ReLU(Conv3x3(ReflectionPad(Upsample2(x))) + bias); also returns the
+    border strips (needed again by the weight gradient).  Every batch of strips [2B,4,L,Cin] is handed to the
+    convolution kernels as ONE tall image [1,8B,L,Cin] (pad 0): the rows between two strips' outputs are slack."""
+    assert x.dtype == torch.bfloat16 and x.is_cuda and x.is_contiguous()
+    B, h, ww, Cin = x.shape
+    Cout = w.shape[0]
+    dev = x.device
+    s_tb = torch.empty((2 * B, 4, 2 * ww + 2, Cin), dtype=torch.bfloat16, device=dev)
+    s_lr = torch.empty((2 * B, 4, 2 * h + 2, Cin), dtype=torch.bfloat16, device=dev)
+    call("livae_upfold_strips", x, B, h, ww, Cin, s_tb, s_lr)
+    p_tb, p_lr = _strip_packs(w, 0)
+    corr_tb = tc_conv(s_tb.view(1, 8 * B, 2 * ww + 2, Cin), p_tb, None, 3, 3, 1, 0, ACT_NONE, out_f32=True)
+    corr_lr = tc_conv(s_lr.view(1, 8 * B, 2 * h + 2, Cin), p_lr, None, 3, 3, 1, 0, ACT_NONE, out_f32=True)
+    y = torch.empty((B, 2 * h, 2 * ww, Cout), dtype=torch.bfloat16, device=dev)
+    call("livae_upfold_fwd", x, upfold_pack(w)[0], bias, B, h, ww, Cin, Cout, y)
+    call("livae_upfold_ring", corr_tb, corr_lr, B, h, ww, Cout, y)
+    return y, s_tb, s_lr
+
+
+def upfold_bwd(x, w, gz, s_tb, s_lr, want_dgrad=True):
+    """x bf16 [B,h,w,Cin] (the layer input, also the ReLU mask of the layer below), gz bf16 [B,2h,2w,Cout]
+    (pre-activation gradient) -> (gw fp32 [Cout,Cin,3,3], gx bf16 [B,h,w,Cin] masked by x > 0 or None)"""
+    assert gz.dtype == torch.bfloat16 and gz.is_contiguous()
+    B, h, ww, Cin = x.shape
+    Cout = w.shape[0]
+    dev = x.device
+    g_tb = torch.empty((2 * B, 4, 2 * ww, Cout), dtype=torch.bfloat16, device=dev)
+    g_lr = torch.empty((2 * B, 4, 2 * h, Cout), dtype=torch.bfloat16, device=dev)
+    call("livae_upfold_gather", gz, B, h, ww, Cout, g_tb, g_lr)
+    # tall images: x side [1,8B,L,Cin], gradient side [1,8B-2,L-2,Cout] (its slack rows are zero)
+    t_tb = g_tb.view(8 * B, 2 * ww, Cout)[:8 * B - 2].unsqueeze(0)
+    t_lr = g_lr.view(8 * B, 2 * h, Cout)[:8 * B - 2].unsqueeze(0)
+    gw_tb, _ = tc_conv_wgrad(s_tb.view(1, 8 * B, 2 * ww + 2, Cin), t_tb, 3, 3, 1, 0, want_bias=False)
+    gw_lr, _ = tc_conv_wgrad(s_lr.view(1, 8 * B, 2 * h + 2, Cin), t_lr, 3, 3, 1, 0, want_bias=False)
+    gw = torch.empty_like(w)
+    ws = torch.empty(L.lib().livae_upfold_wgrad_ws_bytes(Cin, Cout) // 4, dtype=torch.float32, device=dev)
+    call("livae_upfold_wgrad", x, gz, gw_tb, gw_lr, B, h, ww, Cin, Cout, gw, ws)
+    gx = None
+    if want_dgrad:
+        gx = torch.empty_like(x)
+        call("livae_upfold_dgrad", gz, upfold_pack(w)[1], x, B, h, ww, Cin, Cout, gx)
+        p_tb, p_lr = _strip_packs(w, 2)
+        gs_tb = tc_conv_dgrad(t_tb, p_tb, None, 8 * B, 2 * ww + 2, 3, 3, 1, 0, out_f32=True)
+        gs_lr = tc_conv_dgrad(t_lr, p_lr, None, 8 * B, 2 * h + 2, 3, 3, 1, 0, out_f32=True)
+        call("livae_upfold_patch", gs_tb, gs_lr, x, B, h, ww, Cin, gx)
+    return gw, gx

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -221,6 +223,12 @@ class EncoderTc(Function):
         return (None, gw0, gb0, gw3, gb3, gw7.view_as(w7), gb7, gw9, gb9) + (None,) * 13
 
 
+# Decoder block d3 (64 -> 32 channels, the widest map) runs phase-folded onto its low-resolution input (csrc/upfold.cu).
+# LIVAE_UPFOLD=0: always the materialised Upsample -> ReflectionPad path; 2: fold every block the kernels accept (d2 as
+# well -- measured slower there: its 16 x 16 input fills the 8 x 14 halo tiles to 57 %, see profiles/r02_notes.md).
+UPFOLD = int(os.environ.get("LIVAE_UPFOLD", "1"))
+
+
 class DecoderTc(Function):
     """(z, 10 parameters) -> recon [B,1,P,P]; reference Decoder.forward, model.py:375-388"""
 
@@ -233,20 +241,28 @@ class DecoderTc(Function):
         q = int(round((fcw.shape[0] // 256) ** 0.5))
         y0 = _empty((B, q, q, 256), BF, dev)
         call("livae_decfc_fwd_bf16", z, fcw, fcb, B, Ld, 256, q * q, y0)
-        ys, us = [y0], []
+        ys, aux = [y0], []
         cur, hw = y0, q
+        folded = []
         for w, b, cin, cout in ((d1w, d1b, 256, 128), (d2w, d2b, 128, 64), (d3w, d3b, 64, 32)):
-            u = _empty((B, 2 * hw + 2, 2 * hw + 2, cin), BF, dev)
-            call("livae_upsample_pad_fwd_bf16", cur, B, hw, hw, cin, u)
-            cur = ops.tc_conv(u, ops.tc_pack_weights(w, cout, cin, 3, 3, 0), b, 3, 3, 1, 0, ACT_RELU)
-            us.append(u); ys.append(cur)
+            if UPFOLD and (cout == 32 or UPFOLD > 1) and ops.upfold_supported(B, hw, hw, cin, cout):
+                # phase-folded block (csrc/upfold.cu): no up-sampled tensor; the border strips are kept for the weight gradient
+                cur, s_tb, s_lr = ops.upfold_fwd(cur, w, b)
+                aux += [s_tb, s_lr]; folded.append(True)
+            else:
+                u = _empty((B, 2 * hw + 2, 2 * hw + 2, cin), BF, dev)
+                call("livae_upsample_pad_fwd_bf16", cur, B, hw, hw, cin, u)
+                cur = ops.tc_conv(u, ops.tc_pack_weights(w, cout, cin, 3, 3, 0), b, 3, 3, 1, 0, ACT_RELU)
+                aux += [u, u]; folded.append(False)
+            ys.append(cur)
             hw *= 2
         P = 2 * hw
         recon = _empty((B, 1, P, P), torch.float32, dev)
         # d4 (upsample -> pad -> 32->1 conv -> sigmoid) straight from the low-resolution map (csrc/upconv_c1.cu)
         call("livae_upconv_c1_fwd", cur, d4w, d4b, B, hw, hw, ACT_SIGMOID, recon)
-        ctx.save_for_backward(z, fcw, d1w, d2w, d3w, d4w, recon, *ys, *us)
+        ctx.save_for_backward(z, fcw, d1w, d2w, d3w, d4w, recon, *ys, *aux)
         ctx.dims = (B, Ld, q, P)
+        ctx.folded = tuple(folded)
         return recon
 
     @staticmethod
@@ -254,31 +270,46 @@ class DecoderTc(Function):
     def backward(ctx, g_recon):
         saved = ctx.saved_tensors
         z, fcw, d1w, d2w, d3w, d4w, recon = saved[:7]
-        ys, us = saved[7:11], saved[11:14]
+        ys, aux = saved[7:11], saved[11:17]
         B, Ld, q, P = ctx.dims
+        folded = ctx.folded
         dev = z.device
         gpre4 = torch.empty_like(recon)
         call("livae_sigmoid_bwd", recon, g_recon.contiguous(), None, recon.numel(), gpre4)
         gd4w = torch.empty_like(d4w); gd4b = _empty((1,), torch.float32, dev)
         grads = []
         hw = P // 2
-        gu = None
+        gu = gx = None          # gradient handed down by the layer above: w.r.t. its up-sampled input / its low-res input
         for i, (w, cin, cout) in zip((3, 2, 1), ((d3w, 64, 32), (d2w, 128, 64), (d1w, 256, 128))):
-            y, u = ys[i], us[i - 1]
-            gy = torch.empty_like(y)                              # pre-activation gradient of conv i
-            gb = _empty((cout,), torch.float32, dev)           # bias gradient fused into the adjoint kernel
+            y = ys[i]
+            gb = _empty((cout,), torch.float32, dev)
             if i == 3:
                 # the whole backward of d4 (weight, bias, data gradient + upsample/pad adjoint + this layer's bias
                 # gradient) in one kernel over the LOW-resolution tensors (csrc/upconv_c1.cu)
+                gy = torch.empty_like(y)                          # pre-activation gradient of conv i
                 call("livae_upconv_c1_bwd", gpre4, d4w, y, B, hw, hw, gy, gb, gd4w, gd4b)
+            elif gx is not None:                                  # the folded block above already applied this layer's ReLU mask
+                gy = gx
+                call("livae_colsum_bf16", gy, B * hw * hw, cout, gb)
             else:
+                gy = torch.empty_like(y)
                 call("livae_upsample_pad_bwd_bias_bf16", gu, B, hw, hw, cout, y, gy, gb)
-            gw, _ = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0, want_bias=False)
-            gu = ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, cout, cin, 3, 3, 2), None, hw + 2, hw + 2, 3, 3, 1, 0)
+            if folded[i - 1]:
+                gw, gx = ops.upfold_bwd(ys[i - 1], w, gy, aux[2 * (i - 1)], aux[2 * (i - 1) + 1])
+                gu = None
+            else:
+                u = aux[2 * (i - 1)]
+                gw, _ = ops.tc_conv_wgrad(u, gy, 3, 3, 1, 0, want_bias=False)
+                gu = ops.tc_conv_dgrad(gy, ops.tc_pack_weights(w, cout, cin, 3, 3, 2), None, hw + 2, hw + 2, 3, 3, 1, 0)
+                gx = None
             grads.append((gw, gb))
             hw //= 2
-        gy0 = torch.empty_like(ys[0])
-        call("livae_upsample_pad_bwd_bf16", gu, B, q, q, 256, ys[0], gy0)
+        if gx is not None:
+            gy0 = gx
+        else:
+            gy0 = torch.empty_like(ys[0])
+            call("livae_upsample_pad_bwd_bf16", gu, B, q, q, 256, ys[0], gy0)
+
         gfcw = torch.empty_like(fcw); gfcb = _empty((fcw.shape[0],), torch.float32, dev)
         gz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
         call("livae_decfc_bwd_bf16", z, fcw, gy0, B, Ld, 256, q * q, gfcw, gfcb, gz)

@@ -276,3 +276,38 @@ def test_decoder_d4_fused_forward(B, H, W):
         _call("livae_upconv_c1_fwd", _nhwc(x).cuda().to(BF), w.cuda(), bias.cuda(), B, H, W, act, out)
         assert rel_l2(out.cpu(), want) < 2e-5, (act, rel_l2(out.cpu(), want))
         assert (out.cpu() - want).abs().max() < 1e-4 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("B,h,Cin,Cout", [(3, 16, 128, 64), (2, 32, 64, 32), (5, 8, 64, 32), (2, 24, 128, 32)])
+def test_upfold_block_matches_upsample_pad_conv(B, h, Cin, Cout):
+    """decoder blocks d2 / d3 phase-folded onto the low-resolution input (csrc/upfold.cu) against the reference
+    composition Upsample(x2, bilinear) -> ReflectionPad2d(1) -> Conv2d(3x3) -> ReLU (model.py:356-368) on the same
+    bf16-rounded operands: values, data gradient (incl. the ReLU mask of the layer below) and weight gradient, with
+    the border rows / columns checked on their own"""
+    from livae import ops
+    rng = np.random.default_rng(B * h + Cin)
+    x = _bf(torch.tensor(np.maximum(rng.standard_normal((B, Cin, h, h)), 0).astype(np.float32))).requires_grad_(True)
+    w = torch.tensor((rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32), requires_grad=True)
+    b = torch.tensor((rng.standard_normal(Cout) * 0.1).astype(np.float32))
+    up = F.pad(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
+    pre = F.conv2d(up, w, b)
+    y_ref = torch.relu(pre)
+    assert ops.upfold_supported(B, h, h, Cin, Cout)
+    xd = _nhwc(x.detach()).cuda().to(BF)
+    wd = w.detach().cuda()
+    y, s_tb, s_lr = ops.upfold_fwd(xd, wd, b.cuda())
+    got = y.float().cpu()
+    want = _nhwc(y_ref.detach())
+    assert rel_l2(got, want) < 5e-3
+    for sl in (np.s_[:, :2], np.s_[:, -2:], np.s_[:, :, :2], np.s_[:, :, -2:]):       # the corrected border rows / columns
+        assert rel_l2(got[sl], want[sl]) < 5e-3
+    # backward from a pre-activation gradient that already carries this layer's ReLU mask
+    g = _bf(torch.tensor(rng.standard_normal(tuple(pre.shape)).astype(np.float32))) * (pre.detach() > 0)
+    (pre * g).sum().backward()
+    gw, gx = ops.upfold_bwd(xd, wd, _nhwc(g).cuda().to(BF), s_tb, s_lr)
+    assert rel_l2(gw.cpu(), w.grad) < 2e-3
+    gx_ref = _nhwc(x.grad * (x.detach() > 0))
+    gxc = gx.float().cpu()
+    assert rel_l2(gxc, gx_ref) < 6e-3
+    for sl in (np.s_[:, :2], np.s_[:, -2:], np.s_[:, :, :2], np.s_[:, :, -2:]):
+        assert rel_l2(gxc[sl], gx_ref[sl]) < 8e-3

@@ -39,6 +39,24 @@ elif case == "wgrad_d3":
 elif case == "wgrad_d1":
     x = torch.randn(B, 18, 18, 256, device=dev).to(bf); g = torch.randn(B, 16, 16, 128, device=dev).to(bf)
     run = lambda: ops.tc_conv_wgrad(x, g, 3, 3, 1, 0)
+if case.startswith("up_"):
+    # phase-folded decoder blocks (csrc/upfold.cu): up_<fwd|dg|wg>_<d2|d3>
+    _, what, layer = case.split("_")
+    h, ci, co = {"d2": (16, 128, 64), "d3": (32, 64, 32)}[layer]
+    x = torch.randn(B, h, h, ci, device=dev).clamp_min(0).to(bf); wt = torch.randn(co, ci, 3, 3, device=dev) * 0.05
+    bias = torch.zeros(co, device=dev)
+    gz = torch.randn(B, 2 * h, 2 * h, co, device=dev).to(bf)
+    wf, wd = ops.upfold_pack(wt)
+    ctb = torch.zeros(2 * B, 2, 2 * h, co, device=dev); clr = torch.zeros(2 * B, 2, 2 * h, co, device=dev)
+    y = torch.empty(B, 2 * h, 2 * h, co, device=dev, dtype=bf); gx = torch.empty_like(x)
+    from livae._lib import call
+    if what == "fwd":
+        run = lambda: call("livae_upfold_fwd", x, wf, bias, B, h, h, ci, co, y)
+    elif what == "dg":
+        run = lambda: call("livae_upfold_dgrad", gz, wd, x, B, h, h, ci, co, gx)
+    else:
+        gw = torch.empty_like(wt); ws = torch.empty(L.livae_upfold_wgrad_ws_bytes(ci, co) // 4, device=dev)
+        run = lambda: call("livae_upfold_wgrad", x, gz, None, None, B, h, h, ci, co, gw, ws)
 if case.startswith("dg_") or case.startswith("fw_"):
     # generic: dg_/fw_<Cin>_<Cout>_<k>_<stride>_<pad>_<Hin>
     _, ci, co, k, st, pd, hin = case.split("_"); ci, co, k, st, pd, hin = map(int, (ci, co, k, st, pd, hin))
