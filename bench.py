@@ -268,6 +268,12 @@ def describe_call(name, a):
         ints = [v for v in a if isinstance(v, int)]
         Bb, Hin, Win, Cin, Cout = ints[:5]
         return name[6:], 2.0 * Bb * (Hin // 2) * (Win // 2) * Cin * Cout * 16, by
+    if name in ("livae_upfold_fwd", "livae_upfold_dgrad", "livae_upfold_wgrad"):
+        # decoder block folded onto its low-resolution input (csrc/upfold.cu): 3x3 x (Cin -> 4*Cout) MACs per low-res pixel,
+        # i.e. exactly the 3x3 x (Cin -> Cout) MACs per output pixel of the reference's Upsample -> Pad -> Conv2d
+        ints = [v for v in a if isinstance(v, int)]
+        Bb, h, w, Cin, Cout = ints[:5]
+        return f"{name[6:]}[{Cin}->{Cout} {h}x{w}]", 2.0 * Bb * h * w * 9 * Cin * 4 * Cout, by
     if name.startswith("livae_thin_conv"):
         ints = [v for v in a if isinstance(v, int)]
         return f"{name[6:]}[{','.join(str(v) for v in ints[:4])}]", 0.0, by
