@@ -268,8 +268,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 struct HaloGroup { int16_t dy, dx, tap_begin, tap_end; };
 struct ConvTcHaloParams {
   int tiles_x, tiles_y;
-  int tw;                 // valid output columns per tile (16 - max column shift)
-  int box_rows;           // rows of the input box (8 + max row shift)
+  int tw;                 // valid output columns per tile (bw - max column shift)
+  int bw, th;             // box width in grid columns (16..20) and output rows per tile (128 / bw)
+  int box_rows;           // rows of the input box (th + max row shift)
   int Hq, Wq, Ho, Wo, os, oy0, ox0, in_stride;
   int ngroups;
   HaloGroup grp[4];
@@ -542,8 +543,8 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t row_bytes = KSTEPS * 32u;
-  const uint32_t a_bytes = (uint32_t)(p.box_rows * 16) * row_bytes;
-  const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)(p.box_rows * p.bw) * row_bytes;
+  const uint32_t a_slot = ((uint32_t)(p.box_rows * p.bw + p.bw) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.N * row_bytes;
   const uint32_t b_slot = (b_bytes + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
         const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
         const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
         const int b = t3;
-        const int x0 = tx * p.tw * p.in_stride, y0 = ty * 8 * p.in_stride;
+        const int x0 = tx * p.tw * p.in_stride, y0 = ty * p.th * p.in_stride;
         for (int g = 0; g < p.ngroups; ++g) {
           const HaloGroup G = p.grp[g];
           for (int c = 0; c < p.nkc; ++c) {
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int px = row & 15, py = row >> 4;
+    const int py = row / p.bw, px = row - py * p.bw;
     int it = 0, pn = 0;
     long long* pb = (warp == 2 && lane == 0) ? p.probe : nullptr;
     // EPI 3 / 4: eight epilogue warps in two groups, group g owns accumulator g (alternate tiles): a warp's chain per tile
@@ -704,8 +705,8 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
       const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
       const int b = t3;
       const int acc = (int)((uint32_t)it % nacc);
-      const int qy = ty * 8 + py, qx = tx * p.tw + px;
-      const bool valid = px < p.tw && qy < p.Hq && qx < p.Wq;
+      const int qy = ty * p.th + py, qx = tx * p.tw + px;
+      const bool valid = px < p.tw && py < p.th && qy < p.Hq && qx < p.Wq;
       const int64_t pix = ((int64_t)b * p.Ho + (qy * p.os + p.oy0)) * p.Wo + (qx * p.os + p.ox0);
       probe_rec(pb, 2, 0, pn);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
@@ -850,8 +851,10 @@ static bool channels_ok(int Cin, int Cout) {
   return Cin == 16 || Cin == 32;
 }
 
-// 0 = one TMA box per tap (conv_tc_kernel); 1 = one haloed box per tap group (conv_tc_halo_kernel)
+// 0 = one TMA box per tap (conv_tc_kernel); 1 (default) = one haloed box per tap group (conv_tc_halo_kernel), box width
+// chosen per layer; 2 = the same with 16-column boxes only (A/B switch for the box-width choice)
 static int g_halo_mode = 1;
+static int g_halo_wide = 1;
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -882,6 +885,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     gof[t] = g;
   }
   int max_sy = 0, max_sx = 0;
+  int tsy[kMaxTaps], tsx[kMaxTaps];
   for (int g = 0; g < ng; ++g) {
     p.grp[g].tap_begin = (int16_t)n;
     for (int t = 0; t < ntaps; ++t) {
@@ -890,7 +894,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
       if (sy > max_sy) max_sy = sy;
       if (sx > max_sx) max_sx = sx;
       order[n] = t;
-      p.tap_shift[n] = (uint8_t)(sy * 16 + sx);
+      tsy[n] = sy; tsx[n] = sx;
       p.tap_w[n] = (int8_t)tw_idx[t];
       ++n;
     }
@@ -898,12 +902,28 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     p.grp[g].dy = (int16_t)gmin_y[g]; p.grp[g].dx = (int16_t)gmin_x[g];
   }
   (void)order; (void)floordiv;
-  if (max_sx > 8 || max_sy * 16 + max_sx > 200) return 1;
+  if (max_sx > 8) return 1;
   p.ngroups = ng; p.ntaps = ntaps;
-  p.tw = 16 - max_sx;
-  p.box_rows = 8 + max_sy;
-  if ((p.box_rows * s) > 256 || 16 * s > 256) return 1;
-  p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + 7) / 8;
+  // Box width: the tile is 128 consecutive positions of a bw-wide box, i.e. 128 / bw rows of bw - max_sx valid columns.
+  // 16 (8 rows) is the default; a wider box (7 or 6 rows) is taken when it covers the grid with fewer tiles -- a 32-wide
+  // grid under 3x3 taps needs three 14-column tiles per row at bw = 16 (12 tiles per 32 x 32 map) but two 16-column
+  // tiles at bw = 18 (10 tiles).
+  {
+    int best_bw = 16, best_tiles = 1 << 30;
+    for (int bw = 16; bw <= 20; ++bw) {
+      const int tw = bw - max_sx, th = 128 / bw;
+      const int tiles = ((Wq + tw - 1) / tw) * ((Hq + th - 1) / th);
+      if (tiles < best_tiles) { best_tiles = tiles; best_bw = bw; }
+    }
+    if (!g_halo_wide) best_bw = 16;
+    p.bw = best_bw; p.th = 128 / best_bw;
+  }
+  p.tw = p.bw - max_sx;
+  p.box_rows = p.th + max_sy;
+  if (max_sy * p.bw + max_sx > 200) return 1;
+  for (int t = 0; t < ntaps; ++t) p.tap_shift[t] = (uint8_t)(tsy[t] * p.bw + tsx[t]);
+  if ((p.box_rows * s) > 256 || p.bw * s > 256) return 1;
+  p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + p.th - 1) / p.th;
   p.Hq = Hq; p.Wq = Wq; p.Ho = Ho; p.Wo = Wo; p.os = os; p.oy0 = oy0; p.ox0 = ox0; p.in_stride = s;
   p.kc = Cin >= 64 ? 64 : Cin;
   if (opts.a_s2d) {                        // K chunks never straddle a pixel row of the 2x2 block (see the tensor map below)
@@ -927,13 +947,13 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     const uint64_t C = (uint64_t)Cin / 4, Wf = 2 * (uint64_t)Win, Hf = 2 * (uint64_t)Hin;
     uint64_t dims[4] = {2 * C, (uint64_t)Win, Hf, (uint64_t)B};
     uint64_t str[3] = {2 * C * 2, Wf * C * 2, Hf * Wf * C * 2};
-    uint32_t box[4] = {(uint32_t)p.kc, 16u, (uint32_t)(2 * p.box_rows), 1u};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.bw, (uint32_t)(2 * p.box_rows), 1u};
     uint32_t es[4] = {1, 1, 2, 1};
     if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
   } else {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
-    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(16 * s), (uint32_t)(p.box_rows * s), 1u};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.bw * s), (uint32_t)(p.box_rows * s), 1u};
     uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
     if (int e = make_tmap_bf16(&tmA, in, 4, dims, str, box, es, row_bytes)) return e;
   }
@@ -943,7 +963,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.N, 1};
     if (int e = make_tmap_bf16(&tmB, wpacked, 3, dims, str, box, nullptr, row_bytes)) return e;
   }
-  const uint32_t a_slot = ((uint32_t)(p.box_rows * 16 + 16) * row_bytes + 1023u) & ~1023u;
+  const uint32_t a_slot = ((uint32_t)(p.box_rows * p.bw + p.bw) * row_bytes + 1023u) & ~1023u;
   const uint32_t b_slot = ((uint32_t)p.N * row_bytes + 1023u) & ~1023u;
   // keep every weight tile in shared memory for the CTA's lifetime whenever they fit next to the two A slots
   // (even at one CTA per SM: streaming them costs an mbarrier wait + a commit per tap, more than the tap's MMAs)
@@ -1196,4 +1216,4 @@ extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, 
 extern "C" void livae_set_probe(void* dev_ptr) { g_probe = (long long*)dev_ptr; }
 
 // tuning / test hook: 0 = per-tap boxes only, 1 = halo kernel where eligible
-extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; }
+extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; g_halo_wide = mode == 2 ? 0 : 1; }
