@@ -390,9 +390,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the step as two CUDA graphs (livae.train.GraphedRvaeStep): for small per-GPU batches, "
-                         "where the ~190 launches of a step are host-bound (the strong-scaling case)")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=True,
+                    help="(default) the device-timed step is livae.train.GraphedRvaeStep: the same kernels replayed as two "
+                         "CUDA graphs -- the ~200 launches of a step cost 0.4 ms of gaps at 2048 patches per GPU and are "
+                         "the whole cost at 256 (strong scaling)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", help="issue every launch from Python")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -467,8 +469,17 @@ def main():
         gstep = GraphedRvaeStep(model, opt, crit, device, CANON_W, MAX_NORM, reduce_grads)
 
     def step(batch):
+        nonlocal gstep
         if gstep is not None:
-            return gstep(batch)
+            try:
+                return gstep(batch)
+            except Exception as e:          # capture failed: say so and time the eager step instead
+                if gstep.g_fwd is not None and gstep.g_opt is not None:
+                    raise
+                sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n")
+                gstep = None
+                args.cuda_graph = False
+                torch.cuda.synchronize()
         return train_rvae_step(model, opt, crit, batch, device, CANON_W, MAX_NORM, reduce_grads)
 
     def resident_step(i):
@@ -562,7 +573,14 @@ def main():
     # the same step without the encoder convolutions of the x_rot pass, whose mu / logvar the reference's loop discards
     # at the call site (train.py:376-377: `_, _, theta_rotated = model.encoder(x_rotated)`); identical losses and
     # gradients.  Reported NEXT TO the headline, never as it.
+    gstep_el = None
+    if gstep is not None:
+        from livae.train import GraphedRvaeStep
+        gstep_el = GraphedRvaeStep(model, opt, crit, device, CANON_W, MAX_NORM, reduce_grads, elide_dead_encoder=True)
+
     def elided_step(i):
+        if gstep_el is not None:
+            return gstep_el(batches[i % len(batches)])
         return train_rvae_step(model, opt, crit, batches[i % len(batches)], device, CANON_W, MAX_NORM, reduce_grads,
                                elide_dead_encoder=True)
     elided_step(0)

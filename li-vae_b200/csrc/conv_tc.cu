@@ -285,6 +285,7 @@ struct ConvTcHaloParams {
   int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
   int s2d_cpr;                                // a_s2d: K chunks per pixel row of the 2x2 block (2C / kc)
   int up_cout;                                // epi_mode 3 (epilogue_upfold)
+  int nacc;                                   // TMEM accumulators: 2, or up to 4 when the CTA has the SM to itself
 };
 
 static constexpr int kHaloSmemMax = 225 * 1024;     // dynamic shared memory opt-in of the halo kernels (SM: 227 KB = 232448 B incl. ~1.3 KB static)
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   // TMEM accumulators: two (double buffer); EPI 3 / 4: as many as the 512 columns hold, up to four.  One accumulator's
   // cycle is its tile's MMAs plus its epilogue, so with two the kernel ran at (MMA + epilogue) / 2 per tile whenever the
   // epilogue was the longer half (folded decoder: 4000-4700 vs 2400-3800 cycles, mostly the scattered 16-byte stores).
-  const uint32_t nacc = (EPI == 3 || EPI == 4) ? (512u / acc_cols < 4u ? 512u / acc_cols : 4u) : 2u;
+  const uint32_t nacc = (uint32_t)p.nacc;
   const uint32_t ncols = nacc * acc_cols;
 
   if (warp == 0 && lane == 0) {
@@ -998,6 +999,10 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   // (up to the whole 227 KB of the SM when the CTA is alone on it: with resident weights of 144 KB the folded decoder
   // kernels had two slots, i.e. ONE box in flight, and ran at one TMA round trip -- 4000+ cycles -- per tile)
   while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= (size_t)kHaloSmemMax) { smem += a_slot; ++p.nsa; }
+  // TMEM accumulators: two; the folded-decoder kernels (alone on their SM) take up to four.  (Tried for every kernel
+  // that has the SM to itself, together with a six-slot A ring: no gain, 15.68 -> 15.79 ms.)
+  p.nacc = 2;
+  if (opts.epi_mode == 3 || premask) { p.nacc = (int)(512u / acc_cols); if (p.nacc > 4) p.nacc = 4; if (p.nacc < 2) p.nacc = 2; }
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
   const dim3 grid(gx, N / p.N);

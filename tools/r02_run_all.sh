@@ -12,12 +12,12 @@ echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 4 
 echo "== secondary C2 / C4"; (timeout 300 python tools/bench_vae.py; timeout 300 python tools/bench_stn.py) > $O/${T}_secondary_c2_c4.jsonl 2>&1; tail -2 $O/${T}_secondary_c2_c4.jsonl | cut -c1-300
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/${T}_ncu_launches_bench_step.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e > $O/${T}_ncu_launch.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e --no-cuda-graph > $O/${T}_ncu_launch.log 2>&1
 python tools/ncu_times.py $O/${T}_ncu_launches_bench_step.csv > $O/${T}_ncu_launch_summary.txt 2>&1; head -12 $O/${T}_ncu_launch_summary.txt
 echo "== ncu full capture of the top families"
 timeout 1200 ncu --set full --clock-control none --import-source on \
   -k regex:'conv1_wgrad_fold|upconv_c1|rot_sample|upsample_pad_bwd|upsample_pad_fwd|conv_tc_halo|conv1c_tc|elbo|upfold|wgrad_halo' \
-  --launch-skip 170 -c 60 -o $O/${T}_top python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e > $O/${T}_ncu_full.log 2>&1
+  --launch-skip 170 -c 60 -o $O/${T}_top python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-e2e --no-cuda-graph > $O/${T}_ncu_full.log 2>&1
 ncu -i $O/${T}_top.ncu-rep --page raw --csv > $O/${T}_ncu_full_top.csv 2>/dev/null
 python tools/ncu_extract.py $O/${T}_ncu_full_top.csv > $O/${T}_ncu_full_top.txt 2>&1; head -50 $O/${T}_ncu_full_top.txt | cut -c1-220
 rm -f $O/${T}_top.ncu-rep        # tens of MB with --import-source; gpurun copies back at most 64 MiB
