@@ -362,7 +362,9 @@ def check_dp(args, device, rank, world, dist):
         # Adam's first update is lr * g / (|g| + eps): where |g| is within a few eps (1e-8) of zero -- dead units -- the
         # update is decided by summation-order noise (2e-9 absolute here) on BOTH sides, so those elements are reported
         # separately and the parameter comparison is made where the update is a function of the gradient
-        live = opt1.flat_grad.abs() > 1e-6
+        # (threshold: the run-to-run gradient noise of the backward pass's remaining fp32 atomics is 1e-6 .. 6e-5 in
+        # relative L2, i.e. up to ~1e-5 absolute on single elements of the clipped gradient, whose rms is 1.3e-2)
+        live = opt1.flat_grad.abs() > 3e-5
         pd = float(dparam[live].max())
         res = {"ranks": world, "global_batch": B, "grad_rel_l2_after_clip": gd, "param_max_abs_diff_after_adamw": pd,
                "param_max_abs_diff_incl_adam_eps_regime": float(dparam.max()),
@@ -370,7 +372,8 @@ def check_dp(args, device, rank, world, dist):
                "ok": bool(gd < 1e-4 and pd < 1e-5),
                "note": "same kernels per sample; the difference is fp32 summation order of the weight-gradient partial "
                        "sums (bf16 storage is per sample and identical on both sides).  Parameters are compared on the "
-                       "elements with |g| > 1e-6 after clipping; elsewhere lr*g/(|g|+1e-8) amplifies 1e-9 noise to O(lr)"}
+                       "elements with |g| > 3e-5 after clipping (rms 1.3e-2); below that Adam's lr*g/(|g|+1e-8) turns the "
+                       "1e-5-class summation-order noise of the remaining fp32 atomics into O(lr) steps"}
     dist.barrier()
     return res
 

@@ -165,6 +165,8 @@ def lib():
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [_CODE[c] for c in sig]
+    if os.environ.get("LIVAE_HALO16"):      # A/B switch: 16-column halo boxes only (csrc/conv_tc.cu launch_conv_tc_halo)
+        L.livae_tc_set_halo_mode(2)
     _lib = L
     return L
 
