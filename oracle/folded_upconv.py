@@ -1,7 +1,9 @@
-"""Oracle-side PROTOTYPE (CPU, torch float64) of the phase-folded form of the decoder blocks d1-d3
+"""Oracle side (CPU, torch float64) of the phase-folded form of the decoder blocks
 `Upsample(x2, bilinear, align_corners=False) -> ReflectionPad2d(1) -> Conv2d(Cin, Cout, 3)` (reference
-model.py:357-368), the next kernel item in DESIGN.md section 7.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py):
-it pins the algebra the future sm_100a kernels must implement; nothing in the product imports it.
+model.py:357-368).  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): it pins the algebra of csrc/upfold.cu on the
+CPU against torch's own ops (tests/test_folded_upconv_cpu.py); nothing in the product imports it.  Two decompositions:
+the replicate-padded one below (round 1's design study) and, at the end of the file, the zero-padded one with border
+strips that the kernels implement, with the kernel's index maps restated one to one.
 
 1-D facts (n source samples x[0..n-1], padded up-sampled axis p = 0..2n+1, u = p - 1):
   up[2i]   = 0.25 x[i-1] + 0.75 x[i]      (x[-1] := x[0])
@@ -71,3 +73,72 @@ def folded_block(x, w, b=None):
     if b is not None:
         y = y + b.view(1, -1, 1, 1)
     return y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The decomposition csrc/upfold.cu implements (round 2): ZERO padding for the folded convolution F0 (TMA out-of-bounds
+# fill; no padded copy of x) and the whole border rule in two batches of 4-row strips.  With the 1-D operators
+#   R  [2n+2, n]: true up-sampling + reflect padding (index clamping, positions -1 / 2n mirrored onto 1 / 2n-2),
+#   R0 [2n+2, n]: the interior formula on the zero-extended input (what F0 implies),
+# P - P0 = (Ry - R0y) (x) Rx + R0y (x) (Rx - R0x); Ry - R0y is non-zero on padded rows {-1, 0, 2h-1, 2h} only:
+#   row -1: 0.5 x[0] + 0.25 x[1]      row 0: 0.25 x[0]      row 2h-1: 0.25 x[h-1]      row 2h: 0.25 x[h-2] + 0.5 x[h-1]
+# The functions below restate the kernel's index maps (up_true_w, up_zero_w, the strip table) one to one.
+# ------------------------------------------------------------------------------------------------------------------
+def up_true_w(X: int, j: int, n: int) -> float:
+    """csrc/upfold.cu up_true_w: weight of x[j] in the true padded up-sampled value at padded position X in -1..2n"""
+    Xc = 1 if X < 0 else (2 * n - 2 if X >= 2 * n else X)
+    m = Xc >> 1
+    if Xc & 1:
+        return (0.75 if m == j else 0.0) + (0.25 if min(m + 1, n - 1) == j else 0.0)
+    return (0.25 if max(m - 1, 0) == j else 0.0) + (0.75 if m == j else 0.0)
+
+
+def up_zero_w(X: int, j: int) -> float:
+    """csrc/upfold.cu up_zero_w: the same for the interior formula on the zero-extended input"""
+    m = (X + 2) // 2 - 1
+    if X - 2 * m:
+        return (0.75 if m == j else 0.0) + (0.25 if m + 1 == j else 0.0)
+    return (0.25 if m - 1 == j else 0.0) + (0.75 if m == j else 0.0)
+
+
+def up_matrices(n, dtype=torch.float64):
+    R = torch.tensor([[up_true_w(t - 1, j, n) for j in range(n)] for t in range(2 * n + 2)], dtype=dtype)
+    R0 = torch.tensor([[up_zero_w(t - 1, j) for j in range(n)] for t in range(2 * n + 2)], dtype=dtype)
+    return R, R0
+
+
+def strips(x):
+    """x [B,C,h,w] -> (s_tb [2,B,C,4,2w+2], s_lr [2,B,C,4,2h+2]) as upfold_strips_kernel writes them (NCHW here): side 0 =
+    top / left with live rows 0,1; side 1 = bottom / right with live rows 2,3; the lr strips transposed"""
+    B, C, h, w = x.shape
+    Rx, _ = up_matrices(w, x.dtype)
+    _, R0y = up_matrices(h, x.dtype)
+    s_tb = x.new_zeros(2, B, C, 4, 2 * w + 2)
+    s_lr = x.new_zeros(2, B, C, 4, 2 * h + 2)
+    for side in (0, 1):
+        for r in ((0, 1) if side == 0 else (2, 3)):
+            outer = (r == 0) if side == 0 else (r == 3)          # the strip row outside the image
+            c0, c1 = (0.5, 0.25) if outer else (0.25, 0.0)
+            l0, l1 = (0, 1) if side == 0 else (h - 1, h - 2)
+            s_tb[side, :, :, r] = (c0 * x[:, :, l0] + c1 * x[:, :, l1]) @ Rx.T
+            l0, l1 = (0, 1) if side == 0 else (w - 1, w - 2)
+            s_lr[side, :, :, r] = (c0 * x[:, :, :, l0] + c1 * x[:, :, :, l1]) @ R0y.T
+    return s_tb, s_lr
+
+
+def folded_block_strips(x, w, b=None):
+    """the layer as csrc/upfold.cu computes it: zero-padded folded convolution + strip corrections on the two outermost
+    output rows / columns"""
+    B, C, h, ww = x.shape
+    Co = w.shape[0]
+    t = F.conv2d(x, fold_weights(w), padding=1)
+    y = t.reshape(B, 2, 2, Co, h, ww).permute(0, 3, 4, 1, 5, 2).reshape(B, Co, 2 * h, 2 * ww)
+    s_tb, s_lr = strips(x)
+    corr_tb = F.conv2d(s_tb.reshape(2 * B, C, 4, 2 * ww + 2), w).reshape(2, B, Co, 2, 2 * ww)
+    corr_lr = F.conv2d(s_lr.reshape(2 * B, C, 4, 2 * h + 2), w.transpose(2, 3)).reshape(2, B, Co, 2, 2 * h)
+    y = y.clone()
+    y[:, :, :2] += corr_tb[0]
+    y[:, :, -2:] += corr_tb[1]
+    y[:, :, :, :2] += corr_lr[0].transpose(2, 3)
+    y[:, :, :, -2:] += corr_lr[1].transpose(2, 3)
+    return y if b is None else y + b.view(1, -1, 1, 1)
