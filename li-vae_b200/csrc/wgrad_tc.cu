@@ -470,6 +470,49 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// The same for C a multiple of 8 and at most 256 (every layer of the step): a thread owns 8 channels and reads them as
+// one 16-byte load, C/8 threads cover a row, the other thread groups of the CTA walk further rows -- 2-byte loads per
+// thread ran the kernel at 1.7 TB/s.  Same fixed association per CTA (row groups summed in group order).
+__global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const uint4* __restrict__ g, int64_t R, int C8,
+                                                             float* __restrict__ gb, int64_t rows_per_cta, int part_mode) {
+  __shared__ float red[256 * 8];
+  const int rgs = 256 / C8;
+  const int tid = threadIdx.x, cl = tid % C8, rg = tid / C8;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rg < rgs) {
+    int64_t r = r0 + rg;
+    for (; r + 3 * rgs < r1; r += 4 * rgs) {        // four loads in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(g + (r + (int64_t)u * rgs) * C8 + cl);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[2 * k] += __uint_as_float(w[k] << 16); a[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
+      }
+    }
+    for (; r < r1; r += rgs) {
+      const uint4 v = __ldg(g + r * C8 + cl);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[2 * k] += __uint_as_float(w[k] << 16); a[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k * 256 + tid] = a[k];
+  __syncthreads();
+  if (tid < 8 * C8) {                                // one thread per channel: channel c = 8 * (c / 8) + c % 8
+    const int c = tid, lane8 = c >> 3, k = c & 7;
+    float s = 0.f;
+    for (int j = 0; j < rgs; ++j) s += red[k * 256 + j * C8 + lane8];
+    if (part_mode) gb[(int64_t)blockIdx.x * (8 * C8) + c] = s;
+    else atomicAdd(gb + c, s);
+  }
+}
+
 }  // namespace tc
 }  // namespace livae
 
@@ -710,13 +753,16 @@ void colsum_bf16(const void* g, int64_t R, int C, float* gb, cudaStream_t st) {
   int64_t rows = (R + kNumSMs * 4 - 1) / (kNumSMs * 4);
   if (rows < 64) rows = 64;
   const int blocks = (int)((R + rows - 1) / rows);
+  const bool v8 = (C & 7) == 0 && C <= 256 && ((uintptr_t)g & 15) == 0;
   if (float* part = scratch_floats((int64_t)blocks * C)) {       // two fixed-order passes (gb need not be zeroed)
-    colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, part, rows, 1);
+    if (v8) colsum_bf16_v8_kernel<<<blocks, 256, 0, st>>>((const uint4*)g, R, C / 8, part, rows, 1);
+    else colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, part, rows, 1);
     count_launch(1);
     sum_slices(part, blocks, C, gb, st);
     return;
   }
-  colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, gb, rows, 0);
+  if (v8) colsum_bf16_v8_kernel<<<blocks, 256, 0, st>>>((const uint4*)g, R, C / 8, gb, rows, 0);
+  else colsum_bf16_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, R, C, gb, rows, 0);
   count_launch(1);
 }
 }}  // namespace livae::tc
