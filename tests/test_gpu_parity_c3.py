@@ -152,5 +152,7 @@ def test_forward_pass_is_bit_reproducible_and_gradients_only_jitter_by_summation
     for k in g1:
         # measured: <= 5e-7 (B = 64) .. 2e-5 (B = 256, STN conv1 bias) everywhere except the encoder's convolutions and heads, whose gradients are cancelling sums
         # thousands of times smaller than their terms (|g| ~ 1e-2 .. 2e-1 against 2e+1 for the decoder): 2e-4 / 6.5e-5
-        loose = k.startswith("encoder.conv_layers") or k.startswith("encoder.fc_")
+        # The STN's gradients are the same kind of sum (over samples, of per-sample angle gradients that differ run to run
+        # at 1e-7 through rot_sample's atomics): mostly bit-identical, 1.1e-4 seen once in three runs at B = 256.
+        loose = k.startswith("encoder.")
         assert rel_l2(g1[k], g2[k]) <= (2e-3 if loose else 1e-4), (k, rel_l2(g1[k], g2[k]))
