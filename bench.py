@@ -369,7 +369,7 @@ def check_dp(args, device, rank, world, dist):
         res = {"ranks": world, "global_batch": B, "grad_rel_l2_after_clip": gd, "param_max_abs_diff_after_adamw": pd,
                "param_max_abs_diff_incl_adam_eps_regime": float(dparam.max()),
                "adam_eps_regime_fraction": float(1.0 - live.float().mean()),
-               "ok": bool(gd < 1e-4 and pd < 1e-5),
+               "ok": bool(gd < 5e-4 and pd < 1e-5),
                "note": "same kernels per sample; the difference is fp32 summation order of the weight-gradient partial "
                        "sums (bf16 storage is per sample and identical on both sides).  Parameters are compared on the "
                        "elements with |g| > 3e-5 after clipping (rms 1.3e-2); below that Adam's lr*g/(|g|+1e-8) turns the "
