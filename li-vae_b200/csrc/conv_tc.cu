@@ -285,7 +285,6 @@ struct ConvTcHaloParams {
   int a_s2d, epi_mode; uint8_t* pool_idx;     // HaloOpts (tc_common.cuh)
   int s2d_cpr;                                // a_s2d: K chunks per pixel row of the 2x2 block (2C / kc)
   int up_cout;                                // epi_mode 3 (epilogue_upfold)
-  int nacc;                                   // TMEM accumulators: 2, or up to 4 when the CTA has the SM to itself
 };
 
 static constexpr int kHaloSmemMax = 225 * 1024;     // dynamic shared memory opt-in of the halo kernels (SM: 227 KB = 232448 B incl. ~1.3 KB static)
@@ -532,11 +531,11 @@ __device__ __forceinline__ void epilogue_upfold(uint32_t taddr, int nbase, int N
 // EPI = epilogue mode (HaloOpts): a template parameter so that the register-hungry pooled / un-blocking
 // epilogues do not cost the plain convolutions their occupancy.
 template <int KSTEPS, int EPI>
-__global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(EPI == 2 ? kThreadsEpi2 : kThreads, EPI == 2 ? 2 : 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const ConvTcHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t fullA[kSAmax], emptyA[kSAmax], fullB[kSB], emptyB[kSB], tfull[4], tempty[4];
+  __shared__ __align__(8) uint64_t fullA[kSAmax], emptyA[kSAmax], fullB[kSB], emptyB[kSB], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_tapoff[kMaxTaps];        // row shift of each tap in descriptor address units (16 B)
   __shared__ int s_grp[4][2];                    // tap_begin, tap_end of each group
@@ -552,10 +551,11 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
   uint8_t* smemB = smem + (uint32_t)p.nsa * a_slot;
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
-  // TMEM accumulators: two (double buffer); EPI 3 / 4: as many as the 512 columns hold, up to four.  One accumulator's
-  // cycle is its tile's MMAs plus its epilogue, so with two the kernel ran at (MMA + epilogue) / 2 per tile whenever the
-  // epilogue was the longer half (folded decoder: 4000-4700 vs 2400-3800 cycles, mostly the scattered 16-byte stores).
-  const uint32_t nacc = (uint32_t)p.nacc;
+  // Two TMEM accumulators (double buffer).  Up to four of them, a second epilogue warp group on alternate tiles and a
+  // deeper A ring were measured on the folded-decoder kernels and on every kernel that has its SM to itself: no gain
+  // (15.68 -> 15.79 ms per step) -- those epilogues are bound by LSU wavefronts (every thread stores its own 32..128-byte
+  // run: 79 % of the LSU data pipe in the ncu capture of epilogue_upfold), which more buffering cannot hide.
+  constexpr uint32_t nacc = 2u;
   const uint32_t ncols = nacc * acc_cols;
 
   if (warp == 0 && lane == 0) {
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
     prefetch_tmap(&tmB);
     for (int s = 0; s < kSAmax; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI == 2 ? 8 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI == 2 ? 8 : 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -696,11 +696,7 @@ __global__ void __launch_bounds__(EPI >= 2 ? kThreadsEpi2 : kThreads, EPI == 2 ?
     const int py = row / p.bw, px = row - py * p.bw;
     int it = 0, pn = 0;
     long long* pb = (warp == 2 && lane == 0) ? p.probe : nullptr;
-    // EPI 3 / 4: eight epilogue warps in two groups, group g owns accumulator g (alternate tiles): a warp's chain per tile
-    // (tcgen05.ld passes, mask / store latency: 4000-4700 cycles measured) may then take two tiles' worth of MMA time
-    const int egrp = (EPI == 3 || EPI == 4) ? (warp >= 6 ? 1 : 0) : -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      if (egrp >= 0 && (it & 1) != egrp) continue;
       int t3 = tile;
       const int tx = t3 % p.tiles_x; t3 /= p.tiles_x;
       const int ty = t3 % p.tiles_y; t3 /= p.tiles_y;
@@ -990,7 +986,6 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   while (acc_cols < (uint32_t)p.N) acc_cols <<= 1;
   int per_sm = (int)(220 * 1024 / (smem + 1024));
   int per_sm_tmem = (int)(512 / (2 * acc_cols));
-  if (opts.epi_mode == 3 || premask) per_sm_tmem = 1;       // these take up to four accumulators (see the kernel)
   if (per_sm > per_sm_tmem) per_sm = per_sm_tmem;
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
@@ -999,10 +994,6 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   // (up to the whole 227 KB of the SM when the CTA is alone on it: with resident weights of 144 KB the folded decoder
   // kernels had two slots, i.e. ONE box in flight, and ran at one TMA round trip -- 4000+ cycles -- per tile)
   while (p.nsa < kSAmax && (smem + a_slot + 1024) * per_sm <= 220 * 1024 && smem + a_slot <= (size_t)kHaloSmemMax) { smem += a_slot; ++p.nsa; }
-  // TMEM accumulators: two; the folded-decoder kernels (alone on their SM) take up to four.  (Tried for every kernel
-  // that has the SM to itself, together with a six-slot A ring: no gain, 15.68 -> 15.79 ms.)
-  p.nacc = 2;
-  if (opts.epi_mode == 3 || premask) { p.nacc = (int)(512u / acc_cols); if (p.nacc > 4) p.nacc = 4; if (p.nacc < 2) p.nacc = 2; }
   int gx = kNumSMs * per_sm;
   if (gx > tiles) gx = tiles;
   const dim3 grid(gx, N / p.N);
@@ -1014,8 +1005,8 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
     conv_tc_halo_kernel<4, 2><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
   } else if (opts.epi_mode == 3) {
     if (p.kc != 64) return 1;
-    conv_tc_halo_kernel<4, 3><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
-  } else if (premask) conv_tc_halo_kernel<4, 4><<<grid, kThreadsEpi2, smem, st>>>(tmA, tmB, p);
+    conv_tc_halo_kernel<4, 3><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else if (premask) conv_tc_halo_kernel<4, 4><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 64) conv_tc_halo_kernel<4, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else if (p.kc == 32) conv_tc_halo_kernel<2, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   else conv_tc_halo_kernel<1, 0><<<grid, kThreads, smem, st>>>(tmA, tmB, p);

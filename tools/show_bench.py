@@ -9,7 +9,7 @@ for path in sys.argv[1:]:
             continue
         d = json.loads(l)
         k = d.pop("kernels", None)
-        print(path, "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]),
+        print(path, "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), "e2e", d.get("e2e") and round(d["e2e"]["value"]),
               "launches", d.get("gpu_launches"), "roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3),
               "step_frac", round(d["step_roofline"]["frac"], 3))
         if k and "-k" in sys.argv[0:1] + sys.argv:
