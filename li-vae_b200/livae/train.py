@@ -20,6 +20,8 @@ from collections import defaultdict
 from typing import Any
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -295,7 +297,10 @@ class GraphedRvaeStep:
     SURVEY 8e.  The gradient all-reduce (`reduce_grads`) runs eagerly between the two graphs.  Needs
     livae.optim.FlatAdamW (its flat buffers are the static memory the second graph works on) and batches of one fixed
     shape; the first call captures (after two warm-up runs whose effect on parameters and optimiser state is undone).
-    Returns what train_rvae_step returns; the tensors are static graph memory, valid until the next call."""
+    Learning rate, betas, eps, weight decay, the clip norm and the set of trainable parameters are baked into the
+    captured launches, so they are compared on every call and a change (an LR scheduler, --freeze-stn) re-captures.
+    Returns what train_rvae_step returns; the tensors are static graph memory, valid until the next call.
+    `train_rvae_one_epoch` uses this class by itself when the optimiser is a FlatAdamW (LIVAE_CUDA_GRAPH=0 disables)."""
 
     def __init__(self, model, optimizer, criterion, device, canonical_weight: float = 0.2, max_norm: float = 20.0,
                  reduce_grads=None, elide_dead_encoder: bool = False):
@@ -304,6 +309,13 @@ class GraphedRvaeStep:
         self.model, self.opt, self.crit, self.device = model, optimizer, criterion, torch.device(device)
         self.cw, self.max_norm, self.reduce, self.elide = canonical_weight, max_norm, reduce_grads, elide_dead_encoder
         self.g_fwd = self.g_opt = None
+        self.sig = None
+
+    def _sig(self):
+        o = self.opt
+        return (tuple((g.get("lr"), tuple(g.get("betas", ())), g.get("eps"), g.get("weight_decay"), g.get("decoupled"))
+                      for g in o.param_groups),
+                tuple(p.requires_grad for p in self.model.parameters()), self.model.training)
 
     def _fwd_bwd(self):
         self.opt.zero_grad()
@@ -319,6 +331,9 @@ class GraphedRvaeStep:
 
     def _capture(self, x, xr, ang):
         o = self.opt
+        self.g_fwd = self.g_opt = None          # a re-capture: release the old graphs and their pool first
+        self.outs = self.pre = None
+        self.sig = self._sig()
         self.sx, self.sxr, self.sang = x.clone(), xr.clone(), ang.clone()
         keep = [t.clone() for t in (o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_dev)]
         side = torch.cuda.Stream(self.device)
@@ -339,11 +354,17 @@ class GraphedRvaeStep:
             dst.copy_(src)
         ops.invalidate_weight_packs()
 
+    def accepts(self, x, xr, ang) -> bool:
+        """a paired batch of the captured shape (any paired batch before the first capture)"""
+        if xr is None or ang is None or ang.dim() != 1:
+            return False
+        return self.g_fwd is None or (x.shape == self.sx.shape and ang.shape == self.sang.shape)
+
     def __call__(self, batch):
         x, xr, ang = _unpack_rvae_batch(batch, self.device)
         if xr is None or ang is None:
             raise ValueError("GraphedRvaeStep: paired batches (x, x_rotated, angle) only")
-        if self.g_fwd is None:
+        if self.g_fwd is None or self.sig != self._sig():
             self._capture(x, xr, ang)
         elif x.shape != self.sx.shape:
             raise ValueError("GraphedRvaeStep: batch shape changed (drop_last=True keeps it fixed)")
@@ -357,6 +378,23 @@ class GraphedRvaeStep:
         return self.sx, loss, recon_l, kld_l, cycle_l, can_l, outs, self.pre
 
 
+def _graph_step_for(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads):
+    """the GraphedRvaeStep of this (model, optimiser, criterion, ...) combination, kept on the optimiser between epochs;
+    None when the optimiser is not a FlatAdamW (the reference scripts' torch.optim.AdamW: eager launches), when
+    LIVAE_CUDA_GRAPH=0, or after a failed capture"""
+    if getattr(optimizer, "flat_grad", None) is None or os.environ.get("LIVAE_CUDA_GRAPH", "1") == "0":
+        return None
+    ent = getattr(optimizer, "_livae_graph_step", None)
+    if ent is False:
+        return None
+    key = (id(model), id(criterion), str(torch.device(device)), float(canonical_weight), float(max_norm), id(reduce_grads))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    gs = GraphedRvaeStep(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads)
+    optimizer._livae_graph_step = (key, gs)
+    return gs
+
+
 def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger, device,
                          canonical_weight: float = 0.2, scaler=None, grad_max_norm: float | None = None,
                          reduce_grads=None) -> None:
@@ -366,9 +404,30 @@ def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger
     acc = _DevAccum(device)
     n_batches = 0
     max_norm = grad_max_norm if grad_max_norm is not None else 20.0
+    gstep = _graph_step_for(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads)
     for batch in DevicePrefetcher(data_loader, device):
-        x, loss, recon_l, kld_l, cycle_l, _can_l, outs, pre = train_rvae_step(
-            model, optimizer, criterion, batch, device, canonical_weight, max_norm, reduce_grads)
+        step_out = None
+        if gstep is not None:
+            batch = _unpack_rvae_batch(batch, device)
+            if gstep.accepts(*batch):              # ragged last batch, unpaired data: the eager step below
+                try:
+                    step_out = gstep(batch)
+                except Exception as e:             # capture failed (never seen; e.g. out of memory for the graph pool)
+                    if gstep.g_fwd is not None and gstep.g_opt is not None:
+                        raise
+                    import warnings
+                    warnings.warn(f"livae: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                                  "continuing with eager launches")
+                    optimizer._livae_graph_step = False
+                    gstep = None
+                    torch.cuda.synchronize()
+            if batch[1] is None:
+                batch = batch[0]
+            elif batch[2] is None:
+                batch = batch[:2]
+        if step_out is None:
+            step_out = train_rvae_step(model, optimizer, criterion, batch, device, canonical_weight, max_norm, reduce_grads)
+        x, loss, recon_l, kld_l, cycle_l, _can_l, outs, pre = step_out
         rotated_recon, canonical_recon, theta, mu, logvar = outs
         with torch.no_grad():
             m = dict(train_loss=loss, train_recon_loss=recon_l, train_kld_loss=kld_l, train_cycle_loss=cycle_l,

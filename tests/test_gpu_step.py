@@ -474,3 +474,49 @@ def test_cuda_graph_step_equals_eager_step():
         diff = (p0[k] - p1[k]).abs()
         stats = (k, float(diff.max()), float(diff.mean()), float((diff > 2e-5).float().mean()))
         assert float(diff.mean()) <= 5e-6 and float((diff > 2e-5).float().mean()) <= 1e-3 and float(diff.max()) <= 6.1e-3, stats
+
+
+@pytest.mark.tc_engine
+def test_train_rvae_one_epoch_uses_graphs_transparently(monkeypatch):
+    """livae.train.train_rvae_one_epoch with a FlatAdamW replays the step as CUDA graphs by itself (LIVAE_CUDA_GRAPH=0:
+    eager launches): same logged metrics and parameters over two epochs that include a ragged last batch (eager
+    fallback) and a learning-rate change between the epochs (re-capture: the rate is baked into the captured launch)"""
+    import copy
+    import livae
+    from livae.optim import FlatAdamW
+    P, L, B, seed = 32, 2, 16, 91
+    params = O.make_params(O.rvae_param_shapes(P, L), seed=seed, stn_head_std=0.5)
+    full = [tuple(t.cuda() for t in O.make_lattice_batch(B, P, seed=seed + 1 + k)) for k in range(3)]
+    ragged = tuple(t[:B // 2].contiguous() for t in full[0])
+    loader = full + [ragged]
+    eps = torch.from_numpy(np.random.default_rng(seed).standard_normal((B, L))).float().cuda()
+    dev = torch.device("cuda")
+    results = []
+    for graphed in (False, True):
+        monkeypatch.setenv("LIVAE_CUDA_GRAPH", "1" if graphed else "0")
+        m = _rvae(P, L, params)
+        opt = FlatAdamW(m.parameters(), lr=1e-3, weight_decay=1e-5)
+        crit = livae.RVAELoss(beta=10.0, gamma=10.0)
+        log = livae.MetricLogger()
+        orig = torch.randn_like
+        torch.randn_like = lambda t, **k: eps[:t.shape[0]].reshape(t.shape)
+        try:
+            livae.train_rvae_one_epoch(m, loader, opt, crit, log, dev)
+            for g in opt.param_groups:
+                g["lr"] = 3e-3
+            livae.train_rvae_one_epoch(m, loader, opt, crit, log, dev)
+        finally:
+            torch.randn_like = orig
+        used = getattr(opt, "_livae_graph_step", None)
+        assert (used is not None and used is not False and used[1].g_fwd is not None) == graphed
+        results.append((copy.deepcopy(log.metrics), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
+                        float(opt.step_dev)))
+    (m0, p0, s0), (m1, p1, s1) = results
+    assert s0 == s1 == 8.0
+    for k in ("train_loss", "train_recon_loss", "train_kld_loss", "train_cycle_loss", "train_psnr", "train_ssim", "train_grad_norm"):
+        a, b = np.asarray(m0[k], dtype=np.float64), np.asarray(m1[k], dtype=np.float64)
+        assert np.allclose(a, b, rtol=2e-4, atol=1e-6), (k, a, b)
+    # the second epoch ran at three times the rate in both modes: parameters agree in the bulk (cf. the test above)
+    for k in p0:
+        diff = (p0[k] - p1[k]).abs()
+        assert float(diff.mean()) <= 2e-5 and float((diff > 1e-4).float().mean()) <= 2e-3, (k, float(diff.max()), float(diff.mean()))
