@@ -261,7 +261,8 @@ class _DevAccum:
     def add(self, **kw):
         for k, v in kw.items():
             v = v.detach().reshape(()) if isinstance(v, torch.Tensor) else torch.tensor(float(v), device=self.device)
-            self.sums[k] = v if k not in self.sums else self.sums[k] + v
+            # the first value is copied: under GraphedRvaeStep it is a view of static graph memory that the next replay overwrites
+            self.sums[k] = v.clone() if k not in self.sums else self.sums[k] + v
 
     def averages(self, n):
         if not self.sums:
