@@ -515,7 +515,9 @@ def test_train_rvae_one_epoch_uses_graphs_transparently(monkeypatch):
     assert s0 == s1 == 8.0
     for k in ("train_loss", "train_recon_loss", "train_kld_loss", "train_cycle_loss", "train_psnr", "train_ssim", "train_grad_norm"):
         a, b = np.asarray(m0[k], dtype=np.float64), np.asarray(m1[k], dtype=np.float64)
-        assert np.allclose(a, b, rtol=2e-4, atol=1e-6), (k, a, b)
+        # (2e-3: the second epoch's values carry eight steps of Adam-amplified atomic-order noise; the aliasing bug this test
+        # found -- the accumulator keeping a view of static graph memory -- was 1.7e-2)
+        assert np.allclose(a, b, rtol=2e-3, atol=1e-5), (k, a, b)
     # the second epoch ran at three times the rate in both modes: parameters agree in the bulk (cf. the test above)
     for k in p0:
         diff = (p0[k] - p1[k]).abs()
