@@ -510,8 +510,11 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    if args.cuda_graph:
-        os.environ["LIVAE_CUDA_GRAPH"] = "1"      # train_rvae_one_epoch replays the step as CUDA graphs as well (opt-in switch)
+    if args.cuda_graph and world == 1:
+        # train_rvae_one_epoch replays the step as CUDA graphs as well (opt-in switch).  One GPU only: the combination
+        # graphed epoch loop + NCCL all-reduce between the graphs was not measured in round 2 (GraphedRvaeStep itself with
+        # the all-reduce is what the device-timed value runs at every N).
+        os.environ["LIVAE_CUDA_GRAPH"] = "1"
 
     def timed_epoch(loader):
         """the public loop: livae.train.train_rvae_one_epoch over `loader` (args.steps batches), metric block and
@@ -562,7 +565,7 @@ def main():
         # 13 metric floats come back once per epoch
         e2e = {"value": n_patches / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": world * args.batch * 8 * 8, "d2h_bytes_per_step": world * 13 * 4 / args.steps,
-               "path": "livae.train.train_rvae_one_epoch (metric block included; LIVAE_CUDA_GRAPH=1 unless --no-cuda-graph) over livae.data.DevicePatchLoader: "
+               "path": "livae.train.train_rvae_one_epoch (metric block included; LIVAE_CUDA_GRAPH=1 at N = 1 unless --no-cuda-graph) over livae.data.DevicePatchLoader: "
                        "host site indices + Python-random draws in the reference's order -> pinned upload -> ROI gather, "
                        "default_transform, paired rotation, min-max on the GPU from 16 x 4096^2 resident images "
                        "(what scripts/train_rvae.py's DataLoader becomes through this package); metrics are read back "
