@@ -364,6 +364,10 @@ int livae_decfc_bwd_bf16(const float* z, const float* w, const void* gy, int B, 
 /* tuning / test hook: 0 = fetch one TMA box per filter tap; 1 (default) = fetch one haloed box per tap
  * group and address each tap as a row shift of it */
 void livae_tc_set_halo_mode(int mode);
+/* Host-side tile geometry of the halo convolution kernel for an Hq x Wq output grid whose taps shift by up to max_sx
+ * columns inside a tap group (kw - 1 at stride 1): box width (16..20), output rows and valid columns per 128-position
+ * tile, tiles per map.  No device work. */
+int livae_tc_halo_geometry(int Hq, int Wq, int max_sx, int* bw, int* th, int* tw, int* tiles);
 void livae_tc_set_wgrad_halo(int mode);   /* the same switch for the weight-gradient kernel */
 /* 1 (default): the thin 1-channel layers run on tcgen05 (thread-built im2col / col2im operands,
  * csrc/thin_tc.cu) where the shape is eligible; 0: SIMT kernels only */

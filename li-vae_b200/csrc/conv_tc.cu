@@ -855,6 +855,22 @@ static int g_halo_wide = 1;
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
+// Box width of the halo kernel's tile for an Hq x Wq output grid whose taps shift by up to max_sx columns inside a tap
+// group: the width in 16..20 that covers the grid with the fewest 128-position tiles (128 / bw rows of bw - max_sx valid
+// columns each); ties go to the narrower box.  Pure host arithmetic (livae_tc_halo_geometry exposes it to the CPU tests).
+static int halo_box_width(int Hq, int Wq, int max_sx) {
+  int best_bw = 16, best_tiles = 1 << 30;
+  for (int bw = 16; bw <= 20; ++bw) {
+    const int tw = bw - max_sx, th = 128 / bw;
+    if (tw < 1) continue;
+    const int tiles = ((Wq + tw - 1) / tw) * ((Hq + th - 1) / th);
+    if (tiles < best_tiles) { best_tiles = tiles; best_bw = bw; }
+  }
+  return best_bw;
+}
+
+int halo_box_width_public(int Hq, int Wq, int max_sx) { return halo_box_width(Hq, Wq, max_sx); }
+
 // returns 1 when the shape is not eligible for the halo kernel
 int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const void* wpacked, int wtaps, int N,
                         int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
@@ -905,16 +921,8 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
   // 16 (8 rows) is the default; a wider box (7 or 6 rows) is taken when it covers the grid with fewer tiles -- a 32-wide
   // grid under 3x3 taps needs three 14-column tiles per row at bw = 16 (12 tiles per 32 x 32 map) but two 16-column
   // tiles at bw = 18 (10 tiles).
-  {
-    int best_bw = 16, best_tiles = 1 << 30;
-    for (int bw = 16; bw <= 20; ++bw) {
-      const int tw = bw - max_sx, th = 128 / bw;
-      const int tiles = ((Wq + tw - 1) / tw) * ((Hq + th - 1) / th);
-      if (tiles < best_tiles) { best_tiles = tiles; best_bw = bw; }
-    }
-    if (!g_halo_wide) best_bw = 16;
-    p.bw = best_bw; p.th = 128 / best_bw;
-  }
+  p.bw = g_halo_wide ? halo_box_width(Hq, Wq, max_sx) : 16;
+  p.th = 128 / p.bw;
   p.tw = p.bw - max_sx;
   p.box_rows = p.th + max_sy;
   if (max_sy * p.bw + max_sx > 200) return 1;
@@ -1210,6 +1218,16 @@ extern "C" int livae_tc_conv_dgrad(const livae_tc_conv_desc* d, const void* gy, 
 
 // tracing hook (tc_common.cuh): device buffer of 4 x 1024 int64, or NULL to switch tracing off
 extern "C" void livae_set_probe(void* dev_ptr) { g_probe = (long long*)dev_ptr; }
+
+// Host-side tile geometry of the halo kernel (no device work): for an Hq x Wq output grid and a maximum column shift
+// max_sx inside a tap group (kw - 1 for stride 1) -> box width, rows and valid columns per tile, tiles per map
+extern "C" int livae_tc_halo_geometry(int Hq, int Wq, int max_sx, int* bw, int* th, int* tw, int* tiles) {
+  LIVAE_CHECK_ARG(Hq > 0 && Wq > 0 && max_sx >= 0 && max_sx <= 8 && bw && th && tw && tiles, "tc_halo_geometry: bad args");
+  const int b = livae::tc::halo_box_width_public(Hq, Wq, max_sx);
+  *bw = b; *th = 128 / b; *tw = b - max_sx;
+  *tiles = ((Wq + *tw - 1) / *tw) * ((Hq + *th - 1) / *th);
+  return 0;
+}
 
 // tuning / test hook: 0 = per-tap boxes only, 1 = halo kernel where eligible
 extern "C" void livae_tc_set_halo_mode(int mode) { g_halo_mode = mode ? 1 : 0; g_halo_wide = mode == 2 ? 0 : 1; }

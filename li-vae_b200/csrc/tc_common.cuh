@@ -202,6 +202,7 @@ int launch_conv_tc_halo(const void* in, int B, int Hin, int Win, int Cin, const 
                         int Hq, int Wq, int Ho, int Wo, int os, int oy0, int ox0, int in_stride, int ntaps,
                         const int* tdy, const int* tdx, const int* tw_idx, void* out, int out_f32,
                         const float* bias, int act, const void* relu_mask, cudaStream_t st, HaloOpts opts);
+int halo_box_width_public(int Hq, int Wq, int max_sx);   // conv_tc.cu: tile box width of the halo kernel (host arithmetic)
 // returns 0 = launched, 1 = shape not eligible
 int launch_wgrad_halo(const livae_tc_conv_desc* d, const void* x, const void* gy, float* gw_acc, int Ho, int Wo,
                       cudaStream_t st, int x_s2d);   // x_s2d: bit 0 = x, bit 1 = gy read block-wise (2x2 blocks as channels)

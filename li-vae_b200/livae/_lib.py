@@ -149,6 +149,8 @@ def lib():
     L.livae_tc_conv5pool_supported.argtypes = [C.c_int] * 5
     L.livae_tc_conv5pool_wgrad_ws_bytes.restype = C.c_int64
     L.livae_tc_conv5pool_wgrad_ws_bytes.argtypes = [C.c_int, C.c_int]
+    L.livae_tc_halo_geometry.restype = C.c_int
+    L.livae_tc_halo_geometry.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] * 4
     L.livae_upfold_supported.restype = C.c_int
     L.livae_upfold_supported.argtypes = [C.c_int] * 5
     L.livae_upfold_wgrad_ws_bytes.restype = C.c_int64
@@ -175,7 +177,7 @@ def exported_symbols():
     """every entry point include/livae_b200.h declares (used by the CPU symbol test)"""
     return sorted(list(_SIGS) + ["livae_last_error", "livae_abi_version", "livae_device_ok",
                                  "livae_elbo_scratch_floats", "livae_l2norm_scratch_floats",
-                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_upfold_supported", "livae_upfold_wgrad_ws_bytes", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
+                                 "livae_launch_count", "livae_tc_conv_supported", "livae_tc_set_halo_mode", "livae_tc_set_wgrad_halo", "livae_set_scratch", "livae_thin_set_tc", "livae_set_probe", "livae_tc_conv5pool_supported", "livae_tc_halo_geometry", "livae_upfold_supported", "livae_upfold_wgrad_ws_bytes", "livae_tc_dgrad_s2blk_supported", "livae_tc_conv5pool_wgrad_ws_bytes", "livae_tc_wgrad_ws_bytes", "livae_conv_fwd_ws_bytes", "livae_conv_out_shape", "livae_ssim_box_ws_floats"])
 
 
 def ptr(t):

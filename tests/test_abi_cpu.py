@@ -107,3 +107,34 @@ def test_canonical_cache_is_one_shot_and_identity_keyed():
     enc._canonical = (x, th, xr)
     assert enc.take_canonical(x, th) is xr and enc.take_canonical(x, th) is None
     copy.deepcopy(enc)                                            # an idle module carries no batch / graph
+
+
+def test_halo_tile_geometry_chooser(libpath):
+    """host logic of the tcgen05 halo convolution (csrc/conv_tc.cu launch_conv_tc_halo): the tile is 128 consecutive
+    positions of a bw-wide box, bw chosen in 16..20 to cover the output grid with the fewest tiles"""
+    import ctypes as C
+
+    from livae import _lib
+    L = _lib.lib()
+
+    def geo(H, W, sx):
+        out = [C.c_int() for _ in range(4)]
+        assert L.livae_tc_halo_geometry(H, W, sx, *[C.byref(o) for o in out]) == 0
+        return tuple(o.value for o in out)
+
+    def tiles_at(H, W, sx, bw):
+        tw, th = bw - sx, 128 // bw
+        return -(-W // tw) * -(-H // th)
+
+    # the cases the round-2 notes quote: 32 x 32 and 16 x 16 maps under 3x3 taps, the 64-wide strips
+    assert geo(32, 32, 2) == (18, 7, 16, 10) and tiles_at(32, 32, 2, 16) == 12
+    assert geo(16, 16, 2)[3] == 3 and tiles_at(16, 16, 2, 16) == 4
+    assert geo(64, 64, 2)[3] <= tiles_at(64, 64, 2, 16) == 40
+    for H in (4, 8, 9, 16, 31, 32, 64, 100, 16382):
+        for W in (8, 14, 16, 28, 32, 33, 64, 66):
+            for sx in (0, 1, 2, 4):
+                bw, th, tw, tiles = geo(H, W, sx)
+                assert 16 <= bw <= 20 and th == 128 // bw and tw == bw - sx and th * bw <= 128
+                assert tiles == tiles_at(H, W, sx, bw) == min(tiles_at(H, W, sx, b) for b in range(16, 21))
+                assert -(-W // tw) * tw >= W and -(-H // th) * th >= H          # the tiles cover the grid
+    assert L.livae_tc_halo_geometry(0, 8, 2, None, None, None, None) != 0          # argument errors are reported, not crashed on
