@@ -1,0 +1,112 @@
+"""CPU: the part of the reference's own test-suite that needs no GPU (tests/test_filter.py 7 tests,
+tests/test_utils.py 4 tests), against the drop-in package.
+
+* In the build container the reference's test FILES are collected and run as they lie under /root/reference/tests, with
+  this repo's `livae` first on the path (skipped where the tree does not exist).  test_utils.py's noise-fallback test
+  is unseeded there (SURVEY section 4 calls it flaky against the reference itself): it is run on its own and only
+  required not to error.
+* The same behaviours restated here (own inputs, seeded) travel with the repo.
+
+tests/test_train.py's cases need this package's kernels and live in tests/test_gpu_trainer_api.py; tests/test_data.py
+exercises a `generate_lattice_grid(coords, shape, patch_size=, padding=)` signature the reference itself no longer has
+(10 / 10 fail against /root/reference/src too), so there is nothing to keep green there."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REF_TESTS = "/root/reference/tests"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "li-vae_b200")
+
+
+def _run_reference_tests(files, extra=()):
+    env = dict(os.environ, PYTHONPATH=PKG, PYTHONDONTWRITEBYTECODE="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", "/tmp", *extra,
+           *[os.path.join(REF_TESTS, f) for f in files]]
+    return subprocess.run(cmd, cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree only exists in the build container")
+def test_reference_filter_tests_pass_against_the_dropin():
+    r = _run_reference_tests(["test_filter.py"])
+    assert r.returncode == 0 and "7 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree only exists in the build container")
+def test_reference_utils_tests_pass_against_the_dropin():
+    # the three seeded-by-construction tests must pass; the noise-fallback test draws an unseeded image and fails
+    # against the reference itself for some draws, so it is only required not to ERROR
+    r = _run_reference_tests(["test_utils.py"], extra=["-k", "not fallback"])
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    r = _run_reference_tests(["test_utils.py"], extra=["-k", "fallback"])
+    assert r.returncode in (0, 1) and "error" not in r.stdout.lower(), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- the same behaviours, restated (filter.py:42-232, utils.py:12-82 of the reference) ----------------------------
+def _checkerboard(n=64):
+    yy, xx = np.indices((n, n))
+    return np.where((yy + xx) % 2 == 0, -1.0, 1.0)
+
+
+def test_normalize_image_range_and_constant():
+    from livae.filter import normalize_image
+    out = normalize_image(np.array([[0.0, 5.0], [10.0, 15.0]]))
+    assert out.min() == 0.0 and out.max() == 1.0
+    assert np.array_equal(normalize_image(np.full((3, 3), 7.0)), np.zeros((3, 3)))
+
+
+def test_fft_spectra_shapes():
+    from livae.filter import fft_spectra
+    img = np.arange(16.0).reshape(4, 4)
+    mag, phase = fft_spectra(img)
+    assert mag.shape == phase.shape == img.shape and (mag >= 0).all()
+    assert mag[2, 2] == pytest.approx(img.sum())                     # DC bin sits at the centre of the shifted spectrum
+
+
+def test_radial_filters_on_a_checkerboard():
+    from livae.filter import bandpass_filter, highpass_filter, lowpass_filter
+    cb = _checkerboard()
+    assert lowpass_filter(cb, cutoff_radius=5).std() < 0.1 * cb.std()
+    assert highpass_filter(cb, cutoff_radius=5).std() > 0.8 * cb.std()
+    ramp = np.outer(np.linspace(0, 1, 64), np.ones(64))
+    both = ramp + cb
+    bp = bandpass_filter(both, low_cutoff=5, high_cutoff=20)
+    assert 0.05 * cb.std() < bp.std() < both.std()
+    # low-pass + high-pass at the same radius overlap only on the ring r == cutoff
+    lp, hp = lowpass_filter(both, 5.5), highpass_filter(both, 5.5)
+    assert np.allclose(lp + hp, both, atol=1e-9)
+
+
+def test_filter_argument_errors():
+    from livae.filter import bandpass_filter, lowpass_filter
+    with pytest.raises(ValueError):
+        bandpass_filter(np.ones((8, 8)), low_cutoff=10, high_cutoff=5)
+    with pytest.raises(ValueError):
+        lowpass_filter(np.zeros((2, 2, 2)), cutoff_radius=5)
+
+
+def _hex_lattice(size, spacing, noise, seed):
+    y, x = np.mgrid[:size, :size].astype(np.float64)
+    k = 2 * np.pi / spacing
+    img = np.sin(k * x) + np.sin(k * (x / 2 - np.sqrt(3) * y / 2)) + np.sin(k * (x / 2 + np.sqrt(3) * y / 2))
+    return img + np.random.default_rng(seed).normal(0, noise, img.shape)
+
+
+def test_lattice_constant_hexagonal_and_overrides():
+    from livae.utils import estimate_lattice_constant
+    assert 14.0 < estimate_lattice_constant(_hex_lattice(512, 16.0, 0.3, 0)) < 18.0
+    x = np.arange(512.0)[None, :]
+    rng = np.random.default_rng(1)
+    stripes = np.sin(2 * np.pi / 20.0 * x) + rng.normal(0, 0.2, (512, 512))
+    assert 18.0 < estimate_lattice_constant(stripes, min_atom_size=15.0, max_atom_size=30.0) < 22.0
+    noisy = np.sin(2 * np.pi / 12.0 * x) + rng.normal(0, 0.5, (512, 512))
+    assert estimate_lattice_constant(noisy, prominence_factor=0.05) != 15.0
+
+
+def test_lattice_constant_falls_back_without_a_peak():
+    from livae.utils import estimate_lattice_constant
+    # a constant image has no radial-profile peak at all: the documented fallback (utils.py:12-82) is 15.0
+    assert estimate_lattice_constant(np.ones((128, 128))) == 15.0
