@@ -54,6 +54,48 @@ def test_draws_replay_reference_order():
     assert random.random() == nxt
 
 
+def _same_draws(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(a, dict):
+        return a.keys() == b.keys() and all(_same_draws(a[k], b[k]) for k in a)
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("cfg", [(0.5, 4, False, True, True), (0.5, 4, True, True, False), (0.5, 4, False, False, True),
+                                 (0.3, 0, False, True, True), (0.5, 1, True, True, True), (0.9, 100, True, True, True)])
+def test_batch_draws_from_the_word_stream_equal_per_call_draws(cfg):
+    """large batches parse Mersenne-Twister output words instead of calling `random` seven times per patch: the same
+    numbers bit for bit (the oracle-checked per-call loop above is the yardstick) and the same generator state
+    afterwards, so the reference's stream continues unchanged"""
+    from livae import data
+    fp, jitter, rotation, transform, pair = cfg
+    for seed, n in ((0, 64), (1, 257), (2, 2048)):
+        random.seed(seed); random.gauss(0, 1); random.random()            # a pending gauss value must survive
+        want = data._draw_calls(n, fp, jitter, rotation, transform, pair)
+        state, nxt = random.getstate(), random.random()
+        random.seed(seed); random.gauss(0, 1); random.random()
+        got = data._draw(n, fp, jitter, rotation, transform, pair)        # n >= 64: the stream parser
+        assert _same_draws(want[0], got[0]) and _same_draws(want[1], got[1])
+        assert random.getstate() == state and random.random() == nxt
+
+
+def test_word_stream_draws_redraw_a_short_block(monkeypatch):
+    from livae import data
+    monkeypatch.setattr(data, "_DRAW_SLACK", -700)                       # first block too short by construction
+    random.seed(11)
+    want = data._draw_calls(128, 0.5, 4, False, True, True)
+    state = random.getstate()
+    random.seed(11)
+    got = data._draw_stream(128, 0.5, 4, False, True, True)
+    assert _same_draws(want[0], got[0]) and _same_draws(want[1], got[1]) and random.getstate() == state
+    # small batches and DataLoader-worker items (n = 1) keep calling `random`
+    calls = []
+    monkeypatch.setattr(data, "_draw_stream", lambda *a: calls.append(a))
+    data._draw(8, 0.5, 4, False, True, True)
+    assert not calls
+
+
 def test_source_refuses_cpu_and_foreign_transforms():
     from livae import data
     img = np.zeros((64, 64))
