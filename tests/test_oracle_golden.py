@@ -3,13 +3,14 @@
 import hashlib
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import patch as OP
 from oracle import rot_sample as ORS
 from oracle import rvae as O
 from tests.golden.make_golden import synth_image
-from tests.util import check_grads_against_golden, load_golden, rel_l2
+from tests.util import check_grads_against_golden, fp32_noise_floor, load_golden, rel_l2
 
 
 def test_rot_sample_numpy_matches_reference():
@@ -185,3 +186,64 @@ def test_augment_and_paired_rotation_match_reference():
         assert np.abs(got - want).max() < 1e-4, (name, np.abs(got - want).max())
         n += 1
     assert n == 4 + 2 * (10 + 10 + 5)
+
+
+# ---- loss / batch-format branches and further shapes (tests/golden/make_golden_r3.py -> branches.npz) ---------------
+class _Sub:
+    """the entries of one case of branches.npz under their un-prefixed names"""
+
+    def __init__(self, gold, tag):
+        self.gold, self.pre = gold, tag + "/"
+        self.files = [f[len(self.pre):] for f in gold.files if f.startswith(self.pre)]
+
+    def __getitem__(self, k):
+        return self.gold[self.pre + k]
+
+
+def _branch_cases():
+    from tests.golden.make_golden_r3 import RVAE_CASES, VAE_CASES
+    return sorted(RVAE_CASES), sorted(VAE_CASES)
+
+
+@pytest.mark.parametrize("tag", _branch_cases()[0])
+def test_rvae_step_branches_match_reference(tag):
+    """gamma = 0, the diversity loss, canonical_weight = 0, an unpaired batch and a pair without its angle, at latent
+    sizes 2 - 16 and P = 32 / 64: the reference's own trainer (train.py:315-397, loss.py:138-186) against
+    oracle.rvae.rvae_full_step"""
+    from tests.golden.make_golden_r3 import RVAE_CASES, rvae_inputs
+    P, L, B, seed, beta, gamma, div, cw, fmt = RVAE_CASES[tag]
+    g = _Sub(load_golden("branches.npz"), tag)
+    params, x, xr, ang, eps = rvae_inputs(P, L, B, seed)
+    if fmt == "single":
+        xr = ang = None
+    elif fmt == "pair2":
+        ang = None
+    outs, grads = O.rvae_full_step(params, x, xr, ang, eps, beta=beta, gamma=gamma, canonical_weight=cw,
+                                   use_diversity=div)
+    want = float(g["metric/train_loss"])
+    assert abs(float(outs["loss"]) - want) <= 1e-5 * abs(want)
+    assert abs(float(outs["recon_loss"]) - float(g["metric/train_recon_loss"])) <= 1e-5 * float(g["metric/train_recon_loss"])
+    assert abs(float(outs["kld"]) - float(g["metric/train_kld_loss"])) <= 1e-4 * float(g["metric/train_kld_loss"]) + 1e-9
+    assert abs(float(outs["cycle"]) - float(g["metric/train_cycle_loss"])) <= 1e-5
+    if gamma == 0 or fmt != "paired":
+        assert float(outs["cycle"]) == 0.0 and float(g["metric/train_cycle_loss"]) == 0.0
+    # 2e-4 as for the main vectors, or 3x the oracle's own fp32-vs-fp64 distance where that is larger: with two patches of
+    # P = 64 the STN's gradient is a cancelling sum that fp32 itself only defines to 4.5e-4 (the reference sits 7.9e-4 away)
+    floor = fp32_noise_floor(O.rvae_full_step, params, x, xr, ang, eps, beta=beta, gamma=gamma, canonical_weight=cw,
+                             use_diversity=div)
+    check_grads_against_golden(grads, g, rtol={k: max(2e-4, 3.0 * v) for k, v in floor.items()})
+
+
+@pytest.mark.parametrize("tag", _branch_cases()[1])
+def test_vae_step_shapes_match_reference(tag):
+    from tests.golden.make_golden_r3 import VAE_CASES, vae_inputs
+    P, L, B, seed, beta = VAE_CASES[tag]
+    g = _Sub(load_golden("branches.npz"), tag)
+    params, x, eps = vae_inputs(P, L, B, seed)
+    outs, grads = O.vae_full_step(params, x, eps, beta=beta)
+    assert abs(float(outs["loss"]) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert abs(float(outs["recon_loss"]) - float(g["recon_loss"])) <= 1e-5 * float(g["recon_loss"])
+    assert abs(float(outs["kld"]) - float(g["kld"])) <= 1e-4 * abs(float(g["kld"])) + 1e-9
+    assert abs(float(outs["recon"].double().sum()) - float(g["recon_sum"])) <= 1e-5 * float(g["recon_sum"])
+    assert np.abs(outs["mu"].numpy() - g["mu"]).max() < 1e-5
+    check_grads_against_golden(grads, g, rtol=2e-4)
