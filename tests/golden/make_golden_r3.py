@@ -56,6 +56,15 @@ def vae_inputs(P, L, B, seed):
     return params, x, eps
 
 
+def metric_inputs():
+    rng = np.random.default_rng(31)
+    mu = torch.from_numpy(rng.standard_normal((6, 5))).float()
+    logvar = torch.from_numpy(rng.standard_normal((6, 5)) * 0.3 - 1.0).float()
+    a = torch.from_numpy(rng.random((3, 1, 32, 32))).float()
+    b = (a + torch.from_numpy(rng.standard_normal((3, 1, 32, 32))).float() * 0.05).clamp(0, 1)
+    return mu, logvar, a, b
+
+
 def main():
     ref_loader.load()
     from livae.loss import RVAELoss, VAELoss
@@ -93,6 +102,13 @@ def main():
         res[f"{tag}/recon_sum"] = np.array(recon.double().sum().item())
         res[f"{tag}/mu"] = mu.detach().numpy()
         print(tag, float(loss))
+    # livae.metrics.compute_latent_metrics / the pixel part of compute_reconstruction_metrics (metrics.py:116-194)
+    from livae.metrics import compute_latent_metrics, compute_reconstruction_metrics
+    mu, logvar, a, b = metric_inputs()
+    for k, v in compute_latent_metrics(mu, logvar).items():
+        res["metrics/" + k] = np.array(v)
+    for k, v in compute_reconstruction_metrics(a, b).items():
+        res["metrics/" + k] = np.array(v)
     np.savez_compressed(os.path.join(OUT, "branches.npz"), torch_version=torch.__version__, **res)
 
 

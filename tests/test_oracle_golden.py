@@ -247,3 +247,18 @@ def test_vae_step_shapes_match_reference(tag):
     assert abs(float(outs["recon"].double().sum()) - float(g["recon_sum"])) <= 1e-5 * float(g["recon_sum"])
     assert np.abs(outs["mu"].numpy() - g["mu"]).max() < 1e-5
     check_grads_against_golden(grads, g, rtol=2e-4)
+
+
+def test_latent_metric_dictionary_matches_reference():
+    """livae.metrics.compute_latent_metrics is plain tensor arithmetic (no kernels): the reference's values for the same
+    inputs, key for key (metrics.py:153-194).  The pixel metrics of compute_reconstruction_metrics go through the
+    PSNR / SSIM kernels (checked on the GPU in tests/test_gpu_trainer_api.py and against the reference trainer's logged
+    PSNR / SSIM in tests/test_gpu_dropin.py); the reference's values for these inputs are stored next to the latent ones."""
+    from livae.metrics import compute_latent_metrics
+    from tests.golden.make_golden_r3 import metric_inputs
+    g = _Sub(load_golden("branches.npz"), "metrics")
+    mu, logvar, _, _ = metric_inputs()
+    got = compute_latent_metrics(mu, logvar)
+    assert sorted(got) == sorted(k for k in g.files if k.startswith("latent_"))
+    for k, v in got.items():
+        assert abs(v - float(g[k])) <= 1e-6 * max(1.0, abs(float(g[k]))), k
