@@ -57,10 +57,11 @@ def peaks():
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's torch-CPU port of the reference step
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(steps, warmup, sample_b=32):
+def cpu_reference_step_rate(steps, warmup, sample_b=32, max_seconds=None):
     """Times the reference algorithm's CPU path (oracle/rvae.py restatement: the same ATen CPU ops
     the reference's nn.Modules dispatch to) on a bounded sample of the workload: batches of
-    `sample_b` 128x128 patches.  /root/reference does not exist on the GPU box, so the port is used."""
+    `sample_b` 128x128 patches.  /root/reference does not exist on the GPU box, so the port is used.
+    -> (patches/s, ms per step, batch, steps timed); `max_seconds` ends the timed loop early (whole steps only)."""
     from oracle import rvae as O
     torch.manual_seed(0)
     params = O.make_params(O.rvae_param_shapes(P, LATENT), seed=1234, stn_head_std=0.5)
@@ -83,10 +84,14 @@ def cpu_reference_step_rate(steps, warmup, sample_b=32):
     for i in range(warmup):
         one(i + 1)
     t0 = time.perf_counter()
+    done = 0
     for i in range(steps):
         one(warmup + i + 1)
+        done += 1
+        if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
+            break
     dt = time.perf_counter() - t0
-    return sample_b * steps / dt, dt / steps * 1e3, sample_b
+    return sample_b * done / dt, dt / done * 1e3, sample_b, done
 
 
 def run_reference(args):
@@ -102,7 +107,7 @@ def run_reference(args):
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-    rate, ms, sb = cpu_reference_step_rate(steps, warm)
+    rate, ms, sb, steps = cpu_reference_step_rate(steps, warm, max_seconds=240.0)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -685,8 +690,12 @@ def main():
             if best:
                 gb["speedup_vs_best_aten"] = value / best
         if world == 1 and not args.no_cpu_baseline:
-            nb = 40                     # ~6 s of CPU work on the box's 16 threads
-            rate, cms, sb = cpu_reference_step_rate(nb, 2)
+            # ~6 s of CPU work on all the host threads this process may use (a launcher may have exported OMP_NUM_THREADS=1)
+            try:
+                torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+            except Exception:
+                pass
+            rate, cms, sb, nb = cpu_reference_step_rate(40, 2, max_seconds=20.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{nb} steps of batch {sb} of the same FULL step, oracle torch-CPU port, "
                                               f"{cms:.0f} ms/step ({nb * cms / 1e3:.1f} s of CPU work after 2 warm-up steps)"}

@@ -59,7 +59,7 @@ def run_port(steps, batch):
     import torch
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     import bench
-    rate, ms, _ = bench.cpu_reference_step_rate(steps, 1, sample_b=batch)
+    rate, ms, _, _ = bench.cpu_reference_step_rate(steps, 1, sample_b=batch)
     print(json.dumps({"patches_per_s": rate, "ms_per_step": ms, "threads": torch.get_num_threads(),
                       "torch": torch.__version__}))
 
