@@ -1,5 +1,6 @@
 """CPU: the part of the reference's own test-suite that needs no GPU (tests/test_filter.py 7 tests,
-tests/test_utils.py 4 tests), against the drop-in package.
+tests/test_utils.py 4 tests, and the 10 host-only cases of tests/test_train.py: rotation statistics, MetricLogger, atom
+position accuracy, the scalar TensorBoard helper), against the drop-in package.
 
 * In the build container the reference's test FILES are collected and run as they lie under /root/reference/tests, with
   this repo's `livae` first on the path (skipped where the tree does not exist).  test_utils.py's noise-fallback test
@@ -43,6 +44,17 @@ def test_reference_utils_tests_pass_against_the_dropin():
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     r = _run_reference_tests(["test_utils.py"], extra=["-k", "fallback"])
     assert r.returncode in (0, 1) and "error" not in r.stdout.lower(), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+HOST_ONLY_TRAINER_CASES = ("TestGetRotationStats or TestMetricLogger or TestComputeAtomPositionAccuracy "
+                           "or TestLogScalarMetricsTensorboard")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree only exists in the build container")
+def test_reference_trainer_host_cases_pass_against_the_dropin():
+    # the other 24 cases of test_train.py run this package's kernels: tests/test_gpu_trainer_api.py restates them
+    r = _run_reference_tests(["test_train.py"], extra=["-k", HOST_ONLY_TRAINER_CASES])
+    assert r.returncode == 0 and "10 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 # ---- the same behaviours, restated (filter.py:42-232, utils.py:12-82 of the reference) ----------------------------
@@ -110,3 +122,58 @@ def test_lattice_constant_falls_back_without_a_peak():
     from livae.utils import estimate_lattice_constant
     # a constant image has no radial-profile peak at all: the documented fallback (utils.py:12-82) is 15.0
     assert estimate_lattice_constant(np.ones((128, 128))) == 15.0
+
+
+# ---- host-only trainer helpers (train.py:559-580, 856-936 of the reference) ------------------------------------------
+def test_metric_logger_accumulates_and_averages():
+    import torch
+    from livae.train import MetricLogger
+    log = MetricLogger()
+    assert len(log.metrics) == 0
+    log.update(loss=1.0, acc=0.5)
+    log.update(loss=torch.tensor(3.0))                               # tensors are read with .item()
+    assert log.metrics["loss"] == [1.0, 3.0] and log.metrics["acc"] == [0.5]
+    assert log.get_averages() == {"loss": 2.0, "acc": 0.5}
+    log.reset()
+    assert len(log.metrics) == 0 and log.get_averages() == {}
+
+
+def test_rotation_stats_in_degrees():
+    import torch
+    from livae.train import get_rotation_stats
+    rot = torch.randn(7, 2, generator=torch.Generator().manual_seed(0))
+    assert isinstance(get_rotation_stats(rot), tuple) and len(get_rotation_stats(rot)) == 2
+    mean, std = get_rotation_stats(torch.tensor([[0.0, 2.0]] * 6))    # (cos, sin) = (0, 2): 90 degrees, no spread
+    assert abs(mean - 90.0) < 1e-4 and std < 1e-4
+    mean, std = get_rotation_stats(torch.tensor([[1.0, 1.0], [1.0, -1.0]]))
+    assert abs(mean) < 1e-4 and abs(std - 45.0 * 2 ** 0.5) < 1e-3     # +-45 degrees, unbiased std
+    mean, std = get_rotation_stats(torch.randn(100, 2, generator=torch.Generator().manual_seed(1)))
+    assert -180.0 <= mean <= 180.0 and std > 0
+
+
+def test_atom_position_accuracy_and_scalar_logging():
+    import torch
+    from livae.train import compute_atom_position_accuracy, log_scalar_metrics_tensorboard
+    a = torch.zeros(1, 9, 9)
+    b = torch.zeros(1, 9, 9)
+    for (y, x), (yy, xx) in (((2, 2), (2, 2)), ((6, 6), (6, 5))):      # the second atom comes back one pixel off
+        a[0, y, x] = 1.0
+        b[0, yy, xx] = 1.0
+    m = compute_atom_position_accuracy(a, b, lattice_spacing=3.0, threshold_ratio=0.5)
+    assert m["n_original_atoms"] == 2 and m["n_reconstructed_atoms"] == 2 and m["atom_detection_rate"] == 1.0
+    assert m["atom_position_accuracy"] == 1.0 and m["atom_mean_position_error"] == pytest.approx(0.5)
+    m = compute_atom_position_accuracy(a, torch.zeros(1, 9, 9), lattice_spacing=3.0)
+    assert m["atom_detection_rate"] == 0.0 and m["n_reconstructed_atoms"] == 0 and m["atom_mean_position_error"] == float("inf")
+    with pytest.raises(ValueError):
+        compute_atom_position_accuracy(a, b, lattice_spacing=0.0)
+
+    class Writer:
+        def __init__(self):
+            self.rows = []
+
+        def add_scalar(self, tag, value, step):
+            self.rows.append((tag, value, step))
+
+    w = Writer()
+    log_scalar_metrics_tensorboard(w, {"x": 1.0, "y": 2.0}, global_step=9, prefix="val/")
+    assert sorted(w.rows) == [("val/x", 1.0, 9), ("val/y", 2.0, 9)]
