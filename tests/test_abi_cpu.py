@@ -138,3 +138,36 @@ def test_halo_tile_geometry_chooser(libpath):
                 assert tiles == tiles_at(H, W, sx, bw) == min(tiles_at(H, W, sx, b) for b in range(16, 21))
                 assert -(-W // tw) * tw >= W and -(-H // th) * th >= H          # the tiles cover the grid
     assert L.livae_tc_halo_geometry(0, 8, 2, None, None, None, None) != 0          # argument errors are reported, not crashed on
+
+
+def test_benchmarked_layers_are_eligible_for_the_tensor_core_kernels(libpath):
+    """host arithmetic behind the C ABI (no device work): every GEMM-shaped layer of the benchmarked rVAE (C3: P = 128,
+    B = 2048; reference model.py:185-237, 262-300, 330-372) is accepted by the tcgen05 kernels' eligibility checks, so the
+    `tc` engine cannot silently run the exact SIMT path there; shapes outside the kernels' channel rules are refused;
+    the weight-gradient workspace is the fp32 gradient itself"""
+    import ctypes as C
+    from livae import _lib
+    L = _lib.lib()
+
+    def tc(B, H, W, Ci, Co, k, s, p):
+        d = _lib.TcConvDesc(B, H, W, Ci, Co, k, k, s, p, 0, 0)
+        return L.livae_tc_conv_supported(C.byref(d)), L.livae_tc_wgrad_ws_bytes(C.byref(d))
+
+    for B in (2048, 256, 8):
+        # encoder c2 - c4: Conv2d(k 4, s 2, p 1); decoder d1, d2: 3 x 3 over the reflection-padded up-sampled map
+        for H, Ci, Co, k, s, p in ((64, 32, 64, 4, 2, 1), (32, 64, 128, 4, 2, 1), (16, 128, 256, 4, 2, 1),
+                                   (18, 256, 128, 3, 1, 0), (34, 128, 64, 3, 1, 0), (66, 64, 32, 3, 1, 0)):
+            ok, ws = tc(B, H, H, Ci, Co, k, s, p)
+            assert ok == 1 and ws == Co * Ci * k * k * 4, (B, H, Ci, Co)
+        assert L.livae_tc_conv5pool_supported(B, 64, 64, 16, 32) == 1          # STN conv2 + pool on the 64 x 64 pooled map
+        assert L.livae_upfold_supported(B, 32, 32, 64, 32) == 1                 # d3 folded onto its 32 x 32 input
+        assert L.livae_tc_dgrad_s2blk_supported(64, 64, 32, 64) == 1            # encoder c2 data gradient, block form
+    assert L.livae_tc_conv5pool_wgrad_ws_bytes(16, 32) >= 32 * 16 * 25 * 4
+    assert L.livae_upfold_wgrad_ws_bytes(64, 32) >= 32 * 64 * 9 * 4
+    # refused: channel counts the MMA tiling has no layout for, and the 5-channel case of the exact engine's tests
+    assert tc(8, 7, 7, 3, 5, 3, 1, 0)[0] == 0
+    assert tc(8, 32, 32, 48, 64, 3, 1, 1)[0] == 0
+    assert L.livae_tc_conv5pool_supported(8, 64, 64, 3, 32) == 0
+    # scratch sizes the Python side allocates from are positive and stable across calls
+    assert L.livae_elbo_scratch_floats() == L.livae_elbo_scratch_floats() > 0
+    assert L.livae_l2norm_scratch_floats() > 0 and L.livae_ssim_box_ws_floats(2048, 128) > 0
