@@ -171,3 +171,48 @@ def test_benchmarked_layers_are_eligible_for_the_tensor_core_kernels(libpath):
     # scratch sizes the Python side allocates from are positive and stable across calls
     assert L.livae_elbo_scratch_floats() == L.livae_elbo_scratch_floats() > 0
     assert L.livae_l2norm_scratch_floats() > 0 and L.livae_ssim_box_ws_floats(2048, 128) > 0
+
+
+def _call_with(L, _lib, name, size, tc_desc):
+    import ctypes as C
+    args, keep = [], []
+    for c in _lib._SIGS[name]:
+        if c in "ps":
+            args.append(None)
+        elif c in "il":
+            args.append(size)
+        elif c == "f":
+            args.append(1.0)
+        elif c == "t":
+            keep.append(_lib.TcConvDesc(*tc_desc)); args.append(C.byref(keep[-1]))
+        else:
+            keep.append(_lib.ConvDesc()); args.append(C.byref(keep[-1]))
+    rc = getattr(L, name)(*args)
+    return rc, (L.livae_last_error().decode(errors="replace") if rc else "")
+
+
+def test_argument_errors_and_empty_problems_at_the_c_abi(libpath):
+    """Error behaviour of every int-returning entry point, checked without a device: argument validation runs before any
+    CUDA call, so (a) NULL device pointers with non-empty sizes are refused with rc < 0 and a message that names the
+    function, never launched; (b) an empty problem (all sizes 0) is either a no-op (rc 0) or an argument error -- never a
+    CUDA call (rc > 0 is a cudaError_t); nothing crashes."""
+    from livae import _lib
+    L = _lib.lib()
+    noop = []
+
+    def names_it(msg, name):
+        # "<launcher>: what is wrong"; the ROI gather shares the sub-pixel gather's launcher and reports under its name
+        who = msg.split(":")[0]
+        return bool(msg) and (who in name or "_".join(who.split("_")[:2]) in name)
+
+    for name in _lib._SIGS:
+        rc, msg = _call_with(L, _lib, name, 0, (0,) * 11)
+        assert rc <= 0, (name, rc, msg)
+        if rc == 0:
+            noop.append(name)
+        else:
+            assert names_it(msg, name), (name, msg)
+        rc, msg = _call_with(L, _lib, name, 64, (8, 32, 32, 64, 64, 3, 3, 1, 1, 0, 0))
+        assert rc < 0 and names_it(msg, name), (name, rc, msg)
+    # the tensor-core entry points treat an empty batch as nothing to do
+    assert {"livae_tc_conv", "livae_tc_conv_dgrad", "livae_tc_conv_wgrad", "livae_upfold_fwd"} <= set(noop)
