@@ -15,8 +15,9 @@ import torch.nn as nn
 from . import ops, tc
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
 
-# Convolution engine: "tc" = tcgen05/TMA tensor cores with bf16 storage between layers (default;
-# parity class 1e-2, north_star "bf16 GEMM inputs"), "f32" = exact fp32 SIMT engine (1e-4).
+# Convolution engine: "tc" = tcgen05/TMA tensor cores with bf16 storage between layers (default; north_star's "bf16 GEMM
+# inputs": ELBO 1e-3, reconstructions 1e-2, gradients max(1e-2, operand-rounding floor) -- livae/tc.py),
+# "f32" = exact fp32 SIMT engine (1e-4 class).
 _ENGINE = "tc"
 
 
