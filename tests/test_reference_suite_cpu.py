@@ -25,8 +25,10 @@ PKG = os.path.join(ROOT, "li-vae_b200")
 
 def _run_reference_tests(files, extra=()):
     env = dict(os.environ, PYTHONPATH=PKG, PYTHONDONTWRITEBYTECODE="1")
-    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", "/tmp", *extra,
-           *[os.path.join(REF_TESTS, f) for f in files]]
+    # the reference's tests draw their noise from numpy's GLOBAL generator without seeding it (SURVEY section 4 calls one of
+    # them flaky for that reason; another failed here once in five runs): seed it before pytest starts, in that process
+    argv = ["-q", "-p", "no:cacheprovider", "--rootdir", "/tmp", *extra, *[os.path.join(REF_TESTS, f) for f in files]]
+    cmd = [sys.executable, "-c", f"import sys, numpy, pytest; numpy.random.seed(12345); sys.exit(pytest.main({argv!r}))"]
     return subprocess.run(cmd, cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
 
 
@@ -38,8 +40,8 @@ def test_reference_filter_tests_pass_against_the_dropin():
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree only exists in the build container")
 def test_reference_utils_tests_pass_against_the_dropin():
-    # the three seeded-by-construction tests must pass; the noise-fallback test draws an unseeded image and fails
-    # against the reference itself for some draws, so it is only required not to ERROR
+    # the three lattice tests must pass; the noise-fallback test fails against the reference itself for some draws of its
+    # noise image (11.64 instead of 15.0 in SURVEY's probe), so it is only required not to ERROR
     r = _run_reference_tests(["test_utils.py"], extra=["-k", "not fallback"])
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     r = _run_reference_tests(["test_utils.py"], extra=["-k", "fallback"])
