@@ -155,6 +155,57 @@ def test_peak_local_max_semantics():
     assert get_clean_peaks(img, min_distance=4).tolist() == [[10, 10], [25, 30]]
 
 
+def _peak_local_max_loops(img, min_distance, threshold_rel=None):
+    """scikit-image 0.25.2 (the reference's pinned version, uv.lock) `peak_local_max(image, min_distance, threshold_rel)`
+    with its defaults, written out as loops from its published algorithm -- `_get_peak_mask` (pixel equals the maximum of
+    its (2d+1)^2 window, edges replicated; strictly above max(image.min(), threshold_rel * image.max())),
+    `_exclude_border` (d pixels on every side), `_get_high_intensity_peaks` (stable sort by falling intensity) and
+    `ensure_spacing` (walk the sorted list; an accepted peak rejects every other candidate at Chebyshev distance < d)."""
+    h, w = img.shape
+    d = int(min_distance)
+    thr = img.min()
+    if threshold_rel is not None:
+        thr = max(thr, threshold_rel * img.max())
+    cand = []
+    for y in range(d, h - d):
+        for x in range(d, w - d):
+            win = img[max(y - d, 0):y + d + 1, max(x - d, 0):x + d + 1]      # inside the border the window is never clipped
+            if img[y, x] == win.max() and img[y, x] > thr:
+                cand.append((y, x))
+    cand.sort(key=lambda p: -img[p])                                        # list.sort is stable: row-major among equals
+    rejected, out = set(), []
+    for i, p in enumerate(cand):
+        if i in rejected:
+            continue
+        out.append(p)
+        for j, q in enumerate(cand):
+            if j != i and max(abs(p[0] - q[0]), abs(p[1] - q[1])) < d:
+                rejected.add(j)
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+
+
+def test_peak_local_max_equals_the_written_out_algorithm():
+    """the vectorised peak finder against the loop restatement above on noisy lattices, quantised images (plateaus and
+    exact ties) and degenerate inputs; scikit-image itself is not installed, so this pins the implementation to a second,
+    independently written statement of the documented algorithm rather than to the library"""
+    from livae.sites import peak_local_max
+    rng = np.random.default_rng(17)
+    yy, xx = np.mgrid[:48, :56].astype(np.float64)
+    lattice = np.cos(2 * np.pi * xx / 9.0) * np.cos(2 * np.pi * yy / 7.0)
+    cases = [(lattice + rng.normal(0, 0.2, lattice.shape), 3, 0.01),
+             (lattice + rng.normal(0, 0.05, lattice.shape), 2, 0.3),
+             (np.round(rng.random((40, 40)) * 4) / 4, 2, 0.01),              # heavy ties and plateaus
+             (np.round(rng.random((30, 33)) * 3), 1, None),
+             (rng.random((25, 25)), 4, None),
+             (rng.random((12, 12)), 5, 0.5),                                  # border wider than most of the image
+             (np.full((9, 9), 2.5), 2, 0.01)]                                 # constant image: no peaks
+    for img, d, tr in cases:
+        got = peak_local_max(img, min_distance=d, threshold_rel=tr)
+        want = _peak_local_max_loops(img, d, tr)
+        assert got.shape == want.shape and np.array_equal(got, want), (img.shape, d, tr, len(got), len(want))
+    assert len(_peak_local_max_loops(cases[0][0], 3, 0.01)) > 20
+
+
 def _tiny_dataset(kind, transform):
     from livae import data as D
     rng = np.random.default_rng(3)
