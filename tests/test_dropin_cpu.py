@@ -2,6 +2,7 @@
 against vectors produced by the reference (tests/golden/make_golden_r2.py), and the DataLoader-worker recipe
 mechanism of livae.data (workers produce recipes; the pixels are made on the GPU in the main process)."""
 import os
+import sys
 import random
 
 import numpy as np
@@ -293,3 +294,40 @@ def test_tensorboard_helpers_signature():
     w = W()
     log_scalar_metrics_tensorboard(w, {"a": 1.0, "b": 2.0}, 7, prefix="train/")
     assert w.rows == [("train/a", 1.0, 7), ("train/b", 2.0, 7)]
+
+
+def _h5_expectations_hold(load, fake):
+    for contents, name, want in fake.cases():
+        fake.FILES["f.h5"] = contents
+        if isinstance(want, type):
+            with pytest.raises(want):
+                load("f.h5", name)
+        else:
+            got = load("f.h5", name)
+            assert got.shape == contents[want].shape and np.array_equal(got, contents[want]), (name, want)
+
+
+def test_load_image_from_h5_dataset_selection(monkeypatch):
+    """utils.py:111-185 of the reference: explicit path, base-name search, auto-detection (preferred names, then area,
+    ties in visiting order), KeyError without a 2-D dataset -- through an in-memory stand-in for h5py (not installed here)"""
+    from tests import fake_h5py
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py.install())
+    from livae.utils import load_image_from_h5
+    _h5_expectations_hold(load_image_from_h5, fake_h5py)
+    _h5_expectations_hold(lambda p, n: load_image_from_h5(__import__("pathlib").Path(p), n), fake_h5py)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_h5_expectations_are_the_references_behaviour():
+    """the same table against the reference's own load_image_from_h5 (its process: the two packages share a name)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests import fake_h5py as F; F.install()\n"
+            "from oracle import ref_loader; ref_loader.load()\n"
+            "from livae.utils import load_image_from_h5\n"
+            "assert load_image_from_h5.__module__ == 'livae.utils' and '/root/reference' in sys.modules['livae'].__file__\n"
+            "from tests.test_dropin_cpu import _h5_expectations_hold\n"
+            "_h5_expectations_hold(load_image_from_h5, F); print('REF_OK')\n") % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "REF_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
