@@ -487,6 +487,29 @@ class _DeviceDataset(Dataset):
         st["_src"] = None               # device tensors stay in the process that owns the GPU
         return st
 
+    # ---- inspection plots of the reference's dataset classes (data.py:252-289, 562-612): host-side, matplotlib ----
+    def _window(self, img_idx, coords, size, offset):
+        """the displayed region of image `img_idx` and the sites that fall inside it, in the region's own coordinates
+        -> (image view, sites, boolean mask over `coords`)"""
+        img = self.images[img_idx]
+        coords = np.asarray(coords).reshape(-1, 2)
+        if size is None:
+            return img, coords, np.ones(len(coords), dtype=bool)
+        y0, x0 = offset
+        inside = ((coords[:, 0] >= y0) & (coords[:, 0] < y0 + size) & (coords[:, 1] >= x0) & (coords[:, 1] < x0 + size))
+        return img[y0:y0 + size, x0:x0 + size], coords[inside] - np.array([y0, x0]), inside
+
+    @staticmethod
+    def _show(img, groups, figsize, marker_size):
+        import matplotlib.pyplot as plt            # not needed anywhere else in the package
+        plt.figure(figsize=figsize)
+        plt.imshow(img, cmap="gray")
+        for pts in groups:
+            if len(pts) > 0:
+                plt.scatter(pts[:, 1], pts[:, 0], s=marker_size, c="red", marker="o", alpha=0.8)
+        plt.axis("off")
+        plt.show()
+
 
 class PatchDataset(_DeviceDataset):
     """Patches centred on detected atoms (reference data.py:151-250): same constructor, attributes
@@ -507,6 +530,18 @@ class PatchDataset(_DeviceDataset):
             print(f"Detected {len(coords)} atoms, {int(ok.sum())} after edge exclusion.")
             self.atom_coords.append(coords[ok])
         self._register()
+
+    def plot_peaks(self, img_idx: int, size: int | None = None, offset: tuple[int, int] = (0, 0)) -> None:
+        """detected atoms over image `img_idx`, optionally only a size x size region at `offset` = (y, x)
+        (reference data.py:252-289)"""
+        img, pts, _ = self._window(img_idx, self.atom_coords[img_idx], size, offset)
+        # the reference scatters unconditionally: an empty region still draws (an empty) scatter
+        import matplotlib.pyplot as plt
+        plt.figure(figsize=(6, 6))
+        plt.imshow(img, cmap="gray")
+        plt.scatter(pts[:, 1], pts[:, 0], s=30, c="red", marker="o", alpha=0.8)
+        plt.axis("off")
+        plt.show()
 
 
 class AdaptiveLatticeDataset(_DeviceDataset):
@@ -531,6 +566,13 @@ class AdaptiveLatticeDataset(_DeviceDataset):
             self.sample_coords.append(sites)
             self.labels.append(labels)
         self._register()
+
+    def plot_lattice(self, img_idx: int, size: int | None = None, offset: tuple[int, int] = (0, 0)) -> None:
+        """lattice sites over image `img_idx` -- sites with an atom, then empty sites, as two scatters in the same style
+        (reference data.py:562-612)"""
+        img, pts, inside = self._window(img_idx, self.sample_coords[img_idx], size, offset)
+        labels = np.asarray(self.labels[img_idx])[inside]
+        self._show(img, [pts[labels == 1], pts[labels == 0]], (8, 8), 50)
 
     @classmethod
     def from_sites(cls, images, sample_coords, patch_size: int, padding: int = 48, transform=default_transform,

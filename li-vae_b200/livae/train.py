@@ -632,7 +632,8 @@ def evaluate_rotation_invariance(model, images: torch.Tensor, angles=(0, 45, 90,
     """Latent variance / reconstruction error / angle error of the model over rotated copies of a few images
     (reference train.py:680-788).  The rotations (TF.rotate, bilinear, fill 0) run in the `rotate_crop` kernel.
     Deviation, on purpose: the reference reads the predicted angle as atan2(theta[0,1], theta[0,0]), which raises
-    IndexError for the real RVAE's theta [B,1]; a one-column theta is taken as the angle itself."""
+    IndexError for the real RVAE's theta [B,1]; a one-column theta is taken as the angle itself.
+    `device` defaults to cuda (the reference's default is cpu; this package has no CPU path)."""
     model.eval()
     angles = [float(a) for a in angles]
     if images.dim() != 4:

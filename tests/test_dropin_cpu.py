@@ -331,3 +331,81 @@ def test_h5_expectations_are_the_references_behaviour():
             "_h5_expectations_hold(load_image_from_h5, F); print('REF_OK')\n") % root
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
     assert r.returncode == 0 and "REF_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_dataset_plot_helpers_draw_the_sites_of_the_region(monkeypatch):
+    """PatchDataset.plot_peaks / AdaptiveLatticeDataset.plot_lattice (reference data.py:252-289, 562-612) with a
+    recording stand-in for matplotlib.pyplot (matplotlib is not installed here): the cropped image, the sites inside the
+    region in region coordinates, atoms and empty sites as separate scatters"""
+    import types
+    from livae import data as D
+    calls = []
+    plt = types.ModuleType("matplotlib.pyplot")
+    for name in ("figure", "imshow", "scatter", "axis", "show"):
+        setattr(plt, name, lambda *a, _n=name, **k: calls.append((_n, a, k)))
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+
+    img = np.arange(40.0 * 50).reshape(40, 50)
+    sites = np.array([[5.0, 6.0], [12.5, 30.0], [20.0, 21.0], [35.0, 45.0]])
+    ds = D.AdaptiveLatticeDataset.from_sites([img], [sites], patch_size=8, padding=2,
+                                             labels=[np.array([1, 0, 1, 0])])
+    ds.plot_lattice(0, size=20, offset=(4, 5))
+    kinds = [c[0] for c in calls]
+    assert kinds == ["figure", "imshow", "scatter", "axis", "show"]       # no empty site in this region: no second scatter
+    assert calls[0][2] == {"figsize": (8, 8)} and np.array_equal(calls[1][1][0], img[4:24, 5:25])
+    (xs, ys), kw = calls[2][1], calls[2][2]                      # atoms inside the region: (5,6) and (20,21)
+    assert list(xs) == [1.0, 16.0] and list(ys) == [1.0, 16.0] and kw["s"] == 50 and kw["c"] == "red"
+    calls.clear()
+    ds.plot_lattice(0)                                           # whole image: two atoms, two empty sites
+    assert [len(c[1][0]) for c in calls if c[0] == "scatter"] == [2, 2] and calls[1][1][0].shape == (40, 50)
+
+    calls.clear()
+    pd_ = D.PatchDataset.__new__(D.PatchDataset)                 # plot helper only: skip the site finding
+    pd_.images, pd_.atom_coords = [img], [np.array([[5, 6], [30, 40]])]
+    pd_.plot_peaks(0, size=16, offset=(0, 0))
+    assert [c[0] for c in calls] == ["figure", "imshow", "scatter", "axis", "show"]
+    assert calls[0][2] == {"figsize": (6, 6)} and list(calls[2][1][0]) == [6] and list(calls[2][1][1]) == [5]
+    assert calls[2][2]["s"] == 30 and calls[3][1] == ("off",)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_public_surface_and_signatures_match_the_reference_modules():
+    """every public function, class and public method (plus __init__ / forward / __getitem__) defined in the reference's
+    seven modules exists here under the same name with the same positional parameter names in the same order; trailing
+    extra parameters (train_rvae_one_epoch's reduce_grads) are allowed.  Read from the reference's SOURCE (ast): the two
+    packages share the name `livae` and cannot be imported side by side."""
+    import ast
+    import importlib
+    import inspect
+
+    def ref_params(fn):
+        return [a.arg for a in fn.args.posonlyargs + fn.args.args]
+
+    def our_params(obj):
+        ps = inspect.signature(obj).parameters.values()
+        return [p.name for p in ps if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+    problems = []
+    for mod in ("data", "loss", "model", "train", "utils", "filter", "metrics"):
+        tree = ast.parse(open(os.path.join(REF, "src", "livae", mod + ".py")).read())
+        ours = importlib.import_module("livae." + mod)
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and not node.name.startswith("_"):
+                obj = getattr(ours, node.name, None)
+                if obj is None or our_params(obj)[:len(ref_params(node))] != ref_params(node):
+                    problems.append((mod, node.name))
+            elif isinstance(node, ast.ClassDef) and not node.name.startswith("_"):
+                cls = getattr(ours, node.name, None)
+                if cls is None:
+                    problems.append((mod, node.name))
+                    continue
+                for f in node.body:
+                    if isinstance(f, ast.FunctionDef) and (f.name in ("__init__", "forward", "__getitem__", "__len__")
+                                                           or not f.name.startswith("_")):
+                        m = getattr(cls, f.name, None)
+                        if m is None or our_params(m)[:len(ref_params(f))] != ref_params(f):
+                            problems.append((mod, node.name + "." + f.name))
+    assert not problems, problems
