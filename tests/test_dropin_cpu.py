@@ -409,3 +409,25 @@ def test_public_surface_and_signatures_match_the_reference_modules():
                         if m is None or our_params(m)[:len(ref_params(f))] != ref_params(f):
                             problems.append((mod, node.name + "." + f.name))
     assert not problems, problems
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_every_livae_import_of_every_reference_script_resolves():
+    """not only the three training scripts: each `from livae.<module> import <names>` anywhere in the reference's scripts/,
+    top-level helper scripts and verify_*.py (Ray Tune drivers, comparison / t-SNE / visualisation scripts included) names
+    something this package provides"""
+    import ast
+    import glob
+    import importlib
+    files = sorted(glob.glob(os.path.join(REF, "scripts", "*.py")) + glob.glob(os.path.join(REF, "*.py")))
+    assert len(files) >= 10
+    missing, seen = [], 0
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.ImportFrom) and node.module and node.module.split(".")[0] == "livae":
+                mod = importlib.import_module(node.module)
+                for a in node.names:
+                    seen += 1
+                    if not hasattr(mod, a.name):
+                        missing.append((os.path.basename(path), node.module, a.name))
+    assert seen >= 40 and not missing, missing
