@@ -216,3 +216,18 @@ def test_argument_errors_and_empty_problems_at_the_c_abi(libpath):
         assert rc < 0 and names_it(msg, name), (name, rc, msg)
     # the tensor-core entry points treat an empty batch as nothing to do
     assert {"livae_tc_conv", "livae_tc_conv_dgrad", "livae_tc_conv_wgrad", "livae_upfold_fwd"} <= set(noop)
+
+
+def test_the_stub_printed_in_integration_md_binds(libpath):
+    """the reference-side ctypes stub INTEGRATION.md shows a maintainer is executed as written (library path substituted):
+    it binds, its argument list has the header's arity, and livae_last_error comes back as bytes"""
+    import ctypes
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\nimport ctypes, torch\n(.*?)```", doc, re.S).group(1)
+    assert 'ctypes.CDLL("liblivae_sm100.so")' in code
+    ns = {}
+    exec("import ctypes, torch\n" + code.replace('ctypes.CDLL("liblivae_sm100.so")', f"ctypes.CDLL({libpath!r})"), ns)
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "livae_b200.h")).read(), flags=re.S)
+    params = re.search(r"\blivae_rot_sample_fwd\s*\((.*?)\)\s*;", hdr, re.S).group(1)
+    assert len(ns["_lib"].livae_rot_sample_fwd.argtypes) == len([p for p in params.split(",") if p.strip()])
+    assert isinstance(ns["_lib"].livae_last_error(), bytes) and callable(ns["rotate"])
