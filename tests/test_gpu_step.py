@@ -471,7 +471,9 @@ def test_cuda_graph_step_equals_eager_step():
     # (round 2's last GPU session: 3 of 4 runs of the epoch test below at a mean of 2.7e-5 on the STN's first layer, the
     # fourth below 2e-5), so the bounds are stated against the distance Adam CAN travel, lr * steps: what these tests are
     # for -- a stale static input, warm-up steps leaking into the state, a view of graph memory -- moves parameters by
-    # that distance itself (and the loss by percent), the noise by a fraction of a percent of it.
+    # that distance itself (two leaked warm-up steps: 0.25 - 0.67 of it on most elements; a wrong batch: ~0.35 of it on
+    # average) and the loss by percent, the noise by a fraction of a percent of it (0.34 % in the runs above; only the first
+    # tensor in state_dict order was ever seen failing, so the bound leaves a 30x margin for the others).
     _assert_same_trajectory(l0, l1, p0, p1, travel=1e-3 * 3)
 
 
@@ -481,7 +483,7 @@ def _assert_same_trajectory(l0, l1, p0, p1, travel):
     for k in p0:
         diff = (p0[k] - p1[k]).abs()
         stats = (k, float(diff.max()), float(diff.mean()), float((diff > 0.25 * travel).float().mean()))
-        assert float(diff.mean()) <= 0.05 * travel, stats                          # the bulk: within 5 % of the travel
+        assert float(diff.mean()) <= 0.1 * travel, stats                           # the bulk: within 10 % of the travel
         assert float((diff > 0.25 * travel).float().mean()) <= 1e-2, stats        # at most 1 % of a tensor's elements stray
         assert float(diff.max()) <= 2.05 * travel, stats                          # nothing beyond sign flips on every step
 
