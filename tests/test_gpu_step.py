@@ -478,14 +478,23 @@ def test_cuda_graph_step_equals_eager_step():
 
 
 def _assert_same_trajectory(l0, l1, p0, p1, travel):
+    """bounds from tools/trajectory_noise_cpu.py (profiles/r02z_trajectory_noise_cpu.txt): with bf16 GEMM operands and 1e-5
+    gradient noise the worst tensor ends 1.0 % of the travel apart on average, single elements up to 0.9 of it (one of a
+    128-element bias beyond a quarter)"""
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 1e-3 * abs(a), (l0, l1)
+    num = den = 0.0
     for k in p0:
         diff = (p0[k] - p1[k]).abs()
-        stats = (k, float(diff.max()), float(diff.mean()), float((diff > 0.25 * travel).float().mean()))
-        assert float(diff.mean()) <= 0.1 * travel, stats                           # the bulk: within 10 % of the travel
-        assert float((diff > 0.25 * travel).float().mean()) <= 1e-2, stats        # at most 1 % of a tensor's elements stray
-        assert float(diff.max()) <= 2.05 * travel, stats                          # nothing beyond sign flips on every step
+        n = diff.numel()
+        stray = int((diff > 0.25 * travel).sum())
+        stats = (k, n, float(diff.max()), float(diff.mean()), stray)
+        num += float(diff.double().sum()); den += n
+        assert float(diff.max()) <= 2.05 * travel, stats                           # nothing beyond sign flips on every step
+        if n >= 64:                                                                # (a 2-element bias has no 'bulk')
+            assert float(diff.mean()) <= 0.1 * travel, stats                       # the bulk: within 10 % of the travel
+            assert stray <= max(2, int(0.02 * n)), stats                           # a few near-zero-gradient elements stray
+    assert num / den <= 0.1 * travel, (num / den, travel)                          # all parameters together
 
 
 @pytest.mark.tc_engine
